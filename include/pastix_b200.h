@@ -1,0 +1,161 @@
+/*
+ * pastix_b200.h — C ABI of the B200-native sopalin numeric phase.
+ *
+ * This is the drop-in boundary for ONE path of PaStiX 5.2.2.16: the numeric
+ * factorization (API_TASK_NUMFACT) and the up_down triangular solve
+ * (API_TASK_SOLVE).  Everything above it (ordering, symbolic factorization,
+ * blend analysis, the pastix()/pastix_fortran() task driver) stays the
+ * reference's unchanged host code; this library consumes the SolverMatrix
+ * that analysis produced.  Plain pointers and sizes only; all index arrays
+ * are int64_t (the reference built with -DINTSIZE64; a 32-bit build widens
+ * them in the shim).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/src):
+ *   pb200_create        <- sopalin_init / sopalin_init_smp + CoefMatrix_Allocate
+ *                          (sopalin/src/sopalin_init.c:99,865; coefinit.c:104)
+ *   pb200_assemble      <- CoefMatrix_Init + Csc2solv_cblk
+ *                          (sopalin/src/coefinit.c:237; csc_intern_solve.c:65-125)
+ *   pb200_norm1         <- CscNorm1 (sopalin/src/csc_intern_compute.c:120-176),
+ *                          feeding the threshold of init_struct_sopalin
+ *                          (sopalin/src/sopalin3d.c:586-606)
+ *   pb200_factorize     <- {po,sy,he,ge}_sopalin_thread -> sopalin_smp task loop
+ *                          (sopalin/src/sopalin3d.c:1388, 666-1262): compute_1d =
+ *                          factor_diag + factor_trsm1d + compute_1dgemm/add_contrib_local
+ *                          (compute_diag.c:538, compute_trsm.c:128, sopalin_compute.c:747-1032)
+ *   pb200_inertia       <- inertia count (sopalin/src/sopalin3d.c:1145-1161)
+ *   pb200_solve         <- {po,sy,he,ge}_updo_thread -> up_down_smp
+ *                          (sopalin/src/updo.c:67,114-1664; updo_sendrecv.c:496-639)
+ *   pb200_get_coeftab / pb200_set_coeftab
+ *                       <- SolverCblk.coeftab / .ucoeftab contents
+ *                          (blend/src/solver.h:94-117), so host consumers
+ *                          (Schur, dumps, refinement) keep working
+ *   pb200_destroy       <- CoefMatrix_Free + sopalin_clean (coefinit.c:479)
+ *
+ * Error behaviour: every call returns PB200_SUCCESS (0) or a negative code;
+ * pb200_last_error() gives the message.  There is NO CPU fallback: without a
+ * CUDA device (or with the wrong architecture) pb200_create fails with
+ * PB200_ERR_CUDA.
+ */
+#ifndef PASTIX_B200_H
+#define PASTIX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* arithmetic type — values of API_FLOAT (common/src/api.h: API_REALSINGLE..API_COMPLEXDOUBLE) */
+#define PB200_REALSINGLE    0
+#define PB200_REALDOUBLE    1
+#define PB200_COMPLEXSINGLE 2
+#define PB200_COMPLEXDOUBLE 3
+
+/* factorization — values of API_FACT (common/src/api.h:381-384) */
+#define PB200_FACT_LLT  0
+#define PB200_FACT_LDLT 1
+#define PB200_FACT_LU   2
+#define PB200_FACT_LDLH 3
+
+#define PB200_SUCCESS        0
+#define PB200_ERR_BADARG    -1
+#define PB200_ERR_CUDA      -2
+#define PB200_ERR_NOMEM     -3
+#define PB200_ERR_STATE     -4
+#define PB200_ERR_STRUCT    -5   /* SolverMatrix violates an invariant we rely on */
+
+/*
+ * Flat, read-only view of the reference's SolverMatrix for one process
+ * (blend/src/solver.h:94-168).  Field names follow SolverCblk / SolverBlok.
+ * cblk arrays hold cblknbr entries, except bloknum which holds cblknbr+1
+ * (the sentinel = bloknbr).  Indices are 0-based (baseval 0), rows/columns
+ * are numbered in the permuted ordering.
+ */
+typedef struct pb200_solver_s {
+  int64_t        cblknbr;
+  int64_t        bloknbr;
+  const int64_t *fcolnum;   /* SolverCblk.fcolnum */
+  const int64_t *lcolnum;   /* SolverCblk.lcolnum (inclusive) */
+  const int64_t *bloknum;   /* SolverCblk.bloknum: first blok (the diagonal one) */
+  const int64_t *stride;    /* SolverCblk.stride: leading dimension of the panel */
+  const int64_t *frownum;   /* SolverBlok.frownum */
+  const int64_t *lrownum;   /* SolverBlok.lrownum (inclusive) */
+  const int64_t *cblknum;   /* SolverBlok.cblknum: facing column block */
+  const int64_t *coefind;   /* SolverBlok.coefind: row offset inside the panel */
+} pb200_solver_t;
+
+typedef struct pb200_handle_s pb200_handle_t;
+
+/* summary filled by pb200_info */
+typedef struct pb200_info_s {
+  int64_t n;            /* number of unknowns */
+  int64_t coefnbr;      /* elements in one factor slab (sum stride*width) */
+  int64_t nlevels;      /* elimination-tree levels in the launch schedule */
+  int64_t device_bytes; /* bytes of HBM held by the handle */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t sm_count;
+  int32_t cc_major, cc_minor;
+} pb200_info_t;
+
+const char *pb200_last_error(void);
+const char *pb200_version(void);
+
+/* Build the device-side structures, the level schedule and allocate the
+ * factor slab(s) in HBM. `device` < 0 selects the current CUDA device. */
+int pb200_create(pb200_handle_t **h, const pb200_solver_t *solver,
+                 int flttype, int factotype, int device);
+int pb200_destroy(pb200_handle_t *h);
+int pb200_info(const pb200_handle_t *h, pb200_info_t *info);
+
+/* Panel offsets inside the flat slab: offsets[c] = sum_{k<c} stride_k*width_k,
+ * cblknbr+1 entries. The slab passed to get/set_coeftab uses this layout. */
+int pb200_panel_offsets(const pb200_handle_t *h, int64_t *offsets);
+
+/* max_j sum_i |a_ij| over the internal CSC (host arrays). */
+double pb200_norm1(int flttype, int64_t n, const int64_t *colptr, const void *values);
+
+/* Zero the slab(s) and scatter the permuted CSC (0-based, colptr[n+1]) into the
+ * panels. `tvalues` (same pattern, values of A^T) is required for LU and
+ * ignored otherwise. The CSC is copied to HBM and kept for pb200_reassemble. */
+int pb200_assemble(pb200_handle_t *h, const int64_t *colptr, const int64_t *rows,
+                   const void *values, const void *tvalues);
+/* Re-run the device-side zero + scatter from the CSC already resident in HBM. */
+int pb200_reassemble(pb200_handle_t *h);
+
+/* Numeric factorization of the assembled panels.
+ *   critere  : static-pivot threshold (|pivot| < critere => pivot := critere)
+ *   nbpivot  : OUT number of replaced pivots (-> IPARM_STATIC_PIVOTING)
+ *   seconds  : OUT device time of the factorization (-> DPARM_FACT_TIME) */
+int pb200_factorize(pb200_handle_t *h, double critere, int64_t *nbpivot, double *seconds);
+
+/* Number of positive diagonal terms of D (real LDLt; -> IPARM_INERTIA). */
+int pb200_inertia(pb200_handle_t *h, int64_t *inertia);
+
+/* up_down on `nrhs` right-hand sides held in HOST memory, permuted ordering,
+ * column-major with leading dimension ldx (the layout of UpDownVector.sm2xtab,
+ * blend/src/updown.h:69-72). Overwritten by the solution.
+ *   seconds : OUT device time of the sweeps, copies excluded (-> DPARM_SOLV_TIME) */
+int pb200_solve(pb200_handle_t *h, void *x, int64_t ldx, int64_t nrhs, double *seconds);
+/* Same with x already resident in HBM (device pointer). */
+int pb200_solve_device(pb200_handle_t *h, void *x_dev, int64_t ldx, int64_t nrhs, double *seconds);
+
+/* Copy the factor slab(s) device -> host / host -> device. U may be NULL unless LU. */
+int pb200_get_coeftab(pb200_handle_t *h, void *L, void *U);
+int pb200_set_coeftab(pb200_handle_t *h, const void *L, const void *U);
+
+/* Declare panels uploaded with pb200_set_coeftab to be already factorized
+ * (solve-only use: factors computed elsewhere, e.g. by the reference). */
+int pb200_mark_factorized(pb200_handle_t *h);
+
+/* Kernel launches issued by the last factorize / solve call (bench accounting). */
+int64_t pb200_last_launches(const pb200_handle_t *h);
+
+/* FP64 dense-GEMM probe used by bench.py to establish the measured FP64 roof:
+ * runs an m x n x k DGEMM tile loop with this library's own MMA micro-kernel
+ * and returns achieved GFLOP/s (device timed). */
+double pb200_probe_fp64_gflops(int device, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PASTIX_B200_H */

@@ -188,5 +188,13 @@ class RefPastix:
             raise RuntimeError(f"coeftab not allocated (rc={rc})")
         return L, U
 
+    def order(self):
+        """Final permutation kept by the reference after fax/kass (ordemesh, order.h:52-57):
+        permtab[old] = new and peritab[new] = old, 0-based.  KASS amalgamation may
+        re-number inside supernodes, so this can differ from the PERSONAL input."""
+        pt = np.zeros(self.n, dtype=np.int64); pi = np.zeros(self.n, dtype=np.int64)
+        self.lib.refdrv_order_get(self.pd, pt.ctypes.data_as(C.c_void_p), pi.ctypes.data_as(C.c_void_p))
+        return pt, pi
+
     def norm1(self) -> float:
         return float(self.lib.refdrv_norm1(self.pd))

@@ -1,0 +1,36 @@
+"""Builds the in-tree CUDA library pastix_b200/lib/libpastix_b200.so for sm_100a."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "lib", "libpastix_b200.so")
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("engine.cu", "probe.cu")]
+HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("scalar.cuh", "symbol.cuh", "kernels_factor.cuh", "kernels_solve.cuh")] + \
+          [os.path.join(_HERE, "..", "include", "pastix_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "--threads", "4"]
+
+
+def up_to_date() -> bool:
+    if not os.path.exists(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    return all(os.path.getmtime(f) <= t for f in SOURCES + HEADERS + [os.path.abspath(__file__)])
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    print("[pastix_b200] " + " ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv)

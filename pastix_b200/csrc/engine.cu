@@ -1,0 +1,535 @@
+// engine.cu — host side of the C ABI (include/pastix_b200.h): flattens the
+// SolverMatrix into device arrays, builds the elimination-tree level schedule
+// and drives the CUDA kernels.  No CPU compute path exists here: every numeric
+// entry point launches kernels or fails.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pastix_b200.h"
+#include "kernels_factor.cuh"
+#include "kernels_solve.cuh"
+
+using namespace pb200;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(PB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct pb200_handle_s {
+  int flt = 0, facto = 0, device = 0;
+  size_t esize = 0;
+  int64_t cblknbr = 0, bloknbr = 0, n = 0, coefnbr = 0;
+  int wmax = 0, smax = 0, nlevels = 0, sm_count = 0, cc_major = 0, cc_minor = 0;
+  size_t device_bytes = 0;
+  std::vector<int> h_fcol, h_width, h_stride, h_fblok, h_frow, h_nrow, h_fcblk, h_coefind;
+  std::vector<int64_t> h_poff;
+  // level schedule (host copies of the per-level extents)
+  std::vector<int> lvl_ptr;       // cblks of level l: d_lvl_cblk[lvl_ptr[l] .. lvl_ptr[l+1])
+  std::vector<int> trsm_ptr, trsm_tiles, upd_ptr, slv_ptr, slv_tiles;
+  std::vector<long long> upd_tiles;
+  DevSym S{};
+  int *d_lvl_cblk = nullptr;
+  RowTask *d_trsm = nullptr, *d_slv = nullptr;
+  UpdTask *d_upd = nullptr;
+  void *dL = nullptr, *dU = nullptr;
+  // resident CSC
+  int64_t nnz = 0;
+  int64_t *d_colptr = nullptr;
+  int *d_rows = nullptr;
+  void *d_vals = nullptr, *d_tvals = nullptr;
+  unsigned long long *d_cnt = nullptr;  // [0] nbpivot [1] dropped [2] inertia
+  void *d_x = nullptr; size_t x_bytes = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t last_launches = 0;
+  bool assembled = false, factorized = false;
+  std::vector<void *> allocs;
+};
+
+extern "C" const char *pb200_last_error(void) { return g_err.c_str(); }
+extern "C" const char *pb200_version(void) { return "pastix_b200 0.1 (sm_100a)"; }
+
+template <class V>
+static int upload(pb200_handle_t *h, const std::vector<V> &v, V **d) {
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(V);
+  CK(cudaMalloc((void **)d, bytes));
+  h->allocs.push_back(*d);
+  h->device_bytes += bytes;
+  if (!v.empty()) CK(cudaMemcpy(*d, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static size_t elem_size(int flt) {
+  switch (flt) {
+    case PB200_REALSINGLE: return 4;
+    case PB200_REALDOUBLE: return 8;
+    case PB200_COMPLEXSINGLE: return 8;
+    case PB200_COMPLEXDOUBLE: return 16;
+  }
+  return 0;
+}
+
+extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int flttype, int factotype, int device) {
+  if (!out || !s) return fail(PB200_ERR_BADARG, "null argument");
+  if (elem_size(flttype) == 0) return fail(PB200_ERR_BADARG, "bad flttype");
+  if (factotype < 0 || factotype > 3) return fail(PB200_ERR_BADARG, "bad factotype");
+  if (s->cblknbr <= 0 || s->bloknbr < s->cblknbr) return fail(PB200_ERR_BADARG, "empty SolverMatrix");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(PB200_ERR_CUDA, "no CUDA device: pastix_b200 has no CPU fallback");
+  if (device < 0) CK(cudaGetDevice(&device));
+  if (device >= ndev) return fail(PB200_ERR_BADARG, "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+
+  pb200_handle_t *h = new pb200_handle_t();
+  h->flt = flttype; h->facto = factotype; h->device = device; h->esize = elem_size(flttype);
+  h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
+  const int64_t C = s->cblknbr, B = s->bloknbr;
+  h->cblknbr = C; h->bloknbr = B;
+  h->h_fcol.resize(C); h->h_width.resize(C); h->h_stride.resize(C); h->h_fblok.resize(C + 1);
+  h->h_frow.resize(B); h->h_nrow.resize(B); h->h_fcblk.resize(B); h->h_coefind.resize(B);
+  h->h_poff.resize(C + 1);
+  auto bad = [&](const std::string &m) { delete h; return fail(PB200_ERR_STRUCT, m); };
+  h->h_poff[0] = 0;
+  for (int64_t c = 0; c < C; ++c) {
+    int64_t w = s->lcolnum[c] - s->fcolnum[c] + 1;
+    if (w <= 0 || s->stride[c] < w) return bad("cblk with non-positive width or stride < width");
+    if (s->lcolnum[c] >= (int64_t)1 << 31 || s->stride[c] >= (int64_t)1 << 31) return bad("dimension exceeds 2^31");
+    if (c > 0 && s->fcolnum[c] != s->lcolnum[c - 1] + 1) return bad("cblks do not tile the columns contiguously");
+    if (c == 0 && s->fcolnum[0] != 0) return bad("baseval must be 0");
+    h->h_fcol[c] = (int)s->fcolnum[c]; h->h_width[c] = (int)w; h->h_stride[c] = (int)s->stride[c];
+    h->h_fblok[c] = (int)s->bloknum[c];
+    h->h_poff[c + 1] = h->h_poff[c] + s->stride[c] * w;
+    h->wmax = std::max(h->wmax, (int)w); h->smax = std::max(h->smax, (int)s->stride[c]);
+  }
+  h->h_fblok[C] = (int)s->bloknum[C];
+  if (h->h_fblok[C] != B) return bad("bloknum sentinel != bloknbr");
+  h->n = s->lcolnum[C - 1] + 1;
+  h->coefnbr = h->h_poff[C];
+  for (int64_t c = 0; c < C; ++c) {
+    int b0 = h->h_fblok[c], b1 = h->h_fblok[c + 1];
+    if (b1 <= b0) return bad("cblk without diagonal blok");
+    int64_t rows = 0;
+    for (int b = b0; b < b1; ++b) {
+      h->h_frow[b] = (int)s->frownum[b]; h->h_nrow[b] = (int)(s->lrownum[b] - s->frownum[b] + 1);
+      h->h_fcblk[b] = (int)s->cblknum[b]; h->h_coefind[b] = (int)s->coefind[b];
+      if (h->h_nrow[b] <= 0) return bad("blok with no rows");
+      if (s->coefind[b] != rows) return bad("coefind is not the running row count of the panel");
+      if (b > b0 && s->frownum[b] <= s->lrownum[b - 1]) return bad("bloks of a cblk not sorted / overlapping");
+      if (b > b0 && (s->cblknum[b] <= c || s->cblknum[b] >= C)) return bad("off-diagonal blok must face a later cblk");
+      rows += h->h_nrow[b];
+    }
+    if (rows != s->stride[c]) return bad("stride != sum of blok heights");
+    if (s->frownum[b0] != s->fcolnum[c] || s->lrownum[b0] != s->lcolnum[c]) return bad("first blok is not the diagonal blok");
+  }
+  // facing containment: rows of an off-diagonal blok lie inside the facing cblk's columns
+  for (int64_t c = 0; c < C; ++c)
+    for (int b = h->h_fblok[c] + 1; b < h->h_fblok[c + 1]; ++b) {
+      int fc = h->h_fcblk[b];
+      if (h->h_frow[b] < h->h_fcol[fc] || h->h_frow[b] + h->h_nrow[b] > h->h_fcol[fc] + h->h_width[fc])
+        return bad("blok rows not contained in the facing cblk's column range");
+    }
+
+  // ---- elimination-tree levels: level(c) > level(k) for every k with a blok facing c
+  std::vector<int> level(C, 0);
+  for (int64_t c = 0; c < C; ++c)
+    for (int b = h->h_fblok[c] + 1; b < h->h_fblok[c + 1]; ++b) {
+      int fc = h->h_fcblk[b];
+      level[fc] = std::max(level[fc], level[c] + 1);
+    }
+  int nl = 0;
+  for (int64_t c = 0; c < C; ++c) nl = std::max(nl, level[c] + 1);
+  h->nlevels = nl;
+  h->lvl_ptr.assign(nl + 1, 0);
+  for (int64_t c = 0; c < C; ++c) h->lvl_ptr[level[c] + 1]++;
+  for (int l = 0; l < nl; ++l) h->lvl_ptr[l + 1] += h->lvl_ptr[l];
+  std::vector<int> lvl_cblk(C), fill(h->lvl_ptr.begin(), h->lvl_ptr.end() - 1);
+  for (int64_t c = 0; c < C; ++c) lvl_cblk[fill[level[c]]++] = (int)c;
+
+  // ---- per-level task lists
+  std::vector<RowTask> trsm, slv;
+  std::vector<UpdTask> upd;
+  h->trsm_ptr.assign(nl + 1, 0); h->slv_ptr.assign(nl + 1, 0); h->upd_ptr.assign(nl + 1, 0);
+  h->trsm_tiles.assign(nl, 0); h->slv_tiles.assign(nl, 0); h->upd_tiles.assign(nl, 0);
+  for (int l = 0; l < nl; ++l) {
+    int t_tiles = 0, s_tiles = 0; long long u_tiles = 0;
+    for (int q = h->lvl_ptr[l]; q < h->lvl_ptr[l + 1]; ++q) {
+      int c = lvl_cblk[q];
+      int m = h->h_stride[c] - h->h_width[c];
+      if (m <= 0) continue;
+      trsm.push_back({c, t_tiles}); t_tiles += (m + PB200_TRSM_ROWS - 1) / PB200_TRSM_ROWS;
+      slv.push_back({c, s_tiles}); s_tiles += (m + PB200_SLV_ROWS - 1) / PB200_SLV_ROWS;
+      for (int b = h->h_fblok[c] + 1; b < h->h_fblok[c + 1]; ++b) {
+        int mi = h->h_stride[c] - h->h_coefind[b];
+        int ntm = (mi + PB200_UPD_TM - 1) / PB200_UPD_TM, ntn = (h->h_nrow[b] + PB200_UPD_TN - 1) / PB200_UPD_TN;
+        upd.push_back({c, b, (int)u_tiles, ntn}); u_tiles += (long long)ntm * ntn;
+      }
+    }
+    if (u_tiles * 2 >= (1LL << 31)) return bad("too many update tiles in one level");
+    h->trsm_ptr[l + 1] = (int)trsm.size(); h->slv_ptr[l + 1] = (int)slv.size(); h->upd_ptr[l + 1] = (int)upd.size();
+    h->trsm_tiles[l] = t_tiles; h->slv_tiles[l] = s_tiles; h->upd_tiles[l] = u_tiles;
+  }
+
+  // ---- upload
+  std::vector<int> col2cblk(h->n);
+  for (int64_t c = 0; c < C; ++c) for (int j = 0; j < h->h_width[c]; ++j) col2cblk[h->h_fcol[c] + j] = (int)c;
+  int *d; int64_t *d64;
+#define UP(vec, field) { int rc = upload(h, vec, &d); if (rc) { pb200_destroy(h); return rc; } h->S.field = d; }
+  UP(h->h_fcol, fcol) UP(h->h_width, width) UP(h->h_stride, stride) UP(h->h_fblok, fblok)
+  UP(h->h_frow, frow) UP(h->h_nrow, nrow) UP(h->h_fcblk, fcblk) UP(h->h_coefind, coefind) UP(col2cblk, col2cblk)
+#undef UP
+  { int rc = upload(h, h->h_poff, &d64); if (rc) { pb200_destroy(h); return rc; } h->S.poff = d64; }
+  h->S.cblknbr = (int)C; h->S.bloknbr = (int)B;
+  { int rc = upload(h, lvl_cblk, &h->d_lvl_cblk); if (rc) { pb200_destroy(h); return rc; } }
+  { int rc = upload(h, trsm, &h->d_trsm); if (rc) { pb200_destroy(h); return rc; } }
+  { int rc = upload(h, slv, &h->d_slv); if (rc) { pb200_destroy(h); return rc; } }
+  { int rc = upload(h, upd, &h->d_upd); if (rc) { pb200_destroy(h); return rc; } }
+
+  size_t slab = (size_t)h->coefnbr * h->esize;
+  if (cudaMalloc(&h->dL, slab) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(L slab) failed"); }
+  h->device_bytes += slab;
+  if (factotype == PB200_FACT_LU) {
+    if (cudaMalloc(&h->dU, slab) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(U slab) failed"); }
+    h->device_bytes += slab;
+  }
+  CK(cudaMalloc((void **)&h->d_cnt, 4 * sizeof(unsigned long long)));
+  CK(cudaMemset(h->d_cnt, 0, 4 * sizeof(unsigned long long)));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+  *out = h;
+  return PB200_SUCCESS;
+}
+
+extern "C" int pb200_destroy(pb200_handle_t *h) {
+  if (!h) return PB200_SUCCESS;
+  cudaSetDevice(h->device);
+  for (void *p : h->allocs) cudaFree(p);
+  cudaFree(h->dL); cudaFree(h->dU); cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals);
+  cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return PB200_SUCCESS;
+}
+
+extern "C" int pb200_info(const pb200_handle_t *h, pb200_info_t *info) {
+  if (!h || !info) return fail(PB200_ERR_BADARG, "null argument");
+  info->n = h->n; info->coefnbr = h->coefnbr; info->nlevels = h->nlevels; info->device_bytes = (int64_t)h->device_bytes;
+  info->device = h->device; info->sm_count = h->sm_count; info->cc_major = h->cc_major; info->cc_minor = h->cc_minor;
+  return PB200_SUCCESS;
+}
+
+extern "C" int pb200_panel_offsets(const pb200_handle_t *h, int64_t *offsets) {
+  if (!h || !offsets) return fail(PB200_ERR_BADARG, "null argument");
+  memcpy(offsets, h->h_poff.data(), (size_t)(h->cblknbr + 1) * sizeof(int64_t));
+  return PB200_SUCCESS;
+}
+
+extern "C" int64_t pb200_last_launches(const pb200_handle_t *h) { return h ? h->last_launches : 0; }
+
+template <class T>
+static double norm1_t(int64_t n, const int64_t *colptr, const T *v) {
+  double mx = 0;
+  for (int64_t j = 0; j < n; ++j) {
+    double s = 0;
+    for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) s += (double)ST<T>::abs(v[p]);
+    mx = std::max(mx, s);
+  }
+  return mx;
+}
+extern "C" double pb200_norm1(int flttype, int64_t n, const int64_t *colptr, const void *values) {
+  switch (flttype) {
+    case PB200_REALSINGLE: return norm1_t(n, colptr, (const float *)values);
+    case PB200_REALDOUBLE: return norm1_t(n, colptr, (const double *)values);
+    case PB200_COMPLEXSINGLE: return norm1_t(n, colptr, (const cfloat *)values);
+    case PB200_COMPLEXDOUBLE: return norm1_t(n, colptr, (const cdouble *)values);
+  }
+  return -1.0;
+}
+
+// ------------------------------------------------------------------ dispatch helpers
+#define DISPATCH_T(h, FN, ...)                                                    \
+  switch ((h)->flt) {                                                             \
+    case PB200_REALSINGLE: return FN<float>(__VA_ARGS__);                         \
+    case PB200_REALDOUBLE: return FN<double>(__VA_ARGS__);                        \
+    case PB200_COMPLEXSINGLE: return FN<cfloat>(__VA_ARGS__);                     \
+    case PB200_COMPLEXDOUBLE: return FN<cdouble>(__VA_ARGS__);                    \
+  }                                                                               \
+  return fail(PB200_ERR_BADARG, "bad flttype");
+
+template <class T>
+static int reassemble_t(pb200_handle_t *h) {
+  size_t slab = (size_t)h->coefnbr * sizeof(T);
+  CK(cudaMemsetAsync(h->dL, 0, slab, h->stream));
+  if (h->dU) CK(cudaMemsetAsync(h->dU, 0, slab, h->stream));
+  CK(cudaMemsetAsync(h->d_cnt + 1, 0, sizeof(unsigned long long), h->stream));
+  int n = (int)h->n;
+  k_assemble<T><<<(n + 255) / 256, 256, 0, h->stream>>>(h->S, n, h->d_colptr, h->d_rows, (const T *)h->d_vals,
+                                                        (const T *)h->d_tvals, 0, (T *)h->dL, (T *)h->dU, h->d_cnt + 1);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  h->assembled = true; h->factorized = false;
+  return PB200_SUCCESS;
+}
+
+extern "C" int pb200_reassemble(pb200_handle_t *h) {
+  if (!h) return fail(PB200_ERR_BADARG, "null handle");
+  if (!h->d_colptr) return fail(PB200_ERR_STATE, "pb200_assemble has not been called");
+  CK(cudaSetDevice(h->device));
+  DISPATCH_T(h, reassemble_t, h)
+}
+
+extern "C" int pb200_assemble(pb200_handle_t *h, const int64_t *colptr, const int64_t *rows, const void *values,
+                              const void *tvalues) {
+  if (!h || !colptr || !rows || !values) return fail(PB200_ERR_BADARG, "null argument");
+  if (h->facto == PB200_FACT_LU && !tvalues) return fail(PB200_ERR_BADARG, "LU needs the transposed values");
+  CK(cudaSetDevice(h->device));
+  int64_t nnz = colptr[h->n];
+  if (colptr[0] != 0) return fail(PB200_ERR_BADARG, "colptr must be 0-based");
+  if (nnz != h->nnz || !h->d_colptr) {
+    cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals); cudaFree(h->d_tvals);
+    h->d_colptr = nullptr; h->d_rows = nullptr; h->d_vals = nullptr; h->d_tvals = nullptr;
+    CK(cudaMalloc((void **)&h->d_colptr, (size_t)(h->n + 1) * sizeof(int64_t)));
+    CK(cudaMalloc((void **)&h->d_rows, (size_t)std::max<int64_t>(nnz, 1) * sizeof(int)));
+    CK(cudaMalloc(&h->d_vals, (size_t)std::max<int64_t>(nnz, 1) * h->esize));
+    if (h->facto == PB200_FACT_LU) CK(cudaMalloc(&h->d_tvals, (size_t)std::max<int64_t>(nnz, 1) * h->esize));
+    h->nnz = nnz;
+  }
+  std::vector<int> r32((size_t)nnz);
+  for (int64_t i = 0; i < nnz; ++i) r32[i] = (int)rows[i];
+  CK(cudaMemcpyAsync(h->d_colptr, colptr, (size_t)(h->n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_rows, r32.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_vals, values, (size_t)nnz * h->esize, cudaMemcpyHostToDevice, h->stream));
+  if (h->d_tvals) CK(cudaMemcpyAsync(h->d_tvals, tvalues, (size_t)nnz * h->esize, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return pb200_reassemble(h);
+}
+
+// ------------------------------------------------------------------ factorization
+template <class T, int FACTO>
+static int factorize_tf(pb200_handle_t *h, double crit) {
+  T *L = (T *)h->dL, *U = (T *)h->dU;
+  const int lu = (FACTO == F_LU) ? 2 : 1;
+  // dynamic shared memory for the diagonal block: as much as fits
+  int smem_max = 200 * 1024;
+  static bool attr_done[4][4] = {};
+  if (!attr_done[h->flt][FACTO]) {
+    CK(cudaFuncSetAttribute(k_diag_factor<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    attr_done[h->flt][FACTO] = true;
+  }
+  int64_t launches = 0;
+  for (int l = 0; l < h->nlevels; ++l) {
+    int nc = h->lvl_ptr[l + 1] - h->lvl_ptr[l];
+    // smem sized for the widest cblk of this launch would need a per-level max; use global wmax bound
+    int elems = std::min<long long>((long long)h->wmax * h->wmax, smem_max / (long long)sizeof(T));
+    size_t smem = (size_t)elems * sizeof(T);
+    k_diag_factor<T, FACTO><<<nc, 256, smem, h->stream>>>(h->S, L, U, h->d_lvl_cblk + h->lvl_ptr[l], crit, h->d_cnt, elems);
+    ++launches;
+    if (h->trsm_tiles[l] > 0) {
+      k_panel_trsm<T, FACTO><<<h->trsm_tiles[l] * lu, PB200_TRSM_ROWS, 0, h->stream>>>(
+          h->S, L, U, h->d_trsm + h->trsm_ptr[l], h->trsm_ptr[l + 1] - h->trsm_ptr[l]);
+      ++launches;
+    }
+    if (h->upd_tiles[l] > 0) {
+      k_update<T, FACTO><<<(unsigned)(h->upd_tiles[l] * lu), 256, 0, h->stream>>>(
+          h->S, L, U, h->d_upd + h->upd_ptr[l], h->upd_ptr[l + 1] - h->upd_ptr[l]);
+      ++launches;
+    }
+  }
+  CK(cudaGetLastError());
+  h->last_launches = launches;
+  return PB200_SUCCESS;
+}
+
+template <class T>
+static int factorize_t(pb200_handle_t *h, double crit) {
+  switch (h->facto) {
+    case PB200_FACT_LLT: return factorize_tf<T, F_LLT>(h, crit);
+    case PB200_FACT_LDLT: return factorize_tf<T, F_LDLT>(h, crit);
+    case PB200_FACT_LU: return factorize_tf<T, F_LU>(h, crit);
+    case PB200_FACT_LDLH:
+      return ST<T>::is_complex ? factorize_tf<T, F_LDLH>(h, crit) : factorize_tf<T, F_LDLT>(h, crit);
+  }
+  return fail(PB200_ERR_BADARG, "bad factotype");
+}
+
+static int factorize_dispatch(pb200_handle_t *h, double crit) { DISPATCH_T(h, factorize_t, h, crit) }
+
+extern "C" int pb200_factorize(pb200_handle_t *h, double critere, int64_t *nbpivot, double *seconds) {
+  if (!h) return fail(PB200_ERR_BADARG, "null handle");
+  if (!h->assembled) return fail(PB200_ERR_STATE, "panels not assembled (pb200_assemble / pb200_set_coeftab)");
+  if (h->factorized) return fail(PB200_ERR_STATE, "panels already factorized; reassemble first");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(unsigned long long), h->stream));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  int rc = factorize_dispatch(h, critere);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  unsigned long long nb = 0;
+  CK(cudaMemcpy(&nb, h->d_cnt, sizeof(nb), cudaMemcpyDeviceToHost));
+  if (nbpivot) *nbpivot = (int64_t)nb;
+  if (seconds) *seconds = ms * 1e-3;
+  h->factorized = true;
+  return PB200_SUCCESS;
+}
+
+template <class T>
+static int inertia_t(pb200_handle_t *h, int64_t *out) {
+  CK(cudaMemsetAsync(h->d_cnt + 2, 0, sizeof(unsigned long long), h->stream));
+  k_inertia<T><<<(int)((h->cblknbr + 127) / 128), 128, 0, h->stream>>>(h->S, (const T *)h->dL, h->d_cnt + 2);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  unsigned long long v = 0;
+  CK(cudaMemcpy(&v, h->d_cnt + 2, sizeof(v), cudaMemcpyDeviceToHost));
+  *out = (int64_t)v;
+  return PB200_SUCCESS;
+}
+extern "C" int pb200_inertia(pb200_handle_t *h, int64_t *inertia) {
+  if (!h || !inertia) return fail(PB200_ERR_BADARG, "null argument");
+  if (!h->factorized) return fail(PB200_ERR_STATE, "not factorized");
+  CK(cudaSetDevice(h->device));
+  DISPATCH_T(h, inertia_t, h, inertia)
+}
+
+// ------------------------------------------------------------------ solve
+template <class T, int FACTO>
+static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs_total) {
+  const T *L = (const T *)h->dL;
+  const T *Mup = (FACTO == F_LU) ? (const T *)h->dU : L;
+  const int smem_cap = 96 * 1024;
+  static bool attr_done[4][4] = {};
+  if (!attr_done[h->flt][FACTO]) {
+    CK(cudaFuncSetAttribute(k_fwd_diag<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
+    CK(cudaFuncSetAttribute(k_bwd_diag<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
+    attr_done[h->flt][FACTO] = true;
+  }
+  int chunk = (int)std::max<long long>(1, std::min<long long>(nrhs_total, smem_cap / ((long long)h->wmax * (long long)sizeof(T))));
+  if ((size_t)h->wmax * sizeof(T) > (size_t)smem_cap) return fail(PB200_ERR_STRUCT, "cblk too wide for the solve kernels");
+  int64_t launches = 0;
+  for (int r0 = 0; r0 < nrhs_total; r0 += chunk) {
+    const int nrhs = std::min(chunk, nrhs_total - r0);
+    T *xc = x + (size_t)r0 * ldx;
+    const size_t dsm = (size_t)h->wmax * nrhs * sizeof(T);
+    const size_t usm = (size_t)h->wmax * PB200_SLV_NR * sizeof(T);
+    for (int l = 0; l < h->nlevels; ++l) {
+      int nc = h->lvl_ptr[l + 1] - h->lvl_ptr[l];
+      k_fwd_diag<T, FACTO><<<nc, 128, dsm, h->stream>>>(h->S, L, xc, ldx, nrhs, h->d_lvl_cblk + h->lvl_ptr[l]);
+      ++launches;
+      if (h->slv_tiles[l] > 0) {
+        k_fwd_update<T><<<h->slv_tiles[l], PB200_SLV_ROWS, usm, h->stream>>>(h->S, L, xc, ldx, nrhs, h->d_slv + h->slv_ptr[l],
+                                                                            h->slv_ptr[l + 1] - h->slv_ptr[l]);
+        ++launches;
+      }
+    }
+    if (FACTO == F_LDLT || FACTO == F_LDLH) {
+      k_diag_scale<T><<<(int)((h->n + 255) / 256), 256, 0, h->stream>>>(h->S, L, xc, ldx, nrhs, (int)h->n);
+      ++launches;
+    }
+    for (int l = h->nlevels - 1; l >= 0; --l) {
+      int nc = h->lvl_ptr[l + 1] - h->lvl_ptr[l];
+      if (h->slv_tiles[l] > 0) {
+        k_bwd_update<T, FACTO><<<h->slv_tiles[l], PB200_SLV_ROWS, 0, h->stream>>>(h->S, Mup, xc, ldx, nrhs, h->d_slv + h->slv_ptr[l],
+                                                                                  h->slv_ptr[l + 1] - h->slv_ptr[l]);
+        ++launches;
+      }
+      k_bwd_diag<T, FACTO><<<nc, 128, dsm, h->stream>>>(h->S, Mup, xc, ldx, nrhs, h->d_lvl_cblk + h->lvl_ptr[l]);
+      ++launches;
+    }
+  }
+  CK(cudaGetLastError());
+  h->last_launches = launches;
+  return PB200_SUCCESS;
+}
+
+template <class T>
+static int solve_t(pb200_handle_t *h, void *x, int64_t ldx, int nrhs) {
+  switch (h->facto) {
+    case PB200_FACT_LLT: return solve_tf<T, F_LLT>(h, (T *)x, ldx, nrhs);
+    case PB200_FACT_LDLT: return solve_tf<T, F_LDLT>(h, (T *)x, ldx, nrhs);
+    case PB200_FACT_LU: return solve_tf<T, F_LU>(h, (T *)x, ldx, nrhs);
+    case PB200_FACT_LDLH:
+      return ST<T>::is_complex ? solve_tf<T, F_LDLH>(h, (T *)x, ldx, nrhs) : solve_tf<T, F_LDLT>(h, (T *)x, ldx, nrhs);
+  }
+  return fail(PB200_ERR_BADARG, "bad factotype");
+}
+static int solve_dispatch(pb200_handle_t *h, void *x, int64_t ldx, int nrhs) { DISPATCH_T(h, solve_t, h, x, ldx, nrhs) }
+
+extern "C" int pb200_solve_device(pb200_handle_t *h, void *x_dev, int64_t ldx, int64_t nrhs, double *seconds) {
+  if (!h || !x_dev) return fail(PB200_ERR_BADARG, "null argument");
+  if (!h->factorized) return fail(PB200_ERR_STATE, "not factorized");
+  if (ldx < h->n || nrhs <= 0) return fail(PB200_ERR_BADARG, "bad ldx / nrhs");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  int rc = solve_dispatch(h, x_dev, ldx, (int)nrhs);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (seconds) *seconds = ms * 1e-3;
+  return PB200_SUCCESS;
+}
+
+extern "C" int pb200_solve(pb200_handle_t *h, void *x, int64_t ldx, int64_t nrhs, double *seconds) {
+  if (!h || !x) return fail(PB200_ERR_BADARG, "null argument");
+  if (!h->factorized) return fail(PB200_ERR_STATE, "not factorized");
+  if (ldx < h->n || nrhs <= 0) return fail(PB200_ERR_BADARG, "bad ldx / nrhs");
+  CK(cudaSetDevice(h->device));
+  size_t bytes = (size_t)ldx * nrhs * h->esize;
+  if (bytes > h->x_bytes) {
+    cudaFree(h->d_x); h->d_x = nullptr; h->x_bytes = 0;
+    CK(cudaMalloc(&h->d_x, bytes));
+    h->x_bytes = bytes;
+  }
+  CK(cudaMemcpyAsync(h->d_x, x, bytes, cudaMemcpyHostToDevice, h->stream));
+  int rc = pb200_solve_device(h, h->d_x, ldx, nrhs, seconds);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(x, h->d_x, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PB200_SUCCESS;
+}
+
+// ------------------------------------------------------------------ factor slabs <-> host
+extern "C" int pb200_get_coeftab(pb200_handle_t *h, void *L, void *U) {
+  if (!h || !L) return fail(PB200_ERR_BADARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  size_t slab = (size_t)h->coefnbr * h->esize;
+  CK(cudaMemcpy(L, h->dL, slab, cudaMemcpyDeviceToHost));
+  if (U) {
+    if (!h->dU) return fail(PB200_ERR_STATE, "no U slab (not an LU factorization)");
+    CK(cudaMemcpy(U, h->dU, slab, cudaMemcpyDeviceToHost));
+  }
+  return PB200_SUCCESS;
+}
+
+extern "C" int pb200_set_coeftab(pb200_handle_t *h, const void *L, const void *U) {
+  if (!h || !L) return fail(PB200_ERR_BADARG, "null argument");
+  if (h->dU && !U) return fail(PB200_ERR_BADARG, "LU needs both slabs");
+  CK(cudaSetDevice(h->device));
+  size_t slab = (size_t)h->coefnbr * h->esize;
+  CK(cudaMemcpy(h->dL, L, slab, cudaMemcpyHostToDevice));
+  if (h->dU) CK(cudaMemcpy(h->dU, U, slab, cudaMemcpyHostToDevice));
+  h->assembled = true; h->factorized = false;
+  return PB200_SUCCESS;
+}
+
+// set by tests that upload already-factored panels (solve-only parity)
+extern "C" int pb200_mark_factorized(pb200_handle_t *h) {
+  if (!h) return fail(PB200_ERR_BADARG, "null handle");
+  h->factorized = true;
+  return PB200_SUCCESS;
+}

@@ -126,6 +126,24 @@ def nested_dissection_perm(N: int, leaf: int = 8) -> np.ndarray:
     return perm.ravel()
 
 
+def nested_dissection_perm_1d(n: int, leaf: int = 4) -> np.ndarray:
+    """1-D recursive bisection (halves first, the separating vertex last)."""
+    perm = np.empty(n, dtype=np.int64)
+    cnt = 0
+    stack = [(0, 0, n)]
+    while stack:
+        kind, lo, hi = stack.pop()
+        if hi <= lo:
+            continue
+        if kind == 1 or hi - lo <= leaf:
+            perm[lo:hi] = cnt + np.arange(hi - lo)
+            cnt += hi - lo
+            continue
+        mid = lo + (hi - lo) // 2
+        stack.append((1, mid, mid + 1)); stack.append((0, mid + 1, hi)); stack.append((0, lo, mid))
+    return perm
+
+
 def permute_symmetric(A: sp.spmatrix, perm: np.ndarray, full: bool = True) -> sp.csc_matrix:
     """P A P^T in CSC with sorted rows (0-based). If `A` holds only the lower
     triangle of a symmetric matrix and full=True, both triangles are produced —

@@ -1,0 +1,113 @@
+"""Generates the golden fixtures tests/golden/*.npz by RUNNING THE UNMODIFIED
+REFERENCE (oracle/_ref, built by oracle/build_ref.sh from /root/reference).
+Run in the build container:  python tests/golden/make_golden.py
+Each fixture holds: the SolverMatrix arrays and final permutation produced by the
+reference's order/kass/blend analysis, the internal CSC the reference built
+(CscOrdistrib), the pivot threshold, the reference's factor panels
+(coeftab/ucoeftab), IPARM_STATIC_PIVOTING / IPARM_INERTIA, a right-hand side and
+the reference's solution."""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.refpastix import RefPastix  # noqa: E402
+from pastix_b200 import generators as G  # noqa: E402
+from pastix_b200.csc import internal_csc  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+DT = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
+
+
+def case_matrix(kind, N, dt):
+    if kind == "lap1d":
+        return G.laplacian_1d(N, dt), G.nested_dissection_perm_1d(N)
+    if kind == "lap7":
+        return G.laplacian_3d(N, 7, dt), G.nested_dissection_perm(N)
+    if kind == "lap27":
+        return G.laplacian_3d(N, 27, dt), G.nested_dissection_perm(N)
+    if kind == "cd":
+        return G.convection_diffusion_3d(N, dt), G.nested_dissection_perm(N)
+    if kind == "lap7shift":   # complex symmetric: Laplacian + i*0.5 on the diagonal
+        A = G.laplacian_3d(N, 7, dt).tolil()
+        A.setdiag(A.diagonal() + 0.5j)
+        return A.tocsc(), G.nested_dissection_perm(N)
+    if kind == "lap7her":     # hermitian positive definite: off-diagonals -1 +/- 0.3i
+        A = G.laplacian_3d(N, 7, dt).tocoo()
+        v = A.data.copy(); off = A.row != A.col
+        v[off] = v[off] + 0.3j * np.where((A.row[off] - A.col[off]) % 2 == 0, 1, -1)
+        return sp.csc_matrix((v, (A.row, A.col)), shape=A.shape), G.nested_dissection_perm(N)
+    if kind == "lap7sing":    # zero pivots: forces the static-pivoting rule
+        A = G.laplacian_3d(N, 7, dt).tolil()
+        n = N ** 3
+        for i in (0, n // 3, n - 1):
+            A[i, i] = 0.0
+        return A.tocsc(), G.nested_dissection_perm(N)
+    raise ValueError(kind)
+
+
+CASES = [
+    # name, kind, N, prec, facto, iparm overrides, nrhs
+    ("lap1d100_llt_d", "lap1d", 100, "d", "llt", {}, 1),      # BASELINE config 1 (simple -lap 100)
+    ("lap1d100_ldlt_d", "lap1d", 100, "d", "ldlt", {}, 1),
+    ("lap7_8_llt_d", "lap7", 8, "d", "llt", {}, 3),
+    ("lap27_6_ldlt_d", "lap27", 6, "d", "ldlt", {}, 2),
+    ("cd_8_lu_d", "cd", 8, "d", "lu", {}, 2),
+    ("cd_6_lu_z", "cd", 6, "z", "lu", {}, 2),
+    ("lap7shift_6_ldlt_z", "lap7shift", 6, "z", "ldlt", {}, 1),
+    ("lap7her_6_ldlh_z", "lap7her", 6, "z", "ldlh", {}, 1),
+    ("lap7_6_llt_s", "lap7", 6, "s", "llt", {}, 2),
+    ("cd_6_lu_c", "cd", 6, "c", "lu", {}, 1),
+    ("lap7_8_ilu2_llt_d", "lap7", 8, "d", "llt", {"IPARM_INCOMPLETE": 1, "IPARM_LEVEL_OF_FILL": 2}, 1),
+    ("lap7sing_6_ldlt_d", "lap7sing", 6, "d", "ldlt", {}, 1),
+    ("lap7_10_llt_d_bs16", "lap7", 10, "d", "llt", {"IPARM_MIN_BLOCKSIZE": 8, "IPARM_MAX_BLOCKSIZE": 16}, 1),
+]
+
+
+def make(name, kind, N, prec, facto, over, nrhs):
+    dt = DT[prec]
+    A, perm0 = case_matrix(kind, N, dt)
+    n = A.shape[0]
+    sym = {"llt": "yes", "ldlt": "yes", "lu": "no", "ldlh": "her"}[facto]
+    r = RefPastix(prec, threads=1).setup(A, perm0, facto, sym=sym, iparm_over=over).analyze()
+    s = r.solver()
+    permtab, peritab = r.order()
+    r.numfact()
+    csc = r.csc()
+    mine = internal_csc(A, permtab, sym, dt)
+    assert np.array_equal(mine["colptr"], csc["colptr"]) and np.array_equal(mine["rows"], csc["rows"]), name
+    assert np.array_equal(mine["values"], csc["vals"]), name
+    L, U = r.coef()
+    out = r.out()
+    b = G.rhs_vector(n, nrhs, dt)
+    x = r.solve(b)
+    eps = out["epsilon_magn_ctrl"]
+    crit = r.norm1() * np.sqrt(eps)
+    d = dict(cblknbr=s["cblknbr"], bloknbr=s["bloknbr"], fcol=s["fcol"], lcol=s["lcol"], bloknum=s["bloknum"],
+             stride=s["stride"], frow=s["frow"], lrow=s["lrow"], fcblk=s["fcblk"], coefind=s["coefind"],
+             permtab=permtab, colptr=csc["colptr"], rows=csc["rows"], values=csc["vals"],
+             critere=crit, norm1=r.norm1(), L=L, nbpivot=out["static_pivoting"], inertia=out["inertia"],
+             nnzeros=out["nnzeros"], fact_flops=out["fact_flops"], b=b, x=x,
+             prec=prec, facto=facto, sym=sym, kind=kind, N=N)
+    if mine["tvalues"] is not None:
+        d["tvalues"] = mine["tvalues"]
+    if U is not None:
+        d["U"] = U
+    # compact the index arrays
+    for k in ("fcol", "lcol", "bloknum", "stride", "frow", "lrow", "fcblk", "coefind", "permtab", "colptr", "rows"):
+        d[k] = d[k].astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(f"{name}: n={n} cblk={s['cblknbr']} blok={s['bloknbr']} coefnbr={s['coefnbr']} nbpivot={out['static_pivoting']} "
+          f"size={os.path.getsize(os.path.join(OUT, name + '.npz')) / 1024:.0f} KiB")
+    # r.clean() is skipped: the reference frees with its own allocator bookkeeping and the process exits anyway
+
+
+if __name__ == "__main__":
+    only = sys.argv[1:]
+    for c in CASES:
+        if only and c[0] not in only:
+            continue
+        make(*c)
