@@ -1,7 +1,7 @@
 /*
  * TEST INFRASTRUCTURE — the CPU oracle.  Not part of the product path: only
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference leg may
- * load this.  Parity is PINNED: tests/test_oracle_vs_reference.py checks every
+ * load this.  Parity is PINNED: tests/test_oracle.py checks every
  * function below against the unmodified reference built in oracle/_ref and
  * against the committed golden dumps under tests/golden/.
  *

@@ -45,7 +45,8 @@ def test_factor_and_solve_match_reference(name):
     x = permute_rhs(g["b"], g["permtab"])
     s.solve(x)
     xs = unpermute_solution(x, g["permtab"])
-    assert relerr(xs, g["x"]) <= 50 * t
+    # a replaced pivot is ~1e-15: the solution of that (numerically singular) system is not a parity quantity
+    assert relerr(xs, g["x"]) <= (50 * t if g["nbpivot"] == 0 else 1e-1)
     s.close()
 
 
