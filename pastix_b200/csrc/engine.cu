@@ -9,10 +9,12 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <type_traits>
 
 #include "../../include/pastix_b200.h"
 #include "kernels_factor.cuh"
 #include "kernels_solve.cuh"
+#include "kernels_mma.cuh"
 
 using namespace pb200;
 
@@ -53,6 +55,13 @@ struct pb200_handle_s {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t last_launches = 0;
   bool assembled = false, factorized = false;
+  // ---- FP64 tensor-core path (double / complex double, direct factorizations)
+  bool use_mma = false;
+  DevMap M{};
+  struct Step { int kind; int task0, ntasks; long long ntiles; int nbmax; int lvl; };  // kind: 0 diag 1 trsm 2 gemm 3 transpose
+  std::vector<Step> steps;
+  SubTask *d_sub = nullptr;
+  GemmTask *d_gemm = nullptr;
   std::vector<void *> allocs;
 };
 
@@ -77,6 +86,132 @@ static size_t elem_size(int flt) {
     case PB200_COMPLEXDOUBLE: return 16;
   }
   return 0;
+}
+
+// ------------------------------------------------------------------ schedule of the tensor-core path
+// Levels of the elimination tree; inside a level, cblks wider than NBMAX are walked sub-panel by
+// sub-panel ("rounds"): diag -> trsm -> internal update; then one fused GEMM+scatter launch for the level.
+static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, const std::vector<int> &lvl_cblk) {
+  const bool cx = (h->flt == PB200_COMPLEXDOUBLE);
+  const bool lu = (h->facto == PB200_FACT_LU);
+  const int NBMAX = cx ? SubCfg<cdouble>::NBMAX : SubCfg<double>::NBMAX;
+  const int TM = cx ? UpdCfg<cdouble>::TM : UpdCfg<double>::TM;
+  const int TN = cx ? UpdCfg<cdouble>::TN : UpdCfg<double>::TN;
+  const int64_t C = h->cblknbr;
+  // pair tables
+  std::vector<int64_t> pairbase(C + 1, 0);
+  for (int64_t c = 0; c < C; ++c) {
+    int64_t nb = h->h_fblok[c + 1] - h->h_fblok[c] - 1;
+    pairbase[c + 1] = pairbase[c] + nb * (nb + 1) / 2;
+  }
+  int64_t *d_pb; int *d_po = nullptr, *d_napa = nullptr;
+  { int rc = upload(h, pairbase, &d_pb); if (rc) return rc; }
+  size_t pbytes = (size_t)std::max<int64_t>(pairbase[C], 1) * sizeof(int);
+  CK(cudaMalloc((void **)&d_po, pbytes)); h->allocs.push_back(d_po); h->device_bytes += pbytes;
+  CK(cudaMalloc((void **)&d_napa, sizeof(int))); h->allocs.push_back(d_napa);
+  CK(cudaMemset(d_napa, 0, sizeof(int)));
+  k_build_pairs<<<(unsigned)C, 128>>>(h->S, d_pb, d_po, d_napa);
+  CK(cudaGetLastError());
+  int napa = 0;
+  CK(cudaMemcpy(&napa, d_napa, sizeof(int), cudaMemcpyDeviceToHost));
+  if (napa) { h->use_mma = false; return PB200_SUCCESS; }   // incomplete factorization: generic path
+  // per blok: does another cblk of the same level also write into the facing cblk?
+  std::vector<unsigned char> bflag(h->bloknbr, 0);
+  {
+    std::vector<int> stamp(C, -1), cnt(C, 0);
+    for (int l = 0; l < h->nlevels; ++l) {
+      for (int q = h->lvl_ptr[l]; q < h->lvl_ptr[l + 1]; ++q) {
+        int c = lvl_cblk[q];
+        int last = -1;
+        for (int b = h->h_fblok[c] + 1; b < h->h_fblok[c + 1]; ++b) {
+          int fc = h->h_fcblk[b];
+          if (fc == last) continue;   // facing cblks are non-decreasing along a panel
+          last = fc;
+          if (stamp[fc] != l) { stamp[fc] = l; cnt[fc] = 0; }
+          cnt[fc]++;
+        }
+      }
+      for (int q = h->lvl_ptr[l]; q < h->lvl_ptr[l + 1]; ++q) {
+        int c = lvl_cblk[q];
+        for (int b = h->h_fblok[c] + 1; b < h->h_fblok[c + 1]; ++b) bflag[b] = (cnt[h->h_fcblk[b]] > 1);
+      }
+    }
+  }
+  unsigned char *d_bf;
+  { int rc = upload(h, bflag, &d_bf); if (rc) return rc; }
+  h->M.pairbase = d_pb; h->M.pairoff = d_po; h->M.bflag = d_bf;
+
+  std::vector<SubTask> sub;
+  std::vector<GemmTask> gemm;
+  auto subpanel = [&](int w, int r, int &c0, int &c1) {
+    int nsub = (w + NBMAX - 1) / NBMAX;
+    int sw = (((w + nsub - 1) / nsub) + 7) & ~7;
+    c0 = r * sw; c1 = std::min(w, c0 + sw);
+  };
+  for (int l = 0; l < h->nlevels; ++l) {
+    const int q0 = h->lvl_ptr[l], q1 = h->lvl_ptr[l + 1];
+    int rounds = 0;
+    for (int q = q0; q < q1; ++q) rounds = std::max(rounds, (h->h_width[lvl_cblk[q]] + NBMAX - 1) / NBMAX);
+    if (lu) h->steps.push_back({3, q0, q1 - q0, 0, 0, l});
+    for (int r = 0; r < rounds; ++r) {
+      // diag
+      int t0 = (int)sub.size(), nbmax = 0;
+      for (int q = q0; q < q1; ++q) {
+        int c = lvl_cblk[q], w = h->h_width[c];
+        if ((w + NBMAX - 1) / NBMAX <= r) continue;
+        int c0, c1; subpanel(w, r, c0, c1);
+        sub.push_back({c, 0, c0, c1}); nbmax = std::max(nbmax, c1 - c0);
+      }
+      h->steps.push_back({0, t0, (int)sub.size() - t0, (long long)sub.size() - t0, nbmax, l});
+      // trsm
+      t0 = (int)sub.size(); long long tiles = 0; nbmax = 0;
+      for (int q = q0; q < q1; ++q) {
+        int c = lvl_cblk[q], w = h->h_width[c], ld = h->h_stride[c];
+        if ((w + NBMAX - 1) / NBMAX <= r) continue;
+        int c0, c1; subpanel(w, r, c0, c1);
+        if (ld - c1 <= 0) continue;
+        sub.push_back({c, (int)tiles, c0, c1}); tiles += (ld - c1 + PB200_TRSM_TM - 1) / PB200_TRSM_TM;
+        nbmax = std::max(nbmax, c1 - c0);
+      }
+      if (tiles > 0) h->steps.push_back({1, t0, (int)sub.size() - t0, tiles, nbmax, l});
+      // internal update
+      t0 = (int)gemm.size(); tiles = 0;
+      for (int q = q0; q < q1; ++q) {
+        int c = lvl_cblk[q], w = h->h_width[c], ld = h->h_stride[c];
+        if ((w + NBMAX - 1) / NBMAX <= r) continue;
+        int c0, c1; subpanel(w, r, c0, c1);
+        if (c1 >= w) continue;
+        for (int a0 = c1; a0 < ld; a0 += TM) {
+          int ncols = (lu ? w : std::min(w, a0 + TM)) - c1;
+          int ntn = (ncols + TN - 1) / TN;
+          gemm.push_back({c, (int)tiles, ntn, a0, ld, c1, c1 + ncols, c0, c1, 1});
+          tiles += ntn;
+        }
+      }
+      if (tiles > 0) h->steps.push_back({2, t0, (int)gemm.size() - t0, tiles, 0, l});
+    }
+    // external update: fused GEMM + scatter
+    int t0 = (int)gemm.size(); long long tiles = 0;
+    for (int q = q0; q < q1; ++q) {
+      int c = lvl_cblk[q], w = h->h_width[c], ld = h->h_stride[c];
+      if (ld <= w) continue;
+      int b = h->h_fblok[c] + 1;
+      for (int a0 = w; a0 < ld; a0 += TM) {
+        int imax = std::min(ld, a0 + TM) - 1;
+        while (h->h_coefind[b] + h->h_nrow[b] <= imax) ++b;   // blok holding the last row of this tile
+        int ncols = h->h_coefind[b] + h->h_nrow[b] - w;
+        int ntn = (ncols + TN - 1) / TN;
+        gemm.push_back({c, (int)tiles, ntn, a0, ld, w, w + ncols, 0, w, 0});
+        tiles += ntn;
+      }
+    }
+    if (tiles * 2 >= (1LL << 31)) return fail(PB200_ERR_STRUCT, "too many update tiles in one level");
+    if (tiles > 0) h->steps.push_back({2, t0, (int)gemm.size() - t0, tiles, 0, l});
+  }
+  { int rc = upload(h, sub, &h->d_sub); if (rc) return rc; }
+  { int rc = upload(h, gemm, &h->d_gemm); if (rc) return rc; }
+  h->use_mma = true;
+  return PB200_SUCCESS;
 }
 
 extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int flttype, int factotype, int device) {
@@ -196,6 +331,11 @@ extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int f
   { int rc = upload(h, trsm, &h->d_trsm); if (rc) { pb200_destroy(h); return rc; } }
   { int rc = upload(h, slv, &h->d_slv); if (rc) { pb200_destroy(h); return rc; } }
   { int rc = upload(h, upd, &h->d_upd); if (rc) { pb200_destroy(h); return rc; } }
+
+  if (flttype == PB200_REALDOUBLE || flttype == PB200_COMPLEXDOUBLE) {
+    int rc = build_mma_schedule(h, level, lvl_cblk);
+    if (rc) { pb200_destroy(h); return rc; }
+  }
 
   size_t slab = (size_t)h->coefnbr * h->esize;
   if (cudaMalloc(&h->dL, slab) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(L slab) failed"); }
@@ -354,8 +494,61 @@ static int factorize_tf(pb200_handle_t *h, double crit) {
   return PB200_SUCCESS;
 }
 
+// ------------------------------------------------------------------ factorization (tensor-core path)
+template <class T, int FACTO>
+static int factorize_mma(pb200_handle_t *h, double crit) {
+  T *L = (T *)h->dL, *U = (T *)h->dU;
+  const int lu = (FACTO == F_LU) ? 2 : 1;
+  static bool attr_done[4][4] = {};
+  if (!attr_done[h->flt][FACTO]) {
+    CK(cudaFuncSetAttribute(k_gemm_scatter<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem_bytes<T>()));
+    CK(cudaFuncSetAttribute(k_trsm_mma<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)trsm_smem_bytes<T>(SubCfg<T>::NBMAX)));
+    CK(cudaFuncSetAttribute(k_diag_sub<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)((size_t)SubCfg<T>::NBMAX * (SubCfg<T>::NBMAX + 1) * sizeof(T))));
+    attr_done[h->flt][FACTO] = true;
+  }
+  int64_t launches = 0;
+  for (const auto &st : h->steps) {
+    if (st.ntasks == 0) continue;
+    switch (st.kind) {
+      case 0: {
+        size_t smem = (size_t)st.nbmax * (st.nbmax | 1) * sizeof(T);
+        k_diag_sub<T, FACTO><<<st.ntasks, 256, smem, h->stream>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
+      } break;
+      case 1:
+        k_trsm_mma<T, FACTO><<<(unsigned)(st.ntiles * lu), 128, trsm_smem_bytes<T>(st.nbmax), h->stream>>>(
+            h->S, L, U, h->d_sub + st.task0, st.ntasks);
+        break;
+      case 2:
+        k_gemm_scatter<T, FACTO><<<(unsigned)(st.ntiles * lu), 128, upd_smem_bytes<T>(), h->stream>>>(
+            h->S, h->M, L, U, h->d_gemm + st.task0, st.ntasks);
+        break;
+      case 3:
+        if (FACTO == F_LU)
+          k_diag_transpose<T><<<dim3(4, std::min(st.ntasks, 65535)), dim3(32, 8), 0, h->stream>>>(h->S, L, U, h->d_lvl_cblk + st.task0, st.ntasks);
+        break;
+    }
+    ++launches;
+  }
+  CK(cudaGetLastError());
+  h->last_launches = launches;
+  return PB200_SUCCESS;
+}
+
 template <class T>
 static int factorize_t(pb200_handle_t *h, double crit) {
+  if constexpr (std::is_same<T, double>::value || std::is_same<T, cdouble>::value) {
+    if (h->use_mma) {
+      switch (h->facto) {
+        case PB200_FACT_LLT: return factorize_mma<T, F_LLT>(h, crit);
+        case PB200_FACT_LDLT: return factorize_mma<T, F_LDLT>(h, crit);
+        case PB200_FACT_LU: return factorize_mma<T, F_LU>(h, crit);
+        case PB200_FACT_LDLH:
+          return ST<T>::is_complex ? factorize_mma<T, F_LDLH>(h, crit) : factorize_mma<T, F_LDLT>(h, crit);
+      }
+    }
+  }
   switch (h->facto) {
     case PB200_FACT_LLT: return factorize_tf<T, F_LLT>(h, crit);
     case PB200_FACT_LDLT: return factorize_tf<T, F_LDLT>(h, crit);

@@ -1,0 +1,482 @@
+// kernels_mma.cuh — the double-precision hot path: FP64 tensor-core (DMMA)
+// kernels for real and complex double.
+//
+// A column block (cblk) wider than NBMAX columns is processed as a chain of
+// sub-panels J = [c0, c1) of its own columns (right-looking inside the cblk):
+//   k_diag_sub     factor the nb x nb block (c0,c0)            (factor_diag,   compute_diag.c:538)
+//   k_trsm_mma     rows [c1, stride) x J  <-  * W^{-T}          (factor_trsm1d, compute_trsm.c:128)
+//   k_gemm_scatter mode INT: rows [c1, stride) x cols [c1, w) of the cblk's own panel
+//                  -= P[., J] * P[c1:w, J]^T                    (trailing update of PASTIX_*_block,
+//                                                                compute_diag.c:171-203, 262-307, 486-518)
+// and, once the whole cblk is factored,
+//   k_gemm_scatter mode EXT: the fused "GEMM + compacted scatter" of the reference
+//                  C = P[w:, 0:w] * P[w:, 0:w]^T, tile by tile straight from the DMMA accumulators into
+//                  the facing cblks (compute_1dgemm = compute_contrib_compact + add_contrib_local,
+//                  sopalin_compute.c:270-598, 865-1032).  The reference's maxbloktab work buffer and
+//                  the AXPY scatter (dim_dgeam) never touch memory here.
+// LU keeps two panels per cblk, coeftab (L, with the full square A_kk as diagonal blok) and ucoeftab
+// (U^T); while a cblk is being factored ucoeftab's diagonal blok holds the transpose of coeftab's, so
+// both panels go through the same kernels with the B operand taken from the other panel.  At the end
+// ucoeftab's diagonal blok is (LU)^T, which is what DimTrans leaves (compute_diag.c:521-536, 598-603).
+#pragma once
+#include "mma.cuh"
+#include "symbol.cuh"
+#include "kernels_factor.cuh"
+
+namespace pb200 {
+
+// extra device-side maps built once per SolverMatrix (pb200_create)
+struct DevMap {
+  const int64_t *pairbase;      // per cblk: start of its (b2,b1) table in pairoff
+  const int *pairoff;           // tri(lb2,lb1): row offset of blok b2's first row inside fcblk(b1), -1 if none
+  const unsigned char *bflag;   // per blok: 1 = several source cblks of the same level write the facing cblk
+};
+
+struct GemmTask {
+  int cblk;
+  int tile0, ntn;       // first tile of this row tile inside the launch, number of column tiles
+  int arow0, arow1;     // panel rows of A handled by this row tile: [arow0, min(arow0+TM, arow1))
+  int brow0, brow1;     // panel rows forming the columns of C
+  int k0, k1;           // panel columns contracted
+  int mode;             // 0 = EXT (scatter into facing cblks), 1 = INT (own panel)
+};
+struct SubTask {        // diag / trsm work on sub-panel [c0,c1) of a cblk
+  int cblk, tile0, c0, c1;
+};
+
+template <class T> struct UpdCfg;
+template <> struct UpdCfg<double> {
+  static constexpr int TM = 128, TN = 64, KC = 16, STG = 3, WM = 2, WN = 2, PADA = 4, PADB = 4;
+};
+template <> struct UpdCfg<cdouble> {
+  static constexpr int TM = 64, TN = 64, KC = 16, STG = 3, WM = 2, WN = 2, PADA = 2, PADB = 2;
+};
+#define PB200_TABMAX 1536
+
+template <class T>
+constexpr size_t upd_smem_bytes() {
+  using C = UpdCfg<T>;
+  return (size_t)C::STG * C::KC * ((C::TM + C::PADA) + (C::TN + C::PADB) + 1) * sizeof(T) +
+         (size_t)C::TN * 8 + (size_t)(2 * C::TM + 5 * C::TN + PB200_TABMAX) * 4;
+}
+
+__device__ __forceinline__ void plain_sub(double *p, double v) { *p -= v; }
+__device__ __forceinline__ void plain_sub(cdouble *p, cdouble v) {
+  double2 *q = reinterpret_cast<double2 *>(p);
+  double2 o = *q; o.x -= v.x; o.y -= v.y; *q = o;
+}
+
+template <class T, int FACTO>
+__global__ void __launch_bounds__(128, 2)
+k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ tasks, int ntasks) {
+  using C = UpdCfg<T>;
+  constexpr bool CX = ST<T>::is_complex;
+  constexpr int TM = C::TM, TN = C::TN, KC = C::KC, STG = C::STG;
+  constexpr int LDA = TM + C::PADA, LDB = TN + C::PADB;
+  constexpr int MI = TM / C::WM / 16, NI = TN / C::WN / 8;
+  constexpr bool SCALE = (FACTO == F_LDLT || FACTO == F_LDLH);
+  constexpr bool CONJB = (FACTO == F_LDLH || FACTO == F_LLT);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *sA = reinterpret_cast<T *>(smem_raw);
+  T *sB = sA + STG * KC * LDA;
+  T *sD = sB + STG * KC * LDB;
+  int64_t *s_ctgt = reinterpret_cast<int64_t *>(sD + STG * KC);
+  int *s_rb = reinterpret_cast<int *>(s_ctgt + TN);
+  int *s_roff = s_rb + TM;
+  int *s_cb = s_roff + TM;
+  int *s_cj = s_cb + TN;
+  int *s_fc = s_cj + TN;
+  int *s_tw = s_fc + TN;
+  int *s_atom = s_tw + TN;
+  int *s_tab = s_atom + TN;
+
+  int tile = blockIdx.x, part = 0;
+  if (FACTO == F_LU) { part = tile & 1; tile >>= 1; }
+  const int ti = find_task(tasks, ntasks, tile);
+  const GemmTask tk = tasks[ti];
+  const int k = tk.cblk, tn = tile - tk.tile0;
+  const int ld = S.stride[k];
+  const int m0 = tk.arow0, mrows = min(TM, tk.arow1 - m0);
+  const int n0 = tk.brow0 + tn * TN, ncols = min(TN, tk.brow1 - n0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp / C::WN) * (MI * 16), wn0 = (warp % C::WN) * (NI * 8);
+
+  const T *Ap = ((FACTO == F_LU && part == 1) ? U : L) + S.poff[k];
+  const T *Bp = ((FACTO == F_LU && part == 0) ? U : L) + S.poff[k];
+  const T *Dp = L + S.poff[k];
+  const int nchunks = (tk.k1 - tk.k0 + KC - 1) / KC;
+
+  auto load_chunk = [&](int c, int stg) {
+    const int kb = tk.k0 + c * KC;
+    T *a = sA + stg * KC * LDA, *b = sB + stg * KC * LDB;
+    for (int e = tid; e < KC * TM; e += 128) {
+      const int kk = e / TM, i = e % TM;
+      const bool ok = (i < mrows) && (kb + kk < tk.k1);
+      cp_async_elem<sizeof(T)>(a + kk * LDA + i, Ap + (size_t)(ok ? kb + kk : tk.k0) * ld + m0 + (ok ? i : 0), ok);
+    }
+    for (int e = tid; e < KC * TN; e += 128) {
+      const int kk = e / TN, j = e % TN;
+      const bool ok = (j < ncols) && (kb + kk < tk.k1);
+      cp_async_elem<sizeof(T)>(b + kk * LDB + j, Bp + (size_t)(ok ? kb + kk : tk.k0) * ld + n0 + (ok ? j : 0), ok);
+    }
+    if (SCALE && tid < KC)
+      sD[stg * KC + tid] = (kb + tid < tk.k1) ? Dp[(size_t)(kb + tid) * (ld + 1)] : ST<T>::zero();
+  };
+
+#pragma unroll
+  for (int s = 0; s < STG - 1; ++s) {
+    if (s < nchunks) load_chunk(s, s);
+    cp_async_commit();
+  }
+
+  // ---- scatter maps of this tile (overlaps the first loads)
+  if (tk.mode == 0) {
+    const int b0 = S.fblok[k], b1 = S.fblok[k + 1];
+    if (tid < TM) {
+      int rb = 0, roff = 0;
+      if (tid < mrows) {
+        const int m = m0 + tid;
+        const int b = upper_le(S.coefind, b0, b1, m);
+        rb = b - b0 - 1; roff = m - S.coefind[b];
+      }
+      s_rb[tid] = rb; s_roff[tid] = roff;
+    }
+    if (tid < TN) {
+      int cb = 0, cj = 0, fc = 0, tw = 0, at = 0; int64_t ct = 0;
+      if (tid < ncols) {
+        const int n = n0 + tid;
+        const int b = upper_le(S.coefind, b0, b1, n);
+        cb = b - b0 - 1; fc = S.fcblk[b];
+        cj = S.frow[b] + (n - S.coefind[b]) - S.fcol[fc];
+        ct = S.poff[fc] + (int64_t)cj * S.stride[fc];
+        tw = S.width[fc]; at = M.bflag[b];
+      }
+      s_cb[tid] = cb; s_cj[tid] = cj; s_fc[tid] = fc; s_tw[tid] = tw; s_atom[tid] = at; s_ctgt[tid] = ct;
+    }
+  } else {
+    if (tid < TM) { s_rb[tid] = 0; s_roff[tid] = m0 + tid; }
+    if (tid < TN) {
+      const int n = n0 + tid;
+      s_cb[tid] = 0; s_cj[tid] = n; s_fc[tid] = k; s_tw[tid] = 0; s_atom[tid] = 0;
+      s_ctgt[tid] = S.poff[k] + (int64_t)n * ld;
+    }
+  }
+  __syncthreads();
+  int rb_lo = 0, ncb = 1, cb_lo = 0;
+  bool tab_in_smem = false;
+  const int64_t pbase = (tk.mode == 0) ? M.pairbase[k] : 0;
+  if (tk.mode == 0) {
+    rb_lo = s_rb[0]; cb_lo = s_cb[0];
+    const int nrb = s_rb[mrows - 1] - rb_lo + 1;
+    ncb = s_cb[ncols - 1] - cb_lo + 1;
+    tab_in_smem = (nrb * ncb <= PB200_TABMAX);
+    if (tab_in_smem)
+      for (int e = tid; e < nrb * ncb; e += 128) {
+        const int rb = rb_lo + e / ncb, cb = cb_lo + e % ncb;
+        s_tab[e] = (rb >= cb) ? M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb] : -1;
+      }
+  }
+
+  // ---- main loop: C(TM x TN) = A(TM x K) * B(TN x K)^T on DMMA
+  Acc<CX> acc[MI][NI];
+#pragma unroll
+  for (int a = 0; a < MI; ++a)
+#pragma unroll
+    for (int b = 0; b < NI; ++b) acc[a][b].zero();
+
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<STG - 2>();
+    __syncthreads();
+    if (c + STG - 1 < nchunks) load_chunk(c + STG - 1, (c + STG - 1) % STG);
+    cp_async_commit();
+    const int stg = c % STG;
+    const T *a = sA + stg * KC * LDA, *b = sB + stg * KC * LDB, *d = sD + stg * KC;
+#pragma unroll
+    for (int ks = 0; ks < KC; ks += 8) {
+      FragA<CX> fa[MI];
+      FragB<CX> fb[NI];
+#pragma unroll
+      for (int x = 0; x < MI; ++x) load_frag_a<T>(fa[x], a, LDA, wm0 + x * 16, ks, lane);
+#pragma unroll
+      for (int y = 0; y < NI; ++y) load_frag_b<T, CONJB, SCALE>(fb[y], b, LDB, wn0 + y * 8, ks, lane, d);
+#pragma unroll
+      for (int x = 0; x < MI; ++x)
+#pragma unroll
+        for (int y = 0; y < NI; ++y) mma_acc(acc[x][y], fa[x], fb[y]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: subtract the tile from its targets, straight from the accumulators
+  const int g = lane >> 2, t4 = lane & 3;
+  T *TA = ((FACTO == F_LU && part == 1) ? U : L);   // slab updated by the "normal" write of this part
+#pragma unroll
+  for (int x = 0; x < MI; ++x)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int i = wm0 + x * 16 + g + hh * 8;
+      if (i >= mrows) continue;
+      const int rb = s_rb[i], roff = s_roff[i];
+#pragma unroll
+      for (int y = 0; y < NI; ++y)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = wn0 + y * 8 + t4 * 2 + e;
+          if (j >= ncols) continue;
+          T v;
+          if constexpr (CX) v = cdouble(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
+          else v = acc[x][y].re[hh * 2 + e];
+          if (tk.mode == 1) {
+            // own panel: symmetric variants only keep the lower triangle of the diagonal blok
+            if (FACTO == F_LU || roff >= s_cj[j]) plain_sub(TA + s_ctgt[j] + roff, v);
+            continue;
+          }
+          const int cb = s_cb[j];
+          if (rb < cb) continue;
+          int ro = tab_in_smem ? s_tab[(rb - rb_lo) * ncb + (cb - cb_lo)]
+                               : M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb];
+          if (ro < 0) continue;
+          ro += roff;
+          T *dst;
+          if (FACTO != F_LU || part == 0 || ro >= s_tw[j]) {
+            dst = TA + s_ctgt[j] + ro;
+          } else {
+            // U contribution to a diagonal target: stored transposed into coeftab
+            // (sopalin_compute.c:431-435, 572-575); the b1 == b2 square is skipped
+            if (rb == cb) continue;
+            const int fc = s_fc[j];
+            dst = L + S.poff[fc] + (int64_t)ro * S.stride[fc] + s_cj[j];
+          }
+          if (s_atom[j]) atomic_sub(dst, v); else plain_sub(dst, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- panel TRSM on DMMA
+// X (rows [c1, stride) x cols J) <- X * W^{-T}, W = lower triangle of the factored nb x nb block.
+//   LLt  : W = L_JJ                          non-unit
+//   LDLt : W = L_JJ  unit, then X <- X D^{-1} (LDLh: conj(L_JJ))
+//   LU   : part 0  X = coeftab rows,  W = lower(ucoeftab JJ) = U_JJ^T, non-unit   (L <- L U^{-1})
+//          part 1  X = ucoeftab rows, W = lower(coeftab JJ)  = L_JJ,   unit       (U^T <- U^T L^{-T})
+// One CTA owns TRSM_TM rows and all nb columns; each warp owns 16 rows and walks the 8-column blocks
+// left to right: T = X_jb - sum_{kb<jb} Y_kb W[jb,kb]^T, Y_jb = T inv(W[jb,jb])^T, both on DMMA.
+#define PB200_TRSM_TM 64
+template <class T> struct SubCfg;
+template <> struct SubCfg<double> { static constexpr int NBMAX = 128, PADW = 4, PADX = 4; };
+template <> struct SubCfg<cdouble> { static constexpr int NBMAX = 64, PADW = 2, PADX = 2; };
+
+template <class T>
+__host__ __device__ constexpr int trsm_ldw(int nbp) {
+  // LDW = nbp + pad with (LDW mod 16) == 4 for 8-byte and (LDW mod 8) == 2 for 16-byte elements
+  return nbp + SubCfg<T>::PADW;
+}
+template <class T>
+inline size_t trsm_smem_bytes(int nb) {
+  const int nbp = (nb + 7) & ~7;
+  return ((size_t)nbp * trsm_ldw<T>(nbp) + (size_t)nbp * (PB200_TRSM_TM + SubCfg<T>::PADX) + (size_t)nbp * 8) * sizeof(T);
+}
+
+template <class T, int FACTO>
+__global__ void __launch_bounds__(128)
+k_trsm_mma(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, int ntasks) {
+  constexpr bool CX = ST<T>::is_complex;
+  constexpr int TM = PB200_TRSM_TM, LDX = TM + SubCfg<T>::PADX;
+  constexpr bool UNIT_SYM = (FACTO == F_LDLT || FACTO == F_LDLH);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int tile = blockIdx.x, part = 0;
+  if (FACTO == F_LU) { part = tile & 1; tile >>= 1; }
+  const int ti = find_task(tasks, ntasks, tile);
+  const SubTask tk = tasks[ti];
+  const int k = tk.cblk, ld = S.stride[k], c0 = tk.c0, nb = tk.c1 - tk.c0, nbp = (nb + 7) & ~7;
+  const int LDW = trsm_ldw<T>(nbp);
+  const int r_base = tk.c1 + (tile - tk.tile0) * TM, mrows = min(TM, ld - r_base);
+  T *Ws = reinterpret_cast<T *>(smem_raw);
+  T *Xs = Ws + (size_t)nbp * LDW;
+  T *sInv = Xs + (size_t)nbp * LDX;   // [nbp/8][k*8+n] = Inv_jb[n][k]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool unit = UNIT_SYM || (FACTO == F_LU && part == 1);
+  T *Xp = ((FACTO == F_LU && part == 1) ? U : L) + S.poff[k];
+  const T *Wp = ((FACTO == F_LU && part == 0) ? U : L) + S.poff[k] + (size_t)c0 * (ld + 1);
+  const T one = ST<T>::from_real(1.0), zero = ST<T>::zero();
+
+  for (int e = tid; e < nbp * nbp; e += 128) {
+    const int kk = e / nbp, n = e % nbp;
+    T v = (n == kk) ? one : zero;
+    if (n >= kk && n < nb && !(unit && n == kk)) {
+      v = Wp[(size_t)kk * ld + n];
+      if (FACTO == F_LDLH) v = ST<T>::conj(v);
+    }
+    Ws[(size_t)kk * LDW + n] = v;
+  }
+  for (int e = tid; e < nbp * TM; e += 128) {
+    const int kk = e / TM, i = e % TM;
+    Xs[(size_t)kk * LDX + i] = (i < mrows && kk < nb) ? Xp[(size_t)(c0 + kk) * ld + r_base + i] : zero;
+  }
+  __syncthreads();
+  // inverses of the 8x8 diagonal blocks, one thread per block
+  if (tid < nbp / 8) {
+    const T *Wd = Ws + (size_t)(tid * 8) * LDW + tid * 8;   // Wd[r][q] at q*LDW + r
+    T *inv = sInv + tid * 64;
+    for (int c = 0; c < 8; ++c) {
+      T x[8];
+      for (int r = 0; r < 8; ++r) x[r] = zero;
+      x[c] = one / Wd[(size_t)c * LDW + c];
+      for (int r = c + 1; r < 8; ++r) {
+        T s = zero;
+        for (int q = c; q < r; ++q) s += Wd[(size_t)q * LDW + r] * x[q];
+        x[r] = (zero - s) / Wd[(size_t)r * LDW + r];
+      }
+      for (int r = 0; r < 8; ++r) inv[c * 8 + r] = x[r];   // Inv[n=r][k=c] stored at [k*8 + n]
+    }
+  }
+  __syncthreads();
+
+  const int r0 = warp * 16, g = lane >> 2, t4 = lane & 3;
+  if (r0 < mrows) {
+    for (int jb = 0; jb < nbp / 8; ++jb) {
+      Acc<CX> a0, a1;
+      a0.zero(); a1.zero();
+      FragA<CX> fa; FragB<CX> fb;
+      int kb = 0;
+      for (; kb + 1 < jb; kb += 2) {
+        load_frag_a<T>(fa, Xs, LDX, r0, kb * 8, lane);
+        load_frag_b<T, false, false>(fb, Ws, LDW, jb * 8, kb * 8, lane, nullptr);
+        mma_acc(a0, fa, fb);
+        load_frag_a<T>(fa, Xs, LDX, r0, kb * 8 + 8, lane);
+        load_frag_b<T, false, false>(fb, Ws, LDW, jb * 8, kb * 8 + 8, lane, nullptr);
+        mma_acc(a1, fa, fb);
+      }
+      if (kb < jb) {
+        load_frag_a<T>(fa, Xs, LDX, r0, kb * 8, lane);
+        load_frag_b<T, false, false>(fb, Ws, LDW, jb * 8, kb * 8, lane, nullptr);
+        mma_acc(a0, fa, fb);
+      }
+      // T = X_jb - acc, written back in place (C layout), then re-read as an A fragment
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = r0 + g + ((q & 2) ? 8 : 0), kc = jb * 8 + t4 * 2 + (q & 1);
+        T *p = Xs + (size_t)kc * LDX + i;
+        T s;
+        if constexpr (CX) s = cdouble(a0.re[q] + a1.re[q], a0.im[q] + a1.im[q]);
+        else s = a0.re[q] + a1.re[q];
+        *p = *p - s;
+      }
+      __syncwarp();
+      load_frag_a<T>(fa, Xs, LDX, r0, jb * 8, lane);
+      load_frag_b<T, false, false>(fb, sInv + jb * 64, 8, 0, 0, lane, nullptr);
+      a0.zero();
+      mma_acc(a0, fa, fb);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = r0 + g + ((q & 2) ? 8 : 0), kc = jb * 8 + t4 * 2 + (q & 1);
+        T s;
+        if constexpr (CX) s = cdouble(a0.re[q], a0.im[q]);
+        else s = a0.re[q];
+        Xs[(size_t)kc * LDX + i] = s;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  const T *Dp = L + S.poff[k] + (size_t)c0 * (ld + 1);
+  for (int e = tid; e < nb * TM; e += 128) {
+    const int kk = e / TM, i = e % TM;
+    if (i >= mrows) continue;
+    T v = Xs[(size_t)kk * LDX + i];
+    if (UNIT_SYM) v = v / Dp[(size_t)kk * (ld + 1)];
+    Xp[(size_t)(c0 + kk) * ld + r_base + i] = v;
+  }
+}
+
+// ---------------------------------------------------------------- diagonal sub-block
+// Factor the nb x nb block at (c0,c0) of the cblk's diagonal blok in shared memory with the
+// reference's static-pivot rule; LU also mirrors the result transposed into ucoeftab.
+template <class T, int FACTO>
+__global__ void __launch_bounds__(256)
+k_diag_sub(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, double crit, unsigned long long *nbpivot) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *sm = reinterpret_cast<T *>(smem_raw);
+  __shared__ T s_piv;
+  const SubTask tk = tasks[blockIdx.x];
+  const int c = tk.cblk, ld = S.stride[c], nb = tk.c1 - tk.c0;
+  T *A = L + S.poff[c] + (size_t)tk.c0 * (ld + 1);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lds = nb | 1;   // odd leading dimension: conflict-free column and row walks
+  for (int idx = tid; idx < nb * nb; idx += nt) {
+    const int j = idx / nb, i = idx % nb;
+    sm[j * lds + i] = A[(size_t)j * ld + i];
+  }
+  __syncthreads();
+  factor_block<T, FACTO>(sm, nb, lds, crit, nbpivot, &s_piv);
+  for (int idx = tid; idx < nb * nb; idx += nt) {
+    const int j = idx / nb, i = idx % nb;
+    if (FACTO == F_LU || i >= j) A[(size_t)j * ld + i] = sm[j * lds + i];
+  }
+  if (FACTO == F_LU) {
+    T *UA = U + S.poff[c] + (size_t)tk.c0 * (ld + 1);
+    for (int idx = tid; idx < nb * nb; idx += nt) {
+      const int j = idx / nb, i = idx % nb;
+      UA[(size_t)j * ld + i] = sm[i * lds + j];
+    }
+  }
+}
+
+// LU: ucoeftab's diagonal blok <- transpose of coeftab's, for every cblk of the level about to be
+// factored (all external contributions have landed in coeftab by then).
+template <class T>
+__global__ void k_diag_transpose(DevSym S, const T *L, T *U, const int *__restrict__ cblks, int ncblk) {
+  __shared__ T tile[32][33];
+  for (int cc = blockIdx.y; cc < ncblk; cc += gridDim.y) {
+  const int c = cblks[cc];
+  const int w = S.width[c], ld = S.stride[c];
+  const int nt = (w + 31) / 32;
+  const T *A = L + S.poff[c];
+  T *B = U + S.poff[c];
+  for (int tt = blockIdx.x; tt < nt * nt; tt += gridDim.x) {
+    const int bi = (tt / nt) * 32, bj = (tt % nt) * 32;
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+      const int i = bi + threadIdx.x, j = bj + y;
+      if (i < w && j < w) tile[y][threadIdx.x] = A[(size_t)j * ld + i];
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+      const int i = bj + threadIdx.x, j = bi + y;   // B(i,j) = A(j,i)
+      if (i < w && j < w) B[(size_t)j * ld + i] = tile[threadIdx.x][y];
+    }
+  }
+  }
+}
+
+// ---------------------------------------------------------------- pair table
+// pairoff[pairbase[k] + tri(lb2, lb1)] for off-diagonal bloks b1 <= b2 of cblk k: offset, inside the
+// panel of fcblk(b1), of the row that faces b2's first row — what add_contrib_local recomputes for
+// every contribution (sopalin_compute.c:923-945).  -1: no facing blok.  `napa` is raised when a blok
+// is only partially covered (incomplete factorization): those matrices take the generic path.
+__global__ void k_build_pairs(DevSym S, const int64_t *__restrict__ pairbase, int *pairoff, int *napa) {
+  const int k = blockIdx.x;
+  const int b0 = S.fblok[k] + 1, nb = S.fblok[k + 1] - b0;
+  const int64_t base = pairbase[k];
+  for (int e = threadIdx.x; e < nb * (nb + 1) / 2; e += blockDim.x) {
+    // e = tri(lb2, lb1)
+    int lb2 = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+    while (lb2 * (lb2 + 1) / 2 > e) --lb2;
+    while ((lb2 + 1) * (lb2 + 2) / 2 <= e) ++lb2;
+    const int lb1 = e - lb2 * (lb2 + 1) / 2;
+    const int b1 = b0 + lb1, b2 = b0 + lb2;
+    const int fc = S.fcblk[b1];
+    const int r = S.frow[b2], rl = r + S.nrow[b2] - 1;
+    const int tb = upper_le(S.frow, S.fblok[fc], S.fblok[fc + 1], r);
+    int ro = -1;
+    if (tb >= S.fblok[fc] && r < S.frow[tb] + S.nrow[tb]) {
+      ro = S.coefind[tb] + (r - S.frow[tb]);
+      if (rl >= S.frow[tb] + S.nrow[tb]) *napa = 1;
+    } else {
+      *napa = 1;
+    }
+    pairoff[base + e] = ro;
+  }
+}
+
+}  // namespace pb200
