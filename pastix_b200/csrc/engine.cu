@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <type_traits>
@@ -62,6 +63,7 @@ struct pb200_handle_s {
   std::vector<Step> steps;
   SubTask *d_sub = nullptr;
   GemmTask *d_gemm = nullptr;
+  std::vector<int> h_gemm_modes;
   std::vector<void *> allocs;
 };
 
@@ -210,6 +212,8 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
   }
   { int rc = upload(h, sub, &h->d_sub); if (rc) return rc; }
   { int rc = upload(h, gemm, &h->d_gemm); if (rc) return rc; }
+  h->h_gemm_modes.resize(gemm.size());
+  for (size_t i = 0; i < gemm.size(); ++i) h->h_gemm_modes[i] = gemm[i].mode;
   h->use_mma = true;
   return PB200_SUCCESS;
 }
@@ -494,6 +498,7 @@ static int factorize_tf(pb200_handle_t *h, double crit) {
   return PB200_SUCCESS;
 }
 
+static int h_gemm_mode(const pb200_handle_t *h, int task) { return h->h_gemm_modes[task]; }
 // ------------------------------------------------------------------ factorization (tensor-core path)
 template <class T, int FACTO>
 static int factorize_mma(pb200_handle_t *h, double crit) {
@@ -504,17 +509,20 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
     CK(cudaFuncSetAttribute(k_gemm_scatter<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem_bytes<T>()));
     CK(cudaFuncSetAttribute(k_trsm_mma<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)trsm_smem_bytes<T>(SubCfg<T>::NBMAX)));
-    CK(cudaFuncSetAttribute(k_diag_sub<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)((size_t)SubCfg<T>::NBMAX * (SubCfg<T>::NBMAX + 1) * sizeof(T))));
     attr_done[h->flt][FACTO] = true;
   }
   int64_t launches = 0;
+  const bool prof = getenv("PB200_PROFILE") != nullptr;
+  double tkind[4] = {0, 0, 0, 0}; long long nk[4] = {0, 0, 0, 0};
+  double tlevel_max = 0; int lvl_max = -1;
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
   for (const auto &st : h->steps) {
     if (st.ntasks == 0) continue;
+    if (prof) cudaEventRecord(pe0, h->stream);
     switch (st.kind) {
       case 0: {
-        size_t smem = (size_t)st.nbmax * (st.nbmax | 1) * sizeof(T);
-        k_diag_sub<T, FACTO><<<st.ntasks, 256, smem, h->stream>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
+        k_diag_sub<T, FACTO><<<st.ntasks, 256, 0, h->stream>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
       } break;
       case 1:
         k_trsm_mma<T, FACTO><<<(unsigned)(st.ntiles * lu), 128, trsm_smem_bytes<T>(st.nbmax), h->stream>>>(
@@ -530,7 +538,22 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
         break;
     }
     ++launches;
+    if (prof) {
+      cudaEventRecord(pe1, h->stream); cudaEventSynchronize(pe1);
+      float ms = 0; cudaEventElapsedTime(&ms, pe0, pe1);
+      int kd = st.kind;
+      if (kd == 2 && h_gemm_mode(h, st.task0) == 1) kd = 3;   // internal update counted apart
+      tkind[kd] += ms; nk[kd]++;
+      if (getenv("PB200_PROFILE_VERBOSE"))
+        fprintf(stderr, "  lvl %3d kind %d tasks %6d tiles %8lld nbmax %3d : %8.3f ms\n", st.lvl, kd, st.ntasks, st.ntiles, st.nbmax, ms);
+    }
   }
+  if (prof) {
+    fprintf(stderr, "[pb200 profile] diag %.3f ms (%lld)  trsm %.3f ms (%lld)  ext-update %.3f ms (%lld)  int-update/transpose %.3f ms (%lld)\n",
+            tkind[0], nk[0], tkind[1], nk[1], tkind[2], nk[2], tkind[3], nk[3]);
+    cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+  }
+  (void)tlevel_max; (void)lvl_max;
   CK(cudaGetLastError());
   h->last_launches = launches;
   return PB200_SUCCESS;

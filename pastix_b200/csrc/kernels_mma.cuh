@@ -207,49 +207,99 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
   }
   cp_async_wait<0>();
 
-  // ---- epilogue: subtract the tile from its targets, straight from the accumulators
+  // ---- epilogue: subtract the tile from its targets, straight from the accumulators.
+  // Per 16-row MMA slab: resolve the NI*4 target addresses, issue all loads, then all stores, so the
+  // L2 round trips of the read-modify-write overlap instead of serialising.
   const int g = lane >> 2, t4 = lane & 3;
   T *TA = ((FACTO == F_LU && part == 1) ? U : L);   // slab updated by the "normal" write of this part
 #pragma unroll
-  for (int x = 0; x < MI; ++x)
+  for (int x = 0; x < MI; ++x) {
+    T *dst[2][NI][2];
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       const int i = wm0 + x * 16 + g + hh * 8;
-      if (i >= mrows) continue;
-      const int rb = s_rb[i], roff = s_roff[i];
+      const bool rok = i < mrows;
+      const int rb = rok ? s_rb[i] : 0, roff = rok ? s_roff[i] : 0;
 #pragma unroll
       for (int y = 0; y < NI; ++y)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = wn0 + y * 8 + t4 * 2 + e;
-          if (j >= ncols) continue;
-          T v;
-          if constexpr (CX) v = cdouble(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
-          else v = acc[x][y].re[hh * 2 + e];
-          if (tk.mode == 1) {
-            // own panel: symmetric variants only keep the lower triangle of the diagonal blok
-            if (FACTO == F_LU || roff >= s_cj[j]) plain_sub(TA + s_ctgt[j] + roff, v);
-            continue;
+          T *p = nullptr;
+          if (rok && j < ncols) {
+            if (tk.mode == 1) {
+              // own panel: symmetric variants only keep the lower triangle of the diagonal blok
+              if (FACTO == F_LU || roff >= s_cj[j]) p = TA + s_ctgt[j] + roff;
+            } else {
+              const int cb = s_cb[j];
+              if (rb >= cb) {
+                int ro = tab_in_smem ? s_tab[(rb - rb_lo) * ncb + (cb - cb_lo)]
+                                     : M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb];
+                if (ro >= 0) {
+                  ro += roff;
+                  if (FACTO != F_LU || part == 0 || ro >= s_tw[j]) {
+                    p = TA + s_ctgt[j] + ro;
+                  } else if (rb != cb) {
+                    // U contribution to a diagonal target: stored transposed into coeftab
+                    // (sopalin_compute.c:431-435, 572-575); the b1 == b2 square is skipped
+                    const int fc = s_fc[j];
+                    p = L + S.poff[fc] + (int64_t)ro * S.stride[fc] + s_cj[j];
+                  }
+                }
+              }
+            }
           }
-          const int cb = s_cb[j];
-          if (rb < cb) continue;
-          int ro = tab_in_smem ? s_tab[(rb - rb_lo) * ncb + (cb - cb_lo)]
-                               : M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb];
-          if (ro < 0) continue;
-          ro += roff;
-          T *dst;
-          if (FACTO != F_LU || part == 0 || ro >= s_tw[j]) {
-            dst = TA + s_ctgt[j] + ro;
-          } else {
-            // U contribution to a diagonal target: stored transposed into coeftab
-            // (sopalin_compute.c:431-435, 572-575); the b1 == b2 square is skipped
-            if (rb == cb) continue;
-            const int fc = s_fc[j];
-            dst = L + S.poff[fc] + (int64_t)ro * S.stride[fc] + s_cj[j];
-          }
-          if (s_atom[j]) atomic_sub(dst, v); else plain_sub(dst, v);
+          dst[hh][y][e] = p;
         }
     }
+    bool any_atomic = false;
+#pragma unroll
+    for (int y = 0; y < NI; ++y)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = wn0 + y * 8 + t4 * 2 + e;
+        any_atomic |= (j < ncols) && s_atom[j];
+      }
+    if (__any_sync(0xffffffffu, any_atomic)) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int y = 0; y < NI; ++y)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            T *p = dst[hh][y][e];
+            if (p == nullptr) continue;
+            T v;
+            if constexpr (CX) v = cdouble(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
+            else v = acc[x][y].re[hh * 2 + e];
+            atomic_sub(p, v);
+          }
+    } else {
+      T old[2][NI][2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int y = 0; y < NI; ++y)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            T *p = dst[hh][y][e];
+            if (p != nullptr) old[hh][y][e] = *p;
+          }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int y = 0; y < NI; ++y)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            T *p = dst[hh][y][e];
+            if (p == nullptr) continue;
+            T v;
+            if constexpr (CX) v = cdouble(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
+            else v = acc[x][y].re[hh * 2 + e];
+            *p = old[hh][y][e] - v;
+          }
+    }
+  }
 }
 
 // ---------------------------------------------------------------- panel TRSM on DMMA
@@ -273,7 +323,7 @@ __host__ __device__ constexpr int trsm_ldw(int nbp) {
 template <class T>
 inline size_t trsm_smem_bytes(int nb) {
   const int nbp = (nb + 7) & ~7;
-  return ((size_t)nbp * trsm_ldw<T>(nbp) + (size_t)nbp * (PB200_TRSM_TM + SubCfg<T>::PADX) + (size_t)nbp * 8) * sizeof(T);
+  return ((size_t)nbp * trsm_ldw<T>(nbp) + (size_t)nbp * (PB200_TRSM_TM + SubCfg<T>::PADX) + (size_t)nbp * 9) * sizeof(T);
 }
 
 template <class T, int FACTO>
@@ -299,35 +349,48 @@ k_trsm_mma(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, int ntasks) 
   const T *Wp = ((FACTO == F_LU && part == 0) ? U : L) + S.poff[k] + (size_t)c0 * (ld + 1);
   const T one = ST<T>::from_real(1.0), zero = ST<T>::zero();
 
-  for (int e = tid; e < nbp * nbp; e += 128) {
-    const int kk = e / nbp, n = e % nbp;
-    T v = (n == kk) ? one : zero;
-    if (n >= kk && n < nb && !(unit && n == kk)) {
-      v = Wp[(size_t)kk * ld + n];
-      if (FACTO == F_LDLH) v = ST<T>::conj(v);
+  // W: thread n walks row n of the lower triangle (coalesced over n); padding = identity
+  T *rdiag = sInv + (size_t)nbp * 8;   // reciprocals of W's diagonal
+  for (int n = tid; n < nbp; n += 128) {
+    for (int kk = 0; kk < nbp; ++kk) {
+      T v = (n == kk) ? one : zero;
+      if (n >= kk && n < nb && !(unit && n == kk)) {
+        v = Wp[(size_t)kk * ld + n];
+        if (FACTO == F_LDLH) v = ST<T>::conj(v);
+      }
+      Ws[(size_t)kk * LDW + n] = v;
+      if (n == kk) rdiag[n] = one / v;
     }
-    Ws[(size_t)kk * LDW + n] = v;
   }
-  for (int e = tid; e < nbp * TM; e += 128) {
-    const int kk = e / TM, i = e % TM;
-    Xs[(size_t)kk * LDX + i] = (i < mrows && kk < nb) ? Xp[(size_t)(c0 + kk) * ld + r_base + i] : zero;
+  // X: 64 rows x nb columns, thread i%64 walks columns (coalesced over rows)
+  {
+    const int i = tid & (TM - 1);
+    for (int kk = tid / TM; kk < nbp; kk += 128 / TM)
+      Xs[(size_t)kk * LDX + i] = (i < mrows && kk < nb) ? Xp[(size_t)(c0 + kk) * ld + r_base + i] : zero;
   }
   __syncthreads();
-  // inverses of the 8x8 diagonal blocks, one thread per block
-  if (tid < nbp / 8) {
-    const T *Wd = Ws + (size_t)(tid * 8) * LDW + tid * 8;   // Wd[r][q] at q*LDW + r
-    T *inv = sInv + tid * 64;
-    for (int c = 0; c < 8; ++c) {
-      T x[8];
-      for (int r = 0; r < 8; ++r) x[r] = zero;
-      x[c] = one / Wd[(size_t)c * LDW + c];
-      for (int r = c + 1; r < 8; ++r) {
-        T s = zero;
-        for (int q = c; q < r; ++q) s += Wd[(size_t)q * LDW + r] * x[q];
-        x[r] = (zero - s) / Wd[(size_t)r * LDW + r];
+  // inverses of the 8x8 diagonal blocks: one thread per (block, column)
+  for (int e = tid; e < nbp; e += 128) {
+    const int jb = e >> 3, c = e & 7;
+    const T *Wd = Ws + (size_t)(jb * 8) * LDW + jb * 8;   // Wd[r][q] at q*LDW + r
+    const T *rd = rdiag + jb * 8;
+    T *inv = sInv + jb * 64;
+    T x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) x[r] = zero;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r == c) x[r] = rd[r];
+      else if (r > c) {
+        T sacc = zero;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q >= c && q < r) sacc += Wd[(size_t)q * LDW + r] * x[q];
+        x[r] = (zero - sacc) * rd[r];
       }
-      for (int r = 0; r < 8; ++r) inv[c * 8 + r] = x[r];   // Inv[n=r][k=c] stored at [k*8 + n]
     }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) inv[c * 8 + r] = x[r];   // Inv[n=r][k=c] stored at [k*8 + n]
   }
   __syncthreads();
 
@@ -379,46 +442,140 @@ k_trsm_mma(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, int ntasks) 
     }
   }
   __syncthreads();
-  const T *Dp = L + S.poff[k] + (size_t)c0 * (ld + 1);
-  for (int e = tid; e < nb * TM; e += 128) {
-    const int kk = e / TM, i = e % TM;
-    if (i >= mrows) continue;
-    T v = Xs[(size_t)kk * LDX + i];
-    if (UNIT_SYM) v = v / Dp[(size_t)kk * (ld + 1)];
-    Xp[(size_t)(c0 + kk) * ld + r_base + i] = v;
+  {
+    const T *Dp = L + S.poff[k] + (size_t)c0 * (ld + 1);
+    const int i = tid & (TM - 1);
+    if (i < mrows)
+      for (int kk = tid / TM; kk < nb; kk += 128 / TM) {
+        T v = Xs[(size_t)kk * LDX + i];
+        if (UNIT_SYM) v = v / Dp[(size_t)kk * (ld + 1)];
+        Xp[(size_t)(c0 + kk) * ld + r_base + i] = v;
+      }
   }
 }
 
 // ---------------------------------------------------------------- diagonal sub-block
-// Factor the nb x nb block at (c0,c0) of the cblk's diagonal blok in shared memory with the
-// reference's static-pivot rule; LU also mirrors the result transposed into ucoeftab.
+// Factor the nb x nb block at (c0,c0) of the cblk's diagonal blok with the reference's static-pivot
+// rule (|pivot| < critere => pivot := critere, nbpivot++; compute_diag.c:133-137, 232-236, 444-448).
+// One CTA of 256 threads holds the whole block in REGISTERS, 2-D cyclic over a 16 x 16 thread grid
+// (thread (tx,ty) owns rows tx+16a, columns ty+16b), so the right-looking rank-1 updates are pure
+// register FMAs; per pivot only the scaled column (and, for LU, the pivot row) passes through shared
+// memory, double-buffered: one barrier per pivot.
+template <class T> __device__ __forceinline__ bool below_crit(T d, double crit);
+template <> __device__ __forceinline__ bool below_crit<double>(double d, double crit) { return fabs(d) < crit; }
+template <> __device__ __forceinline__ bool below_crit<cdouble>(cdouble d, double crit) {
+  return d.x * d.x + d.y * d.y < crit * crit;
+}
+__device__ __forceinline__ double shfl_t(unsigned m, double v, int src) { return __shfl_sync(m, v, src); }
+__device__ __forceinline__ cdouble shfl_t(unsigned m, cdouble v, int src) {
+  return cdouble(__shfl_sync(m, v.x, src), __shfl_sync(m, v.y, src));
+}
+
+template <class T, int FACTO, int KA, int R>
+__device__ __forceinline__ void diag_steps(T (&a)[R][R], int nb, int tx, int ty, int lane, double crit,
+                                           unsigned long long *nbpivot, T (*colbuf)[16 * R], T (*rowbuf)[16 * R]) {
+  if (KA * 16 >= nb) return;
+  const T zero = ST<T>::zero();
+  for (int kx = 0; kx < 16; ++kx) {
+    const int k = KA * 16 + kx;
+    if (k >= nb) break;
+    const int buf = k & 1;
+    if (ty == kx) {
+      T d = a[KA][KA];
+      if (tx == kx) {
+        if (below_crit<T>(d, crit)) { d = ST<T>::from_real(crit); atomicAdd(nbpivot, 1ULL); }
+        if (FACTO == F_LLT) d = ST<T>::sqrt(d);
+        a[KA][KA] = d;
+      }
+      d = shfl_t(0xFFFFu << (lane & 16), d, (lane & 16) | kx);
+      const T inv = ST<T>::from_real(1.0) / d;
+#pragma unroll
+      for (int ia = KA; ia < R; ++ia) {
+        const int i = tx + 16 * ia;
+        if (i > k) {
+          const T l = a[ia][KA] * inv;
+          a[ia][KA] = l;
+          colbuf[buf][i] = l;
+          if (FACTO == F_LLT) rowbuf[buf][i] = l;
+          else if (FACTO == F_LDLT) rowbuf[buf][i] = d * l;
+          else if (FACTO == F_LDLH) rowbuf[buf][i] = d * ST<T>::conj(l);
+        }
+      }
+    }
+    if (FACTO == F_LU && tx == kx) {
+#pragma unroll
+      for (int jb = KA; jb < R; ++jb) {
+        const int j = ty + 16 * jb;
+        if (j > k) rowbuf[buf][j] = a[KA][jb];
+      }
+    }
+    __syncthreads();
+    T cv[R], rv[R];
+#pragma unroll
+    for (int q = KA; q < R; ++q) {
+      const int i = tx + 16 * q, j = ty + 16 * q;
+      cv[q] = (i > k) ? colbuf[buf][i] : zero;
+      rv[q] = (j > k) ? rowbuf[buf][j] : zero;
+    }
+#pragma unroll
+    for (int ia = KA; ia < R; ++ia)
+#pragma unroll
+      for (int jb = KA; jb < R; ++jb) {
+        if (FACTO != F_LU && jb > ia) continue;   // symmetric variants: lower triangle only
+        a[ia][jb] = a[ia][jb] - cv[ia] * rv[jb];
+      }
+  }
+}
+
 template <class T, int FACTO>
 __global__ void __launch_bounds__(256)
 k_diag_sub(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, double crit, unsigned long long *nbpivot) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *sm = reinterpret_cast<T *>(smem_raw);
-  __shared__ T s_piv;
+  constexpr int R = SubCfg<T>::NBMAX / 16;
+  __shared__ T colbuf[2][16 * R];
+  __shared__ T rowbuf[2][16 * R];
   const SubTask tk = tasks[blockIdx.x];
   const int c = tk.cblk, ld = S.stride[c], nb = tk.c1 - tk.c0;
   T *A = L + S.poff[c] + (size_t)tk.c0 * (ld + 1);
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int lds = nb | 1;   // odd leading dimension: conflict-free column and row walks
-  for (int idx = tid; idx < nb * nb; idx += nt) {
-    const int j = idx / nb, i = idx % nb;
-    sm[j * lds + i] = A[(size_t)j * ld + i];
-  }
-  __syncthreads();
-  factor_block<T, FACTO>(sm, nb, lds, crit, nbpivot, &s_piv);
-  for (int idx = tid; idx < nb * nb; idx += nt) {
-    const int j = idx / nb, i = idx % nb;
-    if (FACTO == F_LU || i >= j) A[(size_t)j * ld + i] = sm[j * lds + i];
-  }
-  if (FACTO == F_LU) {
-    T *UA = U + S.poff[c] + (size_t)tk.c0 * (ld + 1);
-    for (int idx = tid; idx < nb * nb; idx += nt) {
-      const int j = idx / nb, i = idx % nb;
-      UA[(size_t)j * ld + i] = sm[i * lds + j];
+  const int tid = threadIdx.x, lane = tid & 31, tx = tid & 15, ty = tid >> 4;
+  T a[R][R];
+#pragma unroll
+  for (int ia = 0; ia < R; ++ia)
+#pragma unroll
+    for (int jb = 0; jb < R; ++jb) {
+      const int i = tx + 16 * ia, j = ty + 16 * jb;
+      a[ia][jb] = (i < nb && j < nb) ? A[(size_t)j * ld + i] : ST<T>::zero();
     }
+  diag_steps<T, FACTO, 0, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
+  diag_steps<T, FACTO, 1, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
+  diag_steps<T, FACTO, 2, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
+  diag_steps<T, FACTO, 3, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
+  if constexpr (R > 4) {
+    diag_steps<T, FACTO, 4, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
+    diag_steps<T, FACTO, 5, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
+    diag_steps<T, FACTO, 6, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
+    diag_steps<T, FACTO, 7, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
+  }
+#pragma unroll
+  for (int ia = 0; ia < R; ++ia)
+#pragma unroll
+    for (int jb = 0; jb < R; ++jb) {
+      const int i = tx + 16 * ia, j = ty + 16 * jb;
+      if (i < nb && j < nb && (FACTO == F_LU || i >= j)) A[(size_t)j * ld + i] = a[ia][jb];
+    }
+  if (FACTO == F_LU) {
+    // mirror (LU)^T into ucoeftab's diagonal blok through a 16 x 16 shared-memory transpose per register tile
+    __shared__ T tr[16][17];
+    T *UA = U + S.poff[c] + (size_t)tk.c0 * (ld + 1);
+#pragma unroll
+    for (int ia = 0; ia < R; ++ia)
+#pragma unroll
+      for (int jb = 0; jb < R; ++jb) {
+        __syncthreads();
+        tr[ty][tx] = a[ia][jb];                     // element (16ia+tx, 16jb+ty)
+        __syncthreads();
+        const int i = ty + 16 * ia, j = tx + 16 * jb;   // element (i,j) sits in tr[tx][ty]
+        if (i < nb && j < nb) UA[(size_t)i * ld + j] = tr[tx][ty];
+      }
   }
 }
 
