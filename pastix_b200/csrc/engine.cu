@@ -59,10 +59,11 @@ struct pb200_handle_s {
   // ---- FP64 tensor-core path (double / complex double, direct factorizations)
   bool use_mma = false;
   DevMap M{};
-  struct Step { int kind; int task0, ntasks; long long ntiles; int nbmax; int lvl; };  // kind: 0 diag 1 trsm 2 gemm 3 transpose
+  struct Step { int kind; int task0, ntasks; long long ntiles; int nbmax; int lvl; long long t2t0 = 0; };  // kind: 0 diag 1 trsm 2 gemm 3 transpose
   std::vector<Step> steps;
   SubTask *d_sub = nullptr;
   GemmTask *d_gemm = nullptr;
+  int *d_t2t = nullptr;
   std::vector<int> h_gemm_modes;
   std::vector<void *> allocs;
 };
@@ -117,31 +118,20 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
   int napa = 0;
   CK(cudaMemcpy(&napa, d_napa, sizeof(int), cudaMemcpyDeviceToHost));
   if (napa) { h->use_mma = false; return PB200_SUCCESS; }   // incomplete factorization: generic path
-  // per blok: does another cblk of the same level also write into the facing cblk?
-  std::vector<unsigned char> bflag(h->bloknbr, 0);
-  {
-    std::vector<int> stamp(C, -1), cnt(C, 0);
-    for (int l = 0; l < h->nlevels; ++l) {
-      for (int q = h->lvl_ptr[l]; q < h->lvl_ptr[l + 1]; ++q) {
-        int c = lvl_cblk[q];
-        int last = -1;
-        for (int b = h->h_fblok[c] + 1; b < h->h_fblok[c + 1]; ++b) {
-          int fc = h->h_fcblk[b];
-          if (fc == last) continue;   // facing cblks are non-decreasing along a panel
-          last = fc;
-          if (stamp[fc] != l) { stamp[fc] = l; cnt[fc] = 0; }
-          cnt[fc]++;
-        }
-      }
-      for (int q = h->lvl_ptr[l]; q < h->lvl_ptr[l + 1]; ++q) {
-        int c = lvl_cblk[q];
-        for (int b = h->h_fblok[c] + 1; b < h->h_fblok[c + 1]; ++b) bflag[b] = (cnt[h->h_fcblk[b]] > 1);
-      }
+  // per blok: target column origin inside the facing cblk
+  std::vector<BlokTgt> btgt(h->bloknbr);
+  for (int64_t c = 0; c < C; ++c)
+    for (int bb = h->h_fblok[c]; bb < h->h_fblok[c + 1]; ++bb) {
+      int fc = h->h_fcblk[bb];
+      if (bb == h->h_fblok[c]) fc = (int)c;
+      BlokTgt t;
+      t.cj0 = h->h_frow[bb] - h->h_fcol[fc]; t.tld = h->h_stride[fc]; t.tw = h->h_width[fc]; t.fc = fc;
+      t.tgt = h->h_poff[fc] + (int64_t)t.cj0 * t.tld;
+      btgt[bb] = t;
     }
-  }
-  unsigned char *d_bf;
-  { int rc = upload(h, bflag, &d_bf); if (rc) return rc; }
-  h->M.pairbase = d_pb; h->M.pairoff = d_po; h->M.bflag = d_bf;
+  BlokTgt *d_bt;
+  { int rc = upload(h, btgt, &d_bt); if (rc) return rc; }
+  h->M.pairbase = d_pb; h->M.pairoff = d_po; h->M.btgt = d_bt;
 
   std::vector<SubTask> sub;
   std::vector<GemmTask> gemm;
@@ -186,7 +176,7 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
         for (int a0 = c1; a0 < ld; a0 += TM) {
           int ncols = (lu ? w : std::min(w, a0 + TM)) - c1;
           int ntn = (ncols + TN - 1) / TN;
-          gemm.push_back({c, (int)tiles, ntn, a0, ld, c1, c1 + ncols, c0, c1, 1});
+          gemm.push_back({c, (int)tiles, ntn, a0, ld, c1, c1 + ncols, c0, c1, 1, 0, 0});
           tiles += ntn;
         }
       }
@@ -203,7 +193,7 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
         while (h->h_coefind[b] + h->h_nrow[b] <= imax) ++b;   // blok holding the last row of this tile
         int ncols = h->h_coefind[b] + h->h_nrow[b] - w;
         int ntn = (ncols + TN - 1) / TN;
-        gemm.push_back({c, (int)tiles, ntn, a0, ld, w, w + ncols, 0, w, 0});
+        gemm.push_back({c, (int)tiles, ntn, a0, ld, w, w + ncols, 0, w, 0, b, 0});
         tiles += ntn;
       }
     }
@@ -212,6 +202,17 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
   }
   { int rc = upload(h, sub, &h->d_sub); if (rc) return rc; }
   { int rc = upload(h, gemm, &h->d_gemm); if (rc) return rc; }
+  {
+    // tile -> task map of every GEMM launch (task index relative to the launch's first task)
+    std::vector<int> t2t;
+    for (auto &st : h->steps) {
+      if (st.kind != 2) continue;
+      st.t2t0 = (long long)t2t.size();
+      for (int t = 0; t < st.ntasks; ++t)
+        for (int q = 0; q < gemm[st.task0 + t].ntn; ++q) t2t.push_back(t);
+    }
+    int rc = upload(h, t2t, &h->d_t2t); if (rc) return rc;
+  }
   h->h_gemm_modes.resize(gemm.size());
   for (size_t i = 0; i < gemm.size(); ++i) h->h_gemm_modes[i] = gemm[i].mode;
   h->use_mma = true;
@@ -530,7 +531,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
         break;
       case 2:
         k_gemm_scatter<T, FACTO><<<(unsigned)(st.ntiles * lu), 128, upd_smem_bytes<T>(), h->stream>>>(
-            h->S, h->M, L, U, h->d_gemm + st.task0, st.ntasks);
+            h->S, h->M, L, U, h->d_gemm + st.task0, h->d_t2t + st.t2t0);
         break;
       case 3:
         if (FACTO == F_LU)

@@ -25,11 +25,20 @@
 
 namespace pb200 {
 
+// per off-diagonal blok: where its rows land as COLUMNS of the facing cblk (built in pb200_create)
+struct __align__(16) BlokTgt {
+  int64_t tgt;   // poff[fc] + (frow(b) - fcol(fc)) * stride(fc): slab offset of the target column of b's first row
+  int tld;       // stride(fc)
+  int tw;        // width(fc)
+  int cj0;       // frow(b) - fcol(fc)
+  int fc;        // facing cblk
+};
+
 // extra device-side maps built once per SolverMatrix (pb200_create)
 struct DevMap {
   const int64_t *pairbase;      // per cblk: start of its (b2,b1) table in pairoff
   const int *pairoff;           // tri(lb2,lb1): row offset of blok b2's first row inside fcblk(b1), -1 if none
-  const unsigned char *bflag;   // per blok: 1 = several source cblks of the same level write the facing cblk
+  const BlokTgt *btgt;          // per blok
 };
 
 struct GemmTask {
@@ -39,6 +48,8 @@ struct GemmTask {
   int brow0, brow1;     // panel rows forming the columns of C
   int k0, k1;           // panel columns contracted
   int mode;             // 0 = EXT (scatter into facing cblks), 1 = INT (own panel)
+  int rbl;              // EXT: last blok (absolute index) touched by this row tile
+  int pad;
 };
 struct SubTask {        // diag / trsm work on sub-panel [c0,c1) of a cblk
   int cblk, tile0, c0, c1;
@@ -52,23 +63,33 @@ template <> struct UpdCfg<cdouble> {
   static constexpr int TM = 64, TN = 64, KC = 16, STG = 3, WM = 2, WN = 2, PADA = 2, PADB = 2;
 };
 #define PB200_TABMAX 1536
+#define PB200_COEFMAX 1024
 
 template <class T>
 constexpr size_t upd_smem_bytes() {
   using C = UpdCfg<T>;
   return (size_t)C::STG * C::KC * ((C::TM + C::PADA) + (C::TN + C::PADB) + 1) * sizeof(T) +
-         (size_t)C::TN * 8 + (size_t)(2 * C::TM + 5 * C::TN + PB200_TABMAX) * 4;
+         (size_t)C::TN * 8 + (size_t)(2 * C::TM + 5 * C::TN + PB200_TABMAX + PB200_COEFMAX) * 4;
 }
 
-__device__ __forceinline__ void plain_sub(double *p, double v) { *p -= v; }
-__device__ __forceinline__ void plain_sub(cdouble *p, cdouble v) {
-  double2 *q = reinterpret_cast<double2 *>(p);
-  double2 o = *q; o.x -= v.x; o.y -= v.y; *q = o;
+// fire-and-forget reductions (RED.ADD.F64 at L2): the reference serialises these adds with
+// mutex_blok (sopalin_compute.c:563-580)
+__device__ __forceinline__ void red_sub(double *p, double v) { atomicAdd(p, -v); }
+__device__ __forceinline__ void red_sub(cdouble *p, cdouble v) { atomicAdd(&p->x, -v.x); atomicAdd(&p->y, -v.y); }
+
+// last index i in [0, n) with key[i] <= v (keys ascending, key[0] <= v assumed)
+__device__ __forceinline__ int upper_le_s(const int *key, int n, int v) {
+  int l = 0, h = n;
+  while (l < h) {
+    const int mid = (l + h) >> 1;
+    if (key[mid] <= v) l = mid + 1; else h = mid;
+  }
+  return l - 1;
 }
 
 template <class T, int FACTO>
 __global__ void __launch_bounds__(128, 2)
-k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ tasks, int ntasks) {
+k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ tasks, const int *__restrict__ tile2task) {
   using C = UpdCfg<T>;
   constexpr bool CX = ST<T>::is_complex;
   constexpr int TM = C::TM, TN = C::TN, KC = C::KC, STG = C::STG;
@@ -87,13 +108,13 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
   int *s_cj = s_cb + TN;
   int *s_fc = s_cj + TN;
   int *s_tw = s_fc + TN;
-  int *s_atom = s_tw + TN;
-  int *s_tab = s_atom + TN;
+  int *s_tld = s_tw + TN;
+  int *s_tab = s_tld + TN;
+  int *s_coef = s_tab + PB200_TABMAX;
 
   int tile = blockIdx.x, part = 0;
   if (FACTO == F_LU) { part = tile & 1; tile >>= 1; }
-  const int ti = find_task(tasks, ntasks, tile);
-  const GemmTask tk = tasks[ti];
+  const GemmTask tk = tasks[tile2task[tile]];
   const int k = tk.cblk, tn = tile - tk.tile0;
   const int ld = S.stride[k];
   const int m0 = tk.arow0, mrows = min(TM, tk.arow1 - m0);
@@ -129,43 +150,41 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
     cp_async_commit();
   }
 
-  // ---- scatter maps of this tile (overlaps the first loads)
+  // ---- scatter maps of this tile (overlap the first loads): three dependent round trips
+  int rb_lo = 0, ncb = 1, cb_lo = 0;
+  bool tab_in_smem = false;
+  int64_t pbase = 0;
   if (tk.mode == 0) {
-    const int b0 = S.fblok[k], b1 = S.fblok[k + 1];
+    const int bf = S.fblok[k] + 1;          // first off-diagonal blok
+    const int nbk = tk.rbl - bf + 1;        // bloks that rows/columns of this tile can belong to
+    const bool staged = nbk <= PB200_COEFMAX;
+    if (staged) {
+      for (int e = tid; e < nbk; e += 128) s_coef[e] = S.coefind[bf + e];
+      __syncthreads();
+    }
     if (tid < TM) {
       int rb = 0, roff = 0;
       if (tid < mrows) {
         const int m = m0 + tid;
-        const int b = upper_le(S.coefind, b0, b1, m);
-        rb = b - b0 - 1; roff = m - S.coefind[b];
+        rb = staged ? upper_le_s(s_coef, nbk, m) : upper_le(S.coefind, bf, tk.rbl + 1, m) - bf;
+        roff = m - (staged ? s_coef[rb] : S.coefind[bf + rb]);
       }
       s_rb[tid] = rb; s_roff[tid] = roff;
     }
     if (tid < TN) {
-      int cb = 0, cj = 0, fc = 0, tw = 0, at = 0; int64_t ct = 0;
+      int cb = 0, cj = 0, fc = 0, tw = 0, tld = 0; int64_t ct = 0;
       if (tid < ncols) {
         const int n = n0 + tid;
-        const int b = upper_le(S.coefind, b0, b1, n);
-        cb = b - b0 - 1; fc = S.fcblk[b];
-        cj = S.frow[b] + (n - S.coefind[b]) - S.fcol[fc];
-        ct = S.poff[fc] + (int64_t)cj * S.stride[fc];
-        tw = S.width[fc]; at = M.bflag[b];
+        cb = staged ? upper_le_s(s_coef, nbk, n) : upper_le(S.coefind, bf, tk.rbl + 1, n) - bf;
+        const int dn = n - (staged ? s_coef[cb] : S.coefind[bf + cb]);
+        const BlokTgt bt = M.btgt[bf + cb];
+        fc = bt.fc; tw = bt.tw; tld = bt.tld; cj = bt.cj0 + dn;
+        ct = bt.tgt + (int64_t)dn * bt.tld;
       }
-      s_cb[tid] = cb; s_cj[tid] = cj; s_fc[tid] = fc; s_tw[tid] = tw; s_atom[tid] = at; s_ctgt[tid] = ct;
+      s_cb[tid] = cb; s_cj[tid] = cj; s_fc[tid] = fc; s_tw[tid] = tw; s_tld[tid] = tld; s_ctgt[tid] = ct;
     }
-  } else {
-    if (tid < TM) { s_rb[tid] = 0; s_roff[tid] = m0 + tid; }
-    if (tid < TN) {
-      const int n = n0 + tid;
-      s_cb[tid] = 0; s_cj[tid] = n; s_fc[tid] = k; s_tw[tid] = 0; s_atom[tid] = 0;
-      s_ctgt[tid] = S.poff[k] + (int64_t)n * ld;
-    }
-  }
-  __syncthreads();
-  int rb_lo = 0, ncb = 1, cb_lo = 0;
-  bool tab_in_smem = false;
-  const int64_t pbase = (tk.mode == 0) ? M.pairbase[k] : 0;
-  if (tk.mode == 0) {
+    __syncthreads();
+    pbase = M.pairbase[k];
     rb_lo = s_rb[0]; cb_lo = s_cb[0];
     const int nrb = s_rb[mrows - 1] - rb_lo + 1;
     ncb = s_cb[ncols - 1] - cb_lo + 1;
@@ -175,6 +194,13 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
         const int rb = rb_lo + e / ncb, cb = cb_lo + e % ncb;
         s_tab[e] = (rb >= cb) ? M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb] : -1;
       }
+  } else {
+    if (tid < TM) { s_rb[tid] = 0; s_roff[tid] = m0 + tid; }
+    if (tid < TN) {
+      const int n = n0 + tid;
+      s_cb[tid] = 0; s_cj[tid] = n; s_fc[tid] = k; s_tw[tid] = 0; s_tld[tid] = ld;
+      s_ctgt[tid] = S.poff[k] + (int64_t)n * ld;
+    }
   }
 
   // ---- main loop: C(TM x TN) = A(TM x K) * B(TN x K)^T on DMMA
@@ -207,99 +233,46 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
   }
   cp_async_wait<0>();
 
-  // ---- epilogue: subtract the tile from its targets, straight from the accumulators.
-  // Per 16-row MMA slab: resolve the NI*4 target addresses, issue all loads, then all stores, so the
-  // L2 round trips of the read-modify-write overlap instead of serialising.
+  // ---- epilogue: subtract the tile from its targets straight from the accumulators with
+  // fire-and-forget L2 reductions: nothing is read back, so no latency is exposed here.
   const int g = lane >> 2, t4 = lane & 3;
   T *TA = ((FACTO == F_LU && part == 1) ? U : L);   // slab updated by the "normal" write of this part
 #pragma unroll
-  for (int x = 0; x < MI; ++x) {
-    T *dst[2][NI][2];
+  for (int x = 0; x < MI; ++x)
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       const int i = wm0 + x * 16 + g + hh * 8;
-      const bool rok = i < mrows;
-      const int rb = rok ? s_rb[i] : 0, roff = rok ? s_roff[i] : 0;
+      if (i >= mrows) continue;
+      const int rb = s_rb[i], roff = s_roff[i];
 #pragma unroll
       for (int y = 0; y < NI; ++y)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = wn0 + y * 8 + t4 * 2 + e;
-          T *p = nullptr;
-          if (rok && j < ncols) {
-            if (tk.mode == 1) {
-              // own panel: symmetric variants only keep the lower triangle of the diagonal blok
-              if (FACTO == F_LU || roff >= s_cj[j]) p = TA + s_ctgt[j] + roff;
-            } else {
-              const int cb = s_cb[j];
-              if (rb >= cb) {
-                int ro = tab_in_smem ? s_tab[(rb - rb_lo) * ncb + (cb - cb_lo)]
-                                     : M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb];
-                if (ro >= 0) {
-                  ro += roff;
-                  if (FACTO != F_LU || part == 0 || ro >= s_tw[j]) {
-                    p = TA + s_ctgt[j] + ro;
-                  } else if (rb != cb) {
-                    // U contribution to a diagonal target: stored transposed into coeftab
-                    // (sopalin_compute.c:431-435, 572-575); the b1 == b2 square is skipped
-                    const int fc = s_fc[j];
-                    p = L + S.poff[fc] + (int64_t)ro * S.stride[fc] + s_cj[j];
-                  }
-                }
-              }
-            }
+          if (j >= ncols) continue;
+          T v;
+          if constexpr (CX) v = cdouble(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
+          else v = acc[x][y].re[hh * 2 + e];
+          if (tk.mode == 1) {
+            // own panel: symmetric variants only keep the lower triangle of the diagonal blok
+            if (FACTO == F_LU || roff >= s_cj[j]) red_sub(TA + s_ctgt[j] + roff, v);
+            continue;
           }
-          dst[hh][y][e] = p;
+          const int cb = s_cb[j];
+          if (rb < cb) continue;
+          int ro = tab_in_smem ? s_tab[(rb - rb_lo) * ncb + (cb - cb_lo)]
+                               : M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb];
+          if (ro < 0) continue;
+          ro += roff;
+          if (FACTO != F_LU || part == 0 || ro >= s_tw[j]) {
+            red_sub(TA + s_ctgt[j] + ro, v);
+          } else if (rb != cb) {
+            // U contribution to a diagonal target: stored transposed into coeftab
+            // (sopalin_compute.c:431-435, 572-575); the b1 == b2 square is skipped
+            red_sub(L + S.poff[s_fc[j]] + (int64_t)ro * s_tld[j] + s_cj[j], v);
+          }
         }
     }
-    bool any_atomic = false;
-#pragma unroll
-    for (int y = 0; y < NI; ++y)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = wn0 + y * 8 + t4 * 2 + e;
-        any_atomic |= (j < ncols) && s_atom[j];
-      }
-    if (__any_sync(0xffffffffu, any_atomic)) {
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-        for (int y = 0; y < NI; ++y)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            T *p = dst[hh][y][e];
-            if (p == nullptr) continue;
-            T v;
-            if constexpr (CX) v = cdouble(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
-            else v = acc[x][y].re[hh * 2 + e];
-            atomic_sub(p, v);
-          }
-    } else {
-      T old[2][NI][2];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-        for (int y = 0; y < NI; ++y)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            T *p = dst[hh][y][e];
-            if (p != nullptr) old[hh][y][e] = *p;
-          }
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-        for (int y = 0; y < NI; ++y)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            T *p = dst[hh][y][e];
-            if (p == nullptr) continue;
-            T v;
-            if constexpr (CX) v = cdouble(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
-            else v = acc[x][y].re[hh * 2 + e];
-            *p = old[hh][y][e] - v;
-          }
-    }
-  }
 }
 
 // ---------------------------------------------------------------- panel TRSM on DMMA
@@ -349,24 +322,31 @@ k_trsm_mma(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, int ntasks) 
   const T *Wp = ((FACTO == F_LU && part == 0) ? U : L) + S.poff[k] + (size_t)c0 * (ld + 1);
   const T one = ST<T>::from_real(1.0), zero = ST<T>::zero();
 
-  // W: thread n walks row n of the lower triangle (coalesced over n); padding = identity
+  // stage W (lower triangle of the nb x nb block; the upper part is never read) and the X row tile
+  // with cp.async; padding rows/columns are zero-filled, padded diagonal = 1
   T *rdiag = sInv + (size_t)nbp * 8;   // reciprocals of W's diagonal
-  for (int n = tid; n < nbp; n += 128) {
-    for (int kk = 0; kk < nbp; ++kk) {
-      T v = (n == kk) ? one : zero;
-      if (n >= kk && n < nb && !(unit && n == kk)) {
-        v = Wp[(size_t)kk * ld + n];
-        if (FACTO == F_LDLH) v = ST<T>::conj(v);
-      }
-      Ws[(size_t)kk * LDW + n] = v;
-      if (n == kk) rdiag[n] = one / v;
-    }
-  }
-  // X: 64 rows x nb columns, thread i%64 walks columns (coalesced over rows)
   {
+    const int n = tid;
+    if (n < nbp)
+      for (int kk = 0; kk <= n; ++kk)
+        cp_async_elem<sizeof(T)>(Ws + (size_t)kk * LDW + n, Wp + (size_t)(n < nb ? kk : 0) * ld + (n < nb ? n : 0), n < nb);
     const int i = tid & (TM - 1);
-    for (int kk = tid / TM; kk < nbp; kk += 128 / TM)
-      Xs[(size_t)kk * LDX + i] = (i < mrows && kk < nb) ? Xp[(size_t)(c0 + kk) * ld + r_base + i] : zero;
+    for (int kk = tid / TM; kk < nbp; kk += 128 / TM) {
+      const bool ok = (i < mrows && kk < nb);
+      cp_async_elem<sizeof(T)>(Xs + (size_t)kk * LDX + i, Xp + (size_t)(c0 + (ok ? kk : 0)) * ld + r_base + (ok ? i : 0), ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    if (n < nbp) {
+      T dv = one;
+      if (n < nb && !unit) {
+        dv = Ws[(size_t)n * LDW + n];
+        if (FACTO == F_LDLH) dv = ST<T>::conj(dv);
+        dv = one / dv;
+      }
+      if (n >= nb) Ws[(size_t)n * LDW + n] = one;
+      rdiag[n] = dv;
+    }
   }
   __syncthreads();
   // inverses of the 8x8 diagonal blocks: one thread per (block, column)
@@ -385,7 +365,11 @@ k_trsm_mma(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, int ntasks) 
         T sacc = zero;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          if (q >= c && q < r) sacc += Wd[(size_t)q * LDW + r] * x[q];
+          if (q >= c && q < r) {
+            T wv = Wd[(size_t)q * LDW + r];
+            if (FACTO == F_LDLH) wv = ST<T>::conj(wv);
+            sacc += wv * x[q];
+          }
         x[r] = (zero - sacc) * rd[r];
       }
     }
@@ -403,15 +387,15 @@ k_trsm_mma(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, int ntasks) 
       int kb = 0;
       for (; kb + 1 < jb; kb += 2) {
         load_frag_a<T>(fa, Xs, LDX, r0, kb * 8, lane);
-        load_frag_b<T, false, false>(fb, Ws, LDW, jb * 8, kb * 8, lane, nullptr);
+        load_frag_b<T, FACTO == F_LDLH, false>(fb, Ws, LDW, jb * 8, kb * 8, lane, nullptr);
         mma_acc(a0, fa, fb);
         load_frag_a<T>(fa, Xs, LDX, r0, kb * 8 + 8, lane);
-        load_frag_b<T, false, false>(fb, Ws, LDW, jb * 8, kb * 8 + 8, lane, nullptr);
+        load_frag_b<T, FACTO == F_LDLH, false>(fb, Ws, LDW, jb * 8, kb * 8 + 8, lane, nullptr);
         mma_acc(a1, fa, fb);
       }
       if (kb < jb) {
         load_frag_a<T>(fa, Xs, LDX, r0, kb * 8, lane);
-        load_frag_b<T, false, false>(fb, Ws, LDW, jb * 8, kb * 8, lane, nullptr);
+        load_frag_b<T, FACTO == F_LDLH, false>(fb, Ws, LDW, jb * 8, kb * 8, lane, nullptr);
         mma_acc(a0, fa, fb);
       }
       // T = X_jb - acc, written back in place (C layout), then re-read as an A fragment
@@ -471,44 +455,60 @@ __device__ __forceinline__ cdouble shfl_t(unsigned m, cdouble v, int src) {
   return cdouble(__shfl_sync(m, v.x, src), __shfl_sync(m, v.y, src));
 }
 
+// reciprocal of the pivot (and, for LLt, the pivot's square root) off the slow IEEE sqrt/div paths
+template <int FACTO> __device__ __forceinline__ void pivot_inv(double &d, double &inv) {
+  if (FACTO == F_LLT) { inv = rsqrt(d); d = d * inv; inv = inv + inv * fma(-d, inv, 1.0); }   // one Newton step on 1/sqrt
+  else inv = __drcp_rn(d);
+}
+template <int FACTO> __device__ __forceinline__ void pivot_inv(cdouble &d, cdouble &inv) {
+  if (FACTO == F_LLT) d = ST<cdouble>::sqrt(d);
+  inv = cdouble(1.0, 0.0) / d;
+}
+
+// pivot k (column owners: the half-warp with ty == k%16): static-pivot test, scale the column,
+// publish it (and the row factor of the symmetric variants) in buffer k&1
+template <class T, int FACTO, int KA, int R>
+__device__ __forceinline__ void diag_pivot(T (&a)[R][R], int k, int kx, int tx, int lane, double crit,
+                                           unsigned long long *nbpivot, T (*colbuf)[16 * R], T (*rowbuf)[16 * R]) {
+  const int buf = k & 1;
+  T d = a[KA][KA];
+  if (tx == kx && below_crit<T>(d, crit)) { d = ST<T>::from_real(crit); atomicAdd(nbpivot, 1ULL); }
+  d = shfl_t(0xFFFFu << (lane & 16), d, (lane & 16) | kx);
+  T inv;
+  pivot_inv<FACTO>(d, inv);
+  if (tx == kx) a[KA][KA] = d;
+#pragma unroll
+  for (int ia = KA; ia < R; ++ia) {
+    const int i = tx + 16 * ia;
+    if (i > k) {
+      const T l = a[ia][KA] * inv;
+      a[ia][KA] = l;
+      colbuf[buf][i] = l;
+      if (FACTO == F_LLT) rowbuf[buf][i] = l;
+      else if (FACTO == F_LDLT) rowbuf[buf][i] = d * l;
+      else if (FACTO == F_LDLH) rowbuf[buf][i] = d * ST<T>::conj(l);
+    }
+  }
+}
+
 template <class T, int FACTO, int KA, int R>
 __device__ __forceinline__ void diag_steps(T (&a)[R][R], int nb, int tx, int ty, int lane, double crit,
                                            unsigned long long *nbpivot, T (*colbuf)[16 * R], T (*rowbuf)[16 * R]) {
   if (KA * 16 >= nb) return;
   const T zero = ST<T>::zero();
+  // first pivot of this 16-column group (no look-ahead across groups)
+  if (ty == 0) diag_pivot<T, FACTO, KA, R>(a, KA * 16, 0, tx, lane, crit, nbpivot, colbuf, rowbuf);
+  if (FACTO == F_LU && tx == 0) {
+#pragma unroll
+    for (int jb = KA; jb < R; ++jb) {
+      const int j = ty + 16 * jb;
+      if (j > KA * 16) rowbuf[(KA * 16) & 1][j] = a[KA][jb];
+    }
+  }
   for (int kx = 0; kx < 16; ++kx) {
     const int k = KA * 16 + kx;
     if (k >= nb) break;
     const int buf = k & 1;
-    if (ty == kx) {
-      T d = a[KA][KA];
-      if (tx == kx) {
-        if (below_crit<T>(d, crit)) { d = ST<T>::from_real(crit); atomicAdd(nbpivot, 1ULL); }
-        if (FACTO == F_LLT) d = ST<T>::sqrt(d);
-        a[KA][KA] = d;
-      }
-      d = shfl_t(0xFFFFu << (lane & 16), d, (lane & 16) | kx);
-      const T inv = ST<T>::from_real(1.0) / d;
-#pragma unroll
-      for (int ia = KA; ia < R; ++ia) {
-        const int i = tx + 16 * ia;
-        if (i > k) {
-          const T l = a[ia][KA] * inv;
-          a[ia][KA] = l;
-          colbuf[buf][i] = l;
-          if (FACTO == F_LLT) rowbuf[buf][i] = l;
-          else if (FACTO == F_LDLT) rowbuf[buf][i] = d * l;
-          else if (FACTO == F_LDLH) rowbuf[buf][i] = d * ST<T>::conj(l);
-        }
-      }
-    }
-    if (FACTO == F_LU && tx == kx) {
-#pragma unroll
-      for (int jb = KA; jb < R; ++jb) {
-        const int j = ty + 16 * jb;
-        if (j > k) rowbuf[buf][j] = a[KA][jb];
-      }
-    }
     __syncthreads();
     T cv[R], rv[R];
 #pragma unroll
@@ -517,14 +517,32 @@ __device__ __forceinline__ void diag_steps(T (&a)[R][R], int nb, int tx, int ty,
       cv[q] = (i > k) ? colbuf[buf][i] : zero;
       rv[q] = (j > k) ? rowbuf[buf][j] : zero;
     }
+    // the block row / block column holding pivot k+1 first, so that its owners can run ahead
 #pragma unroll
-    for (int ia = KA; ia < R; ++ia)
+    for (int ia = KA; ia < R; ++ia) a[ia][KA] = a[ia][KA] - cv[ia] * rv[KA];
+    if (FACTO == F_LU) {
 #pragma unroll
-      for (int jb = KA; jb < R; ++jb) {
+      for (int jb = KA + 1; jb < R; ++jb) a[KA][jb] = a[KA][jb] - cv[KA] * rv[jb];
+    }
+    if (kx + 1 < 16 && k + 1 < nb) {
+      if (ty == kx + 1) diag_pivot<T, FACTO, KA, R>(a, k + 1, kx + 1, tx, lane, crit, nbpivot, colbuf, rowbuf);
+      if (FACTO == F_LU && tx == kx + 1) {
+#pragma unroll
+        for (int jb = KA; jb < R; ++jb) {
+          const int j = ty + 16 * jb;
+          if (j > k + 1) rowbuf[(k + 1) & 1][j] = a[KA][jb];
+        }
+      }
+    }
+#pragma unroll
+    for (int ia = KA + (FACTO == F_LU ? 1 : 0); ia < R; ++ia)
+#pragma unroll
+      for (int jb = KA + 1; jb < R; ++jb) {
         if (FACTO != F_LU && jb > ia) continue;   // symmetric variants: lower triangle only
         a[ia][jb] = a[ia][jb] - cv[ia] * rv[jb];
       }
   }
+  __syncthreads();   // the next group's first pivot reuses buffer parity 0
 }
 
 template <class T, int FACTO>
