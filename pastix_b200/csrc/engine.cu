@@ -530,7 +530,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
             h->S, L, U, h->d_sub + st.task0, st.ntasks);
         break;
       case 2:
-        k_gemm_scatter<T, FACTO><<<(unsigned)(st.ntiles * lu), 128, upd_smem_bytes<T>(), h->stream>>>(
+        k_gemm_scatter<T, FACTO><<<(unsigned)(st.ntiles * lu), UpdCfg<T>::NT, upd_smem_bytes<T>(), h->stream>>>(
             h->S, h->M, L, U, h->d_gemm + st.task0, h->d_t2t + st.t2t0);
         break;
       case 3:

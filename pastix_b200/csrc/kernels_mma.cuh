@@ -57,10 +57,12 @@ struct SubTask {        // diag / trsm work on sub-panel [c0,c1) of a cblk
 
 template <class T> struct UpdCfg;
 template <> struct UpdCfg<double> {
-  static constexpr int TM = 128, TN = 64, KC = 16, STG = 3, WM = 2, WN = 2, PADA = 4, PADB = 4;
+  static constexpr int TM = 128, TN = 64, KC = 16, STG = 3, WM = 4, WN = 2, PADA = 4, PADB = 4;
+  static constexpr int NT = WM * WN * 32, CTAS = 2;
 };
 template <> struct UpdCfg<cdouble> {
-  static constexpr int TM = 64, TN = 64, KC = 16, STG = 3, WM = 2, WN = 2, PADA = 2, PADB = 2;
+  static constexpr int TM = 64, TN = 64, KC = 16, STG = 3, WM = 4, WN = 2, PADA = 2, PADB = 2;
+  static constexpr int NT = WM * WN * 32, CTAS = 2;
 };
 #define PB200_TABMAX 1536
 #define PB200_COEFMAX 1024
@@ -88,11 +90,11 @@ __device__ __forceinline__ int upper_le_s(const int *key, int n, int v) {
 }
 
 template <class T, int FACTO>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(UpdCfg<T>::NT, UpdCfg<T>::CTAS)
 k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ tasks, const int *__restrict__ tile2task) {
   using C = UpdCfg<T>;
   constexpr bool CX = ST<T>::is_complex;
-  constexpr int TM = C::TM, TN = C::TN, KC = C::KC, STG = C::STG;
+  constexpr int TM = C::TM, TN = C::TN, KC = C::KC, STG = C::STG, NT = C::NT;
   constexpr int LDA = TM + C::PADA, LDB = TN + C::PADB;
   constexpr int MI = TM / C::WM / 16, NI = TN / C::WN / 8;
   constexpr bool SCALE = (FACTO == F_LDLT || FACTO == F_LDLH);
@@ -130,12 +132,12 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
   auto load_chunk = [&](int c, int stg) {
     const int kb = tk.k0 + c * KC;
     T *a = sA + stg * KC * LDA, *b = sB + stg * KC * LDB;
-    for (int e = tid; e < KC * TM; e += 128) {
+    for (int e = tid; e < KC * TM; e += NT) {
       const int kk = e / TM, i = e % TM;
       const bool ok = (i < mrows) && (kb + kk < tk.k1);
       cp_async_elem<sizeof(T)>(a + kk * LDA + i, Ap + (size_t)(ok ? kb + kk : tk.k0) * ld + m0 + (ok ? i : 0), ok);
     }
-    for (int e = tid; e < KC * TN; e += 128) {
+    for (int e = tid; e < KC * TN; e += NT) {
       const int kk = e / TN, j = e % TN;
       const bool ok = (j < ncols) && (kb + kk < tk.k1);
       cp_async_elem<sizeof(T)>(b + kk * LDB + j, Bp + (size_t)(ok ? kb + kk : tk.k0) * ld + n0 + (ok ? j : 0), ok);
@@ -159,7 +161,7 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
     const int nbk = tk.rbl - bf + 1;        // bloks that rows/columns of this tile can belong to
     const bool staged = nbk <= PB200_COEFMAX;
     if (staged) {
-      for (int e = tid; e < nbk; e += 128) s_coef[e] = S.coefind[bf + e];
+      for (int e = tid; e < nbk; e += NT) s_coef[e] = S.coefind[bf + e];
       __syncthreads();
     }
     if (tid < TM) {
@@ -190,7 +192,7 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
     ncb = s_cb[ncols - 1] - cb_lo + 1;
     tab_in_smem = (nrb * ncb <= PB200_TABMAX);
     if (tab_in_smem)
-      for (int e = tid; e < nrb * ncb; e += 128) {
+      for (int e = tid; e < nrb * ncb; e += NT) {
         const int rb = rb_lo + e / ncb, cb = cb_lo + e % ncb;
         s_tab[e] = (rb >= cb) ? M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb] : -1;
       }
@@ -237,6 +239,20 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
   // fire-and-forget L2 reductions: nothing is read back, so no latency is exposed here.
   const int g = lane >> 2, t4 = lane & 3;
   T *TA = ((FACTO == F_LU && part == 1) ? U : L);   // slab updated by the "normal" write of this part
+  // this thread's NI*2 columns: resolved once
+  int c_cb[NI][2], c_cj[NI][2], c_tw[NI][2];
+  int64_t c_tgt[NI][2];
+#pragma unroll
+  for (int y = 0; y < NI; ++y)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = wn0 + y * 8 + t4 * 2 + e;
+      const bool ok = j < ncols;
+      c_cb[y][e] = ok ? s_cb[j] : 0x7fffffff;     // sentinel: never <= a row blok
+      c_cj[y][e] = ok ? s_cj[j] : 0x7fffffff;
+      c_tw[y][e] = s_tw[ok ? j : 0];
+      c_tgt[y][e] = s_ctgt[ok ? j : 0];
+    }
 #pragma unroll
   for (int x = 0; x < MI; ++x)
 #pragma unroll
@@ -244,32 +260,31 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
       const int i = wm0 + x * 16 + g + hh * 8;
       if (i >= mrows) continue;
       const int rb = s_rb[i], roff = s_roff[i];
+      const int trow = (rb - rb_lo) * ncb - cb_lo;
 #pragma unroll
       for (int y = 0; y < NI; ++y)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int j = wn0 + y * 8 + t4 * 2 + e;
-          if (j >= ncols) continue;
           T v;
           if constexpr (CX) v = cdouble(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
           else v = acc[x][y].re[hh * 2 + e];
           if (tk.mode == 1) {
             // own panel: symmetric variants only keep the lower triangle of the diagonal blok
-            if (FACTO == F_LU || roff >= s_cj[j]) red_sub(TA + s_ctgt[j] + roff, v);
+            if (c_cj[y][e] != 0x7fffffff && (FACTO == F_LU || roff >= c_cj[y][e])) red_sub(TA + c_tgt[y][e] + roff, v);
             continue;
           }
-          const int cb = s_cb[j];
+          const int cb = c_cb[y][e];
           if (rb < cb) continue;
-          int ro = tab_in_smem ? s_tab[(rb - rb_lo) * ncb + (cb - cb_lo)]
-                               : M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb];
+          int ro = tab_in_smem ? s_tab[trow + cb] : M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb];
           if (ro < 0) continue;
           ro += roff;
-          if (FACTO != F_LU || part == 0 || ro >= s_tw[j]) {
-            red_sub(TA + s_ctgt[j] + ro, v);
+          if (FACTO != F_LU || part == 0 || ro >= c_tw[y][e]) {
+            red_sub(TA + c_tgt[y][e] + ro, v);
           } else if (rb != cb) {
             // U contribution to a diagonal target: stored transposed into coeftab
             // (sopalin_compute.c:431-435, 572-575); the b1 == b2 square is skipped
-            red_sub(L + S.poff[s_fc[j]] + (int64_t)ro * s_tld[j] + s_cj[j], v);
+            const int j = wn0 + y * 8 + t4 * 2 + e;
+            red_sub(L + S.poff[s_fc[j]] + (int64_t)ro * s_tld[j] + c_cj[y][e], v);
           }
         }
     }

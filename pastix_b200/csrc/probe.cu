@@ -8,7 +8,7 @@
 namespace {
 
 template <int VARIANT>
-__global__ void __launch_bounds__(256) k_probe(double *out, int iters) {
+__global__ void __launch_bounds__(1024) k_probe(double *out, int iters) {
   double c[8][4];
   double a[8], b[4];
 #pragma unroll
@@ -43,14 +43,14 @@ __global__ void __launch_bounds__(256) k_probe(double *out, int iters) {
 }
 
 template <int V>
-double run(int sms) {
+double run(int sms, int bps = 8, int threads = 256) {
   double *d; cudaMalloc(&d, 8);
-  const int iters = 20000, blocks = sms * 8;
-  k_probe<V><<<blocks, 256>>>(d, 100);
+  const int iters = 20000, blocks = sms * bps;
+  k_probe<V><<<blocks, threads>>>(d, 100);
   cudaDeviceSynchronize();
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  k_probe<V><<<blocks, 256>>>(d, iters);
+  k_probe<V><<<blocks, threads>>>(d, iters);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
@@ -61,7 +61,7 @@ double run(int sms) {
   else if (V == 1) per_warp_iter = 8.0 * 8 * 8 * 4 * 2;
   else if (V == 2) per_warp_iter = 8.0 * 16 * 8 * 8 * 2;
   else per_warp_iter = 8.0 * 16 * 8 * 16 * 2;
-  double flops = per_warp_iter * (256 / 32) * (double)blocks * iters;
+  double flops = per_warp_iter * (threads / 32) * (double)blocks * iters;
   return flops / (ms * 1e-3) / 1e9;
 }
 }  // namespace
@@ -71,6 +71,10 @@ extern "C" double pb200_probe_fp64_gflops(int device, int variant) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1.0;
   if (device >= 0) cudaSetDevice(device); else cudaGetDevice(&device);
   cudaDeviceProp p; cudaGetDeviceProperties(&p, device);
+  if (variant >= 100) {   // DMMA m16n8k8 with (variant-100) warps per SM, 8 independent accumulators per warp
+    int warps = variant - 100;
+    return run<2>(p.multiProcessorCount, 1, warps * 32);
+  }
   switch (variant) {
     case 0: return run<0>(p.multiProcessorCount);
     case 1: return run<1>(p.multiProcessorCount);
