@@ -59,11 +59,13 @@ struct pb200_handle_s {
   // ---- FP64 tensor-core path (double / complex double, direct factorizations)
   bool use_mma = false;
   DevMap M{};
-  struct Step { int kind; int task0, ntasks; long long ntiles; int nbmax; int lvl; long long t2t0 = 0; };  // kind: 0 diag 1 trsm 2 gemm 3 transpose
+  struct Step { int kind; int task0, ntasks; long long ntiles; int nbmax; int lvl; long long t2t0 = 0; int strm = 0, wait_ev = -1, rec_ev = -1; };  // kind: 0 diag 1 trsm 2 gemm 3 transpose 4 marker
   std::vector<Step> steps;
   SubTask *d_sub = nullptr;
   GemmTask *d_gemm = nullptr;
   int *d_t2t = nullptr;
+  cudaStream_t stream_u = nullptr;       // second stream: the bulk of the fused GEMM+scatter updates
+  std::vector<cudaEvent_t> sched_ev;     // [l] panel(l) done, [nlevels + l] bulk update of level l done
   std::vector<int> h_gemm_modes;
   std::vector<void *> allocs;
 };
@@ -142,6 +144,7 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
   };
   for (int l = 0; l < h->nlevels; ++l) {
     const int q0 = h->lvl_ptr[l], q1 = h->lvl_ptr[l + 1];
+    const size_t level_first_step = h->steps.size();
     int rounds = 0;
     for (int q = q0; q < q1; ++q) rounds = std::max(rounds, (h->h_width[lvl_cblk[q]] + NBMAX - 1) / NBMAX);
     if (lu) h->steps.push_back({3, q0, q1 - q0, 0, 0, l});
@@ -182,23 +185,55 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
       }
       if (tiles > 0) h->steps.push_back({2, t0, (int)gemm.size() - t0, tiles, 0, l});
     }
-    // external update: fused GEMM + scatter
-    int t0 = (int)gemm.size(); long long tiles = 0;
-    for (int q = q0; q < q1; ++q) {
-      int c = lvl_cblk[q], w = h->h_width[c], ld = h->h_stride[c];
-      if (ld <= w) continue;
-      int b = h->h_fblok[c] + 1;
-      for (int a0 = w; a0 < ld; a0 += TM) {
-        int imax = std::min(ld, a0 + TM) - 1;
-        while (h->h_coefind[b] + h->h_nrow[b] <= imax) ++b;   // blok holding the last row of this tile
-        int ncols = h->h_coefind[b] + h->h_nrow[b] - w;
-        int ntn = (ncols + TN - 1) / TN;
-        gemm.push_back({c, (int)tiles, ntn, a0, ld, w, w + ncols, 0, w, 0, b, 0});
-        tiles += ntn;
+    // external update: fused GEMM + scatter, in two launches.  U1 = the column tiles that hit cblks of
+    // the NEXT level (they gate that level's panel work) stays on the panel stream; U2 = everything else
+    // runs on the second stream underneath the next level's diag/trsm chain.
+    size_t first_p = level_first_step;
+    for (int pass = 0; pass < 2; ++pass) {
+      int t0 = (int)gemm.size(); long long tiles = 0;
+      for (int q = q0; q < q1; ++q) {
+        int c = lvl_cblk[q], w = h->h_width[c], ld = h->h_stride[c];
+        if (ld <= w) continue;
+        int b = h->h_fblok[c] + 1;
+        for (int a0 = w; a0 < ld; a0 += TM) {
+          int imax = std::min(ld, a0 + TM) - 1;
+          while (h->h_coefind[b] + h->h_nrow[b] <= imax) ++b;   // blok holding the last row of this tile
+          int ncols = h->h_coefind[b] + h->h_nrow[b] - w;
+          int ntn = (ncols + TN - 1) / TN;
+          // classify the column tiles, emit maximal runs of the wanted class
+          int run0 = -1, cbk = h->h_fblok[c] + 1;
+          for (int tn = 0; tn <= ntn; ++tn) {
+            bool want = false;
+            if (tn < ntn) {
+              int n_lo = w + tn * TN, n_hi = std::min(w + ncols, n_lo + TN);   // panel rows [n_lo, n_hi)
+              while (h->h_coefind[cbk] + h->h_nrow[cbk] <= n_lo) ++cbk;
+              bool next = false;
+              for (int bb = cbk; bb < h->h_fblok[c + 1] && h->h_coefind[bb] < n_hi; ++bb)
+                if (level[h->h_fcblk[bb]] == l + 1) { next = true; break; }
+              want = (pass == 0) ? next : !next;
+            }
+            if (want && run0 < 0) run0 = tn;
+            if (!want && run0 >= 0) {
+              int rn = tn - run0;
+              int br0 = w + run0 * TN, br1 = std::min(w + ncols, br0 + rn * TN);
+              gemm.push_back({c, (int)tiles, rn, a0, ld, br0, br1, 0, w, 0, b, 0});
+              tiles += rn; run0 = -1;
+            }
+          }
+        }
       }
+      if (tiles * 2 >= (1LL << 31)) return fail(PB200_ERR_STRUCT, "too many update tiles in one level");
+      pb200_handle_t::Step st{tiles > 0 ? 2 : 4, t0, (int)gemm.size() - t0, tiles, 0, l};
+      if (pass == 0) {
+        // the panel steps of this level precede: first one waits for the bulk updates of level l-2
+        if (l >= 2) h->steps[first_p].wait_ev = h->nlevels + (l - 2);
+        h->steps.back().rec_ev = l;          // panel(l) done
+        st.strm = 0;
+      } else {
+        st.strm = 1; st.wait_ev = l; st.rec_ev = h->nlevels + l;
+      }
+      h->steps.push_back(st);
     }
-    if (tiles * 2 >= (1LL << 31)) return fail(PB200_ERR_STRUCT, "too many update tiles in one level");
-    if (tiles > 0) h->steps.push_back({2, t0, (int)gemm.size() - t0, tiles, 0, l});
   }
   { int rc = upload(h, sub, &h->d_sub); if (rc) return rc; }
   { int rc = upload(h, gemm, &h->d_gemm); if (rc) return rc; }
@@ -213,6 +248,9 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
     }
     int rc = upload(h, t2t, &h->d_t2t); if (rc) return rc;
   }
+  CK(cudaStreamCreateWithFlags(&h->stream_u, cudaStreamNonBlocking));
+  h->sched_ev.resize(2 * (size_t)h->nlevels);
+  for (auto &e : h->sched_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   h->h_gemm_modes.resize(gemm.size());
   for (size_t i = 0; i < gemm.size(); ++i) h->h_gemm_modes[i] = gemm[i].mode;
   h->use_mma = true;
@@ -351,7 +389,11 @@ extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int f
   }
   CK(cudaMalloc((void **)&h->d_cnt, 4 * sizeof(unsigned long long)));
   CK(cudaMemset(h->d_cnt, 0, 4 * sizeof(unsigned long long)));
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, hi));   // panel chain: highest priority
+  }
   CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
   *out = h;
   return PB200_SUCCESS;
@@ -363,6 +405,8 @@ extern "C" int pb200_destroy(pb200_handle_t *h) {
   for (void *p : h->allocs) cudaFree(p);
   cudaFree(h->dL); cudaFree(h->dU); cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals);
   cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x);
+  for (auto e : h->sched_ev) cudaEventDestroy(e);
+  if (h->stream_u) cudaStreamDestroy(h->stream_u);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -518,27 +562,34 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   double tlevel_max = 0; int lvl_max = -1;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
+  const bool serial = prof || getenv("PB200_SERIAL") != nullptr;
   for (const auto &st : h->steps) {
-    if (st.ntasks == 0) continue;
+    cudaStream_t sm = (serial || st.strm == 0) ? h->stream : h->stream_u;
+    if (!serial && st.wait_ev >= 0) CK(cudaStreamWaitEvent(sm, h->sched_ev[st.wait_ev], 0));
+    if (st.ntasks == 0 || st.kind == 4) {
+      if (!serial && st.rec_ev >= 0) CK(cudaEventRecord(h->sched_ev[st.rec_ev], sm));
+      continue;
+    }
     if (prof) cudaEventRecord(pe0, h->stream);
     switch (st.kind) {
       case 0: {
-        k_diag_sub<T, FACTO><<<st.ntasks, 256, 0, h->stream>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
+        k_diag_sub<T, FACTO><<<st.ntasks, 256, 0, sm>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
       } break;
       case 1:
-        k_trsm_mma<T, FACTO><<<(unsigned)(st.ntiles * lu), 128, trsm_smem_bytes<T>(st.nbmax), h->stream>>>(
+        k_trsm_mma<T, FACTO><<<(unsigned)(st.ntiles * lu), 128, trsm_smem_bytes<T>(st.nbmax), sm>>>(
             h->S, L, U, h->d_sub + st.task0, st.ntasks);
         break;
       case 2:
-        k_gemm_scatter<T, FACTO><<<(unsigned)(st.ntiles * lu), UpdCfg<T>::NT, upd_smem_bytes<T>(), h->stream>>>(
+        k_gemm_scatter<T, FACTO><<<(unsigned)(st.ntiles * lu), UpdCfg<T>::NT, upd_smem_bytes<T>(), sm>>>(
             h->S, h->M, L, U, h->d_gemm + st.task0, h->d_t2t + st.t2t0);
         break;
       case 3:
         if (FACTO == F_LU)
-          k_diag_transpose<T><<<dim3(4, std::min(st.ntasks, 65535)), dim3(32, 8), 0, h->stream>>>(h->S, L, U, h->d_lvl_cblk + st.task0, st.ntasks);
+          k_diag_transpose<T><<<dim3(4, std::min(st.ntasks, 65535)), dim3(32, 8), 0, sm>>>(h->S, L, U, h->d_lvl_cblk + st.task0, st.ntasks);
         break;
     }
     ++launches;
+    if (!serial && st.rec_ev >= 0) CK(cudaEventRecord(h->sched_ev[st.rec_ev], sm));
     if (prof) {
       cudaEventRecord(pe1, h->stream); cudaEventSynchronize(pe1);
       float ms = 0; cudaEventElapsedTime(&ms, pe0, pe1);
@@ -555,6 +606,10 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
     cudaEventDestroy(pe0); cudaEventDestroy(pe1);
   }
   (void)tlevel_max; (void)lvl_max;
+  if (!serial && h->nlevels > 0) {
+    // join: the panel stream (which carries the timing events) waits for the last bulk update
+    CK(cudaStreamWaitEvent(h->stream, h->sched_ev[2 * (size_t)h->nlevels - 1], 0));
+  }
   CK(cudaGetLastError());
   h->last_launches = launches;
   return PB200_SUCCESS;
