@@ -56,6 +56,15 @@ struct pb200_handle_s {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t last_launches = 0;
   bool assembled = false, factorized = false;
+  // ---- solve schedule (all precisions)
+  struct SlvStep { int task0, ntasks; long long ntiles, t2t0; };
+  std::vector<SlvStep> slv_steps;          // ascending (level, round)
+  SlvTask *d_slvtask = nullptr; int *d_slv_t2t = nullptr;
+  int64_t *d_invoff = nullptr; int64_t inv_elems = 0; int nsubpanels = 0;
+  void *d_inv = nullptr, *d_inv_up = nullptr;   // inverted diagonal triangles (LU: L and U^T)
+  unsigned int *d_slv_cnt = nullptr;
+  void *d_y = nullptr; size_t y_bytes = 0;
+  bool inv_ready = false;
   // ---- FP64 tensor-core path (double / complex double, direct factorizations)
   bool use_mma = false;
   DevMap M{};
@@ -91,6 +100,50 @@ static size_t elem_size(int flt) {
     case PB200_COMPLEXDOUBLE: return 16;
   }
   return 0;
+}
+
+// ------------------------------------------------------------------ schedule of the up_down sweeps
+static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_cblk) {
+  const int NB = (h->flt == PB200_COMPLEXDOUBLE) ? SlvCfg<cdouble>::NB : SlvCfg<double>::NB;
+  std::vector<SlvTask> tasks; std::vector<int> t2t; std::vector<int64_t> invoff;
+  int64_t inv_elems = 0; int sp = 0;
+  for (int l = 0; l < h->nlevels; ++l) {
+    const int q0 = h->lvl_ptr[l], q1 = h->lvl_ptr[l + 1];
+    int rounds = 0;
+    for (int q = q0; q < q1; ++q) rounds = std::max(rounds, (h->h_width[lvl_cblk[q]] + NB - 1) / NB);
+    for (int r = 0; r < rounds; ++r) {
+      int t0 = (int)tasks.size(); long long tiles = 0; long long tt0 = (long long)t2t.size();
+      for (int q = q0; q < q1; ++q) {
+        int c = lvl_cblk[q], w = h->h_width[c], ld = h->h_stride[c];
+        int nsub = (w + NB - 1) / NB;
+        if (nsub <= r) continue;
+        int sw = (w + nsub - 1) / nsub;
+        int c0 = r * sw, c1 = std::min(w, c0 + sw);
+        int nt = std::max(1, (ld - c1 + PB200_SLV_ROWS - 1) / PB200_SLV_ROWS);
+        tasks.push_back({c, (int)tiles, c0, c1, sp, nt});
+        for (int i = 0; i < nt; ++i) t2t.push_back((int)tasks.size() - 1 - t0);
+        tiles += nt;
+        invoff.push_back(inv_elems); inv_elems += (int64_t)(c1 - c0) * (c1 - c0); ++sp;
+      }
+      if (tiles >= (1LL << 31)) return fail(PB200_ERR_STRUCT, "too many solve tiles in one level");
+      h->slv_steps.push_back({t0, (int)tasks.size() - t0, tiles, tt0});
+    }
+  }
+  h->nsubpanels = sp; h->inv_elems = inv_elems;
+  { int rc = upload(h, tasks, &h->d_slvtask); if (rc) return rc; }
+  { int rc = upload(h, t2t, &h->d_slv_t2t); if (rc) return rc; }
+  { int rc = upload(h, invoff, &h->d_invoff); if (rc) return rc; }
+  size_t ib = (size_t)std::max<int64_t>(inv_elems, 1) * h->esize;
+  if (cudaMalloc(&h->d_inv, ib) != cudaSuccess) return fail(PB200_ERR_NOMEM, "cudaMalloc(inverse triangles) failed");
+  h->allocs.push_back(h->d_inv); h->device_bytes += ib;
+  if (h->facto == PB200_FACT_LU) {
+    if (cudaMalloc(&h->d_inv_up, ib) != cudaSuccess) return fail(PB200_ERR_NOMEM, "cudaMalloc(inverse triangles) failed");
+    h->allocs.push_back(h->d_inv_up); h->device_bytes += ib;
+  }
+  CK(cudaMalloc((void **)&h->d_slv_cnt, (size_t)std::max(sp, 1) * sizeof(unsigned int)));
+  h->allocs.push_back(h->d_slv_cnt);
+  CK(cudaMemset(h->d_slv_cnt, 0, (size_t)std::max(sp, 1) * sizeof(unsigned int)));
+  return PB200_SUCCESS;
 }
 
 // ------------------------------------------------------------------ schedule of the tensor-core path
@@ -375,6 +428,7 @@ extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int f
   { int rc = upload(h, slv, &h->d_slv); if (rc) { pb200_destroy(h); return rc; } }
   { int rc = upload(h, upd, &h->d_upd); if (rc) { pb200_destroy(h); return rc; } }
 
+  { int rc = build_solve_schedule(h, lvl_cblk); if (rc) { pb200_destroy(h); return rc; } }
   if (flttype == PB200_REALDOUBLE || flttype == PB200_COMPLEXDOUBLE) {
     int rc = build_mma_schedule(h, level, lvl_cblk);
     if (rc) { pb200_destroy(h); return rc; }
@@ -404,7 +458,7 @@ extern "C" int pb200_destroy(pb200_handle_t *h) {
   cudaSetDevice(h->device);
   for (void *p : h->allocs) cudaFree(p);
   cudaFree(h->dL); cudaFree(h->dU); cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals);
-  cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x);
+  cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x); cudaFree(h->d_y);
   for (auto e : h->sched_ev) cudaEventDestroy(e);
   if (h->stream_u) cudaStreamDestroy(h->stream_u);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -449,6 +503,7 @@ extern "C" double pb200_norm1(int flttype, int64_t n, const int64_t *colptr, con
   return -1.0;
 }
 
+static int invert_dispatch(pb200_handle_t *h, cudaStream_t sm);
 // ------------------------------------------------------------------ dispatch helpers
 #define DISPATCH_T(h, FN, ...)                                                    \
   switch ((h)->flt) {                                                             \
@@ -470,7 +525,7 @@ static int reassemble_t(pb200_handle_t *h) {
                                                         (const T *)h->d_tvals, 0, (T *)h->dL, (T *)h->dU, h->d_cnt + 1);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
-  h->assembled = true; h->factorized = false;
+  h->assembled = true; h->factorized = false; h->inv_ready = false;
   return PB200_SUCCESS;
 }
 
@@ -649,6 +704,8 @@ extern "C" int pb200_factorize(pb200_handle_t *h, double critere, int64_t *nbpiv
   CK(cudaEventRecord(h->ev0, h->stream));
   int rc = factorize_dispatch(h, critere);
   if (rc) return rc;
+  rc = invert_dispatch(h, h->stream);   // diagonal triangles inverted once, for the up_down sweeps
+  if (rc) return rc;
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -679,49 +736,46 @@ extern "C" int pb200_inertia(pb200_handle_t *h, int64_t *inertia) {
 }
 
 // ------------------------------------------------------------------ solve
+// invert the diagonal triangles of the freshly factored panels (one CTA per sub-panel)
+template <class T>
+static int invert_t(pb200_handle_t *h, cudaStream_t sm) {
+  static bool attr_done[4] = {};
+  const int NB = SlvCfg<T>::NB;
+  const size_t smem = (size_t)NB * (NB | 1) * sizeof(T);
+  if (!attr_done[h->flt]) {
+    CK(cudaFuncSetAttribute(k_tri_inverse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[h->flt] = true;
+  }
+  if (h->nsubpanels == 0) return PB200_SUCCESS;
+  const int unit_down = (h->facto != PB200_FACT_LLT);   // LDLt / LDLh / LU-L: unit lower triangle
+  k_tri_inverse<T><<<h->nsubpanels, 128, smem, sm>>>(h->S, (const T *)h->dL, h->d_slvtask, h->d_invoff, (T *)h->d_inv, unit_down);
+  if (h->facto == PB200_FACT_LU)   // up sweep: lower triangle of ucoeftab's diagonal blok = U^T, non-unit
+    k_tri_inverse<T><<<h->nsubpanels, 128, smem, sm>>>(h->S, (const T *)h->dU, h->d_slvtask, h->d_invoff, (T *)h->d_inv_up, 0);
+  CK(cudaGetLastError());
+  h->inv_ready = true;
+  return PB200_SUCCESS;
+}
+static int invert_dispatch(pb200_handle_t *h, cudaStream_t sm) { DISPATCH_T(h, invert_t, h, sm) }
+
 template <class T, int FACTO>
-static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs_total) {
+static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
   const T *L = (const T *)h->dL;
   const T *Mup = (FACTO == F_LU) ? (const T *)h->dU : L;
-  const int smem_cap = 96 * 1024;
-  static bool attr_done[4][4] = {};
-  if (!attr_done[h->flt][FACTO]) {
-    CK(cudaFuncSetAttribute(k_fwd_diag<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
-    CK(cudaFuncSetAttribute(k_bwd_diag<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
-    attr_done[h->flt][FACTO] = true;
-  }
-  int chunk = (int)std::max<long long>(1, std::min<long long>(nrhs_total, smem_cap / ((long long)h->wmax * (long long)sizeof(T))));
-  if ((size_t)h->wmax * sizeof(T) > (size_t)smem_cap) return fail(PB200_ERR_STRUCT, "cblk too wide for the solve kernels");
+  const T *inv = (const T *)h->d_inv;
+  const T *inv_up = (FACTO == F_LU) ? (const T *)h->d_inv_up : inv;
+  T *y = (T *)h->d_y;
   int64_t launches = 0;
-  for (int r0 = 0; r0 < nrhs_total; r0 += chunk) {
-    const int nrhs = std::min(chunk, nrhs_total - r0);
-    T *xc = x + (size_t)r0 * ldx;
-    const size_t dsm = (size_t)h->wmax * nrhs * sizeof(T);
-    const size_t usm = (size_t)h->wmax * PB200_SLV_NR * sizeof(T);
-    for (int l = 0; l < h->nlevels; ++l) {
-      int nc = h->lvl_ptr[l + 1] - h->lvl_ptr[l];
-      k_fwd_diag<T, FACTO><<<nc, 128, dsm, h->stream>>>(h->S, L, xc, ldx, nrhs, h->d_lvl_cblk + h->lvl_ptr[l]);
-      ++launches;
-      if (h->slv_tiles[l] > 0) {
-        k_fwd_update<T><<<h->slv_tiles[l], PB200_SLV_ROWS, usm, h->stream>>>(h->S, L, xc, ldx, nrhs, h->d_slv + h->slv_ptr[l],
-                                                                            h->slv_ptr[l + 1] - h->slv_ptr[l]);
-        ++launches;
-      }
-    }
-    if (FACTO == F_LDLT || FACTO == F_LDLH) {
-      k_diag_scale<T><<<(int)((h->n + 255) / 256), 256, 0, h->stream>>>(h->S, L, xc, ldx, nrhs, (int)h->n);
-      ++launches;
-    }
-    for (int l = h->nlevels - 1; l >= 0; --l) {
-      int nc = h->lvl_ptr[l + 1] - h->lvl_ptr[l];
-      if (h->slv_tiles[l] > 0) {
-        k_bwd_update<T, FACTO><<<h->slv_tiles[l], PB200_SLV_ROWS, 0, h->stream>>>(h->S, Mup, xc, ldx, nrhs, h->d_slv + h->slv_ptr[l],
-                                                                                  h->slv_ptr[l + 1] - h->slv_ptr[l]);
-        ++launches;
-      }
-      k_bwd_diag<T, FACTO><<<nc, 128, dsm, h->stream>>>(h->S, Mup, xc, ldx, nrhs, h->d_lvl_cblk + h->lvl_ptr[l]);
-      ++launches;
-    }
+  for (size_t i = 0; i < h->slv_steps.size(); ++i) {
+    const auto &st = h->slv_steps[i];
+    k_fwd<T, FACTO><<<(unsigned)st.ntiles, PB200_SLV_ROWS, 0, h->stream>>>(h->S, L, inv, h->d_invoff, x, y, ldx, nrhs,
+                                                                         h->d_slvtask + st.task0, h->d_slv_t2t + st.t2t0);
+    ++launches;
+  }
+  for (size_t i = h->slv_steps.size(); i-- > 0;) {
+    const auto &st = h->slv_steps[i];
+    k_bwd<T, FACTO><<<(unsigned)st.ntiles, 256, 0, h->stream>>>(h->S, Mup, inv_up, h->d_invoff, x, y, ldx, nrhs,
+                                                               h->d_slvtask + st.task0, h->d_slv_t2t + st.t2t0, h->d_slv_cnt);
+    ++launches;
   }
   CK(cudaGetLastError());
   h->last_launches = launches;
@@ -746,6 +800,15 @@ extern "C" int pb200_solve_device(pb200_handle_t *h, void *x_dev, int64_t ldx, i
   if (!h->factorized) return fail(PB200_ERR_STATE, "not factorized");
   if (ldx < h->n || nrhs <= 0) return fail(PB200_ERR_BADARG, "bad ldx / nrhs");
   CK(cudaSetDevice(h->device));
+  {
+    size_t yb = (size_t)ldx * nrhs * h->esize;
+    if (yb > h->y_bytes) {
+      cudaFree(h->d_y); h->d_y = nullptr; h->y_bytes = 0;
+      if (cudaMalloc(&h->d_y, yb) != cudaSuccess) return fail(PB200_ERR_NOMEM, "cudaMalloc(work vector) failed");
+      h->y_bytes = yb;
+    }
+    if (!h->inv_ready) { int rc0 = invert_dispatch(h, h->stream); if (rc0) return rc0; }
+  }
   CK(cudaEventRecord(h->ev0, h->stream));
   int rc = solve_dispatch(h, x_dev, ldx, (int)nrhs);
   if (rc) return rc;
@@ -795,7 +858,7 @@ extern "C" int pb200_set_coeftab(pb200_handle_t *h, const void *L, const void *U
   size_t slab = (size_t)h->coefnbr * h->esize;
   CK(cudaMemcpy(h->dL, L, slab, cudaMemcpyHostToDevice));
   if (h->dU) CK(cudaMemcpy(h->dU, U, slab, cudaMemcpyHostToDevice));
-  h->assembled = true; h->factorized = false;
+  h->assembled = true; h->factorized = false; h->inv_ready = false;
   return PB200_SUCCESS;
 }
 
