@@ -150,6 +150,15 @@ int pb200_mark_factorized(pb200_handle_t *h);
 /* Kernel launches issued by the last factorize / solve call (bench accounting). */
 int64_t pb200_last_launches(const pb200_handle_t *h);
 
+/* Measurement support (bench.py roofline): with profiling on, pb200_factorize serialises its
+ * launches and times every kernel kind with CUDA events on the launching stream.
+ *   kind_ms / kind_launches [4]: 0 diagonal blocks, 1 panel TRSM, 2 fused GEMM+scatter (updates into
+ *   facing cblks), 3 in-panel trailing updates / transposes.
+ *   gemm_flops: algorithmic flops of kind 2 for one factorization, PaStiX's own GEMM count
+ *   (blend/src/blend_symbol_cost.c:382-430). */
+int pb200_set_profile(pb200_handle_t *h, int on);
+int pb200_get_profile(const pb200_handle_t *h, double *kind_ms, int64_t *kind_launches, double *gemm_flops);
+
 /* FP64 dense-GEMM probe used by bench.py to establish the measured FP64 roof:
  * runs an m x n x k DGEMM tile loop with this library's own MMA micro-kernel
  * and returns achieved GFLOP/s (device timed). */

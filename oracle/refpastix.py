@@ -16,6 +16,10 @@ import os
 import numpy as np
 import scipy.sparse as sp
 
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pastix_b200.pastix_api import PastixLib  # noqa: E402  (the same pastix() binding, pointed at the reference build)
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REF = os.path.join(_HERE, "_ref")
 
@@ -31,112 +35,13 @@ def enums() -> dict:
     return json.load(open(os.path.join(_REF, "api_enums.json")))
 
 
-class RefPastix:
-    """One reference pastix_data_t instance (one matrix)."""
+class RefPastix(PastixLib):
+    """One reference pastix_data_t instance (one matrix), plus read access to its internals."""
 
     def __init__(self, prec: str = "d", threads: int = 1, verbose: int = 0):
-        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")  # PaStiX threads itself (SURVEY §8c)
-        self.prec = prec
-        self.dtype = np.dtype(_DTYPES[prec])
-        self.lib = C.CDLL(os.path.join(_REF, f"libpastix_ref_{prec}.so"), mode=C.RTLD_LOCAL)
-        self.E = enums()
+        super().__init__(prec, os.path.join(_REF, f"libpastix_ref_{prec}.so"), enums(), threads=threads, verbose=verbose)
         assert self.lib.refdrv_int_size() == 8
         self.lib.refdrv_norm1.restype = C.c_double
-        self.pd = C.c_void_p(None)
-        self.iparm = np.zeros(self.E["IPARM_SIZE"], dtype=np.int64)
-        self.dparm = np.zeros(self.E["DPARM_SIZE"], dtype=np.float64)
-        self.threads = threads
-        self.verbose = verbose
-        self._init_done = False
-
-    # -- raw call ---------------------------------------------------------
-    def _call(self, start: int, end: int, b=None, nrhs: int = 1):
-        E = self.E
-        self.iparm[E["IPARM_START_TASK"]] = start
-        self.iparm[E["IPARM_END_TASK"]] = end
-        bp = b.ctypes.data_as(C.c_void_p) if b is not None else None
-        self.lib.pastix(C.byref(self.pd), C.c_int(0), C.c_int64(self.n),
-                        self.colptr.ctypes.data_as(C.c_void_p), self.rows.ctypes.data_as(C.c_void_p),
-                        self.vals.ctypes.data_as(C.c_void_p), self.perm.ctypes.data_as(C.c_void_p),
-                        self.invp.ctypes.data_as(C.c_void_p), bp, C.c_int64(nrhs),
-                        self.iparm.ctypes.data_as(C.c_void_p), self.dparm.ctypes.data_as(C.c_void_p))
-        err = int(self.iparm[E["IPARM_ERROR_NUMBER"]])
-        if err != 0:
-            raise RuntimeError(f"reference pastix() returned IPARM_ERROR_NUMBER={err}")
-
-    # -- setup ------------------------------------------------------------
-    def setup(self, A: sp.spmatrix, perm0: np.ndarray, facto: str, sym: str = None, iparm_over: dict = None,
-              dparm_over: dict = None):
-        """A: CSC, lower triangle for symmetric ('sym'/'her'), full for 'no'.
-        perm0: 0-based perm[old]=new.  facto in {'llt','ldlt','lu','ldlh'}."""
-        E = self.E
-        A = sp.csc_matrix(A)
-        A.sort_indices()
-        self.n = A.shape[0]
-        self.colptr = (A.indptr.astype(np.int64) + 1)
-        self.rows = (A.indices.astype(np.int64) + 1)
-        self.vals = np.ascontiguousarray(A.data.astype(self.dtype))
-        self.perm = perm0.astype(np.int64) + 1
-        self.invp = np.empty_like(self.perm)
-        self.invp[self.perm - 1] = np.arange(1, self.n + 1)
-        # defaults (pastix.c:334-456)
-        self.iparm[E["IPARM_MODIFY_PARAMETER"]] = E["API_NO"]
-        self._call(E["API_TASK_INIT"], E["API_TASK_INIT"])
-        fact = {"llt": "API_FACT_LLT", "ldlt": "API_FACT_LDLT", "lu": "API_FACT_LU", "ldlh": "API_FACT_LDLH"}[facto]
-        if sym is None:
-            sym = {"llt": "yes", "ldlt": "yes", "lu": "no", "ldlh": "her"}[facto]
-        self.facto, self.sym = facto, sym
-        ip = self.iparm
-        ip[E["IPARM_THREAD_NBR"]] = self.threads
-        ip[E["IPARM_SYM"]] = {"yes": E["API_SYM_YES"], "no": E["API_SYM_NO"], "her": E["API_SYM_HER"]}[sym]
-        ip[E["IPARM_FACTORIZATION"]] = E[fact]
-        ip[E["IPARM_VERBOSE"]] = self.verbose
-        ip[E["IPARM_ORDERING"]] = E["API_ORDER_PERSONAL"]
-        ip[E["IPARM_MATRIX_VERIFICATION"]] = E["API_NO"]
-        ip[E["IPARM_LEVEL_OF_FILL"]] = -1
-        ip[E["IPARM_RHS_MAKING"]] = E["API_RHS_B"]
-        for k, v in (iparm_over or {}).items():
-            ip[E[k]] = v
-        for k, v in (dparm_over or {}).items():
-            self.dparm[E[k]] = v
-        return self
-
-    def analyze(self):
-        E = self.E
-        self._call(E["API_TASK_ORDERING"], E["API_TASK_ANALYSE"])
-        return self
-
-    def numfact(self):
-        E = self.E
-        self._call(E["API_TASK_NUMFACT"], E["API_TASK_NUMFACT"])
-        return self
-
-    def solve(self, b: np.ndarray) -> np.ndarray:
-        """b: (n,) or (n,nrhs) in the USER ordering; returns x likewise."""
-        E = self.E
-        x = np.array(b, dtype=self.dtype, order="F", copy=True)
-        nrhs = 1 if x.ndim == 1 else x.shape[1]
-        self._call(E["API_TASK_SOLVE"], E["API_TASK_SOLVE"], b=x, nrhs=nrhs)
-        return x
-
-    def clean(self):
-        E = self.E
-        if self.pd:
-            self._call(E["API_TASK_CLEAN"], E["API_TASK_CLEAN"])
-            self.pd = C.c_void_p(None)
-
-    # -- outputs ----------------------------------------------------------
-    def out(self) -> dict:
-        E = self.E
-        return {
-            "nnzeros": int(self.iparm[E["IPARM_NNZEROS"]]),
-            "static_pivoting": int(self.iparm[E["IPARM_STATIC_PIVOTING"]]),
-            "inertia": int(self.iparm[E["IPARM_INERTIA"]]),
-            "fact_flops": float(self.dparm[E["DPARM_FACT_FLOPS"]]),
-            "fact_time": float(self.dparm[E["DPARM_FACT_TIME"]]),
-            "solv_time": float(self.dparm[E["DPARM_SOLV_TIME"]]),
-            "epsilon_magn_ctrl": float(self.dparm[E["DPARM_EPSILON_MAGN_CTRL"]]),
-        }
 
     def solver(self) -> dict:
         """Flat copy of the SolverMatrix (blend/src/solver.h:94-168)."""

@@ -13,7 +13,7 @@ SYMBOLS = [
     "pb200_last_error", "pb200_version", "pb200_create", "pb200_destroy", "pb200_info", "pb200_panel_offsets",
     "pb200_norm1", "pb200_assemble", "pb200_reassemble", "pb200_factorize", "pb200_inertia", "pb200_solve",
     "pb200_solve_device", "pb200_get_coeftab", "pb200_set_coeftab", "pb200_mark_factorized",
-    "pb200_last_launches", "pb200_probe_fp64_gflops",
+    "pb200_last_launches", "pb200_probe_fp64_gflops", "pb200_set_profile", "pb200_get_profile",
 ]
 
 
@@ -60,6 +60,8 @@ def lib() -> C.CDLL:
     L.pb200_mark_factorized.argtypes = [C.c_void_p]
     L.pb200_last_launches.argtypes = [C.c_void_p]
     L.pb200_last_launches.restype = C.c_int64
+    L.pb200_set_profile.argtypes = [C.c_void_p, C.c_int]
+    L.pb200_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
     L.pb200_probe_fp64_gflops.argtypes = [C.c_int, C.c_int]
     L.pb200_probe_fp64_gflops.restype = C.c_double
     _lib = L

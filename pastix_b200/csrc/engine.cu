@@ -73,6 +73,9 @@ struct pb200_handle_s {
   SubTask *d_sub = nullptr;
   GemmTask *d_gemm = nullptr;
   int *d_t2t = nullptr;
+  bool prof_on = false;                  // pb200_set_profile: serialise the launches and time each kind
+  double prof_ms[4] = {0, 0, 0, 0}; int64_t prof_n[4] = {0, 0, 0, 0};
+  double gemm_flops = 0;                 // algorithmic flops of the fused GEMM+scatter launches (PaStiX's GEMM term)
   cudaStream_t stream_u = nullptr;       // second stream: the bulk of the fused GEMM+scatter updates
   std::vector<cudaEvent_t> sched_ev;     // [l] panel(l) done, [nlevels + l] bulk update of level l done
   std::vector<int> h_gemm_modes;
@@ -373,6 +376,14 @@ extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int f
         return bad("blok rows not contained in the facing cblk's column range");
     }
 
+  // algorithmic flops of the update GEMMs as PaStiX counts them (blend_symbol_cost.c:382-430:
+  // sum over off-diagonal bloks of 2*M_k*N_k*w, M_k = rows from blok k down; complex x4, LU x2)
+  for (int64_t c = 0; c < C; ++c)
+    for (int b = h->h_fblok[c] + 1; b < h->h_fblok[c + 1]; ++b)
+      h->gemm_flops += 2.0 * (double)(h->h_stride[c] - h->h_coefind[b]) * (double)h->h_nrow[b] * (double)h->h_width[c];
+  if (flttype == PB200_COMPLEXSINGLE || flttype == PB200_COMPLEXDOUBLE) h->gemm_flops *= 4.0;
+  if (factotype == PB200_FACT_LU) h->gemm_flops *= 2.0;
+
   // ---- elimination-tree levels: level(c) > level(k) for every k with a blok facing c
   std::vector<int> level(C, 0);
   for (int64_t c = 0; c < C; ++c)
@@ -482,6 +493,18 @@ extern "C" int pb200_panel_offsets(const pb200_handle_t *h, int64_t *offsets) {
 }
 
 extern "C" int64_t pb200_last_launches(const pb200_handle_t *h) { return h ? h->last_launches : 0; }
+
+extern "C" int pb200_set_profile(pb200_handle_t *h, int on) {
+  if (!h) return fail(PB200_ERR_BADARG, "null handle");
+  h->prof_on = (on != 0);
+  return PB200_SUCCESS;
+}
+extern "C" int pb200_get_profile(const pb200_handle_t *h, double *kind_ms, int64_t *kind_launches, double *gemm_flops) {
+  if (!h) return fail(PB200_ERR_BADARG, "null handle");
+  for (int q = 0; q < 4; ++q) { if (kind_ms) kind_ms[q] = h->prof_ms[q]; if (kind_launches) kind_launches[q] = h->prof_n[q]; }
+  if (gemm_flops) *gemm_flops = h->gemm_flops;
+  return PB200_SUCCESS;
+}
 
 template <class T>
 static double norm1_t(int64_t n, const int64_t *colptr, const T *v) {
@@ -612,7 +635,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
     attr_done[h->flt][FACTO] = true;
   }
   int64_t launches = 0;
-  const bool prof = getenv("PB200_PROFILE") != nullptr;
+  const bool prof = h->prof_on || getenv("PB200_PROFILE") != nullptr;
   double tkind[4] = {0, 0, 0, 0}; long long nk[4] = {0, 0, 0, 0};
   double tlevel_max = 0; int lvl_max = -1;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
@@ -656,6 +679,8 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
     }
   }
   if (prof) {
+    for (int q = 0; q < 4; ++q) { h->prof_ms[q] = tkind[q]; h->prof_n[q] = nk[q]; }
+    if (getenv("PB200_PROFILE") != nullptr)
     fprintf(stderr, "[pb200 profile] diag %.3f ms (%lld)  trsm %.3f ms (%lld)  ext-update %.3f ms (%lld)  int-update/transpose %.3f ms (%lld)\n",
             tkind[0], nk[0], tkind[1], nk[1], tkind[2], nk[2], tkind[3], nk[3]);
     cudaEventDestroy(pe0); cudaEventDestroy(pe1);

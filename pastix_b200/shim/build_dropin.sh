@@ -1,0 +1,74 @@
+#!/bin/bash
+# Builds the drop-in host library pastix_b200/lib/libpastix_dropin_<p>.so (p in d z s c):
+# the UNMODIFIED reference (PaStiX 5.2.2.16, compiled from its sources where they lie under
+# $PASTIX_REFERENCE/src — nothing is copied into this repo) with ONE object replaced:
+# sopalin3d.o (x4 factorization variants) -> pastix_b200/shim/sopalin_b200_shim.c, which routes
+# API_TASK_NUMFACT / API_TASK_SOLVE to the CUDA layer libpastix_b200.so.
+# Recipe = SURVEY.md §8c: -DFORCE_NOMPI, no Scotch/METIS (API_ORDER_PERSONAL + KASS), 64-bit
+# PASTIX_INT, -DMULT_SMX (multi-RHS), Fortran-ABI BLAS (only the reference's host-side refinement
+# and analysis use it) = the OpenBLAS shipped inside the opencv_python_headless wheel.
+# Without the reference tree (GPU box) the prebuilt .so files are kept.
+# usage: pastix_b200/shim/build_dropin.sh [precisions...]      (default: d z s c)
+set -u
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+R=${PASTIX_REFERENCE:-/root/reference}/src
+OUT="$ROOT/pastix_b200/lib"
+[ -d "$R" ] || { echo "reference sources not found at $R — keeping prebuilt drop-in libraries"; exit 0; }
+[ -f "$OUT/libpastix_b200.so" ] || { echo "build libpastix_b200.so first (python -m pastix_b200.build)"; exit 1; }
+PRECS="${*:-d z s c}"
+BLASDIR=$(python - <<'PY'
+import glob, os, sysconfig
+sp = sysconfig.get_paths()["purelib"]
+c = glob.glob(os.path.join(sp, "opencv_python_headless.libs", "libopenblas*.so"))
+print(os.path.dirname(c[0]) if c else "")
+PY
+)
+[ -n "$BLASDIR" ] || { echo "no Fortran-ABI OpenBLAS found"; exit 1; }
+BLASLIB=$(ls "$BLASDIR"/libopenblas*.so | head -1)
+INC="-I$HERE -I$R/common/src -I$R/symbol/src -I$R/order/src -I$R/sopalin/src -I$R/blend/src -I$R/fax/src -I$R/kass/src -I$R/perf/src -I$R/sparse-matrix/src -I$ROOT/include"
+CC="gcc -O2 -w -std=gnu99 -fcommon -fPIC"
+
+for P in $PRECS; do
+  case $P in
+    d) TDEF="-DPREC_DOUBLE";;
+    z) TDEF="-DPREC_DOUBLE -DTYPE_COMPLEX";;
+    s) TDEF="";;
+    c) TDEF="-DTYPE_COMPLEX";;
+  esac
+  LIB="$OUT/libpastix_dropin_$P.so"
+  if [ -f "$LIB" ] && [ "$LIB" -nt "$HERE/sopalin_b200_shim.c" ] && [ "$LIB" -nt "$HERE/shim_hooks.c" ] && [ "$LIB" -nt "$0" ] && [ "$LIB" -nt "$ROOT/include/pastix_b200.h" ]; then
+    echo "[$P] up to date"; continue
+  fi
+  DEF="-DFORCE_NOMPI $TDEF -DINTSIZE64 -DMULT_SMX -DX_ARCHi686_pc_linux -DDOF_CONSTANT -DFORCE_NO_CUDA -DVERSION=\"pastix_b200\""
+  OBJ="$OUT/_dropin_obj_$P"; mkdir -p "$OBJ"
+  JOBS="$OBJ/jobs.txt"; : > "$JOBS"
+  add() { echo "$CC $INC $DEF $3 -c $1 -o $OBJ/$2.o" >> "$JOBS"; }
+  for f in common_integer common_error common_memory trace common; do add $R/common/src/$f.c c_$f -DCHOL_SOPALIN; done
+  for f in dof dof_io symbol symbol_base symbol_check symbol_cost symbol_draw symbol_io symbol_keep symbol_levf symbol_nonzeros symbol_tree; do add $R/symbol/src/$f.c s_$f -DCHOL_SOPALIN; done
+  for f in order order_base order_check order_io; do add $R/order/src/$f.c o_$f -DCHOL_SOPALIN; done
+  for f in assemblyGener blend blend_symbol_cost blendctrl bulles cost costfunc distribPart elimin eliminfunc extendVector extrastruct fanboth2 param_blend partbuild queue simu smart_cblk_split solverMatrixGen solverRealloc solver_check solver_io splitfunc splitpart splitpartlocal symbolrand task write_ps blend_distributeOnGPU; do add $R/blend/src/$f.c b_$f -DCHOL_SOPALIN; done
+  for f in symbol_compact symbol_costi symbol_fax_graph symbol_fax symbol_faxi_graph symbol_faxi; do add $R/fax/src/$f.c f_$f -DCHOL_SOPALIN; done
+  for f in kass compact_graph amalgamate ifax sparRow SF_Direct SF_level find_supernodes KSupernodes sort_row; do add $R/kass/src/$f.c k_$f -DCHOL_SOPALIN; done
+  add $R/sparse-matrix/src/pastix_sparse_matrix.c sm_psm -DCHOL_SOPALIN
+  for f in bordi sopalin_thread compute_context_nbr coefinit csc_intern_build csc_intern_io csc_intern_solve csc_intern_updown csc_utils cscd_utils cscd_utils_fortran debug_dump ooc pastix pastix_fortran sopalin_init sopalin_option sparse_gemm_cpu tools; do add $R/sopalin/src/$f.c p_$f -DCHOL_SOPALIN; done
+  # the reference compiles these four times (src/CMakeLists.txt:40-62); sopalin3d.c is the one we replace
+  for f in starpu_submit_tasks csc_intern_compute raff_functions starpu_updo; do
+    add $R/sopalin/src/$f.c p_${f}_po -DCHOL_SOPALIN
+    add $R/sopalin/src/$f.c p_${f}_ge -DSOPALIN_LU
+    add $R/sopalin/src/$f.c p_${f}_sy -DNOEXTRADEF_SY
+    add $R/sopalin/src/$f.c p_${f}_he -DHERMITIAN
+  done
+  add "$HERE/sopalin_b200_shim.c" x_shim_po -DCHOL_SOPALIN
+  add "$HERE/sopalin_b200_shim.c" x_shim_ge -DSOPALIN_LU
+  add "$HERE/sopalin_b200_shim.c" x_shim_sy -DNOEXTRADEF_SY
+  add "$HERE/sopalin_b200_shim.c" x_shim_he -DHERMITIAN
+  add "$HERE/shim_hooks.c" x_shim_hooks -DCHOL_SOPALIN
+  xargs -P "$(nproc)" -I{} sh -c '{} 2>>'"$OBJ"'/err.log || echo "FAIL: {}"' < "$JOBS" | tee "$OBJ/fail.log"
+  if [ -s "$OBJ/fail.log" ]; then echo "[$P] compile failures (see $OBJ/err.log)"; tail -20 "$OBJ/err.log"; exit 1; fi
+  gcc -shared -o "$LIB" "$OBJ"/*.o -L"$OUT" -lpastix_b200 "$BLASLIB" -lpthread -lm \
+      -Wl,--disable-new-dtags -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$BLASDIR" -Wl,-rpath-link,"$BLASDIR" -Wl,--no-undefined 2> "$OBJ/link.log" \
+      || { echo "[$P] link failed"; head -30 "$OBJ/link.log"; exit 1; }
+  rm -rf "$OBJ"
+  echo "[$P] built $LIB"
+done

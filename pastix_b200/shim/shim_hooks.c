@@ -1,0 +1,85 @@
+/*
+ * shim_hooks.c — measurement / lifetime hooks of the drop-in library, compiled once per precision.
+ * They expose the device handle that sopalin_b200_shim.c keeps for the SolverMatrix inside a
+ * pastix_data_t (src/sopalin/src/pastixstr.h), so that bench.py can re-run the kernels on inputs
+ * already resident in HBM, and let a host application release the HBM explicitly.
+ */
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdint.h>
+#include "nompi.h"
+#include "common_pastix.h"
+#include "tools.h"
+#include "sopalin_define.h"
+#include "dof.h"
+#include "ftgt.h"
+#include "symbol.h"
+#include "csc.h"
+#include "updown.h"
+#include "queue.h"
+#include "bulles.h"
+#include "solver.h"
+#include "assembly.h"
+#include "param_blend.h"
+#include "order.h"
+#include "fax.h"
+#include "kass.h"
+#include "blend.h"
+#include "solverRealloc.h"
+#include "sopalin_thread.h"
+#include "stack.h"
+#include "sopalin3d.h"
+#include "sopalin_init.h"
+#include "sopalin_option.h"
+#include "csc_intern_updown.h"
+#include "csc_intern_build.h"
+#include "coefinit.h"
+#include "out.h"
+#include "pastix.h"
+#include "pastix_internal.h"
+#include "pastixstr.h"
+#include "shim_table.h"
+
+static pb200_shim_entry_t *hook_find(const SolverMatrix *m)
+{
+  int i; pb200_shim_entry_t *e = NULL;
+  pthread_mutex_lock(&shim_mutex);
+  for (i = 0; i < PB200_SHIM_MAX; i++)
+    if (shim_table[i].m == m) { e = &shim_table[i]; break; }
+  pthread_mutex_unlock(&shim_mutex);
+  return e;
+}
+
+/* pb200_handle_t* behind a pastix_data_t (NULL before the first API_TASK_NUMFACT) */
+void *pb200_shim_get_handle(void *pastix_data)
+{
+  pb200_shim_entry_t *e = hook_find(&((pastix_data_t *)pastix_data)->solvmatr);
+  return e ? (void *)e->h : NULL;
+}
+
+/* static-pivot threshold used by the last factorization (sopalin3d.c:586-606) */
+double pb200_shim_get_critere(void *pastix_data)
+{
+  pb200_shim_entry_t *e = hook_find(&((pastix_data_t *)pastix_data)->solvmatr);
+  return e ? e->critere : 0.0;
+}
+
+/* final permutation kept by the reference (order.h:52-57), 0-based, n entries each */
+void pb200_shim_get_order(void *pastix_data, int64_t *permtab, int64_t *peritab)
+{
+  pastix_data_t *pd = (pastix_data_t *)pastix_data;
+  PASTIX_INT i, n = pd->n2 > 0 ? pd->n2 : pd->n;
+  for (i = 0; i < n; i++) { permtab[i] = pd->ordemesh.permtab[i]; peritab[i] = pd->ordemesh.peritab[i]; }
+}
+
+/* release the HBM held for this pastix_data_t (call before API_TASK_CLEAN) */
+void pb200_shim_release_data(void *pastix_data)
+{
+  pb200_shim_entry_t *e = hook_find(&((pastix_data_t *)pastix_data)->solvmatr);
+  if (e == NULL) return;
+  if (e->h) pb200_destroy(e->h);
+  pthread_mutex_lock(&shim_mutex);
+  e->m = NULL; e->h = NULL; e->factorized = 0;
+  pthread_mutex_unlock(&shim_mutex);
+}

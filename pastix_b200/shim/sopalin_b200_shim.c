@@ -1,0 +1,345 @@
+/*
+ * sopalin_b200_shim.c — the drop-in: PaStiX's numeric-phase entry points on the B200.
+ *
+ * Compiled against the UNMODIFIED reference headers (read where they lie under
+ * $PASTIX_REFERENCE/src, nothing is copied) and linked in place of the reference's
+ * sopalin3d.o, four times like it (-DCHOL_SOPALIN / -DSOPALIN_LU / none / -DHERMITIAN give the
+ * po_/ge_/sy_/he_ variants, src/CMakeLists.txt:40-62; precision prefix S_/D_/C_/Z_ from
+ * common/src/redefine_functions.h:84-101).  Everything else of libpastix — pastix(),
+ * pastix_fortran(), ordering, fax/kass, blend, the internal CSC, refinement — stays the
+ * reference's own code, so iparm/dparm and the API_TASK_* semantics are untouched.
+ *
+ * Entry points replaced (reference: src/sopalin/src/sopalin3d.c):
+ *   API_CALL(sopalin_thread)        :1388   numeric factorization        (API_TASK_NUMFACT)
+ *   API_CALL(sopalin_updo_thread)   :1467   factorization + up_down      (NUMFACT..SOLVE)
+ *   API_CALL(updo_thread)           updo.c:67  up_down                   (API_TASK_SOLVE)
+ *   API_CALL(up_down_smp)           updo.c:114 up_down inside the reference's thread pool — the
+ *                                   preconditioner call of the refinement drivers
+ *                                   (raff_functions.c:408-437)
+ *   API_CALL(sopalin_updo_{gmres,grad,pivot,bicgstab}_thread) :1549-1900 = ours + the reference's
+ *                                   host refinement loop (raff_*.c, included below as sopalin3d.c does)
+ * What it does: flattens the SolverMatrix (blend/src/solver.h:94-168) and the internal CSC
+ * (blend/src/csc.h) into the plain arrays of include/pastix_b200.h, computes the static-pivot
+ * threshold exactly as init_struct_sopalin (sopalin3d.c:586-606), runs the CUDA layer, and writes
+ * back sopar->diagchange, DPARM_FACT_TIME, DPARM_SOLV_TIME, IPARM_INERTIA and the solution in
+ * updovct.sm2xtab.  Factors stay resident in HBM, keyed by SolverMatrix*; set PB200_HOST_COEFTAB=1
+ * to also mirror them into cblktab[].coeftab/ucoeftab (malloc'ed like CoefMatrix_Allocate,
+ * coefinit.c:104, so CoefMatrix_Free keeps working) for Schur/dump consumers.
+ * No CPU fallback: a CUDA failure is a fatal error (errorPrint + EXIT, like the reference's own
+ * fatal paths, common/src/errors.h:161-165).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <assert.h>
+#include <pthread.h>
+#include <math.h>
+#include <stdint.h>
+
+#ifdef FORCE_NOMPI
+#include "nompi.h"
+#else
+#include <mpi.h>
+#endif
+#include <signal.h>
+#include "common_pastix.h"
+#include "tools.h"
+#include "trace.h"
+#include "sopalin_define.h"
+#include "symbol.h"
+#include "ftgt.h"
+#include "csc.h"
+#include "updown.h"
+#include "queue.h"
+#include "bulles.h"
+#include "solver.h"
+#include "sopalin_thread.h"
+#include "stack.h"
+#include "sopalin3d.h"
+#include "sopalin_init.h"
+#include "perf.h"
+#include "out.h"
+#include "coefinit.h"
+#include "ooc.h"
+#include "order.h"
+#include "debug_dump.h"
+#include "sopalin_acces.h"
+#include "csc_intern_compute.h"
+
+#include "pastix_b200.h"
+
+#if defined(TYPE_COMPLEX) && defined(PREC_DOUBLE)
+#define PB200_FLT PB200_COMPLEXDOUBLE
+#elif defined(TYPE_COMPLEX)
+#define PB200_FLT PB200_COMPLEXSINGLE
+#elif defined(PREC_DOUBLE)
+#define PB200_FLT PB200_REALDOUBLE
+#else
+#define PB200_FLT PB200_REALSINGLE
+#endif
+
+#if defined(SOPALIN_LU)
+#define PB200_FACTO PB200_FACT_LU
+#elif defined(CHOL_SOPALIN)
+#define PB200_FACTO PB200_FACT_LLT
+#elif defined(HERMITIAN)
+#define PB200_FACTO PB200_FACT_LDLH
+#else
+#define PB200_FACTO PB200_FACT_LDLT
+#endif
+
+/* ---- side table: SolverMatrix* -> device handle (shared by the four variants of one precision) */
+#include "shim_table.h"
+#ifdef CHOL_SOPALIN
+#ifndef SOPALIN_LU
+pb200_shim_entry_t shim_table[PB200_SHIM_MAX];
+pthread_mutex_t    shim_mutex = PTHREAD_MUTEX_INITIALIZER;
+#endif
+#endif
+extern pb200_shim_entry_t shim_table[PB200_SHIM_MAX];
+extern pthread_mutex_t    shim_mutex;
+
+static void shim_fatal(const char *what)
+{
+  errorPrint("pastix_b200: %s: %s", what, pb200_last_error());
+  EXIT(MOD_SOPALIN, INTERNAL_ERR);
+}
+
+static pb200_shim_entry_t *shim_find(const SolverMatrix *m, int create)
+{
+  int i; pb200_shim_entry_t *e = NULL;
+  pthread_mutex_lock(&shim_mutex);
+  for (i = 0; i < PB200_SHIM_MAX; i++)
+    if (shim_table[i].m == m) { e = &shim_table[i]; break; }
+  if (e == NULL && create)
+    for (i = 0; i < PB200_SHIM_MAX; i++)
+      if (shim_table[i].m == NULL) { e = &shim_table[i]; e->m = m; e->h = NULL; e->factorized = 0; break; }
+  pthread_mutex_unlock(&shim_mutex);
+  return e;
+}
+
+/* release the HBM held for one SolverMatrix (call before freeing it; also run on re-analysis) */
+#define pb200_shim_release PASTIX_PREFIX_F(API_CALL(pb200_shim_release))
+void pb200_shim_release(const SolverMatrix *m)
+{
+  pb200_shim_entry_t *e = shim_find(m, 0);
+  if (e == NULL) return;
+  if (e->h) pb200_destroy(e->h);
+  pthread_mutex_lock(&shim_mutex);
+  e->m = NULL; e->h = NULL; e->factorized = 0;
+  pthread_mutex_unlock(&shim_mutex);
+}
+
+/* SolverMatrix -> flat arrays -> device handle */
+static pb200_handle_t *shim_create(SolverMatrix *datacode)
+{
+  pb200_solver_t s; pb200_handle_t *h = NULL;
+  int64_t *buf, *fcol, *lcol, *bnum, *strd, *frow, *lrow, *fcb, *cind;
+  PASTIX_INT i, C = SYMB_CBLKNBR, B = SYMB_BLOKNBR;
+  buf = (int64_t *)malloc(sizeof(int64_t) * (size_t)(4 * (C + 1) + 4 * B + 8));
+  if (buf == NULL) { errorPrint("pastix_b200: out of memory"); EXIT(MOD_SOPALIN, OUTOFMEMORY_ERR); }
+  fcol = buf; lcol = fcol + C + 1; bnum = lcol + C + 1; strd = bnum + C + 1;
+  frow = strd + C + 1; lrow = frow + B; fcb = lrow + B; cind = fcb + B;
+  for (i = 0; i < C; i++) {
+    fcol[i] = SYMB_FCOLNUM(i); lcol[i] = SYMB_LCOLNUM(i); bnum[i] = SYMB_BLOKNUM(i); strd[i] = SOLV_STRIDE(i);
+  }
+  bnum[C] = SYMB_BLOKNUM(C);
+  for (i = 0; i < B; i++) {
+    frow[i] = SYMB_FROWNUM(i); lrow[i] = SYMB_LROWNUM(i); fcb[i] = SYMB_CBLKNUM(i); cind[i] = SOLV_COEFIND(i);
+  }
+  s.cblknbr = C; s.bloknbr = B;
+  s.fcolnum = fcol; s.lcolnum = lcol; s.bloknum = bnum; s.stride = strd;
+  s.frownum = frow; s.lrownum = lrow; s.cblknum = fcb; s.coefind = cind;
+  if (pb200_create(&h, &s, PB200_FLT, PB200_FACTO, -1) != PB200_SUCCESS) shim_fatal("pb200_create");
+  free(buf);
+  return h;
+}
+
+/* internal block-CSC (CscOrdistrib, csc_intern_build.c:352) -> flat colptr/rows/values -> panels in HBM */
+static void shim_assemble(pb200_handle_t *h, SolverMatrix *datacode, SopalinParam *sopar)
+{
+  const CscMatrix *csc = sopar->cscmtx;
+  PASTIX_INT i, j, ncol = 0, nnz = 0, col = 0;
+  int64_t *colptr, *rows;
+  for (i = 0; i < CSC_FNBR(csc); i++) { ncol += CSC_COLNBR(csc, i); nnz = CSC_COL(csc, i, CSC_COLNBR(csc, i)); }
+  colptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ncol + 1));
+  rows   = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nnz + 1));
+  if (colptr == NULL || rows == NULL) { errorPrint("pastix_b200: out of memory"); EXIT(MOD_SOPALIN, OUTOFMEMORY_ERR); }
+  for (i = 0; i < CSC_FNBR(csc); i++)
+    for (j = 0; j < CSC_COLNBR(csc, i); j++) colptr[col++] = CSC_COL(csc, i, j);
+  colptr[col] = nnz;
+  for (i = 0; i < nnz; i++) rows[i] = CSC_ROW(csc, i);
+  if (pb200_assemble(h, colptr, rows, CSC_VALTAB(csc), sopar->transcsc) != PB200_SUCCESS) shim_fatal("pb200_assemble");
+  free(colptr); free(rows);
+  (void)datacode;
+}
+
+/* static-pivot threshold, init_struct_sopalin (sopalin3d.c:586-606) */
+static double shim_critere(SolverMatrix *datacode, SopalinParam *sopar)
+{
+  double crit = sopar->espilondiag;
+  if (crit < 0.0) return -crit;
+  if (sopar->usenocsc == 1) return crit;
+  if (sopar->fakefact == 1)
+    return (double)(UPDOWN_GNODENBR * UPDOWN_GNODENBR + UPDOWN_GNODENBR) * sqrt(sopar->espilondiag);
+  return CscNorm1(sopar->cscmtx, sopar->pastix_comm) * sqrt(sopar->espilondiag);
+}
+
+/* mirror the factors into cblktab[].coeftab / .ucoeftab (only when asked: PB200_HOST_COEFTAB=1) */
+static void shim_mirror_coeftab(pb200_handle_t *h, SolverMatrix *datacode)
+{
+  PASTIX_INT c; size_t off = 0, total = 0;
+  PASTIX_FLOAT *L, *U = NULL;
+  for (c = 0; c < SYMB_CBLKNBR; c++) total += (size_t)SOLV_STRIDE(c) * (size_t)(SYMB_LCOLNUM(c) - SYMB_FCOLNUM(c) + 1);
+  L = (PASTIX_FLOAT *)malloc(total * sizeof(PASTIX_FLOAT));
+  if (PB200_FACTO == PB200_FACT_LU) U = (PASTIX_FLOAT *)malloc(total * sizeof(PASTIX_FLOAT));
+  if (L == NULL || (PB200_FACTO == PB200_FACT_LU && U == NULL)) { errorPrint("pastix_b200: out of memory"); EXIT(MOD_SOPALIN, OUTOFMEMORY_ERR); }
+  if (pb200_get_coeftab(h, L, U) != PB200_SUCCESS) shim_fatal("pb200_get_coeftab");
+  for (c = 0; c < SYMB_CBLKNBR; c++) {
+    size_t sz = (size_t)SOLV_STRIDE(c) * (size_t)(SYMB_LCOLNUM(c) - SYMB_FCOLNUM(c) + 1);
+    if (SOLV_COEFTAB(c) == NULL) { MALLOC_INTERN(SOLV_COEFTAB(c), sz, PASTIX_FLOAT); }
+    memcpy(SOLV_COEFTAB(c), L + off, sz * sizeof(PASTIX_FLOAT));
+    if (U != NULL) {
+      if (SOLV_UCOEFTAB(c) == NULL) { MALLOC_INTERN(SOLV_UCOEFTAB(c), sz, PASTIX_FLOAT); }
+      memcpy(SOLV_UCOEFTAB(c), U + off, sz * sizeof(PASTIX_FLOAT));
+    }
+    off += sz;
+  }
+  free(L); if (U) free(U);
+}
+
+static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
+{
+  pb200_shim_entry_t *e = shim_find(datacode, 1);
+  int64_t nbpivot = 0; double seconds = 0.0, crit;
+  if (e == NULL) { errorPrint("pastix_b200: too many live SolverMatrix instances"); EXIT(MOD_SOPALIN, INTERNAL_ERR); }
+  if (sopar->iparm[IPARM_SCHUR] == API_YES || sopar->iparm[IPARM_DISTRIBUTION_LEVEL] != 0 || SOLV_PROCNBR > 1) {
+    errorPrint("pastix_b200: Schur / 2D distribution / multi-process SolverMatrix are not handled by this shim");
+    EXIT(MOD_SOPALIN, BADPARAMETER_ERR);
+  }
+  if (e->h != NULL && e->facto != PB200_FACTO) { pb200_destroy(e->h); e->h = NULL; }
+  if (e->h == NULL) { e->h = shim_create(datacode); e->facto = PB200_FACTO; }
+  e->factorized = 0;
+  shim_assemble(e->h, datacode, sopar);
+  crit = shim_critere(datacode, sopar);
+  e->critere = crit;
+  if (sopar->iparm[IPARM_VERBOSE] > API_VERBOSE_YES)
+    fprintf(stdout, "Pivoting criterium (||A||*sqrt(epsilon)) = %g\n", crit);
+  if (pb200_factorize(e->h, crit, &nbpivot, &seconds) != PB200_SUCCESS) shim_fatal("pb200_factorize");
+  e->factorized = 1;
+  sopar->diagchange = (PASTIX_INT)nbpivot;                       /* -> IPARM_STATIC_PIVOTING (pastix.c:3853) */
+  sopar->dparm[DPARM_FACT_TIME] = seconds;                       /* sopalin3d.c:1125-1132 */
+#if !defined(TYPE_COMPLEX) && !defined(CHOL_SOPALIN)
+  { int64_t inertia = 0;                                         /* sopalin3d.c:1145-1161 */
+    if (pb200_inertia(e->h, &inertia) != PB200_SUCCESS) shim_fatal("pb200_inertia");
+    sopar->iparm[IPARM_INERTIA] = (PASTIX_INT)inertia; }
+#endif
+  if (getenv("PB200_HOST_COEFTAB") != NULL) shim_mirror_coeftab(e->h, datacode);
+}
+
+static void shim_updown(SolverMatrix *datacode, SopalinParam *sopar)
+{
+  pb200_shim_entry_t *e = shim_find(datacode, 0);
+  double seconds = 0.0;
+  if (e == NULL || e->h == NULL || !e->factorized) {
+    errorPrint("pastix_b200: up_down called before a numeric factorization on this SolverMatrix");
+    EXIT(MOD_SOPALIN, BADPARAMETER_ERR);
+  }
+  if (sopar->iparm[IPARM_TRANSPOSE_SOLVE] == API_YES) {
+    errorPrint("pastix_b200: IPARM_TRANSPOSE_SOLVE is not handled by this shim");
+    EXIT(MOD_SOPALIN, BADPARAMETER_ERR);
+  }
+  if (pb200_solve(e->h, UPDOWN_SM2XTAB, (int64_t)UPDOWN_SM2XSZE, (int64_t)UPDOWN_SM2XNBR, &seconds) != PB200_SUCCESS)
+    shim_fatal("pb200_solve");
+  sopar->dparm[DPARM_SOLV_TIME] = seconds;                       /* updo.c:1495 */
+}
+
+/* ---------------------------------------------------------------- entry points */
+void API_CALL(sopalin_thread)(SolverMatrix *m, SopalinParam *sopaparam)
+{
+  shim_numfact(m, sopaparam);
+}
+
+void API_CALL(updo_thread)(SolverMatrix *m, SopalinParam *sopaparam)
+{
+  shim_updown(m, sopaparam);
+}
+
+void API_CALL(sopalin_updo_thread)(SolverMatrix *m, SopalinParam *sopaparam)
+{
+  shim_numfact(m, sopaparam);
+  shim_updown(m, sopaparam);
+}
+
+/* up_down from inside the reference's thread pool (refinement preconditioner): thread 0 drives the GPU,
+ * the callers bracket this with SYNCHRO_THREAD (raff_functions.c:423-428) */
+void *API_CALL(up_down_smp)(void *arg)
+{
+  sopthread_data_t *argument     = (sopthread_data_t *)arg;
+  Sopalin_Data_t   *sopalin_data = (Sopalin_Data_t *)(argument->data);
+  if (argument->me == 0) shim_updown(sopalin_data->datacode, sopalin_data->sopar);
+  return NULL;
+}
+
+/* no communication thread: one process drives the GPUs */
+void *API_CALL(sopalin_updo_comm)(void *arg)
+{
+  (void)arg;
+  return NULL;
+}
+
+/* ---------------------------------------------------------------- refinement: the reference's host loops,
+ * included exactly as sopalin3d.c:409-434 does, running on top of our up_down_smp */
+void *API_CALL(pivotstatique_smp)(void *arg);
+void *API_CALL(gmres_smp)(void *arg);
+void *API_CALL(grad_smp)(void *arg);
+void *API_CALL(bicgstab_smp)(void *arg);
+void  API_CALL(pivot_thread)(SolverMatrix *datacode, SopalinParam *sopaparam);
+void  API_CALL(gmres_thread)(SolverMatrix *datacode, SopalinParam *sopaparam);
+void  API_CALL(grad_thread)(SolverMatrix *datacode, SopalinParam *sopaparam);
+void  API_CALL(bicgstab_thread)(SolverMatrix *datacode, SopalinParam *sopaparam);
+
+/* file-scope constants the included refinement sources expect from sopalin3d.c:171-186 */
+#include "sopalin_compute.h"
+static PASTIX_INT   iun   = 1;
+#ifdef TYPE_COMPLEX
+static PASTIX_FLOAT fun   = 1.0 + 0.0 * I;
+#else
+static PASTIX_FLOAT fun   = 1.0;
+#endif
+static PASTIX_FLOAT fzero = 0.0;
+
+#define RAFF_CLOCK_INIT {clockInit(&raff_clk);clockStart(&raff_clk);}
+#define RAFF_CLOCK_STOP {clockStop(&(raff_clk));}
+#define RAFF_CLOCK_GET  clockVal(&(raff_clk))
+#include "raff_functions.h"
+#include "raff_grad.c"
+#include "raff_gmres.c"
+#include "raff_pivot.c"
+#include "raff_bicgstab.c"
+
+void API_CALL(sopalin_updo_gmres_thread)(SolverMatrix *m, SopalinParam *sopaparam)
+{
+  shim_numfact(m, sopaparam);
+  shim_updown(m, sopaparam);
+  API_CALL(gmres_thread)(m, sopaparam);
+}
+void API_CALL(sopalin_updo_grad_thread)(SolverMatrix *m, SopalinParam *sopaparam)
+{
+  shim_numfact(m, sopaparam);
+  shim_updown(m, sopaparam);
+  API_CALL(grad_thread)(m, sopaparam);
+}
+void API_CALL(sopalin_updo_pivot_thread)(SolverMatrix *m, SopalinParam *sopaparam)
+{
+  shim_numfact(m, sopaparam);
+  shim_updown(m, sopaparam);
+  API_CALL(pivot_thread)(m, sopaparam);
+}
+void API_CALL(sopalin_updo_bicgstab_thread)(SolverMatrix *m, SopalinParam *sopaparam)
+{
+  shim_numfact(m, sopaparam);
+  shim_updown(m, sopaparam);
+  API_CALL(bicgstab_thread)(m, sopaparam);
+}

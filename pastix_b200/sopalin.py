@@ -75,7 +75,39 @@ def critere_from_norm(norm1: float, epsilon_magn_ctrl: float = DPARM_EPSILON_MAG
 class Sopalin:
     """GPU numeric phase bound to one SolverMatrix."""
 
+    @classmethod
+    def from_handle(cls, handle: int, prec: str, facto: str) -> "Sopalin":
+        """Wrap a pb200_handle_t* owned by someone else (the drop-in shim keeps one per SolverMatrix)."""
+        self = cls.__new__(cls)
+        self.solver, self.prec, self.facto = None, prec, facto
+        self.dtype = np.dtype(DTYPE[prec])
+        self.L = _lib.lib()
+        self.h = C.c_void_p(handle)
+        self._borrowed = True
+        self._read_info()
+        return self
+
+    def _read_info(self):
+        info = _lib.Info()
+        _check(self.L.pb200_info(self.h, C.byref(info)))
+        self.n, self.coefnbr, self.nlevels = int(info.n), int(info.coefnbr), int(info.nlevels)
+        self.device_bytes, self.device, self.sm_count = int(info.device_bytes), int(info.device), int(info.sm_count)
+        self.cc = (int(info.cc_major), int(info.cc_minor))
+        self.nbpivot = 0
+        self.fact_time = 0.0
+        self.solv_time = 0.0
+
+    def set_profile(self, on: bool):
+        _check(self.L.pb200_set_profile(self.h, int(on)))
+
+    def get_profile(self) -> dict:
+        ms = (C.c_double * 4)(); n = (C.c_int64 * 4)(); fl = C.c_double(0)
+        _check(self.L.pb200_get_profile(self.h, ms, n, C.byref(fl)))
+        names = ("diag", "trsm", "gemm_scatter", "inpanel_update")
+        return {"ms": dict(zip(names, list(ms))), "launches": dict(zip(names, [int(v) for v in n])), "gemm_flops": float(fl.value)}
+
     def __init__(self, solver: SolverMatrix | dict, prec: str = "d", facto: str = "llt", device: int = -1):
+        self._borrowed = False
         if isinstance(solver, dict):
             solver = SolverMatrix.from_dict(solver)
         self.solver, self.prec, self.facto = solver, prec, facto
@@ -87,17 +119,10 @@ class Sopalin:
                                      p(solver.cblknum), p(solver.coefind))
         self.h = C.c_void_p(None)
         _check(self.L.pb200_create(C.byref(self.h), C.byref(self._desc), FLTTYPE[prec], FACTO[facto], device))
-        info = _lib.Info()
-        _check(self.L.pb200_info(self.h, C.byref(info)))
-        self.n, self.coefnbr, self.nlevels = int(info.n), int(info.coefnbr), int(info.nlevels)
-        self.device_bytes, self.device, self.sm_count = int(info.device_bytes), int(info.device), int(info.sm_count)
-        self.cc = (int(info.cc_major), int(info.cc_minor))
-        self.nbpivot = 0
-        self.fact_time = 0.0
-        self.solv_time = 0.0
+        self._read_info()
 
     def close(self):
-        if self.h:
+        if self.h and not self._borrowed:
             self.L.pb200_destroy(self.h)
             self.h = C.c_void_p(None)
 

@@ -1,0 +1,77 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/pastix_b200.h
+declares; the drop-in host library exports the reference's numeric-phase entry points; without a
+GPU the product path fails loudly (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    from pastix_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "pastix_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pb200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/pastix_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert b"sm_100a" in lib.pb200_version()
+
+
+@pytest.mark.parametrize("prec,P", [("d", "D"), ("z", "Z"), ("s", "S"), ("c", "C")])
+def test_dropin_exports_reference_entry_points(prec, P):
+    """Names from sopalin3d.h:290-467 with the variant prefixes of sopalin_define.h:453-465; the
+    precision prefix of redefine_functions.h:84-101 is empty in a one-precision-per-library build
+    (no -DMULTIPLE_TYPE_DEFINE), which is how both the oracle and the drop-in are built."""
+    from pastix_b200.pastix_api import dropin_path
+    path = dropin_path(prec)
+    if not os.path.exists(path):
+        pytest.skip("drop-in library not built (needs the reference tree at build time)")
+    lib = C.CDLL(path)
+    names = ["pastix", "dpastix", "pastix_fortran"]
+    for v in ("po", "sy", "he", "ge"):
+        names += [f"{v}_sopalin_thread", f"{v}_sopalin_updo_thread", f"{v}_updo_thread", f"{v}_up_down_smp"]
+        names += [f"{v}_sopalin_updo_gmres_thread", f"{v}_gmres_thread"]
+    names += ["ge_sopalin_updo_pivot_thread", "ge_sopalin_updo_bicgstab_thread", "po_sopalin_updo_grad_thread"]
+    names += ["pb200_shim_get_handle", "pb200_shim_get_critere", "pb200_shim_release_data"]
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from conftest import load_golden
+    from pastix_b200 import Sopalin, PastixB200Error
+    g = load_golden("lap7_6_llt_s")
+    with pytest.raises(PastixB200Error, match="no CUDA device|CUDA"):
+        Sopalin(g, "s", "llt")
+
+
+def test_flop_model_matches_reference_count():
+    """DPARM_FACT_FLOPS of the golden fixtures (the metric's numerator, blend_symbol_cost.c:52-88)
+    re-derived from the SolverMatrix arrays with the formulas of flops.h:74-117."""
+    from conftest import golden_names, load_golden
+    for name in golden_names():
+        g = load_golden(name)
+        if g["facto"] != "llt" or "ilu" in name:
+            continue
+        cb = g["cblknbr"]
+        tot = 0.0
+        for c in range(cb):
+            n = int(g["lcol"][c] - g["fcol"][c] + 1); ld = int(g["stride"][c]); m = ld - n
+            potrf = (n ** 3 / 6 + n ** 2 / 2 + n / 3) + (n ** 3 / 6 - n / 6)           # FMULS+FADDS_POTRF
+            trsm = m * n * (n + 1)                                   # FADDS_TRSM is defined as FMULS_TRMM (flops.h:99-100)
+            gemm = 0.0
+            for b in range(int(g["bloknum"][c]) + 1, int(g["bloknum"][c + 1])):
+                nk = int(g["lrow"][b] - g["frow"][b] + 1); mk = ld - int(g["coefind"][b])
+                gemm += 2.0 * mk * nk * n
+            tot += potrf + trsm + gemm
+        assert abs(tot - g["fact_flops"]) <= 1e-9 * g["fact_flops"], (name, tot, g["fact_flops"])

@@ -1,0 +1,109 @@
+"""GPU parity through the reference-facing boundary: the SAME pastix() calls (iparm/dparm,
+API_TASK_* sequence) served by (a) the drop-in library = reference host code + B200 numeric phase
+and (b) the unmodified reference built in oracle/_ref (CPU sopalin).  Reads like the reference's
+own examples (src/example/src/simple.c:60-256 + CHECK_SOL utils.h:74-137), with asserts."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from conftest import relerr, tol  # noqa: E402
+
+CASES = [
+    # kind, N, prec, facto, iparm overrides, nrhs
+    ("lap1d", 100, "d", "llt", {}, 1),          # BASELINE config 1: simple -lap 100
+    ("lap1d", 100, "d", "ldlt", {}, 1),
+    ("lap7", 12, "d", "llt", {}, 3),
+    ("lap27", 10, "d", "ldlt", {}, 2),
+    ("cd", 10, "d", "lu", {}, 2),
+    ("cd", 8, "z", "lu", {}, 1),
+    ("lap7shift", 8, "z", "ldlt", {}, 1),
+    ("lap7her", 8, "z", "ldlh", {}, 1),
+    ("lap7", 8, "s", "llt", {}, 1),
+    ("cd", 6, "c", "lu", {}, 1),
+    ("lap7", 20, "d", "llt", {"IPARM_MIN_BLOCKSIZE": 160, "IPARM_MAX_BLOCKSIZE": 320}, 1),   # wide cblks: sub-panel path
+    ("lap7", 10, "d", "llt", {"IPARM_INCOMPLETE": 1, "IPARM_LEVEL_OF_FILL": 2}, 1),        # ILU(2): generic path
+]
+
+
+def full_matrix(A, sym):
+    if sym == "no":
+        return A
+    lo = sp.tril(A, -1)
+    return (A + (lo.conj().T if sym == "her" else lo.T)).tocsc()
+
+
+@pytest.mark.parametrize("kind,N,prec,facto,over,nrhs", CASES)
+def test_pastix_dropin_matches_reference(kind, N, prec, facto, over, nrhs):
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    if not available(prec):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix(kind, N, DT[prec])
+    sym = {"llt": "yes", "ldlt": "yes", "lu": "no", "ldlh": "her"}[facto]
+    b = G.rhs_vector(A.shape[0], nrhs, DT[prec])
+    ref = RefPastix(prec, threads=1).setup(A, perm0, facto, sym=sym, iparm_over=over).analyze().numfact()
+    xr = ref.solve(b)
+    gpu = Pastix(prec, threads=1).setup(A, perm0, facto, sym=sym, iparm_over=over).analyze().numfact()
+    xg = gpu.solve(b)
+    og, orf = gpu.out(), ref.out()
+    # analysis is the same unchanged host code: identical structure-derived outputs
+    assert og["nnzeros"] == orf["nnzeros"] and og["fact_flops"] == orf["fact_flops"]
+    assert og["static_pivoting"] == orf["static_pivoting"]
+    if facto == "ldlt" and prec in ("s", "d"):
+        assert og["inertia"] == orf["inertia"]
+    assert og["fact_time"] > 0 and og["solv_time"] > 0
+    incomplete = bool(over.get("IPARM_INCOMPLETE"))
+    t = tol(prec)
+    assert relerr(xg, xr) <= 50 * t, "solution differs from the reference's"
+    if not incomplete:
+        Af = full_matrix(A, sym)
+        res = np.linalg.norm(Af @ xg - b) / np.linalg.norm(b)
+        assert res <= (1e-12 if prec in ("d", "z") else 1e-4), res     # north_star: ||b-Ax||/||b|| <= 1e-12 in double
+    gpu.release()
+
+
+def test_factors_match_reference_through_handle():
+    """coeftab read back from HBM through the handle the shim keeps == the reference's panels."""
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    from conftest import lower_mask
+    if not available("d"):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix("lap27", 8, DT["d"])
+    ref = RefPastix("d", threads=1).setup(A, perm0, "ldlt").analyze().numfact()
+    Lr, _ = ref.coef()
+    gpu = Pastix("d", threads=1).setup(A, perm0, "ldlt").analyze().numfact()
+    Lg, _ = gpu.sopalin().get_coeftab()
+    m = lower_mask(ref.solver())
+    assert relerr(Lg[m], Lr[m]) <= tol("d")
+    assert abs(gpu.critere() - ref.norm1() * np.sqrt(ref.out()["epsilon_magn_ctrl"])) <= 1e-15 * ref.norm1()
+    gpu.release()
+
+
+def test_refinement_runs_on_top_of_gpu_updown():
+    """API_TASK_REFINE: the reference's host GMRES loop preconditioned by the GPU up_down (ILU(1) factor)."""
+    from make_golden import case_matrix, DT
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    A, perm0 = case_matrix("lap7", 10, DT["d"])
+    over = {"IPARM_INCOMPLETE": 1, "IPARM_LEVEL_OF_FILL": 1, "IPARM_REFINEMENT": None}
+    gpu = Pastix("d", threads=1)
+    over["IPARM_REFINEMENT"] = gpu.E["API_RAF_GMRES"]
+    gpu.setup(A, perm0, "llt", iparm_over=over, dparm_over={"DPARM_EPSILON_REFINEMENT": 1e-10}).analyze().numfact()
+    b = G.rhs_vector(A.shape[0], 1, DT["d"])[:, 0].copy()
+    x = gpu.solve(b)
+    x = gpu.refine(b, x)
+    Af = full_matrix(A, "yes")
+    res = np.linalg.norm(Af @ x - b) / np.linalg.norm(b)
+    assert res <= 1e-8, res
+    assert gpu.out()["nbiter"] >= 1
+    gpu.release()
