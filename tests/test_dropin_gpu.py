@@ -19,7 +19,7 @@ CASES = [
     ("lap1d", 100, "d", "llt", {}, 1),          # BASELINE config 1: simple -lap 100
     ("lap1d", 100, "d", "ldlt", {}, 1),
     ("lap7", 12, "d", "llt", {}, 3),
-    ("lap27", 10, "d", "ldlt", {}, 2),
+    ("lap27", 14, "d", "ldlt", {}, 2),       # (the unmodified reference itself corrupts its heap on 27-pt LDLt for N in 7..12)
     ("cd", 10, "d", "lu", {}, 2),
     ("cd", 8, "z", "lu", {}, 1),
     ("lap7shift", 8, "z", "ldlt", {}, 1),
@@ -78,7 +78,7 @@ def test_factors_match_reference_through_handle():
     from conftest import lower_mask
     if not available("d"):
         pytest.skip("oracle/_ref not built")
-    A, perm0 = case_matrix("lap27", 8, DT["d"])
+    A, perm0 = case_matrix("lap27", 14, DT["d"])
     ref = RefPastix("d", threads=1).setup(A, perm0, "ldlt").analyze().numfact()
     Lr, _ = ref.coef()
     gpu = Pastix("d", threads=1).setup(A, perm0, "ldlt").analyze().numfact()
