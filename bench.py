@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on the B200: numeric factorization GFLOP/s (PaStiX's own flop
+count, DPARM_FACT_FLOPS) and % of measured FP64 peak on the 3-D Laplacian, plus solve ms/RHS.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|...] [--impl reference]
+
+One "step" = one pass of the sopalin numeric phase over the synthetic matrix: device-side assembly
+of the panels from the CSC resident in HBM, numeric factorization, one up_down solve.  `value`
+follows SURVEY.md §8(d): DPARM_FACT_FLOPS / the DPARM_FACT_TIME interval (factorization only,
+device-timed with CUDA events on the launching stream; assembly and solve are reported beside it and
+all three are inside `ms_per_step`).  `e2e` is the same metric through the reference-facing call a
+PaStiX user makes — pastix(API_TASK_NUMFACT) then pastix(API_TASK_SOLVE) on the drop-in library with
+HOST buffers (host CSC/RHS -> HBM and the solution back inside the timed region).
+`roofline` is for the dominant kernel (k_gemm_scatter, the fused GEMM + scatter-add of the
+supernodal updates): its algorithmic flops (PaStiX's GEMM term) / its summed CUDA-event duration.
+`cpu_baseline` / `--impl reference` time the UNMODIFIED reference's threaded CPU sopalin
+(oracle/_ref, built from /root/reference in the build container) on the box's host cores.
+
+Multi-GPU (--gpus N>1, launched by torch.distributed.run): see DESIGN.md "Multi-GPU".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# name -> (description, stencil kind, N, precision, factorization, nrhs, iparm overrides)
+WORKLOADS = {
+    "c1": ("1-D Laplacian n=100 LLt double (example/bin/simple -lap 100)", "lap1d", 100, "d", "llt", 1, {}),
+    "c2": ("3-D 7-point Laplacian 64^3 (n=262144) LLt double, nested dissection", "lap7", 64, "d", "llt", 1, {}),
+    "c3": ("3-D 27-point Laplacian 100^3 (n=1000000) LDLt double, nested dissection", "lap27", 100, "d", "ldlt", 1, {}),
+    "c4s": ("complex-double convection-diffusion 64^3 LU static pivoting (config 4 at single-GPU size)", "cd", 64, "z", "lu", 1, {}),
+    "c4": ("complex-double convection-diffusion 128^3 LU static pivoting", "cd", 128, "z", "lu", 1, {}),
+    "c5s": ("blockwise ILU(2) + 64-RHS solve, 3-D 7-point Laplacian 64^3", "lap7", 64, "d", "llt", 64,
+            {"IPARM_INCOMPLETE": 1, "IPARM_LEVEL_OF_FILL": 2}),
+    "c5": ("blockwise ILU(2) + 64-RHS solve, 3-D 7-point Laplacian 200^3", "lap7", 200, "d", "llt", 64,
+           {"IPARM_INCOMPLETE": 1, "IPARM_LEVEL_OF_FILL": 2}),
+}
+DT = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
+SYM = {"llt": "yes", "ldlt": "yes", "lu": "no", "ldlh": "her"}
+ESIZE = {"s": 4, "d": 8, "c": 8, "z": 16}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def case_matrix(kind, N, dt):
+    from pastix_b200 import generators as G
+    if kind == "lap1d":
+        return G.laplacian_1d(N, dt), G.nested_dissection_perm_1d(N)
+    if kind == "lap7":
+        return G.laplacian_3d(N, 7, dt), G.nested_dissection_perm(N)
+    if kind == "lap27":
+        return G.laplacian_3d(N, 27, dt), G.nested_dissection_perm(N)
+    if kind == "cd":
+        return G.convection_diffusion_3d(N, dt), G.nested_dissection_perm(N)
+    raise ValueError(kind)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w": float(np.median(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- FP64 roof
+def measure_fp64_peak(device: int) -> dict:
+    """MEASURED_PEAKS.json carries HBM GB/s and bf16 TF/s only; the FP64 denominators are measured here,
+    live: our own DMMA (mma.sync.m16n8k8.f64) issue-rate probe and a cuBLAS DGEMM 8192^3 burst."""
+    import torch
+    from pastix_b200 import _lib
+    L = _lib.lib()
+    out = {"dmma_probe_tflops": L.pb200_probe_fp64_gflops(device, 2) / 1e3,
+           "dfma_probe_tflops": L.pb200_probe_fp64_gflops(device, 0) / 1e3}
+    n = 8192
+    a = torch.randn(n, n, device=f"cuda:{device}", dtype=torch.float64)
+    b = torch.randn(n, n, device=f"cuda:{device}", dtype=torch.float64)
+    for _ in range(2):
+        c = a @ b
+    torch.cuda.synchronize(device)
+    best = 1e30
+    for _ in range(3):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); c = a @ b; e1.record(); torch.cuda.synchronize(device)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    torch.cuda.empty_cache()
+    out["cublas_dgemm_tflops"] = 2.0 * n ** 3 / best / 1e9
+    out["peak_tflops"] = max(out["dmma_probe_tflops"], out["cublas_dgemm_tflops"])
+    out["source"] = "measured live in bench.py (max of own DMMA probe and cuBLAS DGEMM 8192^3 burst); MEASURED_PEAKS.json has no FP64 figure"
+    return out
+
+
+def measured_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p)); d["_which"] = "measured"
+            return d
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "_which": "fallback"}
+
+
+# ----------------------------------------------------------------------------- reference (CPU) arm
+def run_reference_fact(wl: str, threads: int, steps: int, warmup: int, budget_s: float, N_override: int | None = None):
+    """The UNMODIFIED reference (oracle/_ref) through its own pastix(): analysis once, then NUMFACT + SOLVE
+    per step, timed by the reference's own DPARM_FACT_TIME / DPARM_SOLV_TIME."""
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200 import generators as G
+    desc, kind, N, prec, facto, nrhs, over = WORKLOADS[wl]
+    if N_override:
+        N = N_override
+    if not available(prec):
+        return None
+    A, perm0 = case_matrix(kind, N, DT[prec])
+    over = dict(over)
+    r = RefPastix(prec, threads=threads).setup(A, perm0, facto, sym=SYM[facto], iparm_over=over).analyze()
+    flops = r.out()["fact_flops"]
+    b = G.rhs_vector(A.shape[0], nrhs, DT[prec])
+    ft, st, wall = [], [], []
+    t_begin = time.time()
+    done = 0
+    for it in range(warmup + steps):
+        t0 = time.time()
+        r.numfact()
+        x = r.solve(b)
+        o = r.out()
+        if it >= warmup:
+            ft.append(o["fact_time"]); st.append(o["solv_time"]); wall.append(time.time() - t0); done += 1
+        if time.time() - t_begin > budget_s and done >= 1:
+            break
+    Af = A if SYM[facto] == "no" else None
+    return {"flops": flops, "fact_s": float(np.mean(ft)), "solve_s": float(np.mean(st)), "wall_s": float(np.mean(wall)),
+            "steps_run": done, "N": N, "n": A.shape[0], "nrhs": nrhs, "x": x, "A": A, "b": b, "threads": threads}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    cores = os.cpu_count() or 1
+    desc, kind, N, prec, facto, nrhs, over = WORKLOADS[args.workload]
+    r = run_reference_fact(args.workload, cores, args.steps, args.warmup, float(os.environ.get("PB200_REF_BUDGET_S", "240")))
+    if r is None:
+        return {"impl": "reference", "unavailable": "oracle/_ref (the reference compiled from /root/reference) is not present"}
+    gf = r["flops"] / r["fact_s"] / 1e9
+    unit = "GFLOP/s"
+    sample = f"full numeric factorization of the workload, {r['steps_run']} timed step(s) (DPARM_FACT_TIME)"
+    return {
+        "impl": "reference", "metric": "numeric factorization throughput (PaStiX flop count)", "value": gf, "unit": unit,
+        "n_gpus": args.gpus, "steps": args.steps, "steps_run": r["steps_run"], "warmup": args.warmup,
+        "ms_per_step": r["wall_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"d": "f64", "z": "c128", "s": "f32", "c": "c64"}[prec], "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "threads": cores},
+        "fact_ms": r["fact_s"] * 1e3, "solve_ms_per_rhs": r["solve_s"] * 1e3 / r["nrhs"],
+        "cpu_baseline": {"value": gf, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": gf, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+# ----------------------------------------------------------------------------- our arm
+def our_arm(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — pastix_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(local)
+
+    def maxr(v: float) -> float:
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    from pastix_b200.csc import permute_rhs, unpermute_solution
+
+    desc, kind, N, prec, facto, nrhs, over = WORKLOADS[args.workload]
+    dt = DT[prec]
+    A, perm0 = case_matrix(kind, N, dt)
+    n = A.shape[0]
+    b = G.rhs_vector(n, nrhs, dt)
+    t0 = time.time()
+    gpu = Pastix(prec, threads=1).setup(A, perm0, facto, sym=SYM[facto], iparm_over=dict(over)).analyze()
+    t_analysis = time.time() - t0
+    flops = gpu.out()["fact_flops"]
+    nnzL = gpu.out()["nnzeros"]
+    log(f"[rank {rank}] {args.workload}: n={n} nnz(A)={A.nnz} nnzL={nnzL} flops={flops:.4g} analysis {t_analysis:.1f}s")
+
+    # ---- e2e: the reference-facing call with host buffers
+    e2e_fact, e2e_solve = [], []
+    x = None
+    for it in range(args.warmup + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        gpu.numfact()                     # pastix(API_TASK_NUMFACT): host CSC -> HBM, assembly, factorization
+        t1 = time.perf_counter()
+        x = gpu.solve(b)                  # pastix(API_TASK_SOLVE): host b -> HBM, up_down, x back
+        t2 = time.perf_counter()
+        if it >= args.warmup:
+            e2e_fact.append(t1 - t0); e2e_solve.append(t2 - t1)
+    e2e_fact_s = maxr(float(np.mean(e2e_fact))); e2e_solve_s = maxr(float(np.mean(e2e_solve)))
+    # backward error of the solution the user got (north_star: <= 1e-12 in double, direct factorizations)
+    import scipy.sparse as sp
+    Af = A if SYM[facto] == "no" else (A + (sp.tril(A, -1).conj().T if SYM[facto] == "her" else sp.tril(A, -1).T)).tocsc()
+    berr = float(np.linalg.norm(Af @ x - b) / np.linalg.norm(b))
+    nnzA_int = Af.nnz
+    h2d = (n + 1) * 8 + nnzA_int * 4 + nnzA_int * ESIZE[prec] * (2 if facto == "lu" else 1) + n * nrhs * ESIZE[prec]
+    d2h = n * nrhs * ESIZE[prec] + 8
+
+    # ---- device-resident steps (inputs already in HBM)
+    s = gpu.sopalin()
+    crit = gpu.critere()
+    permtab, _ = gpu.order()
+    xp = permute_rhs(b, permtab)
+    x_src = torch.from_numpy(np.ascontiguousarray(xp.T)).to(f"cuda:{local}")      # (nrhs, n) row-major == n x nrhs column-major
+    x_dev = torch.empty_like(x_src)
+    fact_s, solve_s, asm_s, launches = [], [], [], 0
+    sampler = ClockSampler(local)
+    for it in range(args.warmup):
+        s.reassemble(); s.factorize(crit); x_dev.copy_(x_src); torch.cuda.synchronize(local)
+        s.solve_device(x_dev.data_ptr(), n, nrhs)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_begin = time.perf_counter()
+    for it in range(args.steps):
+        ta = time.perf_counter()
+        s.reassemble()
+        asm_s.append(time.perf_counter() - ta)
+        s.factorize(crit)
+        fact_s.append(s.fact_time)
+        launches += s.last_launches() + 1 + 2   # + assembly + triangle inversions
+        x_dev.copy_(x_src); torch.cuda.synchronize(local)
+        s.solve_device(x_dev.data_ptr(), n, nrhs)
+        solve_s.append(s.solv_time)
+        launches += s.last_launches()
+    barrier()
+    t_region = maxr(time.perf_counter() - t_begin)
+    clocks = sampler.stop() if rank == 0 else None
+    fact_mean = maxr(float(np.mean(fact_s)))
+    solve_mean = maxr(float(np.mean(solve_s)))
+    # solution check of the device-resident path
+    xh = x_dev.cpu().numpy()
+    xs = unpermute_solution(xh.T if xh.ndim == 2 else xh.reshape(n, 1), permtab)
+    berr_dev = float(np.linalg.norm(Af @ xs.reshape(n, -1) - b) / np.linalg.norm(b))
+
+    # ---- roofline of the dominant kernel: serialised launches, CUDA events per kernel kind
+    roof = None
+    prof = None
+    if rank == 0:
+        s.set_profile(True)
+        for _ in range(2):
+            s.reassemble(); s.factorize(crit)
+        prof = s.get_profile()
+        s.set_profile(False)
+        s.reassemble(); s.factorize(crit)
+        peak = measure_fp64_peak(local)
+        gms = prof["ms"]["gemm_scatter"]
+        tot = sum(prof["ms"].values())
+        ach = prof["gemm_flops"] / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        roof = {"kernel": "k_gemm_scatter (fused DMMA GEMM + scatter-add into facing cblks)", "bound": "tensor",
+                "achieved": ach, "peak": peak["peak_tflops"], "unit": "TFLOP/s", "frac": ach / peak["peak_tflops"],
+                "traffic": None, "peak_source": peak["source"], "fp64_peaks": {k: v for k, v in peak.items() if k.endswith("tflops")},
+                "kernel_share_of_step": gms / tot if tot > 0 else None,
+                "kind_ms_serialised": prof["ms"], "kind_launches": prof["launches"],
+                "algorithmic_flops_per_factorization": prof["gemm_flops"]}
+        hp = measured_peaks()
+        bytes_solve = 2.0 * nnzL * ESIZE[prec] * (1 if facto != "lu" else 1) + 6.0 * n * nrhs * ESIZE[prec]
+        roof["solve"] = {"bound": "hbm", "achieved": bytes_solve / solve_mean / 1e9, "peak": hp.get("hbm_gbs"),
+                         "unit": "GB/s", "frac": bytes_solve / solve_mean / 1e9 / hp.get("hbm_gbs", 6650.0),
+                         "peak_source": f"MEASURED_PEAKS.json ({hp['_which']})", "algorithmic_bytes": bytes_solve}
+    gf_total = world * flops / fact_mean / 1e9
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "numeric factorization throughput (PaStiX flop count)", "value": gf_total, "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_region / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"d": "f64", "z": "c128", "s": "f32", "c": "c64"}[prec], "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "n": n, "nnzL": nnzL, "fact_flops": flops, "nrhs": nrhs,
+                       "ordering": "geometric nested dissection passed as API_ORDER_PERSONAL (Scotch is not in the image)",
+                       "l2": "inputs larger than L2: the factor slab (%.2f GB) is rewritten by the device-side assembly every step"
+                             % (s.coefnbr * ESIZE[prec] * (2 if facto == "lu" else 1) / 1e9),
+                       "multi_gpu": "replicas" if world > 1 else "single"},
+            "fact_ms": fact_mean * 1e3, "assemble_ms": float(np.mean(asm_s)) * 1e3,
+            "solve_ms_per_rhs": solve_mean * 1e3 / nrhs,
+            "pct_fp64_peak": 100.0 * (flops / fact_mean / 1e12) / roof["peak"],
+            "backward_error": berr_dev,
+            "e2e": {"value": world * flops / e2e_fact_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "numfact_call_ms": e2e_fact_s * 1e3, "solve_call_ms": e2e_solve_s * 1e3,
+                    "backward_error": berr, "host_memory": "pageable (the reference's own CSC/RHS buffers)",
+                    "call": "pastix(API_TASK_NUMFACT) + pastix(API_TASK_SOLVE) on libpastix_dropin"},
+            "gpu_launches": int(launches),
+            "roofline": roof, "clocks": clocks, "analysis_s": t_analysis,
+        }
+    gpu.release()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def cpu_baseline_for(args) -> dict:
+    """Reference CPU sopalin on the host cores, bounded sample (rank 0, N=1 only)."""
+    cores = os.cpu_count() or 1
+    desc, kind, N, prec, facto, nrhs, over = WORKLOADS[args.workload]
+    # bounded sample: the full workload when it is <= ~1e12 flop, else the same stencil on a smaller grid
+    Ns = None
+    sample = "the full workload's numeric factorization, one run"
+    if args.workload == "c3":
+        Ns = 64; sample = "same 27-point LDLt problem on a 64^3 grid (bounded sample), one run"
+    elif args.workload in ("c4", "c4s"):
+        Ns = 32; sample = "same complex LU problem on a 32^3 grid (bounded sample), one run"
+    elif args.workload == "c5":
+        Ns = 64; sample = "same ILU(2) problem on a 64^3 grid (bounded sample), one run"
+    try:
+        r = run_reference_fact(args.workload, cores, 1, 0, 120.0, N_override=Ns)
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+    if r is None:
+        return {"value": None, "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref not present"}
+    return {"value": r["flops"] / r["fact_s"] / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "reference",
+            "sample": sample, "fact_s": r["fact_s"], "solve_ms_per_rhs": r["solve_s"] * 1e3 / r["nrhs"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("PB200_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    # the reference's analysis prints to stdout: keep fd 1 for the single JSON line
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        line = reference_arm(args)
+    else:
+        line = our_arm(args)
+        if line is not None and args.gpus == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_for(args)
+        elif line is not None:
+            line["cpu_baseline"] = None
+    sys.stdout.flush()
+    if rank == 0 and line is not None:
+        os.write(real_out, (json.dumps(line) + "\n").encode())
+
+
+if __name__ == "__main__":
+    main()
