@@ -374,6 +374,116 @@ def our_arm(args):
     return line
 
 
+def our_arm_dist(args):
+    """N > 1: ONE factorization spread over the N GPUs of the box (strong scaling): proportional subtree
+    mapping of the column blocks, fan-in contributions pulled by the owner over NVLink peer memory
+    (DESIGN.md §6).  Every rank runs the same deterministic host analysis; `value` = the whole job's
+    DPARM_FACT_FLOPS / max over ranks of the device-timed factorization."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — pastix_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    def barrier():
+        dist.barrier(); torch.cuda.synchronize(local)
+
+    def maxr(v: float) -> float:
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import Sopalin, critere_from_norm, generators as G
+    from pastix_b200.csc import internal_csc, permute_rhs, unpermute_solution
+    import scipy.sparse as sp
+    desc, kind, N, prec, facto, nrhs, over = WORKLOADS[args.workload]
+    dt = DT[prec]
+    A, perm0 = case_matrix(kind, N, dt)
+    n = A.shape[0]
+    b = G.rhs_vector(n, nrhs, dt)
+    t0 = time.time()
+    an = Pastix(prec, threads=1).setup(A, perm0, facto, sym=SYM[facto], iparm_over=dict(over)).analyze()
+    t_analysis = time.time() - t0
+    flops = an.out()["fact_flops"]; nnzL = an.out()["nnzeros"]
+    solver = an.solver(); permtab, _ = an.order()
+    csc = internal_csc(A, permtab, SYM[facto], dt)
+    s = Sopalin(solver, prec, facto, device=local, rank=rank, nranks=world).attach()
+    owner, contrib, load = Sopalin.dist_plan(solver, facto, world)
+    crit = critere_from_norm(s.norm1(csc["colptr"], csc["values"]))
+    xp = permute_rhs(b, permtab)
+    Af = A if SYM[facto] == "no" else (A + (sp.tril(A, -1).conj().T if SYM[facto] == "her" else sp.tril(A, -1).T)).tocsc()
+    log(f"[rank {rank}] {args.workload}: n={n} nnzL={nnzL} flops={flops:.4g} analysis {t_analysis:.1f}s "
+        f"load share {load[rank] / load.sum():.3f} device_bytes {s.device_bytes / 1e9:.2f} GB")
+    # ---- e2e: host CSC -> HBM, factorization, host rhs -> solution (public API of this package)
+    e2e_fact, e2e_solve = [], []
+    for it in range(args.warmup + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        s.assemble(csc["colptr"], csc["rows"], csc["values"], csc["tvalues"])
+        s.factorize(crit)
+        barrier()
+        t1 = time.perf_counter()
+        x = xp.copy(order="F"); s.solve(x)
+        t2 = time.perf_counter()
+        if it >= args.warmup:
+            e2e_fact.append(t1 - t0); e2e_solve.append(t2 - t1)
+    berr = float(np.linalg.norm(Af @ unpermute_solution(x, permtab) - b) / np.linalg.norm(b))
+    e2e_fact_s = maxr(float(np.mean(e2e_fact))); e2e_solve_s = maxr(float(np.mean(e2e_solve)))
+    nnzA = Af.nnz
+    h2d = (n + 1) * 8 + nnzA * 8 + nnzA * ESIZE[prec] * (2 if facto == "lu" else 1) + n * nrhs * ESIZE[prec]
+    d2h = n * nrhs * ESIZE[prec] + 8
+    # ---- device-resident steps
+    x_src = torch.from_numpy(np.ascontiguousarray(xp.T)).to(f"cuda:{local}"); x_dev = torch.empty_like(x_src)
+    fact_s, solve_s, launches = [], [], 0
+    sampler = ClockSampler(local)
+    for it in range(args.warmup):
+        s.reassemble(); s.factorize(crit)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_begin = time.perf_counter()
+    for it in range(args.steps):
+        s.reassemble()
+        s.factorize(crit)
+        fact_s.append(s.fact_time); launches += s.last_launches() + 1
+        x_dev.copy_(x_src); torch.cuda.synchronize(local)
+        s.solve_device(x_dev.data_ptr(), n, nrhs)      # first solve after a factorization pulls the peers' panels
+        solve_s.append(s.solv_time); launches += s.last_launches() + 3
+    barrier()
+    t_region = maxr(time.perf_counter() - t_begin)
+    clocks = sampler.stop() if rank == 0 else None
+    fact_mean = maxr(float(np.mean(fact_s))); solve_mean = maxr(float(np.mean(solve_s)))
+    xh = x_dev.cpu().numpy()
+    xs = unpermute_solution(xh.T if xh.ndim == 2 else xh.reshape(n, 1), permtab)
+    berr_dev = float(np.linalg.norm(Af @ xs.reshape(n, -1) - b) / np.linalg.norm(b))
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "numeric factorization throughput (PaStiX flop count)", "value": flops / fact_mean / 1e9, "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_region / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": {"d": "f64", "z": "c128", "s": "f32", "c": "c64"}[prec], "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "n": n, "nnzL": nnzL, "fact_flops": flops, "nrhs": nrhs,
+                       "ordering": "geometric nested dissection passed as API_ORDER_PERSONAL (Scotch is not in the image)",
+                       "l2": "inputs larger than L2: the factor slab is rewritten by the device-side assembly every step",
+                       "multi_gpu": "one factorization over %d GPUs: proportional subtree mapping + fan-in over NVLink peer memory" % world,
+                       "load_share": [float(v) for v in load / load.sum()]},
+            "fact_ms": fact_mean * 1e3, "solve_ms_per_rhs": solve_mean * 1e3 / nrhs, "backward_error": berr_dev,
+            "e2e": {"value": flops / e2e_fact_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "numfact_call_ms": e2e_fact_s * 1e3, "solve_call_ms": e2e_solve_s * 1e3, "backward_error": berr,
+                    "call": "Sopalin.assemble(host CSC) + factorize + solve(host rhs) on every rank (pb200_create_dist path)"},
+            "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None, "clocks": clocks, "analysis_s": t_analysis,
+        }
+    s.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return line
+
+
 def cpu_baseline_for(args) -> dict:
     """Reference CPU sopalin on the host cores, bounded sample (rank 0, N=1 only)."""
     cores = os.cpu_count() or 1
@@ -405,7 +515,16 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("PB200_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--iparm", action="append", default=[], metavar="IPARM_NAME=VALUE",
+                    help="extra iparm override for the analysis (e.g. IPARM_MAX_BLOCKSIZE=240); applied to both arms")
     args = ap.parse_args()
+    if args.iparm:
+        d, k, N, p, f, nr, over = WORKLOADS[args.workload]
+        over = dict(over)
+        for kv in args.iparm:
+            key, val = kv.split("=")
+            over[key] = int(val)
+        WORKLOADS[args.workload] = (d + " [" + ",".join(args.iparm) + "]", k, N, p, f, nr, over)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     # the reference's analysis prints to stdout: keep fd 1 for the single JSON line
@@ -415,7 +534,8 @@ def main():
     if args.impl == "reference":
         line = reference_arm(args)
     else:
-        line = our_arm(args)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        line = our_arm_dist(args) if (world > 1 and not os.environ.get("PB200_REPLICAS")) else our_arm(args)
         if line is not None and args.gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_for(args)
         elif line is not None:

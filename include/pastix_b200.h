@@ -105,6 +105,30 @@ const char *pb200_version(void);
 int pb200_create(pb200_handle_t **h, const pb200_solver_t *solver,
                  int flttype, int factotype, int device);
 int pb200_destroy(pb200_handle_t *h);
+
+/* ---- multi-GPU: one process per GPU of one box, `nranks` <= 8 (the reference's distributed mode:
+ * dpastix + MPI, one SolverMatrix per process with fan-in targets, blend/src/ftgt.h:68-127).
+ * Every process builds the SAME single-process SolverMatrix (the analysis is deterministic) and passes
+ * its rank; column blocks are mapped to GPUs by proportional subtree mapping (blend/src/splitpart.c:752-1012)
+ * computed inside; contributions to column blocks owned by another GPU are summed in a local fan-in
+ * region and pulled by the owner over NVLink peer memory (add_contrib_target sopalin_compute.c:600-733,
+ * recv_handle_fanin sopalin_sendrecv.c:182).  After pb200_create_dist the caller exchanges the opaque
+ * IPC blobs (pb200_ipc_size() bytes per rank, e.g. MPI_Allgather / torch.distributed.all_gather) and
+ * hands all of them, ordered by rank, to pb200_ipc_attach.  pb200_(re)assemble, pb200_factorize and
+ * pb200_destroy are then collective calls.  nbpivot is this GPU's share (sum over ranks =
+ * IPARM_STATIC_PIVOTING, the reference's MPI_Allreduce sopalin3d.c:1138).  The first pb200_solve /
+ * pb200_get_coeftab / pb200_inertia after a factorization copies the other GPUs' factored panels into
+ * the local slab, after which every GPU can solve its own share of the right-hand sides. */
+int pb200_create_dist(pb200_handle_t **h, const pb200_solver_t *solver, int flttype, int factotype,
+                      int device, int rank, int nranks);
+int pb200_ipc_size(void);
+int pb200_ipc_export(pb200_handle_t *h, void *blob);
+int pb200_ipc_attach(pb200_handle_t *h, const void *all_blobs);
+int pb200_dist_barrier(pb200_handle_t *h);
+/* The mapping alone (host only, no GPU): owner[cblknbr] = rank of each column block; optional
+ * contrib[cblknbr] = bit mask of the other ranks that contribute to it, load[nranks] = flops mapped. */
+int pb200_dist_plan(const pb200_solver_t *solver, int factotype, int nranks,
+                    int32_t *owner, uint32_t *contrib, double *load);
 int pb200_info(const pb200_handle_t *h, pb200_info_t *info);
 
 /* Panel offsets inside the flat slab: offsets[c] = sum_{k<c} stride_k*width_k,

@@ -14,6 +14,7 @@ SYMBOLS = [
     "pb200_norm1", "pb200_assemble", "pb200_reassemble", "pb200_factorize", "pb200_inertia", "pb200_solve",
     "pb200_solve_device", "pb200_get_coeftab", "pb200_set_coeftab", "pb200_mark_factorized",
     "pb200_last_launches", "pb200_probe_fp64_gflops", "pb200_set_profile", "pb200_get_profile",
+    "pb200_create_dist", "pb200_ipc_size", "pb200_ipc_export", "pb200_ipc_attach", "pb200_dist_barrier", "pb200_dist_plan",
 ]
 
 
@@ -44,6 +45,11 @@ def lib() -> C.CDLL:
     L.pb200_last_error.restype = C.c_char_p
     L.pb200_version.restype = C.c_char_p
     L.pb200_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(SolverDesc), C.c_int, C.c_int, C.c_int]
+    L.pb200_create_dist.argtypes = [C.POINTER(C.c_void_p), C.POINTER(SolverDesc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.pb200_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.pb200_ipc_attach.argtypes = [C.c_void_p, C.c_void_p]
+    L.pb200_dist_barrier.argtypes = [C.c_void_p]
+    L.pb200_dist_plan.argtypes = [C.POINTER(SolverDesc), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pb200_destroy.argtypes = [C.c_void_p]
     L.pb200_info.argtypes = [C.c_void_p, C.POINTER(Info)]
     L.pb200_panel_offsets.argtypes = [C.c_void_p, C.c_void_p]

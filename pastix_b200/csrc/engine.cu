@@ -16,6 +16,8 @@
 #include "kernels_factor.cuh"
 #include "kernels_solve.cuh"
 #include "kernels_mma.cuh"
+#include "kernels_dist.cuh"
+#include "dist_plan.h"
 
 using namespace pb200;
 
@@ -68,7 +70,7 @@ struct pb200_handle_s {
   // ---- FP64 tensor-core path (double / complex double, direct factorizations)
   bool use_mma = false;
   DevMap M{};
-  struct Step { int kind; int task0, ntasks; long long ntiles; int nbmax; int lvl; long long t2t0 = 0; int strm = 0, wait_ev = -1, rec_ev = -1; };  // kind: 0 diag 1 trsm 2 gemm 3 transpose 4 marker
+  struct Step { int kind; int task0, ntasks; long long ntiles; int nbmax; int lvl; long long t2t0 = 0; int strm = 0, wait_ev = -1, rec_ev = -1; };  // kind: 0 diag 1 trsm 2 gemm 3 transpose 4 marker 5 fan-in
   std::vector<Step> steps;
   SubTask *d_sub = nullptr;
   GemmTask *d_gemm = nullptr;
@@ -80,6 +82,18 @@ struct pb200_handle_s {
   std::vector<cudaEvent_t> sched_ev;     // [l] panel(l) done, [nlevels + l] bulk update of level l done
   std::vector<int> h_gemm_modes;
   std::vector<void *> allocs;
+  // ---- multi-GPU (one process per GPU; see kernels_dist.cuh)
+  int rank = 0, nranks = 1;
+  DistPlan plan;
+  int *d_owner = nullptr;
+  Peers peers{};
+  bool attached = false, gathered = true;
+  unsigned int *d_flags = nullptr, *d_dist_err = nullptr;   // flags: [0,nlevels) level ready, [nlevels] factorization done, [nlevels+1] barrier
+  unsigned int epoch = 0, bar_epoch = 0;
+  struct DistLevel { int sig = 0; unsigned int wait_mask = 0; int task0 = 0, ntasks = 0; long long ntiles = 0; };
+  std::vector<DistLevel> dist_lvl;
+  FanTask *d_fan = nullptr, *d_pull = nullptr; int npull = 0; long long pull_tiles = 0;
+  std::vector<void *> ipc_opened;
 };
 
 extern "C" const char *pb200_last_error(void) { return g_err.c_str(); }
@@ -203,6 +217,8 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
     const size_t level_first_step = h->steps.size();
     int rounds = 0;
     for (int q = q0; q < q1; ++q) rounds = std::max(rounds, (h->h_width[lvl_cblk[q]] + NBMAX - 1) / NBMAX);
+    if (h->nranks > 1 && (h->dist_lvl[l].sig || h->dist_lvl[l].ntasks))
+      h->steps.push_back({5, 0, 1, 0, 0, l});   // fan-in: publish our contributions, pull the peers' (kernels_dist.cuh)
     if (lu) h->steps.push_back({3, q0, q1 - q0, 0, 0, l});
     for (int r = 0; r < rounds; ++r) {
       // diag
@@ -313,8 +329,15 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
   return PB200_SUCCESS;
 }
 
+static int dist_barrier(pb200_handle_t *h);
 extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int flttype, int factotype, int device) {
+  return pb200_create_dist(out, s, flttype, factotype, device, 0, 1);
+}
+
+extern "C" int pb200_create_dist(pb200_handle_t **out, const pb200_solver_t *s, int flttype, int factotype, int device,
+                                 int rank, int nranks) {
   if (!out || !s) return fail(PB200_ERR_BADARG, "null argument");
+  if (nranks < 1 || nranks > PB200_MAXRANKS || rank < 0 || rank >= nranks) return fail(PB200_ERR_BADARG, "bad rank / nranks");
   if (elem_size(flttype) == 0) return fail(PB200_ERR_BADARG, "bad flttype");
   if (factotype < 0 || factotype > 3) return fail(PB200_ERR_BADARG, "bad factotype");
   if (s->cblknbr <= 0 || s->bloknbr < s->cblknbr) return fail(PB200_ERR_BADARG, "empty SolverMatrix");
@@ -330,6 +353,7 @@ extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int f
   pb200_handle_t *h = new pb200_handle_t();
   h->flt = flttype; h->facto = factotype; h->device = device; h->esize = elem_size(flttype);
   h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
+  h->rank = rank; h->nranks = nranks; h->gathered = (nranks == 1);
   const int64_t C = s->cblknbr, B = s->bloknbr;
   h->cblknbr = C; h->bloknbr = B;
   h->h_fcol.resize(C); h->h_width.resize(C); h->h_stride.resize(C); h->h_fblok.resize(C + 1);
@@ -400,6 +424,49 @@ extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int f
   std::vector<int> lvl_cblk(C), fill(h->lvl_ptr.begin(), h->lvl_ptr.end() - 1);
   for (int64_t c = 0; c < C; ++c) lvl_cblk[fill[level[c]]++] = (int)c;
 
+  // up_down runs over every cblk on every GPU (factors are gathered after a distributed factorization)
+  { int rc = build_solve_schedule(h, lvl_cblk); if (rc) { pb200_destroy(h); return rc; } }
+
+  // ---- multi-GPU: proportional subtree mapping; the factorization schedule keeps the owned cblks only
+  h->plan = dist_plan(C, h->h_fblok.data(), h->h_fcblk.data(), h->h_width.data(), h->h_stride.data(), h->h_nrow.data(),
+                      h->h_coefind.data(), nranks, factotype == PB200_FACT_LU);
+  if (nranks > 1) {
+    std::vector<int> optr(nl + 1, 0), ocblk;
+    std::vector<FanTask> fan, pull;
+    h->dist_lvl.assign(nl, pb200_handle_t::DistLevel());
+    for (int l = 0; l < nl; ++l) {
+      auto &D = h->dist_lvl[l];
+      D.task0 = (int)fan.size();
+      for (int q = h->lvl_ptr[l]; q < h->lvl_ptr[l + 1]; ++q) {
+        const int c = lvl_cblk[q];
+        const int64_t len = h->h_poff[c + 1] - h->h_poff[c];
+        const int nt = (int)((len + PB200_FAN_ELEMS - 1) / PB200_FAN_ELEMS);
+        if (h->plan.owner[c] == rank) {
+          ocblk.push_back(c);
+          if (h->plan.contrib[c]) {
+            fan.push_back({c, (int)D.ntiles, h->plan.contrib[c], 0});
+            D.ntiles += nt; D.wait_mask |= h->plan.contrib[c];
+          }
+        } else {
+          if ((h->plan.contrib[c] >> rank) & 1u) D.sig = 1;
+          pull.push_back({c, (int)h->pull_tiles, 0u, 0});
+          h->pull_tiles += nt;
+        }
+      }
+      D.ntasks = (int)fan.size() - D.task0;
+      optr[l + 1] = (int)ocblk.size();
+    }
+    h->lvl_ptr = optr; lvl_cblk = ocblk;
+    h->npull = (int)pull.size();
+    { int rc = upload(h, fan, &h->d_fan); if (rc) { pb200_destroy(h); return rc; } }
+    { int rc = upload(h, pull, &h->d_pull); if (rc) { pb200_destroy(h); return rc; } }
+    { int rc = upload(h, h->plan.owner, &h->d_owner); if (rc) { pb200_destroy(h); return rc; } }
+    CK(cudaMalloc((void **)&h->d_flags, (size_t)(nl + 2) * sizeof(unsigned int)));
+    CK(cudaMemset(h->d_flags, 0, (size_t)(nl + 2) * sizeof(unsigned int)));
+    CK(cudaMalloc((void **)&h->d_dist_err, sizeof(unsigned int)));
+    CK(cudaMemset(h->d_dist_err, 0, sizeof(unsigned int)));
+  }
+
   // ---- per-level task lists
   std::vector<RowTask> trsm, slv;
   std::vector<UpdTask> upd;
@@ -439,7 +506,6 @@ extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int f
   { int rc = upload(h, slv, &h->d_slv); if (rc) { pb200_destroy(h); return rc; } }
   { int rc = upload(h, upd, &h->d_upd); if (rc) { pb200_destroy(h); return rc; } }
 
-  { int rc = build_solve_schedule(h, lvl_cblk); if (rc) { pb200_destroy(h); return rc; } }
   if (flttype == PB200_REALDOUBLE || flttype == PB200_COMPLEXDOUBLE) {
     int rc = build_mma_schedule(h, level, lvl_cblk);
     if (rc) { pb200_destroy(h); return rc; }
@@ -467,6 +533,9 @@ extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int f
 extern "C" int pb200_destroy(pb200_handle_t *h) {
   if (!h) return PB200_SUCCESS;
   cudaSetDevice(h->device);
+  if (h->attached) dist_barrier(h);   // collective: no peer is still reading our slab
+  for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  cudaFree(h->d_flags); cudaFree(h->d_dist_err);
   for (void *p : h->allocs) cudaFree(p);
   cudaFree(h->dL); cudaFree(h->dU); cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals);
   cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x); cudaFree(h->d_y);
@@ -527,6 +596,8 @@ extern "C" double pb200_norm1(int flttype, int64_t n, const int64_t *colptr, con
 }
 
 static int invert_dispatch(pb200_handle_t *h, cudaStream_t sm);
+static int dist_barrier(pb200_handle_t *h);
+static int ensure_gathered(pb200_handle_t *h);
 // ------------------------------------------------------------------ dispatch helpers
 #define DISPATCH_T(h, FN, ...)                                                    \
   switch ((h)->flt) {                                                             \
@@ -537,18 +608,73 @@ static int invert_dispatch(pb200_handle_t *h, cudaStream_t sm);
   }                                                                               \
   return fail(PB200_ERR_BADARG, "bad flttype");
 
+// ------------------------------------------------------------------ multi-GPU helpers
+static const unsigned long long kDistTimeoutNs = 60ULL * 1000000000ULL;
+template <class T>
+static int64_t launch_fanin(pb200_handle_t *h, int l, cudaStream_t sm) {
+  const auto &D = h->dist_lvl[l];
+  int64_t n = 0;
+  if (D.sig) { k_dist_signal<<<1, 32, 0, sm>>>(h->d_flags, l, h->epoch); ++n; }
+  if (D.ntasks) {
+    k_dist_wait<<<1, 32, 0, sm>>>(h->peers, D.wait_mask, l, h->epoch, kDistTimeoutNs, h->d_dist_err);
+    k_fanin_gather<T><<<(unsigned)D.ntiles, 256, 0, sm>>>(h->S, h->peers, (T *)h->dL, (T *)h->dU, h->d_fan + D.task0, D.ntasks);
+    n += 2;
+  }
+  return n;
+}
+static int dist_check(pb200_handle_t *h) {
+  unsigned int e = 0;
+  CK(cudaMemcpy(&e, h->d_dist_err, sizeof(e), cudaMemcpyDeviceToHost));
+  if (e) return fail(PB200_ERR_STATE, "multi-GPU wait timed out on rank " + std::to_string(e - 1) + " (peer did not reach the same step)");
+  return PB200_SUCCESS;
+}
+// device-side barrier over the peers' flag arrays: everything this process launched before is finished on
+// every GPU when it returns (collective: every rank calls it the same number of times)
+static int dist_barrier(pb200_handle_t *h) {
+  if (h->nranks == 1) return PB200_SUCCESS;
+  if (!h->attached) return fail(PB200_ERR_STATE, "pb200_ipc_attach has not been called");
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->stream_u) CK(cudaStreamSynchronize(h->stream_u));
+  ++h->bar_epoch;
+  k_dist_signal<<<1, 32, 0, h->stream>>>(h->d_flags, h->nlevels + 1, h->bar_epoch);
+  k_dist_wait<<<1, 32, 0, h->stream>>>(h->peers, (1u << h->nranks) - 1u, h->nlevels + 1, h->bar_epoch, kDistTimeoutNs, h->d_dist_err);
+  CK(cudaStreamSynchronize(h->stream));
+  return dist_check(h);
+}
+// copy the other GPUs' factored panels into the local slab (once per factorization, before the first
+// up_down / read-back)
+template <class T>
+static int gather_t(pb200_handle_t *h) {
+  k_dist_wait<<<1, 32, 0, h->stream>>>(h->peers, (1u << h->nranks) - 1u, h->nlevels, h->epoch, kDistTimeoutNs, h->d_dist_err);
+  if (h->npull > 0)
+    k_pull_panels<T><<<(unsigned)h->pull_tiles, 256, 0, h->stream>>>(h->S, h->peers, (T *)h->dL, (T *)h->dU, h->d_owner, h->d_pull, h->npull);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return dist_check(h);
+}
+static int gather_dispatch(pb200_handle_t *h) { DISPATCH_T(h, gather_t, h) }
+static int ensure_gathered(pb200_handle_t *h) {
+  if (h->nranks == 1 || h->gathered) return PB200_SUCCESS;
+  if (!h->factorized) return fail(PB200_ERR_STATE, "not factorized");
+  int rc = gather_dispatch(h);
+  if (rc) return rc;
+  h->gathered = true;
+  return PB200_SUCCESS;
+}
 template <class T>
 static int reassemble_t(pb200_handle_t *h) {
   size_t slab = (size_t)h->coefnbr * sizeof(T);
+  { int rc = dist_barrier(h); if (rc) return rc; }   // peers may still be reading our panels / fan-in buffers
   CK(cudaMemsetAsync(h->dL, 0, slab, h->stream));
   if (h->dU) CK(cudaMemsetAsync(h->dU, 0, slab, h->stream));
   CK(cudaMemsetAsync(h->d_cnt + 1, 0, sizeof(unsigned long long), h->stream));
   int n = (int)h->n;
   k_assemble<T><<<(n + 255) / 256, 256, 0, h->stream>>>(h->S, n, h->d_colptr, h->d_rows, (const T *)h->d_vals,
-                                                        (const T *)h->d_tvals, 0, (T *)h->dL, (T *)h->dU, h->d_cnt + 1);
+                                                        (const T *)h->d_tvals, 0, (T *)h->dL, (T *)h->dU, h->d_cnt + 1,
+                                                        h->d_owner, h->rank);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
-  h->assembled = true; h->factorized = false; h->inv_ready = false;
+  h->assembled = true; h->factorized = false; h->inv_ready = false; h->gathered = (h->nranks == 1);
   return PB200_SUCCESS;
 }
 
@@ -600,6 +726,8 @@ static int factorize_tf(pb200_handle_t *h, double crit) {
   int64_t launches = 0;
   for (int l = 0; l < h->nlevels; ++l) {
     int nc = h->lvl_ptr[l + 1] - h->lvl_ptr[l];
+    if (h->nranks > 1) launches += launch_fanin<T>(h, l, h->stream);
+    if (nc == 0) continue;
     // smem sized for the widest cblk of this launch would need a per-level max; use global wmax bound
     int elems = std::min<long long>((long long)h->wmax * h->wmax, smem_max / (long long)sizeof(T));
     size_t smem = (size_t)elems * sizeof(T);
@@ -622,6 +750,7 @@ static int factorize_tf(pb200_handle_t *h, double crit) {
 }
 
 static int h_gemm_mode(const pb200_handle_t *h, int task) { return h->h_gemm_modes[task]; }
+
 // ------------------------------------------------------------------ factorization (tensor-core path)
 template <class T, int FACTO>
 static int factorize_mma(pb200_handle_t *h, double crit) {
@@ -636,7 +765,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   }
   int64_t launches = 0;
   const bool prof = h->prof_on || getenv("PB200_PROFILE") != nullptr;
-  double tkind[4] = {0, 0, 0, 0}; long long nk[4] = {0, 0, 0, 0};
+  double tkind[6] = {0, 0, 0, 0, 0, 0}; long long nk[6] = {0, 0, 0, 0, 0, 0};
   double tlevel_max = 0; int lvl_max = -1;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
@@ -665,6 +794,9 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
         if (FACTO == F_LU)
           k_diag_transpose<T><<<dim3(4, std::min(st.ntasks, 65535)), dim3(32, 8), 0, sm>>>(h->S, L, U, h->d_lvl_cblk + st.task0, st.ntasks);
         break;
+      case 5:
+        launches += launch_fanin<T>(h, st.lvl, sm) - 1;
+        break;
     }
     ++launches;
     if (!serial && st.rec_ev >= 0) CK(cudaEventRecord(h->sched_ev[st.rec_ev], sm));
@@ -680,6 +812,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   }
   if (prof) {
     for (int q = 0; q < 4; ++q) { h->prof_ms[q] = tkind[q]; h->prof_n[q] = nk[q]; }
+    h->prof_ms[3] += tkind[5]; h->prof_n[3] += nk[5];
     if (getenv("PB200_PROFILE") != nullptr)
     fprintf(stderr, "[pb200 profile] diag %.3f ms (%lld)  trsm %.3f ms (%lld)  ext-update %.3f ms (%lld)  int-update/transpose %.3f ms (%lld)\n",
             tkind[0], nk[0], tkind[1], nk[1], tkind[2], nk[2], tkind[3], nk[3]);
@@ -725,14 +858,24 @@ extern "C" int pb200_factorize(pb200_handle_t *h, double critere, int64_t *nbpiv
   if (!h->assembled) return fail(PB200_ERR_STATE, "panels not assembled (pb200_assemble / pb200_set_coeftab)");
   if (h->factorized) return fail(PB200_ERR_STATE, "panels already factorized; reassemble first");
   CK(cudaSetDevice(h->device));
+  if (h->nranks > 1) {
+    if (!h->attached) return fail(PB200_ERR_STATE, "pb200_ipc_attach has not been called");
+    ++h->epoch;
+  }
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(unsigned long long), h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
   int rc = factorize_dispatch(h, critere);
   if (rc) return rc;
-  rc = invert_dispatch(h, h->stream);   // diagonal triangles inverted once, for the up_down sweeps
-  if (rc) return rc;
+  if (h->nranks == 1) {
+    rc = invert_dispatch(h, h->stream);   // diagonal triangles inverted once, for the up_down sweeps
+    if (rc) return rc;
+  } else {
+    k_dist_signal<<<1, 32, 0, h->stream>>>(h->d_flags, h->nlevels, h->epoch);   // our share of the factorization is done
+    h->gathered = false;
+  }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->nranks > 1) { rc = dist_check(h); if (rc) return rc; }
   float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   unsigned long long nb = 0;
   CK(cudaMemcpy(&nb, h->d_cnt, sizeof(nb), cudaMemcpyDeviceToHost));
@@ -757,6 +900,7 @@ extern "C" int pb200_inertia(pb200_handle_t *h, int64_t *inertia) {
   if (!h || !inertia) return fail(PB200_ERR_BADARG, "null argument");
   if (!h->factorized) return fail(PB200_ERR_STATE, "not factorized");
   CK(cudaSetDevice(h->device));
+  { int rc = ensure_gathered(h); if (rc) return rc; }
   DISPATCH_T(h, inertia_t, h, inertia)
 }
 
@@ -825,6 +969,7 @@ extern "C" int pb200_solve_device(pb200_handle_t *h, void *x_dev, int64_t ldx, i
   if (!h->factorized) return fail(PB200_ERR_STATE, "not factorized");
   if (ldx < h->n || nrhs <= 0) return fail(PB200_ERR_BADARG, "bad ldx / nrhs");
   CK(cudaSetDevice(h->device));
+  { int rc = ensure_gathered(h); if (rc) return rc; }
   {
     size_t yb = (size_t)ldx * nrhs * h->esize;
     if (yb > h->y_bytes) {
@@ -867,6 +1012,7 @@ extern "C" int pb200_solve(pb200_handle_t *h, void *x, int64_t ldx, int64_t nrhs
 extern "C" int pb200_get_coeftab(pb200_handle_t *h, void *L, void *U) {
   if (!h || !L) return fail(PB200_ERR_BADARG, "null argument");
   CK(cudaSetDevice(h->device));
+  if (h->factorized) { int rc = ensure_gathered(h); if (rc) return rc; }
   size_t slab = (size_t)h->coefnbr * h->esize;
   CK(cudaMemcpy(L, h->dL, slab, cudaMemcpyDeviceToHost));
   if (U) {
@@ -883,8 +1029,63 @@ extern "C" int pb200_set_coeftab(pb200_handle_t *h, const void *L, const void *U
   size_t slab = (size_t)h->coefnbr * h->esize;
   CK(cudaMemcpy(h->dL, L, slab, cudaMemcpyHostToDevice));
   if (h->dU) CK(cudaMemcpy(h->dU, U, slab, cudaMemcpyHostToDevice));
-  h->assembled = true; h->factorized = false; h->inv_ready = false;
+  h->assembled = true; h->factorized = false; h->inv_ready = false; h->gathered = true;
   return PB200_SUCCESS;
+}
+
+// ------------------------------------------------------------------ multi-GPU plumbing (C ABI)
+extern "C" int pb200_dist_plan(const pb200_solver_t *s, int factotype, int nranks, int32_t *owner, uint32_t *contrib, double *load) {
+  if (!s || !owner || nranks < 1 || nranks > PB200_MAXRANKS) return fail(PB200_ERR_BADARG, "bad argument");
+  const int64_t C = s->cblknbr, B = s->bloknbr;
+  std::vector<int> fblok(C + 1), fcblk(B), width(C), stride(C), nrow(B), coefind(B);
+  for (int64_t c = 0; c < C; ++c) { fblok[c] = (int)s->bloknum[c]; width[c] = (int)(s->lcolnum[c] - s->fcolnum[c] + 1); stride[c] = (int)s->stride[c]; }
+  fblok[C] = (int)s->bloknum[C];
+  for (int64_t b = 0; b < B; ++b) { fcblk[b] = (int)s->cblknum[b]; nrow[b] = (int)(s->lrownum[b] - s->frownum[b] + 1); coefind[b] = (int)s->coefind[b]; }
+  DistPlan P = dist_plan(C, fblok.data(), fcblk.data(), width.data(), stride.data(), nrow.data(), coefind.data(), nranks,
+                         factotype == PB200_FACT_LU);
+  for (int64_t c = 0; c < C; ++c) { owner[c] = P.owner[c]; if (contrib) contrib[c] = P.contrib[c]; }
+  if (load) for (int p = 0; p < nranks; ++p) load[p] = P.load[p];
+  return PB200_SUCCESS;
+}
+
+extern "C" int pb200_ipc_size(void) { return (int)(3 * sizeof(cudaIpcMemHandle_t)); }
+
+extern "C" int pb200_ipc_export(pb200_handle_t *h, void *buf) {
+  if (!h || !buf) return fail(PB200_ERR_BADARG, "null argument");
+  if (h->nranks == 1) return fail(PB200_ERR_STATE, "not a multi-GPU handle");
+  CK(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t *o = (cudaIpcMemHandle_t *)buf;
+  memset(o, 0, 3 * sizeof(cudaIpcMemHandle_t));
+  CK(cudaIpcGetMemHandle(&o[0], h->dL));
+  if (h->dU) CK(cudaIpcGetMemHandle(&o[1], h->dU));
+  CK(cudaIpcGetMemHandle(&o[2], h->d_flags));
+  return PB200_SUCCESS;
+}
+
+extern "C" int pb200_ipc_attach(pb200_handle_t *h, const void *all_handles) {
+  if (!h || !all_handles) return fail(PB200_ERR_BADARG, "null argument");
+  if (h->nranks == 1) return fail(PB200_ERR_STATE, "not a multi-GPU handle");
+  if (h->attached) return PB200_SUCCESS;
+  CK(cudaSetDevice(h->device));
+  const cudaIpcMemHandle_t *in = (const cudaIpcMemHandle_t *)all_handles;
+  h->peers.rank = h->rank; h->peers.nranks = h->nranks;
+  for (int p = 0; p < h->nranks; ++p) {
+    if (p == h->rank) { h->peers.L[p] = h->dL; h->peers.U[p] = h->dU; h->peers.flags[p] = h->d_flags; continue; }
+    void *q = nullptr;
+    CK(cudaIpcOpenMemHandle(&q, in[3 * p + 0], cudaIpcMemLazyEnablePeerAccess)); h->ipc_opened.push_back(q); h->peers.L[p] = q;
+    h->peers.U[p] = nullptr;
+    if (h->dU) { CK(cudaIpcOpenMemHandle(&q, in[3 * p + 1], cudaIpcMemLazyEnablePeerAccess)); h->ipc_opened.push_back(q); h->peers.U[p] = q; }
+    CK(cudaIpcOpenMemHandle(&q, in[3 * p + 2], cudaIpcMemLazyEnablePeerAccess)); h->ipc_opened.push_back(q);
+    h->peers.flags[p] = (unsigned int *)q;
+  }
+  h->attached = true;
+  return PB200_SUCCESS;
+}
+
+extern "C" int pb200_dist_barrier(pb200_handle_t *h) {
+  if (!h) return fail(PB200_ERR_BADARG, "null handle");
+  CK(cudaSetDevice(h->device));
+  return dist_barrier(h);
 }
 
 // set by tests that upload already-factored panels (solve-only parity)

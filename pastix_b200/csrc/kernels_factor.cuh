@@ -22,10 +22,11 @@ enum { F_LLT = 0, F_LDLT = 1, F_LU = 2, F_LDLH = 3 };
 template <class T>
 __global__ void k_assemble(DevSym S, int n, const int64_t *__restrict__ colptr, const int *__restrict__ rows,
                            const T *__restrict__ vals, const T *__restrict__ tvals, int herm, T *L, T *U,
-                           unsigned long long *dropped) {
+                           unsigned long long *dropped, const int *__restrict__ owner, int rank) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   int c = S.col2cblk[j];
+  if (owner != nullptr && owner[c] != rank) return;   // multi-GPU: that panel is a (zero) fan-in buffer here
   int fcol = S.fcol[c], ld = S.stride[c], b0 = S.fblok[c], b1 = S.fblok[c + 1];
   int64_t base = S.poff[c] + (int64_t)ld * (j - fcol);
   for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {

@@ -168,6 +168,21 @@ class Pastix(PastixLib):
         self.lib.pb200_shim_get_order(self.pd, pt.ctypes.data, pi.ctypes.data)
         return pt, pi
 
+    def solver(self) -> dict:
+        """Flat copy of the SolverMatrix produced by the analysis (blend/src/solver.h:94-168), keys as in
+        pb200_solver_t — the input of `Sopalin(...)` / pb200_create_dist for the multi-GPU path."""
+        sz = np.zeros(2, dtype=np.int64)
+        self.lib.pb200_shim_solver_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.pb200_shim_solver_sizes(self.pd, sz.ctypes.data)
+        cb, bl = int(sz[0]), int(sz[1])
+        a = {k: np.zeros(cb + 1, dtype=np.int64) for k in ("fcolnum", "lcolnum", "bloknum", "stride")}
+        b = {k: np.zeros(bl, dtype=np.int64) for k in ("frownum", "lrownum", "cblknum", "coefind")}
+        self.lib.pb200_shim_solver_get.argtypes = [C.c_void_p] * 9
+        self.lib.pb200_shim_solver_get(self.pd, *[a[k].ctypes.data for k in ("fcolnum", "lcolnum", "bloknum", "stride")],
+                                       *[b[k].ctypes.data for k in ("frownum", "lrownum", "cblknum", "coefind")])
+        d = dict(cblknbr=cb, bloknbr=bl); d.update(a); d.update(b)
+        return d
+
     def sopalin(self):
         """The GPU numeric phase behind this pastix_data as a `Sopalin` (borrowed handle)."""
         from .sopalin import Sopalin

@@ -73,6 +73,29 @@ void pb200_shim_get_order(void *pastix_data, int64_t *permtab, int64_t *peritab)
   for (i = 0; i < n; i++) { permtab[i] = pd->ordemesh.permtab[i]; peritab[i] = pd->ordemesh.peritab[i]; }
 }
 
+/* flat copy of the SolverMatrix the analysis left in this pastix_data_t (blend/src/solver.h:94-168), in the
+ * layout of pb200_solver_t — what a multi-GPU host (one process per GPU, same analysis everywhere) hands to
+ * pb200_create_dist.  sizes[0..1] = cblknbr, bloknbr; cblk arrays hold cblknbr+1 entries. */
+void pb200_shim_solver_sizes(void *pastix_data, int64_t *sizes)
+{
+  SolverMatrix *m = &((pastix_data_t *)pastix_data)->solvmatr;
+  sizes[0] = m->cblknbr; sizes[1] = m->bloknbr;
+}
+void pb200_shim_solver_get(void *pastix_data, int64_t *fcolnum, int64_t *lcolnum, int64_t *bloknum, int64_t *stride,
+                           int64_t *frownum, int64_t *lrownum, int64_t *cblknum, int64_t *coefind)
+{
+  SolverMatrix *m = &((pastix_data_t *)pastix_data)->solvmatr;
+  PASTIX_INT i;
+  for (i = 0; i <= m->cblknbr; i++) {
+    fcolnum[i] = m->cblktab[i].fcolnum; lcolnum[i] = m->cblktab[i].lcolnum;
+    bloknum[i] = m->cblktab[i].bloknum; stride[i] = (i < m->cblknbr) ? m->cblktab[i].stride : 0;
+  }
+  for (i = 0; i < m->bloknbr; i++) {
+    frownum[i] = m->bloktab[i].frownum; lrownum[i] = m->bloktab[i].lrownum;
+    cblknum[i] = m->bloktab[i].cblknum; coefind[i] = m->bloktab[i].coefind;
+  }
+}
+
 /* release the HBM held for this pastix_data_t (call before API_TASK_CLEAN) */
 void pb200_shim_release_data(void *pastix_data)
 {

@@ -106,8 +106,11 @@ class Sopalin:
         names = ("diag", "trsm", "gemm_scatter", "inpanel_update")
         return {"ms": dict(zip(names, list(ms))), "launches": dict(zip(names, [int(v) for v in n])), "gemm_flops": float(fl.value)}
 
-    def __init__(self, solver: SolverMatrix | dict, prec: str = "d", facto: str = "llt", device: int = -1):
+    def __init__(self, solver: SolverMatrix | dict, prec: str = "d", facto: str = "llt", device: int = -1,
+                 rank: int = 0, nranks: int = 1):
+        """rank/nranks > 1: one process per GPU; call `attach()` (collective) before assembling."""
         self._borrowed = False
+        self.rank, self.nranks = rank, nranks
         if isinstance(solver, dict):
             solver = SolverMatrix.from_dict(solver)
         self.solver, self.prec, self.facto = solver, prec, facto
@@ -118,8 +121,48 @@ class Sopalin:
                                      p(solver.bloknum), p(solver.stride), p(solver.frownum), p(solver.lrownum),
                                      p(solver.cblknum), p(solver.coefind))
         self.h = C.c_void_p(None)
-        _check(self.L.pb200_create(C.byref(self.h), C.byref(self._desc), FLTTYPE[prec], FACTO[facto], device))
+        _check(self.L.pb200_create_dist(C.byref(self.h), C.byref(self._desc), FLTTYPE[prec], FACTO[facto], device,
+                                        rank, nranks))
         self._read_info()
+
+    # -- multi-GPU plumbing ----------------------------------------------------
+    def attach(self, dist=None):
+        """Exchange the CUDA IPC blobs of the slabs over torch.distributed (any backend; the blobs are
+        192 opaque bytes per rank) and map every peer's slab (pb200_ipc_attach).  Collective."""
+        if self.nranks == 1:
+            return self
+        import torch
+        import torch.distributed as td
+        dist = dist or td
+        nb = int(self.L.pb200_ipc_size())
+        blob = (C.c_ubyte * nb)()
+        _check(self.L.pb200_ipc_export(self.h, blob))
+        mine = torch.tensor(list(bytes(blob)), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda()
+        allb = [torch.empty_like(mine) for _ in range(self.nranks)]
+        dist.all_gather(allb, mine)
+        raw = b"".join(bytes(t.cpu().tolist()) for t in allb)
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        _check(self.L.pb200_ipc_attach(self.h, buf))
+        return self
+
+    def barrier(self):
+        _check(self.L.pb200_dist_barrier(self.h))
+
+    @staticmethod
+    def dist_plan(solver, facto: str, nranks: int):
+        """The column-block -> GPU mapping alone (host only): (owner, contrib mask, flops per rank)."""
+        if isinstance(solver, dict):
+            solver = SolverMatrix.from_dict(solver)
+        L = _lib.lib()
+        p = lambda a: a.ctypes.data
+        desc = _lib.SolverDesc(solver.cblknbr, solver.bloknbr, p(solver.fcolnum), p(solver.lcolnum), p(solver.bloknum),
+                               p(solver.stride), p(solver.frownum), p(solver.lrownum), p(solver.cblknum), p(solver.coefind))
+        owner = np.zeros(solver.cblknbr, dtype=np.int32); contrib = np.zeros(solver.cblknbr, dtype=np.uint32)
+        load = np.zeros(nranks, dtype=np.float64)
+        _check(L.pb200_dist_plan(C.byref(desc), FACTO[facto], nranks, owner.ctypes.data, contrib.ctypes.data, load.ctypes.data))
+        return owner, contrib, load
 
     def close(self):
         if self.h and not self._borrowed:
