@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpastix_b200.so")
+LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(_HERE, "lib", "libpastix_b200.so")   # PB200_LIB: tuning variants
 
 # every symbol include/pastix_b200.h declares
 SYMBOLS = [

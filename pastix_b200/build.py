@@ -8,7 +8,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "lib", "libpastix_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("engine.cu", "probe.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("scalar.cuh", "symbol.cuh", "kernels_factor.cuh", "kernels_solve.cuh", "kernels_mma.cuh", "mma.cuh")] + \
+HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("scalar.cuh", "symbol.cuh", "kernels_factor.cuh", "kernels_solve.cuh", "kernels_mma.cuh", "mma.cuh", "kernels_dist.cuh", "dist_plan.h")] + \
           [os.path.join(_HERE, "..", "include", "pastix_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--threads", "4"]
@@ -21,16 +21,20 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(f) <= t for f in SOURCES + HEADERS + [os.path.abspath(__file__)])
 
 
-def build_cuda(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build_cuda(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """`defines`/`out`: tuning variants (e.g. -DPB200_NBMAX_D=64 into lib/libpastix_b200_nb64.so, selected at
+    run time with PB200_LIB=<path>); the default build is the product."""
+    if out is None and not force and up_to_date():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] + SOURCES
     print("[pastix_b200] " + " ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
-    build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None)

@@ -52,42 +52,67 @@ inline DistPlan dist_plan(int64_t C, const int *fblok, const int *fcblk, const i
   { std::vector<int> fill(cptr.begin(), cptr.end() - 1);
     for (int64_t c = 0; c < C; ++c) if (parent[c] >= 0) child[fill[parent[c]]++] = (int)c; }
   if (nranks > 1) {
-    // top-down over the forest; roots share [0, nranks) in proportion like children of a virtual root
-    struct Item { int c; double lo, hi; int depth; };
-    std::vector<Item> stack;
-    auto split = [&](std::vector<int> kids, double lo, double hi, int depth) {
-      std::sort(kids.begin(), kids.end(), [&](int a, int b) { return sub[a] != sub[b] ? sub[a] > sub[b] : a < b; });
-      double tot = 0; for (int k : kids) tot += sub[k];
-      double pos = lo;
-      for (int k : kids) {
-        const double wdt = (hi - lo) * sub[k] / tot;
-        stack.push_back({k, pos, pos + wdt, depth});
-        pos += wdt;
+    // Pass 1 (top-down): a subtree heavier than one GPU's fair share stays shared over a candidate interval
+    // (several such children split the interval in proportion to their cost); lighter subtrees become
+    // single-GPU subtrees, placed in pass 2.  Pass 2: subtrees, heaviest first, go to the least-loaded GPU
+    // of their interval; pass 3: the shared column blocks, heaviest first, likewise — they are about half
+    // of the flops, so they level what the subtrees left uneven.
+    double total = 0;
+    for (int64_t c = 0; c < C; ++c) if (parent[c] < 0) total += sub[c];
+    const double fair = total / nranks;
+    struct Item { int c, a, b; };
+    std::vector<Item> stack, subtrees, shared;
+    {
+      std::vector<int> roots;
+      for (int64_t c = 0; c < C; ++c) if (parent[c] < 0) roots.push_back((int)c);
+      // virtual root over the forest
+      std::vector<int> big, small;
+      for (int r : roots) (sub[r] > fair ? big : small).push_back(r);
+      double tot = 0; for (int k : big) tot += sub[k];
+      double pos = 0;
+      for (int k : big) {
+        const double wdt = nranks * sub[k] / tot;
+        int lo = (int)(pos + 0.5), hi = (int)(pos + wdt + 0.5);
+        lo = std::min(lo, nranks - 1); if (hi <= lo) hi = lo + 1; hi = std::min(hi, nranks);
+        stack.push_back({k, lo, hi}); pos += wdt;
       }
-    };
-    std::vector<int> roots;
-    for (int64_t c = 0; c < C; ++c) if (parent[c] < 0) roots.push_back((int)c);
-    split(roots, 0.0, (double)nranks, 0);
+      for (int k : small) subtrees.push_back({k, 0, nranks});
+    }
     while (!stack.empty()) {
       const Item it = stack.back(); stack.pop_back();
-      // integer candidate interval [a, b): ranks whose unit interval is covered by at least half, at least one
-      int a = (int)(it.lo + 0.5), b = (int)(it.hi + 0.5);
-      a = std::min(std::max(a, 0), nranks - 1);
-      if (b <= a) { a = std::min((int)it.lo, nranks - 1); b = a + 1; }
-      b = std::min(b, nranks);
-      if (b - a == 1) {
-        // whole subtree on rank a
-        std::vector<int> st2{it.c};
-        while (!st2.empty()) {
-          const int c = st2.back(); st2.pop_back();
-          P.owner[c] = a;
-          for (int q = cptr[c]; q < cptr[c + 1]; ++q) st2.push_back(child[q]);
-        }
-        continue;
+      if (it.b - it.a == 1) { subtrees.push_back(it); continue; }
+      shared.push_back(it);
+      std::vector<int> big, small;
+      for (int q = cptr[it.c]; q < cptr[it.c + 1]; ++q) (sub[child[q]] > fair ? big : small).push_back(child[q]);
+      std::sort(big.begin(), big.end(), [&](int x, int y) { return sub[x] != sub[y] ? sub[x] > sub[y] : x < y; });
+      double tot = 0; for (int k : big) tot += sub[k];
+      double pos = it.a;
+      for (int k : big) {
+        const double wdt = (it.b - it.a) * sub[k] / tot;
+        int lo = (int)(pos + 0.5), hi = (int)(pos + wdt + 0.5);
+        lo = std::min(std::max(lo, it.a), it.b - 1); if (hi <= lo) hi = lo + 1; hi = std::min(hi, it.b);
+        stack.push_back({k, lo, hi}); pos += wdt;
       }
-      P.owner[it.c] = a + (it.depth % (b - a));
-      std::vector<int> kids(child.begin() + cptr[it.c], child.begin() + cptr[it.c + 1]);
-      if (!kids.empty()) split(kids, (double)a, (double)b, it.depth + 1);
+      for (int k : small) subtrees.push_back({k, it.a, it.b});
+    }
+    std::vector<double> L(nranks, 0.0);
+    auto least = [&](int a2, int b2) { int best = a2; for (int p = a2 + 1; p < b2; ++p) if (L[p] < L[best]) best = p; return best; };
+    std::sort(subtrees.begin(), subtrees.end(), [&](const Item &x, const Item &y) { return sub[x.c] != sub[y.c] ? sub[x.c] > sub[y.c] : x.c < y.c; });
+    for (const Item &it : subtrees) {
+      const int p = least(it.a, it.b);
+      L[p] += sub[it.c];
+      std::vector<int> st2{it.c};
+      while (!st2.empty()) {
+        const int c = st2.back(); st2.pop_back();
+        P.owner[c] = p;
+        for (int q = cptr[c]; q < cptr[c + 1]; ++q) st2.push_back(child[q]);
+      }
+    }
+    std::sort(shared.begin(), shared.end(), [&](const Item &x, const Item &y) { return cost[x.c] != cost[y.c] ? cost[x.c] > cost[y.c] : x.c < y.c; });
+    for (const Item &it : shared) {
+      const int p = least(it.a, it.b);
+      L[p] += cost[it.c];
+      P.owner[it.c] = p;
     }
   }
   for (int64_t c = 0; c < C; ++c) {

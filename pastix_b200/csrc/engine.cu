@@ -67,6 +67,9 @@ struct pb200_handle_s {
   unsigned int *d_slv_cnt = nullptr;
   void *d_y = nullptr; size_t y_bytes = 0;
   bool inv_ready = false;
+  std::vector<int> inv_lvl_ptr;            // sub-panels of level l: [inv_lvl_ptr[l], inv_lvl_ptr[l+1])
+  cudaStream_t stream_i = nullptr;         // low priority: triangle inversions underneath the factorization
+  cudaEvent_t ev_inv = nullptr;
   // ---- FP64 tensor-core path (double / complex double, direct factorizations)
   bool use_mma = false;
   DevMap M{};
@@ -124,9 +127,11 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
   const int NB = (h->flt == PB200_COMPLEXDOUBLE) ? SlvCfg<cdouble>::NB : SlvCfg<double>::NB;
   std::vector<SlvTask> tasks; std::vector<int> t2t; std::vector<int64_t> invoff;
   int64_t inv_elems = 0; int sp = 0;
+  h->inv_lvl_ptr.assign(h->nlevels + 1, 0);
   for (int l = 0; l < h->nlevels; ++l) {
     const int q0 = h->lvl_ptr[l], q1 = h->lvl_ptr[l + 1];
     int rounds = 0;
+    h->inv_lvl_ptr[l] = sp;
     for (int q = q0; q < q1; ++q) rounds = std::max(rounds, (h->h_width[lvl_cblk[q]] + NB - 1) / NB);
     for (int r = 0; r < rounds; ++r) {
       int t0 = (int)tasks.size(); long long tiles = 0; long long tt0 = (long long)t2t.size();
@@ -146,7 +151,7 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
       h->slv_steps.push_back({t0, (int)tasks.size() - t0, tiles, tt0});
     }
   }
-  h->nsubpanels = sp; h->inv_elems = inv_elems;
+  h->nsubpanels = sp; h->inv_elems = inv_elems; h->inv_lvl_ptr[h->nlevels] = sp;
   { int rc = upload(h, tasks, &h->d_slvtask); if (rc) return rc; }
   { int rc = upload(h, t2t, &h->d_slv_t2t); if (rc) return rc; }
   { int rc = upload(h, invoff, &h->d_invoff); if (rc) return rc; }
@@ -220,6 +225,7 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
     if (h->nranks > 1 && (h->dist_lvl[l].sig || h->dist_lvl[l].ntasks))
       h->steps.push_back({5, 0, 1, 0, 0, l});   // fan-in: publish our contributions, pull the peers' (kernels_dist.cuh)
     if (lu) h->steps.push_back({3, q0, q1 - q0, 0, 0, l});
+    if (rounds == 0) h->steps.push_back({4, 0, 0, 0, 0, l});   // multi-GPU: no cblk of this level lives here; keeps the level's events
     for (int r = 0; r < rounds; ++r) {
       // diag
       int t0 = (int)sub.size(), nbmax = 0;
@@ -321,6 +327,12 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
     int rc = upload(h, t2t, &h->d_t2t); if (rc) return rc;
   }
   CK(cudaStreamCreateWithFlags(&h->stream_u, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->stream_i, cudaStreamNonBlocking, lo));
+    CK(cudaEventCreateWithFlags(&h->ev_inv, cudaEventDisableTiming));
+  }
   h->sched_ev.resize(2 * (size_t)h->nlevels);
   for (auto &e : h->sched_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   h->h_gemm_modes.resize(gemm.size());
@@ -541,6 +553,8 @@ extern "C" int pb200_destroy(pb200_handle_t *h) {
   cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x); cudaFree(h->d_y);
   for (auto e : h->sched_ev) cudaEventDestroy(e);
   if (h->stream_u) cudaStreamDestroy(h->stream_u);
+  if (h->stream_i) cudaStreamDestroy(h->stream_i);
+  if (h->ev_inv) cudaEventDestroy(h->ev_inv);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -750,6 +764,7 @@ static int factorize_tf(pb200_handle_t *h, double crit) {
 }
 
 static int h_gemm_mode(const pb200_handle_t *h, int task) { return h->h_gemm_modes[task]; }
+template <class T> static int invert_range(pb200_handle_t *h, int sp0, int sp1, cudaStream_t sm);
 
 // ------------------------------------------------------------------ factorization (tensor-core path)
 template <class T, int FACTO>
@@ -770,6 +785,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
   const bool serial = prof || getenv("PB200_SERIAL") != nullptr;
+  const bool overlap_inv = !serial && h->nranks == 1 && getenv("PB200_INV_OVERLAP") != nullptr;   // opt-in: measured slower (r01)
   for (const auto &st : h->steps) {
     cudaStream_t sm = (serial || st.strm == 0) ? h->stream : h->stream_u;
     if (!serial && st.wait_ev >= 0) CK(cudaStreamWaitEvent(sm, h->sched_ev[st.wait_ev], 0));
@@ -800,6 +816,16 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
     }
     ++launches;
     if (!serial && st.rec_ev >= 0) CK(cudaEventRecord(h->sched_ev[st.rec_ev], sm));
+    if (overlap_inv && st.rec_ev >= 0 && st.rec_ev < h->nlevels) {
+      // panel(l) is final: invert its diagonal triangles (up_down preparation) underneath the rest
+      const int l = st.rec_ev;
+      if (h->inv_lvl_ptr[l + 1] > h->inv_lvl_ptr[l]) {
+        CK(cudaStreamWaitEvent(h->stream_i, h->sched_ev[l], 0));
+        int rc = invert_range<T>(h, h->inv_lvl_ptr[l], h->inv_lvl_ptr[l + 1], h->stream_i);
+        if (rc) return rc;
+        launches += lu;
+      }
+    }
     if (prof) {
       cudaEventRecord(pe1, h->stream); cudaEventSynchronize(pe1);
       float ms = 0; cudaEventElapsedTime(&ms, pe0, pe1);
@@ -822,6 +848,11 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   if (!serial && h->nlevels > 0) {
     // join: the panel stream (which carries the timing events) waits for the last bulk update
     CK(cudaStreamWaitEvent(h->stream, h->sched_ev[2 * (size_t)h->nlevels - 1], 0));
+    if (overlap_inv) {
+      CK(cudaEventRecord(h->ev_inv, h->stream_i));
+      CK(cudaStreamWaitEvent(h->stream, h->ev_inv, 0));
+      h->inv_ready = true;
+    }
   }
   CK(cudaGetLastError());
   h->last_launches = launches;
@@ -867,7 +898,7 @@ extern "C" int pb200_factorize(pb200_handle_t *h, double critere, int64_t *nbpiv
   int rc = factorize_dispatch(h, critere);
   if (rc) return rc;
   if (h->nranks == 1) {
-    rc = invert_dispatch(h, h->stream);   // diagonal triangles inverted once, for the up_down sweeps
+    if (!h->inv_ready) rc = invert_dispatch(h, h->stream);   // diagonal triangles inverted once, for the up_down sweeps
     if (rc) return rc;
   } else {
     k_dist_signal<<<1, 32, 0, h->stream>>>(h->d_flags, h->nlevels, h->epoch);   // our share of the factorization is done
@@ -906,8 +937,9 @@ extern "C" int pb200_inertia(pb200_handle_t *h, int64_t *inertia) {
 
 // ------------------------------------------------------------------ solve
 // invert the diagonal triangles of the freshly factored panels (one CTA per sub-panel)
+// sub-panels [sp0, sp1) (tasks are ordered by level, so a level is one contiguous range)
 template <class T>
-static int invert_t(pb200_handle_t *h, cudaStream_t sm) {
+static int invert_range(pb200_handle_t *h, int sp0, int sp1, cudaStream_t sm) {
   static bool attr_done[4] = {};
   const int NB = SlvCfg<T>::NB;
   const size_t smem = (size_t)NB * (NB | 1) * sizeof(T);
@@ -915,11 +947,17 @@ static int invert_t(pb200_handle_t *h, cudaStream_t sm) {
     CK(cudaFuncSetAttribute(k_tri_inverse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[h->flt] = true;
   }
-  if (h->nsubpanels == 0) return PB200_SUCCESS;
+  if (sp1 <= sp0) return PB200_SUCCESS;
   const int unit_down = (h->facto != PB200_FACT_LLT);   // LDLt / LDLh / LU-L: unit lower triangle
-  k_tri_inverse<T><<<h->nsubpanels, 128, smem, sm>>>(h->S, (const T *)h->dL, h->d_slvtask, h->d_invoff, (T *)h->d_inv, unit_down);
+  k_tri_inverse<T><<<sp1 - sp0, 128, smem, sm>>>(h->S, (const T *)h->dL, h->d_slvtask + sp0, h->d_invoff, (T *)h->d_inv, unit_down);
   if (h->facto == PB200_FACT_LU)   // up sweep: lower triangle of ucoeftab's diagonal blok = U^T, non-unit
-    k_tri_inverse<T><<<h->nsubpanels, 128, smem, sm>>>(h->S, (const T *)h->dU, h->d_slvtask, h->d_invoff, (T *)h->d_inv_up, 0);
+    k_tri_inverse<T><<<sp1 - sp0, 128, smem, sm>>>(h->S, (const T *)h->dU, h->d_slvtask + sp0, h->d_invoff, (T *)h->d_inv_up, 0);
+  return PB200_SUCCESS;
+}
+template <class T>
+static int invert_t(pb200_handle_t *h, cudaStream_t sm) {
+  int rc = invert_range<T>(h, 0, h->nsubpanels, sm);
+  if (rc) return rc;
   CK(cudaGetLastError());
   h->inv_ready = true;
   return PB200_SUCCESS;

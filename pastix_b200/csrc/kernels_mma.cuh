@@ -300,7 +300,10 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
 // left to right: T = X_jb - sum_{kb<jb} Y_kb W[jb,kb]^T, Y_jb = T inv(W[jb,jb])^T, both on DMMA.
 #define PB200_TRSM_TM 64
 template <class T> struct SubCfg;
-template <> struct SubCfg<double> { static constexpr int NBMAX = 128, PADW = 4, PADX = 4; };
+#ifndef PB200_NBMAX_D
+#define PB200_NBMAX_D 64
+#endif
+template <> struct SubCfg<double> { static constexpr int NBMAX = PB200_NBMAX_D, PADW = 4, PADX = 4; };
 template <> struct SubCfg<cdouble> { static constexpr int NBMAX = 64, PADW = 2, PADX = 2; };
 
 template <class T>
@@ -578,16 +581,9 @@ k_diag_sub(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, double crit,
       const int i = tx + 16 * ia, j = ty + 16 * jb;
       a[ia][jb] = (i < nb && j < nb) ? A[(size_t)j * ld + i] : ST<T>::zero();
     }
-  diag_steps<T, FACTO, 0, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
-  diag_steps<T, FACTO, 1, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
-  diag_steps<T, FACTO, 2, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
-  diag_steps<T, FACTO, 3, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
-  if constexpr (R > 4) {
-    diag_steps<T, FACTO, 4, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
-    diag_steps<T, FACTO, 5, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
-    diag_steps<T, FACTO, 6, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
-    diag_steps<T, FACTO, 7, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
-  }
+#define PB200_DS(KA) if constexpr (R > KA) diag_steps<T, FACTO, KA, R>(a, nb, tx, ty, lane, crit, nbpivot, colbuf, rowbuf);
+  PB200_DS(0) PB200_DS(1) PB200_DS(2) PB200_DS(3) PB200_DS(4) PB200_DS(5) PB200_DS(6) PB200_DS(7)
+#undef PB200_DS
 #pragma unroll
   for (int ia = 0; ia < R; ++ia)
 #pragma unroll

@@ -1,17 +1,21 @@
 set -x
 export PYTHONUNBUFFERED=1
-PB200_PROFILE=1 PB200_PROFILE_VERBOSE=1 timeout 300 python tools/run_case.py 64 7 llt d > gpurun_out/levels_c2.txt 2>&1
-PB200_PROFILE=1 PB200_PROFILE_VERBOSE=1 timeout 400 python tools/run_case.py 100 27 ldlt d > gpurun_out/levels_c3.txt 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_c2.csv python tools/profile_step.py c2 > gpurun_out/ncu_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_gemm_scatter -s 24 -c 8 -o /tmp/prof_gs python tools/profile_step.py c2 > gpurun_out/ncu_full.log 2>&1
-ncu -i /tmp/prof_gs.ncu-rep --page raw --csv > gpurun_out/prof_gemm_scatter_c2_raw.csv 2>/dev/null
-ncu -i /tmp/prof_gs.ncu-rep --page details --csv > gpurun_out/prof_gemm_scatter_c2_details.csv 2>/dev/null
-ncu -i /tmp/prof_gs.ncu-rep --page source --csv --print-source sass > gpurun_out/prof_gemm_scatter_c2_source.csv 2>/dev/null
-ls -la /tmp/prof_gs.ncu-rep
-SZ=$(stat -c %s /tmp/prof_gs.ncu-rep); if [ "$SZ" -lt 30000000 ]; then cp /tmp/prof_gs.ncu-rep gpurun_out/prof_gemm_scatter_c2.ncu-rep; fi
-for bs in "120 240" "240 480"; do set -- $bs
-  timeout 300 python bench.py --workload c2 --steps 3 --no-cpu-baseline --iparm IPARM_MIN_BLOCKSIZE=$1 --iparm IPARM_MAX_BLOCKSIZE=$2 > gpurun_out/bench_c2_bs$2.json 2> gpurun_out/bench_c2_bs$2.log
-  timeout 400 python bench.py --workload c3 --steps 3 --no-cpu-baseline --iparm IPARM_MIN_BLOCKSIZE=$1 --iparm IPARM_MAX_BLOCKSIZE=$2 > gpurun_out/bench_c3_bs$2.json 2> gpurun_out/bench_c3_bs$2.log
-done
-cat gpurun_out/bench_c*_bs*.json
-du -sh gpurun_out; ls -la gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/dist_debug.py > gpurun_out/dist_debug.log 2>&1; echo "rc=$?"
+grep "bad=" gpurun_out/dist_debug.log
+timeout 600 python -m pytest tests/test_dist.py -m gpu -x -q > gpurun_out/pytest_dist.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_dist.log
+tail -5 gpurun_out/pytest_dist.log
+(
+export CUDA_VISIBLE_DEVICES=0
+for st in 0 3000 6000 10000; do echo "== C3 stagger $st"; PB200_STAGGER_NS=$st timeout 300 python tools/run_case.py 100 27 ldlt d 2>&1 | grep -E "factorize|solve|backward"; done
+) > gpurun_out/ab_gpu0.log 2>&1 &
+(
+export CUDA_VISIBLE_DEVICES=1
+for st in 0 3000 6000; do echo "== C2 stagger $st"; PB200_STAGGER_NS=$st timeout 300 python tools/run_case.py 64 7 llt d 2>&1 | grep -E "factorize|solve|backward"; done
+echo "== C2 no inv overlap"; PB200_NO_INV_OVERLAP=1 timeout 300 python tools/run_case.py 64 7 llt d 2>&1 | grep -E "factorize|solve|backward"
+echo "== C2 nb64"; PB200_LIB=$PWD/pastix_b200/lib/libpastix_b200_nb64.so timeout 300 python tools/run_case.py 64 7 llt d 2>&1 | grep -E "factorize|solve|backward"
+echo "== C3 nb64"; PB200_LIB=$PWD/pastix_b200/lib/libpastix_b200_nb64.so timeout 300 python tools/run_case.py 100 27 ldlt d 2>&1 | grep -E "factorize|solve|backward"
+) > gpurun_out/ab_gpu1.log 2>&1 &
+wait
+cat gpurun_out/ab_gpu0.log gpurun_out/ab_gpu1.log
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_c2_n2.json 2> gpurun_out/bench_c2_n2.log; echo "rc=$?"
+cat gpurun_out/bench_c2_n2.json
