@@ -67,6 +67,8 @@ struct pb200_handle_s {
   unsigned int *d_slv_cnt = nullptr;
   void *d_y = nullptr; size_t y_bytes = 0;
   bool inv_ready = false;
+  std::vector<int64_t> h_rmbase;           // per cblk: first entry of its off-diagonal rows in d_rowglob
+  int *d_rowglob = nullptr;                // global row of every off-diagonal panel row
   std::vector<int> inv_lvl_ptr;            // sub-panels of level l: [inv_lvl_ptr[l], inv_lvl_ptr[l+1])
   cudaStream_t stream_i = nullptr;         // low priority: triangle inversions underneath the factorization
   cudaEvent_t ev_inv = nullptr;
@@ -78,6 +80,7 @@ struct pb200_handle_s {
   SubTask *d_sub = nullptr;
   GemmTask *d_gemm = nullptr;
   int *d_t2t = nullptr;
+  TileDesc *d_desc = nullptr;
   bool prof_on = false;                  // pb200_set_profile: serialise the launches and time each kind
   double prof_ms[4] = {0, 0, 0, 0}; int64_t prof_n[4] = {0, 0, 0, 0};
   double gemm_flops = 0;                 // algorithmic flops of the fused GEMM+scatter launches (PaStiX's GEMM term)
@@ -127,6 +130,8 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
   const int NB = (h->flt == PB200_COMPLEXDOUBLE) ? SlvCfg<cdouble>::NB : SlvCfg<double>::NB;
   std::vector<SlvTask> tasks; std::vector<int> t2t; std::vector<int64_t> invoff;
   int64_t inv_elems = 0; int sp = 0;
+  std::vector<int64_t> rmbase((size_t)h->cblknbr + 1, 0);
+  for (int64_t c = 0; c < h->cblknbr; ++c) rmbase[c + 1] = rmbase[c] + (h->h_stride[c] - h->h_width[c]);
   h->inv_lvl_ptr.assign(h->nlevels + 1, 0);
   for (int l = 0; l < h->nlevels; ++l) {
     const int q0 = h->lvl_ptr[l], q1 = h->lvl_ptr[l + 1];
@@ -142,7 +147,7 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
         int sw = (w + nsub - 1) / nsub;
         int c0 = r * sw, c1 = std::min(w, c0 + sw);
         int nt = std::max(1, (ld - c1 + PB200_SLV_ROWS - 1) / PB200_SLV_ROWS);
-        tasks.push_back({c, (int)tiles, c0, c1, sp, nt});
+        tasks.push_back({c, (int)tiles, c0, c1, sp, nt, ld, h->h_fcol[c], w, 0, h->h_poff[c], rmbase[c] - w, inv_elems});
         for (int i = 0; i < nt; ++i) t2t.push_back((int)tasks.size() - 1 - t0);
         tiles += nt;
         invoff.push_back(inv_elems); inv_elems += (int64_t)(c1 - c0) * (c1 - c0); ++sp;
@@ -152,6 +157,7 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
     }
   }
   h->nsubpanels = sp; h->inv_elems = inv_elems; h->inv_lvl_ptr[h->nlevels] = sp;
+  h->h_rmbase = rmbase;
   { int rc = upload(h, tasks, &h->d_slvtask); if (rc) return rc; }
   { int rc = upload(h, t2t, &h->d_slv_t2t); if (rc) return rc; }
   { int rc = upload(h, invoff, &h->d_invoff); if (rc) return rc; }
@@ -209,6 +215,20 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
   BlokTgt *d_bt;
   { int rc = upload(h, btgt, &d_bt); if (rc) return rc; }
   h->M.pairbase = d_pb; h->M.pairoff = d_po; h->M.btgt = d_bt;
+  {
+    // static row/column scatter maps, one entry per off-diagonal panel row
+    std::vector<int64_t> rmbase(C + 1, 0);
+    for (int64_t c = 0; c < C; ++c) rmbase[c + 1] = rmbase[c] + (h->h_stride[c] - h->h_width[c]);
+    int64_t *d_rb; RowMap *d_rm = nullptr; ColMap *d_cm = nullptr;
+    { int rc = upload(h, rmbase, &d_rb); if (rc) return rc; }
+    const size_t nrow = (size_t)std::max<int64_t>(rmbase[C], 1);
+    if (cudaMalloc((void **)&d_rm, nrow * sizeof(RowMap)) != cudaSuccess || cudaMalloc((void **)&d_cm, nrow * sizeof(ColMap)) != cudaSuccess)
+      return fail(PB200_ERR_NOMEM, "cudaMalloc(scatter maps) failed");
+    h->allocs.push_back(d_rm); h->allocs.push_back(d_cm); h->device_bytes += nrow * (sizeof(RowMap) + sizeof(ColMap));
+    k_build_maps<<<(unsigned)C, 128>>>(h->S, d_bt, d_rb, d_rm, d_cm);
+    CK(cudaGetLastError());
+    h->M.rmbase = d_rb; h->M.rm = d_rm; h->M.cm = d_cm;
+  }
 
   std::vector<SubTask> sub;
   std::vector<GemmTask> gemm;
@@ -263,6 +283,7 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
       }
       if (tiles > 0) h->steps.push_back({2, t0, (int)gemm.size() - t0, tiles, 0, l});
     }
+    if (lu && rounds > 1) h->steps.push_back({6, q0, q1 - q0, 0, 0, l});   // complete the diagonal bloks of the multi-round cblks
     // external update: fused GEMM + scatter, in two launches.  U1 = the column tiles that hit cblks of
     // the NEXT level (they gate that level's panel work) stays on the panel stream; U2 = everything else
     // runs on the second stream underneath the next level's diag/trsm chain.
@@ -325,6 +346,18 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
         for (int q = 0; q < gemm[st.task0 + t].ntn; ++q) t2t.push_back(t);
     }
     int rc = upload(h, t2t, &h->d_t2t); if (rc) return rc;
+    // one TileDesc per tile of every launch, filled on the device
+    const size_t nt = std::max<size_t>(t2t.size(), 1);
+    if (cudaMalloc((void **)&h->d_desc, nt * sizeof(TileDesc)) != cudaSuccess) return fail(PB200_ERR_NOMEM, "cudaMalloc(tile descriptors) failed");
+    h->allocs.push_back(h->d_desc); h->device_bytes += nt * sizeof(TileDesc);
+    for (const auto &st : h->steps) {
+      if (st.kind != 2 || st.ntiles == 0) continue;
+      const int n = (int)st.ntiles;
+      if (cx) k_build_tiledesc<UpdCfg<cdouble>::TM, UpdCfg<cdouble>::TN><<<(n + 127) / 128, 128>>>(h->S, h->M, h->d_gemm + st.task0, h->d_t2t + st.t2t0, n, h->d_desc + st.t2t0);
+      else k_build_tiledesc<UpdCfg<double>::TM, UpdCfg<double>::TN><<<(n + 127) / 128, 128>>>(h->S, h->M, h->d_gemm + st.task0, h->d_t2t + st.t2t0, n, h->d_desc + st.t2t0);
+    }
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
   }
   CK(cudaStreamCreateWithFlags(&h->stream_u, cudaStreamNonBlocking));
   {
@@ -514,6 +547,15 @@ extern "C" int pb200_create_dist(pb200_handle_t **out, const pb200_solver_t *s, 
   { int rc = upload(h, h->h_poff, &d64); if (rc) { pb200_destroy(h); return rc; } h->S.poff = d64; }
   h->S.cblknbr = (int)C; h->S.bloknbr = (int)B;
   { int rc = upload(h, lvl_cblk, &h->d_lvl_cblk); if (rc) { pb200_destroy(h); return rc; } }
+  {
+    int64_t *d_rb = nullptr;
+    { int rc = upload(h, h->h_rmbase, &d_rb); if (rc) { pb200_destroy(h); return rc; } }
+    const size_t nrow = (size_t)std::max<int64_t>(h->h_rmbase[C], 1);
+    if (cudaMalloc((void **)&h->d_rowglob, nrow * sizeof(int)) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(row map) failed"); }
+    h->allocs.push_back(h->d_rowglob); h->device_bytes += nrow * sizeof(int);
+    k_build_rowglob<<<(unsigned)C, 128>>>(h->S, d_rb, h->d_rowglob);
+    CK(cudaGetLastError());
+  }
   { int rc = upload(h, trsm, &h->d_trsm); if (rc) { pb200_destroy(h); return rc; } }
   { int rc = upload(h, slv, &h->d_slv); if (rc) { pb200_destroy(h); return rc; } }
   { int rc = upload(h, upd, &h->d_upd); if (rc) { pb200_destroy(h); return rc; } }
@@ -780,7 +822,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   }
   int64_t launches = 0;
   const bool prof = h->prof_on || getenv("PB200_PROFILE") != nullptr;
-  double tkind[6] = {0, 0, 0, 0, 0, 0}; long long nk[6] = {0, 0, 0, 0, 0, 0};
+  double tkind[7] = {0, 0, 0, 0, 0, 0, 0}; long long nk[7] = {0, 0, 0, 0, 0, 0, 0};
   double tlevel_max = 0; int lvl_max = -1;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
@@ -804,7 +846,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
         break;
       case 2:
         k_gemm_scatter<T, FACTO><<<(unsigned)(st.ntiles * lu), UpdCfg<T>::NT, upd_smem_bytes<T>(), sm>>>(
-            h->S, h->M, L, U, h->d_gemm + st.task0, h->d_t2t + st.t2t0);
+            h->M, L, U, h->d_desc + st.t2t0);
         break;
       case 3:
         if (FACTO == F_LU)
@@ -812,6 +854,11 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
         break;
       case 5:
         launches += launch_fanin<T>(h, st.lvl, sm) - 1;
+        break;
+      case 6:
+        if (FACTO == F_LU)
+          k_diag_complete_lu<T><<<dim3(8, std::min(st.ntasks, 65535)), dim3(32, 8), 0, sm>>>(h->S, L, U, h->d_lvl_cblk + st.task0, st.ntasks,
+                                                                                         SubCfg<T>::NBMAX);
         break;
     }
     ++launches;
@@ -838,7 +885,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   }
   if (prof) {
     for (int q = 0; q < 4; ++q) { h->prof_ms[q] = tkind[q]; h->prof_n[q] = nk[q]; }
-    h->prof_ms[3] += tkind[5]; h->prof_n[3] += nk[5];
+    h->prof_ms[3] += tkind[5] + tkind[6]; h->prof_n[3] += nk[5] + nk[6];
     if (getenv("PB200_PROFILE") != nullptr)
     fprintf(stderr, "[pb200 profile] diag %.3f ms (%lld)  trsm %.3f ms (%lld)  ext-update %.3f ms (%lld)  int-update/transpose %.3f ms (%lld)\n",
             tkind[0], nk[0], tkind[1], nk[1], tkind[2], nk[2], tkind[3], nk[3]);
@@ -949,9 +996,9 @@ static int invert_range(pb200_handle_t *h, int sp0, int sp1, cudaStream_t sm) {
   }
   if (sp1 <= sp0) return PB200_SUCCESS;
   const int unit_down = (h->facto != PB200_FACT_LLT);   // LDLt / LDLh / LU-L: unit lower triangle
-  k_tri_inverse<T><<<sp1 - sp0, 128, smem, sm>>>(h->S, (const T *)h->dL, h->d_slvtask + sp0, h->d_invoff, (T *)h->d_inv, unit_down);
+  k_tri_inverse<T><<<sp1 - sp0, 128, smem, sm>>>((const T *)h->dL, h->d_slvtask + sp0, (T *)h->d_inv, unit_down);
   if (h->facto == PB200_FACT_LU)   // up sweep: lower triangle of ucoeftab's diagonal blok = U^T, non-unit
-    k_tri_inverse<T><<<sp1 - sp0, 128, smem, sm>>>(h->S, (const T *)h->dU, h->d_slvtask + sp0, h->d_invoff, (T *)h->d_inv_up, 0);
+    k_tri_inverse<T><<<sp1 - sp0, 128, smem, sm>>>((const T *)h->dU, h->d_slvtask + sp0, (T *)h->d_inv_up, 0);
   return PB200_SUCCESS;
 }
 template <class T>
@@ -974,14 +1021,14 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
   int64_t launches = 0;
   for (size_t i = 0; i < h->slv_steps.size(); ++i) {
     const auto &st = h->slv_steps[i];
-    k_fwd<T, FACTO><<<(unsigned)st.ntiles, PB200_SLV_ROWS, 0, h->stream>>>(h->S, L, inv, h->d_invoff, x, y, ldx, nrhs,
-                                                                         h->d_slvtask + st.task0, h->d_slv_t2t + st.t2t0);
+    k_fwd<T, FACTO><<<(unsigned)st.ntiles, PB200_SLV_NT, 0, h->stream>>>(L, inv, x, y, ldx, nrhs, h->d_slvtask + st.task0,
+                                                                       h->d_slv_t2t + st.t2t0, h->d_rowglob);
     ++launches;
   }
   for (size_t i = h->slv_steps.size(); i-- > 0;) {
     const auto &st = h->slv_steps[i];
-    k_bwd<T, FACTO><<<(unsigned)st.ntiles, 256, 0, h->stream>>>(h->S, Mup, inv_up, h->d_invoff, x, y, ldx, nrhs,
-                                                               h->d_slvtask + st.task0, h->d_slv_t2t + st.t2t0, h->d_slv_cnt);
+    k_bwd<T, FACTO><<<(unsigned)st.ntiles, PB200_BWD_NT, 0, h->stream>>>(Mup, inv_up, x, y, ldx, nrhs, h->d_slvtask + st.task0,
+                                                                       h->d_slv_t2t + st.t2t0, h->d_rowglob, h->d_slv_cnt);
     ++launches;
   }
   CK(cudaGetLastError());

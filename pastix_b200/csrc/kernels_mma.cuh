@@ -35,10 +35,27 @@ struct __align__(16) BlokTgt {
 };
 
 // extra device-side maps built once per SolverMatrix (pb200_create)
+// static scatter maps, one entry per off-diagonal panel row of every cblk (built once, k_build_maps):
+// what add_contrib_local derives per contribution from frownum/coefind (sopalin_compute.c:427-435)
+struct RowMap { int rb, roff; };            // local off-diagonal blok of the row, offset of the row inside it
+struct __align__(16) ColMap {               // the same panel row seen as a COLUMN of the facing cblk
+  int64_t ctgt;                             // slab offset of that target column: poff[fc] + cj * tld
+  int cb, cj, tw, tld;                      // local blok, column inside fc, width(fc), stride(fc)
+  int pad0, pad1;
+};
 struct DevMap {
   const int64_t *pairbase;      // per cblk: start of its (b2,b1) table in pairoff
   const int *pairoff;           // tri(lb2,lb1): row offset of blok b2's first row inside fcblk(b1), -1 if none
   const BlokTgt *btgt;          // per blok
+  const int64_t *rmbase;        // per cblk: first entry of its rows in rm / cm (entry index = rmbase[k] + m - w)
+  const RowMap *rm;
+  const ColMap *cm;
+};
+// everything one CTA of k_gemm_scatter needs to start, in ONE load (built once per launch, k_build_tiledesc)
+struct __align__(16) TileDesc {
+  int64_t poff, pbase, rmrow;   // panel offset of the source cblk; pairbase; rmbase - width (index by panel row)
+  int ld, m0, mrows, n0, ncols, k0, k1, mode;
+  int rb_lo, nrb, cb_lo, ncb;   // local blok ranges covered by the tile's rows / columns
 };
 
 struct GemmTask {
@@ -71,7 +88,7 @@ template <class T>
 constexpr size_t upd_smem_bytes() {
   using C = UpdCfg<T>;
   return (size_t)C::STG * C::KC * ((C::TM + C::PADA) + (C::TN + C::PADB) + 1) * sizeof(T) +
-         (size_t)C::TN * 8 + (size_t)(2 * C::TM + 5 * C::TN + PB200_TABMAX + PB200_COEFMAX) * 4;
+         (size_t)C::TN * sizeof(ColMap) + (size_t)C::TM * sizeof(RowMap) + (size_t)PB200_TABMAX * 4;
 }
 
 // fire-and-forget reductions (RED.ADD.F64 at L2): the reference serialises these adds with
@@ -89,9 +106,15 @@ __device__ __forceinline__ int upper_le_s(const int *key, int n, int v) {
   return l - 1;
 }
 
+template <int BYTES>
+__device__ __forceinline__ void cp_async_raw(void *smem_dst, const void *gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(gmem_src), "n"(BYTES));
+}
+
 template <class T, int FACTO>
 __global__ void __launch_bounds__(UpdCfg<T>::NT, UpdCfg<T>::CTAS)
-k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ tasks, const int *__restrict__ tile2task) {
+k_gemm_scatter(DevMap M, T *L, T *U, const TileDesc *__restrict__ descs) {
   using C = UpdCfg<T>;
   constexpr bool CX = ST<T>::is_complex;
   constexpr int TM = C::TM, TN = C::TN, KC = C::KC, STG = C::STG, NT = C::NT;
@@ -103,30 +126,24 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
   T *sA = reinterpret_cast<T *>(smem_raw);
   T *sB = sA + STG * KC * LDA;
   T *sD = sB + STG * KC * LDB;
-  int64_t *s_ctgt = reinterpret_cast<int64_t *>(sD + STG * KC);
-  int *s_rb = reinterpret_cast<int *>(s_ctgt + TN);
-  int *s_roff = s_rb + TM;
-  int *s_cb = s_roff + TM;
-  int *s_cj = s_cb + TN;
-  int *s_fc = s_cj + TN;
-  int *s_tw = s_fc + TN;
-  int *s_tld = s_tw + TN;
-  int *s_tab = s_tld + TN;
-  int *s_coef = s_tab + PB200_TABMAX;
+  ColMap *s_cm = reinterpret_cast<ColMap *>(sD + STG * KC);
+  RowMap *s_rm = reinterpret_cast<RowMap *>(s_cm + TN);
+  int *s_tab = reinterpret_cast<int *>(s_rm + TM);
 
   int tile = blockIdx.x, part = 0;
   if (FACTO == F_LU) { part = tile & 1; tile >>= 1; }
-  const GemmTask tk = tasks[tile2task[tile]];
-  const int k = tk.cblk, tn = tile - tk.tile0;
-  const int ld = S.stride[k];
-  const int m0 = tk.arow0, mrows = min(TM, tk.arow1 - m0);
-  const int n0 = tk.brow0 + tn * TN, ncols = min(TN, tk.brow1 - n0);
+  // the whole tile description in one (broadcast) load: no dependent index chasing before the first
+  // operand bytes are requested
+  const TileDesc tk = descs[tile];
+  const int ld = tk.ld;
+  const int m0 = tk.m0, mrows = tk.mrows;
+  const int n0 = tk.n0, ncols = tk.ncols;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm0 = (warp / C::WN) * (MI * 16), wn0 = (warp % C::WN) * (NI * 8);
 
-  const T *Ap = ((FACTO == F_LU && part == 1) ? U : L) + S.poff[k];
-  const T *Bp = ((FACTO == F_LU && part == 0) ? U : L) + S.poff[k];
-  const T *Dp = L + S.poff[k];
+  const T *Ap = ((FACTO == F_LU && part == 1) ? U : L) + tk.poff;
+  const T *Bp = ((FACTO == F_LU && part == 0) ? U : L) + tk.poff;
+  const T *Dp = L + tk.poff;
   const int nchunks = (tk.k1 - tk.k0 + KC - 1) / KC;
 
   auto load_chunk = [&](int c, int stg) {
@@ -146,63 +163,37 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
       sD[stg * KC + tid] = (kb + tid < tk.k1) ? Dp[(size_t)(kb + tid) * (ld + 1)] : ST<T>::zero();
   };
 
+  // ---- scatter maps of this tile: static tables copied asynchronously into shared memory, in the same
+  // cp.async group as the first operand chunk (they land while the pipeline fills; the first barrier of
+  // the main loop publishes them)
+  const int rb_lo = tk.rb_lo, cb_lo = tk.cb_lo, ncb = tk.ncb;
+  const bool tab_in_smem = (tk.mode == 0) && (tk.nrb * ncb <= PB200_TABMAX);
+  if (tk.mode == 0) {
+    if (tid < mrows) cp_async_raw<8>(s_rm + tid, M.rm + tk.rmrow + m0 + tid);
+    if (tid < ncols) {
+      const ColMap *src = M.cm + tk.rmrow + n0 + tid;
+      cp_async_raw<16>(s_cm + tid, src);
+      cp_async_raw<16>(reinterpret_cast<char *>(s_cm + tid) + 16, reinterpret_cast<const char *>(src) + 16);
+    }
+    if (tab_in_smem)
+      for (int e = tid; e < tk.nrb * ncb; e += NT) {
+        const int rb = rb_lo + e / ncb, cb = cb_lo + e % ncb;
+        if (rb >= cb) cp_async_raw<4>(s_tab + e, M.pairoff + tk.pbase + (int64_t)rb * (rb + 1) / 2 + cb);
+        else s_tab[e] = -1;
+      }
+  } else {
+    if (tid < TM) { s_rm[tid].rb = 0; s_rm[tid].roff = m0 + tid; }
+    if (tid < TN) {
+      const int n = n0 + tid;
+      ColMap cmv; cmv.ctgt = tk.poff + (int64_t)n * ld; cmv.cb = 0; cmv.cj = n; cmv.tw = 0; cmv.tld = ld; cmv.pad0 = cmv.pad1 = 0;
+      s_cm[tid] = cmv;
+    }
+  }
+
 #pragma unroll
   for (int s = 0; s < STG - 1; ++s) {
     if (s < nchunks) load_chunk(s, s);
     cp_async_commit();
-  }
-
-  // ---- scatter maps of this tile (overlap the first loads): three dependent round trips
-  int rb_lo = 0, ncb = 1, cb_lo = 0;
-  bool tab_in_smem = false;
-  int64_t pbase = 0;
-  if (tk.mode == 0) {
-    const int bf = S.fblok[k] + 1;          // first off-diagonal blok
-    const int nbk = tk.rbl - bf + 1;        // bloks that rows/columns of this tile can belong to
-    const bool staged = nbk <= PB200_COEFMAX;
-    if (staged) {
-      for (int e = tid; e < nbk; e += NT) s_coef[e] = S.coefind[bf + e];
-      __syncthreads();
-    }
-    if (tid < TM) {
-      int rb = 0, roff = 0;
-      if (tid < mrows) {
-        const int m = m0 + tid;
-        rb = staged ? upper_le_s(s_coef, nbk, m) : upper_le(S.coefind, bf, tk.rbl + 1, m) - bf;
-        roff = m - (staged ? s_coef[rb] : S.coefind[bf + rb]);
-      }
-      s_rb[tid] = rb; s_roff[tid] = roff;
-    }
-    if (tid < TN) {
-      int cb = 0, cj = 0, fc = 0, tw = 0, tld = 0; int64_t ct = 0;
-      if (tid < ncols) {
-        const int n = n0 + tid;
-        cb = staged ? upper_le_s(s_coef, nbk, n) : upper_le(S.coefind, bf, tk.rbl + 1, n) - bf;
-        const int dn = n - (staged ? s_coef[cb] : S.coefind[bf + cb]);
-        const BlokTgt bt = M.btgt[bf + cb];
-        fc = bt.fc; tw = bt.tw; tld = bt.tld; cj = bt.cj0 + dn;
-        ct = bt.tgt + (int64_t)dn * bt.tld;
-      }
-      s_cb[tid] = cb; s_cj[tid] = cj; s_fc[tid] = fc; s_tw[tid] = tw; s_tld[tid] = tld; s_ctgt[tid] = ct;
-    }
-    __syncthreads();
-    pbase = M.pairbase[k];
-    rb_lo = s_rb[0]; cb_lo = s_cb[0];
-    const int nrb = s_rb[mrows - 1] - rb_lo + 1;
-    ncb = s_cb[ncols - 1] - cb_lo + 1;
-    tab_in_smem = (nrb * ncb <= PB200_TABMAX);
-    if (tab_in_smem)
-      for (int e = tid; e < nrb * ncb; e += NT) {
-        const int rb = rb_lo + e / ncb, cb = cb_lo + e % ncb;
-        s_tab[e] = (rb >= cb) ? M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb] : -1;
-      }
-  } else {
-    if (tid < TM) { s_rb[tid] = 0; s_roff[tid] = m0 + tid; }
-    if (tid < TN) {
-      const int n = n0 + tid;
-      s_cb[tid] = 0; s_cj[tid] = n; s_fc[tid] = k; s_tw[tid] = 0; s_tld[tid] = ld;
-      s_ctgt[tid] = S.poff[k] + (int64_t)n * ld;
-    }
   }
 
   // ---- main loop: C(TM x TN) = A(TM x K) * B(TN x K)^T on DMMA
@@ -234,6 +225,7 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
     }
   }
   cp_async_wait<0>();
+  if (nchunks == 0) __syncthreads();   // (never: K >= 1) maps are published by the main loop's first barrier
 
   // ---- epilogue: subtract the tile from its targets straight from the accumulators with
   // fire-and-forget L2 reductions: nothing is read back, so no latency is exposed here.
@@ -248,10 +240,11 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
     for (int e = 0; e < 2; ++e) {
       const int j = wn0 + y * 8 + t4 * 2 + e;
       const bool ok = j < ncols;
-      c_cb[y][e] = ok ? s_cb[j] : 0x7fffffff;     // sentinel: never <= a row blok
-      c_cj[y][e] = ok ? s_cj[j] : 0x7fffffff;
-      c_tw[y][e] = s_tw[ok ? j : 0];
-      c_tgt[y][e] = s_ctgt[ok ? j : 0];
+      const ColMap cmv = s_cm[ok ? j : 0];
+      c_cb[y][e] = ok ? cmv.cb : 0x7fffffff;     // sentinel: never <= a row blok
+      c_cj[y][e] = ok ? cmv.cj : 0x7fffffff;
+      c_tw[y][e] = cmv.tw;
+      c_tgt[y][e] = cmv.ctgt;
     }
 #pragma unroll
   for (int x = 0; x < MI; ++x)
@@ -259,7 +252,7 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
     for (int hh = 0; hh < 2; ++hh) {
       const int i = wm0 + x * 16 + g + hh * 8;
       if (i >= mrows) continue;
-      const int rb = s_rb[i], roff = s_roff[i];
+      const int rb = s_rm[i].rb, roff = s_rm[i].roff;
       const int trow = (rb - rb_lo) * ncb - cb_lo;
 #pragma unroll
       for (int y = 0; y < NI; ++y)
@@ -275,7 +268,7 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
           }
           const int cb = c_cb[y][e];
           if (rb < cb) continue;
-          int ro = tab_in_smem ? s_tab[trow + cb] : M.pairoff[pbase + (int64_t)rb * (rb + 1) / 2 + cb];
+          int ro = tab_in_smem ? s_tab[trow + cb] : M.pairoff[tk.pbase + (int64_t)rb * (rb + 1) / 2 + cb];
           if (ro < 0) continue;
           ro += roff;
           if (FACTO != F_LU || part == 0 || ro >= c_tw[y][e]) {
@@ -284,7 +277,8 @@ k_gemm_scatter(DevSym S, DevMap M, T *L, T *U, const GemmTask *__restrict__ task
             // U contribution to a diagonal target: stored transposed into coeftab
             // (sopalin_compute.c:431-435, 572-575); the b1 == b2 square is skipped
             const int j = wn0 + y * 8 + t4 * 2 + e;
-            red_sub(L + S.poff[s_fc[j]] + (int64_t)ro * s_tld[j] + c_cj[y][e], v);
+            const int tld = s_cm[j].tld;
+            red_sub(L + (c_tgt[y][e] - (int64_t)c_cj[y][e] * tld) + (int64_t)ro * tld + c_cj[y][e], v);
           }
         }
     }
@@ -633,6 +627,81 @@ __global__ void k_diag_transpose(DevSym S, const T *L, T *U, const int *__restri
     }
   }
   }
+}
+
+// LU, cblks factored in several sub-panel rounds: the rounds leave U12 only as its transpose in ucoeftab's
+// diagonal blok (and L21 only in coeftab's).  Complete both diagonal bloks to the full LU / (LU)^T that
+// PASTIX_getrf_block + DimTrans leave (compute_diag.c:486-536), so that coeftab/ucoeftab read back equal
+// the reference's element for element.
+template <class T>
+__global__ void k_diag_complete_lu(DevSym S, T *L, T *U, const int *__restrict__ cblks, int ncblk, int nbmax) {
+  __shared__ T tl[32][33], tu[32][33];
+  for (int cc = blockIdx.y; cc < ncblk; cc += gridDim.y) {
+    const int c = cblks[cc];
+    const int w = S.width[c], ld = S.stride[c];
+    if (w <= nbmax) continue;
+    const int nt = (w + 31) / 32;
+    T *A = L + S.poff[c];
+    T *B = U + S.poff[c];
+    for (int tt = blockIdx.x; tt < nt * nt; tt += gridDim.x) {
+      const int bi = (tt / nt) * 32, bj = (tt % nt) * 32;   // target tile: rows bi.., cols bj.. with bi <= bj (upper part)
+      if (bi > bj) continue;
+      __syncthreads();
+      for (int y = threadIdx.y; y < 32; y += blockDim.y) {   // source tile: rows bj.., cols bi.. (lower part)
+        const int i = bj + threadIdx.x, j = bi + y;
+        if (i < w && j < w) { tl[y][threadIdx.x] = A[(size_t)j * ld + i]; tu[y][threadIdx.x] = B[(size_t)j * ld + i]; }
+      }
+      __syncthreads();
+      for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int i = bi + threadIdx.x, j = bj + y;           // element (i, j), strictly upper only
+        if (i < w && j < w && i < j) { A[(size_t)j * ld + i] = tu[threadIdx.x][y]; B[(size_t)j * ld + i] = tl[threadIdx.x][y]; }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- static scatter maps
+// one CTA per cblk, threads over its off-diagonal panel rows
+__global__ void k_build_maps(DevSym S, const BlokTgt *__restrict__ btgt, const int64_t *__restrict__ rmbase,
+                             RowMap *rm, ColMap *cm) {
+  const int k = blockIdx.x;
+  const int w = S.width[k], ld = S.stride[k], bf = S.fblok[k] + 1, be = S.fblok[k + 1];
+  const int64_t base = rmbase[k];
+  for (int m = w + threadIdx.x; m < ld; m += blockDim.x) {
+    const int b = upper_le(S.coefind, bf, be, m);
+    const int roff = m - S.coefind[b];
+    const BlokTgt bt = btgt[b];
+    RowMap r; r.rb = b - bf; r.roff = roff;
+    ColMap c; c.ctgt = bt.tgt + (int64_t)roff * bt.tld; c.cb = b - bf; c.cj = bt.cj0 + roff; c.tw = bt.tw; c.tld = bt.tld;
+    c.pad0 = c.pad1 = 0;
+    rm[base + m - w] = r;
+    cm[base + m - w] = c;
+  }
+}
+
+// one thread per tile of one k_gemm_scatter launch
+template <int TM, int TN>
+__global__ void k_build_tiledesc(DevSym S, DevMap M, const GemmTask *__restrict__ tasks, const int *__restrict__ tile2task,
+                                 int ntiles, TileDesc *out) {
+  const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= ntiles) return;
+  const GemmTask tk = tasks[tile2task[tile]];
+  const int k = tk.cblk, tn = tile - tk.tile0;
+  TileDesc d;
+  d.poff = S.poff[k]; d.pbase = M.pairbase[k]; d.rmrow = M.rmbase[k] - S.width[k];
+  d.ld = S.stride[k];
+  d.m0 = tk.arow0; d.mrows = min(TM, tk.arow1 - tk.arow0);
+  d.n0 = tk.brow0 + tn * TN; d.ncols = min(TN, tk.brow1 - d.n0);
+  d.k0 = tk.k0; d.k1 = tk.k1; d.mode = tk.mode;
+  d.rb_lo = d.cb_lo = 0; d.nrb = d.ncb = 1;
+  if (tk.mode == 0) {
+    const int bf = S.fblok[k] + 1, be = S.fblok[k + 1];
+    d.rb_lo = upper_le(S.coefind, bf, be, d.m0) - bf;
+    d.nrb = upper_le(S.coefind, bf, be, d.m0 + d.mrows - 1) - bf - d.rb_lo + 1;
+    d.cb_lo = upper_le(S.coefind, bf, be, d.n0) - bf;
+    d.ncb = upper_le(S.coefind, bf, be, d.n0 + d.ncols - 1) - bf - d.cb_lo + 1;
+  }
+  out[tile] = d;
 }
 
 // ---------------------------------------------------------------- pair table

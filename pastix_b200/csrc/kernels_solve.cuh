@@ -33,6 +33,11 @@ struct SlvTask {
   int cblk, tile0, c0, c1;
   int sp;        // sub-panel id: index into invoff / counters
   int ntiles;
+  // static copies of what the kernels need, so that a CTA starts after two dependent loads
+  int ld, fcol, w, pad;
+  int64_t poff;    // panel offset in the slab
+  int64_t rgbase;  // rowglob index of panel row 0 (= rmbase[cblk] - w); rows < w are the cblk's own columns
+  int64_t invoff;  // offset of the inverted triangle of this sub-panel
 };
 
 // L2 (cache-global) loads: values other CTAs produced with L2 reductions
@@ -53,13 +58,12 @@ __device__ __forceinline__ int panel_row_to_global(const DevSym &S, int c, int m
 // One CTA per sub-panel, thread j builds column j by forward substitution into shared memory.
 template <class T>
 __global__ void __launch_bounds__(128)
-k_tri_inverse(DevSym S, const T *__restrict__ M, const SlvTask *__restrict__ tasks, const int64_t *__restrict__ invoff,
-              T *inv, int unit) {
+k_tri_inverse(const T *__restrict__ M, const SlvTask *__restrict__ tasks, T *inv, int unit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *Xs = reinterpret_cast<T *>(smem_raw);
   const SlvTask tk = tasks[blockIdx.x];
-  const int c = tk.cblk, ld = S.stride[c], nb = tk.c1 - tk.c0;
-  const T *W = M + S.poff[c] + (size_t)tk.c0 * (ld + 1);
+  const int ld = tk.ld, nb = tk.c1 - tk.c0;
+  const T *W = M + tk.poff + (size_t)tk.c0 * (ld + 1);
   const int ldx = nb | 1;
   const int j = threadIdx.x;
   const T one = ST<T>::from_real(1.0), zero = ST<T>::zero();
@@ -74,140 +78,186 @@ k_tri_inverse(DevSym S, const T *__restrict__ M, const SlvTask *__restrict__ tas
     }
   }
   __syncthreads();
-  T *out = inv + invoff[tk.sp];
+  T *out = inv + tk.invoff;
   for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
     const int jj = e / nb, i = e % nb;
     out[e] = (i >= jj) ? Xs[(size_t)jj * ldx + i] : zero;
   }
 }
 
-// ---- forward: one launch per (level, round); CTA = (sub-panel, 128-row tile of rows [c1, stride))
+// global row of every off-diagonal panel row, built once (one CTA per cblk)
+__global__ void k_build_rowglob(DevSym S, const int64_t *__restrict__ rmbase, int *rowglob) {
+  const int k = blockIdx.x;
+  const int w = S.width[k], ld = S.stride[k], bf = S.fblok[k] + 1, be = S.fblok[k + 1];
+  const int64_t base = rmbase[k];
+  for (int m = w + threadIdx.x; m < ld; m += blockDim.x) {
+    const int b = upper_le(S.coefind, bf, be, m);
+    rowglob[base + m - w] = S.frow[b] + (m - S.coefind[b]);
+  }
+}
+
+#define PB200_SLV_CG 4                      // column groups per CTA (k_fwd): 128 rows x 4 groups = 512 threads
+#define PB200_SLV_NT (PB200_SLV_ROWS * PB200_SLV_CG)
+#define PB200_SLV_MLP 16                    // independent loads in flight per thread
+
+// ---- forward: one launch per (level, round); CTA = (sub-panel, 128-row tile of rows [c1, stride)).
+// Thread (r, cg) owns panel row r of the tile and every 4th... the cg-th quarter of the nb columns; the
+// loads of a batch are issued together (latency of a level = a few memory round trips, not nb of them).
 template <class T, int FACTO>
-__global__ void __launch_bounds__(PB200_SLV_ROWS)
-k_fwd(DevSym S, const T *__restrict__ L, const T *__restrict__ inv, const int64_t *__restrict__ invoff,
-      T *x, T *y, int64_t ldx, int nrhs, const SlvTask *__restrict__ tasks, const int *__restrict__ tile2task) {
-  constexpr int NB = SlvCfg<T>::NB, NR = PB200_SLV_NR;
+__global__ void __launch_bounds__(PB200_SLV_NT, 1)
+k_fwd(const T *__restrict__ L, const T *__restrict__ inv, T *x, T *y, int64_t ldx, int nrhs,
+      const SlvTask *__restrict__ tasks, const int *__restrict__ tile2task, const int *__restrict__ rowglob) {
+  constexpr int NB = SlvCfg<T>::NB, NR = PB200_SLV_NR, CG = PB200_SLV_CG, ML = sizeof(T) >= 16 ? PB200_SLV_MLP / 2 : PB200_SLV_MLP;
   __shared__ T xs[NR][NB];
   __shared__ T ys[NR][NB];
+  __shared__ T part[CG][NR][PB200_SLV_ROWS];
   const SlvTask tk = tasks[tile2task[blockIdx.x]];
-  const int c = tk.cblk, ld = S.stride[c], fcol = S.fcol[c], nb = tk.c1 - tk.c0;
+  const int ld = tk.ld, fcol = tk.fcol, nb = tk.c1 - tk.c0;
   const int tile = blockIdx.x - tk.tile0;
-  const int tid = threadIdx.x;
-  const T *P = L + S.poff[c];
-  const T *Inv = inv + invoff[tk.sp];
-  const int m = tk.c1 + tile * PB200_SLV_ROWS + tid;
+  const int tid = threadIdx.x, r = tid & (PB200_SLV_ROWS - 1), cg = tid / PB200_SLV_ROWS;
+  const T *P = L + tk.poff;
+  const T *Inv = inv + tk.invoff;
+  const int m = tk.c1 + tile * PB200_SLV_ROWS + r;
   const bool rowok = m < ld;
-  const int grow = rowok ? panel_row_to_global(S, c, m) : 0;
+  const int cgn = (nb + CG - 1) / CG, j_lo = cg * cgn, j_hi = min(nb, j_lo + cgn);
+  int grow = 0;
+  if (rowok && cg == 0) grow = (m < tk.w) ? fcol + m : rowglob[tk.rgbase + m];
   for (int r0 = 0; r0 < nrhs; r0 += NR) {
     const int nr = min(NR, nrhs - r0);
     __syncthreads();
-    for (int e = tid; e < NR * NB; e += PB200_SLV_ROWS) {
-      const int r = e / NB, j = e % NB;
-      xs[r][j] = (r < nr && j < nb) ? x[(size_t)(r0 + r) * ldx + fcol + tk.c0 + j] : ST<T>::zero();
+    for (int e = tid; e < NR * NB; e += PB200_SLV_NT) {
+      const int rr = e / NB, j = e % NB;
+      xs[rr][j] = (rr < nr && j < nb) ? x[(size_t)(r0 + rr) * ldx + fcol + tk.c0 + j] : ST<T>::zero();
     }
     __syncthreads();
-    // y_J = Inv * x_J (lower triangular): thread i builds row i, coalesced column walk
-    if (tid < nb) {
+    // y_J = Inv * x_J (the strict upper triangle of Inv is stored as zeros: uniform trip count)
+    {
       T acc[NR];
 #pragma unroll
-      for (int r = 0; r < NR; ++r) acc[r] = ST<T>::zero();
-      // (the strict upper triangle of Inv is stored as zeros: uniform trip count, deep unrolling)
-#pragma unroll 16
-      for (int j = 0; j < nb; ++j) {
-        const T a = Inv[(size_t)j * nb + tid];
+      for (int rr = 0; rr < NR; ++rr) acc[rr] = ST<T>::zero();
+      if (r < nb)
+        for (int j0 = j_lo; j0 < j_hi; j0 += ML) {
+          T a[ML];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) fma_acc(acc[r], a, xs[r][j]);
-      }
+          for (int q = 0; q < ML; ++q) a[q] = (j0 + q < j_hi) ? Inv[(size_t)(j0 + q) * nb + r] : ST<T>::zero();
 #pragma unroll
-      for (int r = 0; r < NR; ++r) ys[r][tid] = acc[r];
-      if (tile == 0) {
+          for (int q = 0; q < ML; ++q)
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) fma_acc(acc[rr], a[q], xs[rr][min(j0 + q, NB - 1)]);
+        }
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) part[cg][rr][r] = acc[rr];
+    }
+    __syncthreads();
+    if (cg == 0 && r < nb) {
+      T d = ST<T>::from_real(1.0);
+      if ((FACTO == F_LDLT || FACTO == F_LDLH) && tile == 0) d = P[(size_t)(tk.c0 + r) * (ld + 1)];
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        T v = part[0][rr][r];
+#pragma unroll
+        for (int g = 1; g < CG; ++g) v += part[g][rr][r];
+        ys[rr][r] = v;
         // write-back; LDLt/LDLh: the diagonal step x_k /= D_kk folded in (updo.c:948-984)
-        T d = ST<T>::from_real(1.0);
-        if (FACTO == F_LDLT || FACTO == F_LDLH) d = P[(size_t)(tk.c0 + tid) * (ld + 1)];
-#pragma unroll
-        for (int r = 0; r < NR; ++r)
-          if (r < nr) y[(size_t)(r0 + r) * ldx + fcol + tk.c0 + tid] =
-              (FACTO == F_LDLT || FACTO == F_LDLH) ? acc[r] / d : acc[r];
+        if (tile == 0 && rr < nr)
+          y[(size_t)(r0 + rr) * ldx + fcol + tk.c0 + r] = (FACTO == F_LDLT || FACTO == F_LDLH) ? v / d : v;
       }
     }
     __syncthreads();
-    if (rowok) {
+    {
       T acc[NR];
 #pragma unroll
-      for (int r = 0; r < NR; ++r) acc[r] = ST<T>::zero();
-      const T *col = P + (size_t)tk.c0 * ld + m;
-#pragma unroll 16
-      for (int j = 0; j < nb; ++j) {
-        const T a = col[(size_t)j * ld];
+      for (int rr = 0; rr < NR; ++rr) acc[rr] = ST<T>::zero();
+      if (rowok) {
+        const T *col = P + (size_t)tk.c0 * ld + m;
+        for (int j0 = j_lo; j0 < j_hi; j0 += ML) {
+          T a[ML];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) fma_acc(acc[r], a, ys[r][j]);
+          for (int q = 0; q < ML; ++q) a[q] = (j0 + q < j_hi) ? col[(size_t)(j0 + q) * ld] : ST<T>::zero();
+#pragma unroll
+          for (int q = 0; q < ML; ++q)
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) fma_acc(acc[rr], a[q], ys[rr][min(j0 + q, NB - 1)]);
+        }
       }
 #pragma unroll
-      for (int r = 0; r < NR; ++r)
-        if (r < nr) atomic_sub(&x[(size_t)(r0 + r) * ldx + grow], acc[r]);
+      for (int rr = 0; rr < NR; ++rr) part[cg][rr][r] = acc[rr];
+    }
+    __syncthreads();
+    if (cg == 0 && rowok) {
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        T v = part[0][rr][r];
+#pragma unroll
+        for (int g = 1; g < CG; ++g) v += part[g][rr][r];
+        if (rr < nr) atomic_sub(&x[(size_t)(r0 + rr) * ldx + grow], v);
+      }
     }
   }
 }
 
 // ---- backward: one launch per (level, round), descending.  M is coeftab (ucoeftab for LU).
+#define PB200_BWD_NT 512
 template <class T, int FACTO>
-__global__ void __launch_bounds__(256)
-k_bwd(DevSym S, const T *__restrict__ M, const T *__restrict__ inv, const int64_t *__restrict__ invoff,
-      T *x, T *y, int64_t ldx, int nrhs, const SlvTask *__restrict__ tasks, const int *__restrict__ tile2task,
+__global__ void __launch_bounds__(PB200_BWD_NT, 1)
+k_bwd(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t ldx, int nrhs,
+      const SlvTask *__restrict__ tasks, const int *__restrict__ tile2task, const int *__restrict__ rowglob,
       unsigned int *counters) {
   constexpr int NB = SlvCfg<T>::NB, NR = PB200_SLV_NR;
   constexpr bool CONJ = (FACTO == F_LDLH);
+  constexpr int RI = PB200_SLV_ROWS / 32;   // row chunks per lane
   __shared__ T xr[NR][PB200_SLV_ROWS];
   __shared__ T yj[NR][NB];
   __shared__ int s_last;
   const SlvTask tk = tasks[tile2task[blockIdx.x]];
-  const int c = tk.cblk, ld = S.stride[c], fcol = S.fcol[c], nb = tk.c1 - tk.c0;
+  const int ld = tk.ld, fcol = tk.fcol, nb = tk.c1 - tk.c0;
   const int tile = blockIdx.x - tk.tile0;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  const T *P = M + S.poff[c];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = PB200_BWD_NT / 32;
+  const T *P = M + tk.poff;
   const int mbase = tk.c1 + tile * PB200_SLV_ROWS;
   const int mrows = max(0, min(PB200_SLV_ROWS, ld - mbase));
   int grow = 0;
-  if (tid < mrows) grow = panel_row_to_global(S, c, mbase + tid);
+  if (tid < mrows) { const int m = mbase + tid; grow = (m < tk.w) ? fcol + m : rowglob[tk.rgbase + m]; }
   if (mrows > 0) {
     for (int r0 = 0; r0 < nrhs; r0 += NR) {
       const int nr = min(NR, nrhs - r0);
       __syncthreads();
       if (tid < PB200_SLV_ROWS)
 #pragma unroll
-        for (int r = 0; r < NR; ++r)
-          xr[r][tid] = (tid < mrows && r < nr) ? x[(size_t)(r0 + r) * ldx + grow] : ST<T>::zero();
+        for (int rr = 0; rr < NR; ++rr)
+          xr[rr][tid] = (tid < mrows && rr < nr) ? x[(size_t)(r0 + rr) * ldx + grow] : ST<T>::zero();
       __syncthreads();
-      constexpr int JC = 4;   // columns per warp pass: JC * (rows/32) loads in flight
+      constexpr int JC = 4;   // columns per warp pass: JC * RI loads in flight per lane
       for (int j0 = warp * JC; j0 < nb; j0 += nwarp * JC) {
+        T a[JC][RI];
+#pragma unroll
+        for (int q = 0; q < JC; ++q)
+#pragma unroll
+          for (int ii = 0; ii < RI; ++ii) {
+            const int i = lane + 32 * ii;
+            a[q][ii] = (j0 + q < nb && i < mrows) ? P[(size_t)(tk.c0 + j0 + q) * ld + mbase + i] : ST<T>::zero();
+            if (CONJ) a[q][ii] = ST<T>::conj(a[q][ii]);
+          }
         T acc[JC][NR];
 #pragma unroll
         for (int q = 0; q < JC; ++q)
 #pragma unroll
-          for (int r = 0; r < NR; ++r) acc[q][r] = ST<T>::zero();
-        for (int i = lane; i < mrows; i += 32) {
-          T a[JC];
+          for (int rr = 0; rr < NR; ++rr) {
+            acc[q][rr] = ST<T>::zero();
 #pragma unroll
-          for (int q = 0; q < JC; ++q) {
-            a[q] = (j0 + q < nb) ? P[(size_t)(tk.c0 + j0 + q) * ld + mbase + i] : ST<T>::zero();
-            if (CONJ) a[q] = ST<T>::conj(a[q]);
+            for (int ii = 0; ii < RI; ++ii) fma_acc(acc[q][rr], a[q][ii], xr[rr][lane + 32 * ii]);
           }
-#pragma unroll
-          for (int q = 0; q < JC; ++q)
-#pragma unroll
-            for (int r = 0; r < NR; ++r) fma_acc(acc[q][r], a[q], xr[r][i]);
-        }
 #pragma unroll
         for (int q = 0; q < JC; ++q)
 #pragma unroll
-          for (int r = 0; r < NR; ++r) {
+          for (int rr = 0; rr < NR; ++rr) {
             typedef typename ST<T>::real R;
-            R *p = reinterpret_cast<R *>(&acc[q][r]);
+            R *p = reinterpret_cast<R *>(&acc[q][rr]);
             for (int o = 16; o > 0; o >>= 1) {
               p[0] += __shfl_down_sync(0xffffffffu, p[0], o);
               if (ST<T>::is_complex) p[1] += __shfl_down_sync(0xffffffffu, p[1], o);
             }
-            if (lane == 0 && r < nr && j0 + q < nb) atomic_sub(&y[(size_t)(r0 + r) * ldx + fcol + tk.c0 + j0 + q], acc[q][r]);
+            if (lane == 0 && rr < nr && j0 + q < nb) atomic_sub(&y[(size_t)(r0 + rr) * ldx + fcol + tk.c0 + j0 + q], acc[q][rr]);
           }
       }
     }
@@ -223,46 +273,42 @@ k_bwd(DevSym S, const T *__restrict__ M, const T *__restrict__ inv, const int64_
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const T *Inv = inv + invoff[tk.sp];
+  const T *Inv = inv + tk.invoff;
+  constexpr int NJ = NB / 32;
   for (int r0 = 0; r0 < nrhs; r0 += NR) {
     const int nr = min(NR, nrhs - r0);
     __syncthreads();
-    for (int e = tid; e < NR * NB; e += blockDim.x) {
-      const int r = e / NB, j = e % NB;
-      yj[r][j] = (r < nr && j < nb) ? ld_cg(&y[(size_t)(r0 + r) * ldx + fcol + tk.c0 + j]) : ST<T>::zero();
+    for (int e = tid; e < NR * NB; e += PB200_BWD_NT) {
+      const int rr = e / NB, j = e % NB;
+      yj[rr][j] = (rr < nr && j < nb) ? ld_cg(&y[(size_t)(r0 + rr) * ldx + fcol + tk.c0 + j]) : ST<T>::zero();
     }
     __syncthreads();
     // x_i = sum_{j >= i} op(Inv[j][i]) y_j : warp per output, lanes along the contiguous j
     constexpr int IC = 4;
     for (int i0 = warp * IC; i0 < nb; i0 += nwarp * IC) {
-      T acc[IC][NR];
+      T a[IC][NJ];
 #pragma unroll
       for (int q = 0; q < IC; ++q)
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[q][r] = ST<T>::zero();
-      for (int j = lane; j < nb; j += 32) {   // entries with j < i are stored zeros
-        T a[IC];
-#pragma unroll
-        for (int q = 0; q < IC; ++q) {
-          a[q] = (i0 + q < nb) ? Inv[(size_t)(i0 + q) * nb + j] : ST<T>::zero();
-          if (CONJ) a[q] = ST<T>::conj(a[q]);
+        for (int jj = 0; jj < NJ; ++jj) {
+          const int j = lane + 32 * jj;   // entries with j < i are stored zeros
+          a[q][jj] = (i0 + q < nb && j < nb) ? Inv[(size_t)(i0 + q) * nb + j] : ST<T>::zero();
+          if (CONJ) a[q][jj] = ST<T>::conj(a[q][jj]);
         }
 #pragma unroll
-        for (int q = 0; q < IC; ++q)
-#pragma unroll
-          for (int r = 0; r < NR; ++r) fma_acc(acc[q][r], a[q], yj[r][j]);
-      }
-#pragma unroll
       for (int q = 0; q < IC; ++q)
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
+        for (int rr = 0; rr < NR; ++rr) {
+          T acc = ST<T>::zero();
+#pragma unroll
+          for (int jj = 0; jj < NJ; ++jj) fma_acc(acc, a[q][jj], yj[rr][lane + 32 * jj]);
           typedef typename ST<T>::real R;
-          R *p = reinterpret_cast<R *>(&acc[q][r]);
+          R *p = reinterpret_cast<R *>(&acc);
           for (int o = 16; o > 0; o >>= 1) {
             p[0] += __shfl_down_sync(0xffffffffu, p[0], o);
             if (ST<T>::is_complex) p[1] += __shfl_down_sync(0xffffffffu, p[1], o);
           }
-          if (lane == 0 && r < nr && i0 + q < nb) x[(size_t)(r0 + r) * ldx + fcol + tk.c0 + i0 + q] = acc[q][r];
+          if (lane == 0 && rr < nr && i0 + q < nb) x[(size_t)(r0 + rr) * ldx + fcol + tk.c0 + i0 + q] = acc;
         }
     }
   }
