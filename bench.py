@@ -149,6 +149,18 @@ def measure_fp64_peak(device: int) -> dict:
     return out
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant k_gemm_scatter launch, from the committed
+    `ncu --set full` capture (profiles/r01/ncu_gemm_scatter_c3_summary.json); None when absent."""
+    p = os.path.join(ROOT, "profiles", "r01", "ncu_gemm_scatter_c3_summary.json")
+    try:
+        d = json.load(open(p))["dominant"]
+        return {"dram_bytes": d["dram_bytes_read"] + d["dram_bytes_write"], "launch_tiles": d["grid_tiles"],
+                "launch_ms": d["duration_s"] * 1e3, "capture": "c3, one launch (ncu --set full)"}
+    except Exception:
+        return None
+
+
 def measured_peaks() -> dict:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -334,7 +346,7 @@ def our_arm(args):
         ach = prof["gemm_flops"] / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         roof = {"kernel": "k_gemm_scatter (fused DMMA GEMM + scatter-add into facing cblks)", "bound": "tensor",
                 "achieved": ach, "peak": peak["peak_tflops"], "unit": "TFLOP/s", "frac": ach / peak["peak_tflops"],
-                "traffic": None, "peak_source": peak["source"], "fp64_peaks": {k: v for k, v in peak.items() if k.endswith("tflops")},
+                "traffic": ncu_traffic(), "peak_source": peak["source"], "fp64_peaks": {k: v for k, v in peak.items() if k.endswith("tflops")},
                 "kernel_share_of_step": gms / tot if tot > 0 else None,
                 "kind_ms_serialised": prof["ms"], "kind_launches": prof["launches"],
                 "algorithmic_flops_per_factorization": prof["gemm_flops"]}

@@ -73,15 +73,30 @@ struct SubTask {        // diag / trsm work on sub-panel [c0,c1) of a cblk
 };
 
 template <class T> struct UpdCfg;
+// tile shape of the real-double update kernel (tuning variants: python -m pastix_b200.build -DPB200_UPD_TM=64 ...)
+#ifndef PB200_UPD_D_TM
+// measured (r01, C3): 128x64/256 thr/2 CTAs 371 ms; 64x64/128 thr/4 CTAs/2 stages 341 ms; 64x64/3 CTAs/3 stages 370 ms;
+// 128x64 KC=32 2 stages 360 ms.  Four small CTAs per SM give the one DMMA pipe four independent phase contexts.
+#define PB200_UPD_D_TM 64
+#define PB200_UPD_D_TN 64
+#define PB200_UPD_D_KC 16
+#define PB200_UPD_D_STG 2
+#define PB200_UPD_D_WM 2
+#define PB200_UPD_D_WN 2
+#define PB200_UPD_D_CTAS 4
+#endif
 template <> struct UpdCfg<double> {
-  static constexpr int TM = 128, TN = 64, KC = 16, STG = 3, WM = 4, WN = 2, PADA = 4, PADB = 4;
-  static constexpr int NT = WM * WN * 32, CTAS = 2;
+  static constexpr int TM = PB200_UPD_D_TM, TN = PB200_UPD_D_TN, KC = PB200_UPD_D_KC, STG = PB200_UPD_D_STG,
+                       WM = PB200_UPD_D_WM, WN = PB200_UPD_D_WN, PADA = 4, PADB = 4;
+  static constexpr int NT = WM * WN * 32, CTAS = PB200_UPD_D_CTAS;
 };
 template <> struct UpdCfg<cdouble> {
   static constexpr int TM = 64, TN = 64, KC = 16, STG = 3, WM = 4, WN = 2, PADA = 2, PADB = 2;
   static constexpr int NT = WM * WN * 32, CTAS = 2;
 };
+#ifndef PB200_TABMAX
 #define PB200_TABMAX 1536
+#endif
 #define PB200_COEFMAX 1024
 
 template <class T>
