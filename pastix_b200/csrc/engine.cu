@@ -17,6 +17,7 @@
 #include "kernels_solve.cuh"
 #include "kernels_mma.cuh"
 #include "kernels_dist.cuh"
+#include "kernels_small.cuh"
 #include "dist_plan.h"
 
 using namespace pb200;
@@ -88,6 +89,11 @@ struct pb200_handle_s {
   std::vector<cudaEvent_t> sched_ev;     // [l] panel(l) done, [nlevels + l] bulk update of level l done
   std::vector<int> h_gemm_modes;
   std::vector<void *> allocs;
+  // ---- small-supernode path of the generic factorization (kernels_small.cuh)
+  struct GStep { int kind; int l0, l1; };   // 0: classic level (diag / trsm / update launches), 1: one fused launch, 2: single-CTA chain of thin levels
+  std::vector<GStep> gsteps;
+  int *d_lvl_ptr = nullptr;
+  int64_t *d_sm_pbase = nullptr, *d_sm_tabL = nullptr, *d_sm_tabU = nullptr;
   // ---- multi-GPU (one process per GPU; see kernels_dist.cuh)
   int rank = 0, nranks = 1;
   DistPlan plan;
@@ -374,6 +380,60 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
   return PB200_SUCCESS;
 }
 
+// ------------------------------------------------------------------ schedule of the generic factorization
+// Levels whose (local) cblks are all small run the fused warp-per-cblk kernel; consecutive thin ones are chained
+// inside one CTA (kernels_small.cuh).  Everything else keeps the three launches per level.
+static int build_small_schedule(pb200_handle_t *h, const std::vector<int> &lvl_cblk) {
+  const int nl = h->nlevels;
+  const bool cx16 = (h->esize >= 16);
+  const int chain_warps = cx16 ? SmChain<cdouble>::WARPS : SmChain<double>::WARPS;
+  const bool off = getenv("PB200_NO_SMALL_PATH") != nullptr;
+  std::vector<char> small(nl, 0);
+  std::vector<int64_t> pbase(lvl_cblk.size() + 1, 0);
+  for (int l = 0; l < nl; ++l) {
+    const int q0 = h->lvl_ptr[l], q1 = h->lvl_ptr[l + 1];
+    bool ok = !off && q1 > q0;
+    for (int q = q0; q < q1 && ok; ++q) {
+      const int c = lvl_cblk[q];
+      ok = h->h_width[c] <= PB200_SM_WMAX && h->h_stride[c] - h->h_width[c] <= PB200_SM_RMAX;
+    }
+    small[l] = ok;
+    for (int q = q0; q < q1; ++q) {
+      const int c = lvl_cblk[q];
+      const int64_t mr = h->h_stride[c] - h->h_width[c];
+      pbase[q + 1] = pbase[q] + (ok ? mr * (mr + 1) / 2 : 0);
+    }
+  }
+  for (int l = 0; l < nl;) {
+    const int nc = h->lvl_ptr[l + 1] - h->lvl_ptr[l];
+    if (!small[l]) { h->gsteps.push_back({0, l, l + 1}); ++l; continue; }
+    if (h->nranks == 1 && nc <= 2 * chain_warps) {
+      int e = l + 1;
+      while (e < nl && small[e] && h->lvl_ptr[e + 1] - h->lvl_ptr[e] <= 2 * chain_warps) ++e;
+      h->gsteps.push_back({2, l, e}); l = e;
+    } else { h->gsteps.push_back({1, l, l + 1}); ++l; }
+  }
+  const int64_t npairs = pbase.back();
+  if (npairs == 0) return PB200_SUCCESS;
+  { int rc = upload(h, pbase, &h->d_sm_pbase); if (rc) return rc; }
+  { int rc = upload(h, h->lvl_ptr, &h->d_lvl_ptr); if (rc) return rc; }
+  const size_t tb = (size_t)npairs * sizeof(int64_t);
+  if (cudaMalloc((void **)&h->d_sm_tabL, tb) != cudaSuccess) return fail(PB200_ERR_NOMEM, "cudaMalloc(small-cblk contribution table) failed");
+  h->allocs.push_back(h->d_sm_tabL); h->device_bytes += tb;
+  if (h->facto == PB200_FACT_LU) {
+    if (cudaMalloc((void **)&h->d_sm_tabU, tb) != cudaSuccess) return fail(PB200_ERR_NOMEM, "cudaMalloc(small-cblk contribution table) failed");
+    h->allocs.push_back(h->d_sm_tabU); h->device_bytes += tb;
+  }
+  for (int l = 0; l < nl; ++l) {
+    if (!small[l]) continue;
+    const int q0 = h->lvl_ptr[l], nc = h->lvl_ptr[l + 1] - q0;
+    k_build_small_pairs<<<(nc * 32 + 255) / 256, 256>>>(h->S, h->d_lvl_cblk + q0, nc, h->d_sm_pbase + q0, h->d_sm_tabL, h->d_sm_tabU);
+  }
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  return PB200_SUCCESS;
+}
+
 static int dist_barrier(pb200_handle_t *h);
 extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int flttype, int factotype, int device) {
   return pb200_create_dist(out, s, flttype, factotype, device, 0, 1);
@@ -562,6 +622,10 @@ extern "C" int pb200_create_dist(pb200_handle_t **out, const pb200_solver_t *s, 
 
   if (flttype == PB200_REALDOUBLE || flttype == PB200_COMPLEXDOUBLE) {
     int rc = build_mma_schedule(h, level, lvl_cblk);
+    if (rc) { pb200_destroy(h); return rc; }
+  }
+  if (!h->use_mma) {
+    int rc = build_small_schedule(h, lvl_cblk);
     if (rc) { pb200_destroy(h); return rc; }
   }
 
@@ -779,11 +843,34 @@ static int factorize_tf(pb200_handle_t *h, double crit) {
     CK(cudaFuncSetAttribute(k_diag_factor<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     attr_done[h->flt][FACTO] = true;
   }
+  static bool sm_attr_done[4][4] = {};
+  const size_t sm_lvl_smem = (size_t)PB200_SM_WARPS * sizeof(SmallWs<T>), sm_chain_smem = (size_t)SmChain<T>::WARPS * sizeof(SmallWs<T>);
+  if (!sm_attr_done[h->flt][FACTO]) {
+    CK(cudaFuncSetAttribute(k_small_level<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_lvl_smem));
+    CK(cudaFuncSetAttribute(k_small_chain<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chain_smem));
+    sm_attr_done[h->flt][FACTO] = true;
+  }
   int64_t launches = 0;
-  for (int l = 0; l < h->nlevels; ++l) {
+  for (const auto &gs : h->gsteps) {
+    if (gs.kind == 2) {   // run of thin small levels: one CTA walks them
+      const int q0 = h->lvl_ptr[gs.l0];
+      k_small_chain<T, FACTO><<<1, SmChain<T>::WARPS * 32, sm_chain_smem, h->stream>>>(
+          h->S, L, U, h->d_lvl_cblk, h->d_lvl_ptr + gs.l0, gs.l1 - gs.l0, h->d_sm_pbase, h->d_sm_tabL, h->d_sm_tabU, crit, h->d_cnt);
+      (void)q0;
+      ++launches;
+      continue;
+    }
+    const int l = gs.l0;
     int nc = h->lvl_ptr[l + 1] - h->lvl_ptr[l];
     if (h->nranks > 1) launches += launch_fanin<T>(h, l, h->stream);
     if (nc == 0) continue;
+    if (gs.kind == 1) {   // every cblk of the level is small: diag + trsm + updates fused, one warp per cblk
+      const int q0 = h->lvl_ptr[l];
+      k_small_level<T, FACTO><<<(nc + PB200_SM_WARPS - 1) / PB200_SM_WARPS, PB200_SM_WARPS * 32, sm_lvl_smem, h->stream>>>(
+          h->S, L, U, h->d_lvl_cblk + q0, nc, h->d_sm_pbase + q0, h->d_sm_tabL, h->d_sm_tabU, crit, h->d_cnt);
+      ++launches;
+      continue;
+    }
     // smem sized for the widest cblk of this launch would need a per-level max; use global wmax bound
     int elems = std::min<long long>((long long)h->wmax * h->wmax, smem_max / (long long)sizeof(T));
     size_t smem = (size_t)elems * sizeof(T);

@@ -218,11 +218,20 @@ static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
     errorPrint("pastix_b200: Schur / 2D distribution / multi-process SolverMatrix are not handled by this shim");
     EXIT(MOD_SOPALIN, BADPARAMETER_ERR);
   }
+  {
+  double t0 = clockGet(), t1, t2, t3;
   if (e->h != NULL && e->facto != PB200_FACTO) { pb200_destroy(e->h); e->h = NULL; }
   if (e->h == NULL) { e->h = shim_create(datacode); e->facto = PB200_FACTO; }
   e->factorized = 0;
+  t1 = clockGet();
   shim_assemble(e->h, datacode, sopar);
+  t2 = clockGet();
   crit = shim_critere(datacode, sopar);
+  t3 = clockGet();
+  if (getenv("PB200_SHIM_TIMING") != NULL)
+    fprintf(stderr, "[pb200 shim] create %.1f ms, CSC flatten + H2D + device assembly %.1f ms, CscNorm1 %.1f ms\n",
+            (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3);
+  }
   e->critere = crit;
   if (sopar->iparm[IPARM_VERBOSE] > API_VERBOSE_YES)
     fprintf(stdout, "Pivoting criterium (||A||*sqrt(epsilon)) = %g\n", crit);

@@ -1,14 +1,10 @@
 set -x
 export PYTHONUNBUFFERED=1
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
-for v in "" vE vF; do
-  echo "== variant '$v'"
-  if [ -n "$v" ]; then export PB200_LIB=$PWD/pastix_b200/lib/libpastix_b200_$v.so; else unset PB200_LIB; fi
-  timeout 300 python tools/run_case.py 64 7 llt d 2>&1 | grep -E "factorize|backward" | tail -2
-  timeout 300 python tools/run_case.py 100 27 ldlt d 2>&1 | grep -E "factorize|backward" | tail -2
-done > gpurun_out/variants.log 2>&1
-unset PB200_LIB
-cat gpurun_out/variants.log
-timeout 600 python bench.py > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.log; echo "rc=$?"; cat gpurun_out/bench_c2.json
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_c2_ref.json 2> gpurun_out/bench_c2_ref.log; echo "rc=$?"; cat gpurun_out/bench_c2_ref.json
+timeout 900 python -m pytest tests/test_dist.py -m gpu -q > gpurun_out/pytest_dist.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_dist.log
+tail -5 gpurun_out/pytest_dist.log
+for wl in c2 c3; do
+for n in 4 2; do
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 3 --warmup 3 --workload $wl > gpurun_out/bench_${wl}_n$n.json 2> gpurun_out/bench_${wl}_n$n.log; echo "rc=$?"
+python -c "
+import json; d=json.load(open('gpurun_out/bench_${wl}_n$n.json')); print('$wl n=$n', 'fact_ms', d['fact_ms'], 'GF', d['value'], 'solve', d['solve_ms_per_rhs'], 'berr', d['backward_error'], 'e2e', d['e2e']['value'], d['e2e']['numfact_call_ms'])"
+done; done
