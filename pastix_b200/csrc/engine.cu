@@ -60,7 +60,14 @@ struct pb200_handle_s {
   int64_t last_launches = 0;
   bool assembled = false, factorized = false;
   // ---- solve schedule (all precisions)
+  struct GStep { int kind; int l0, l1; };   // 0: classic level (separate launches), 1: one fused small-cblk launch, 2: single-CTA chain of thin levels
   struct SlvStep { int task0, ntasks; long long ntiles, t2t0; };
+  std::vector<int> slv_lvl_ptr, slv_lvl_step;   // full (all-GPU) level lists; slv_steps of level l: [slv_lvl_step[l], slv_lvl_step[l+1])
+  std::vector<GStep> sgsteps;                  // up_down schedule over levels (kinds as gsteps)
+  int *d_slv_cblk = nullptr, *d_slv_lvl_ptr = nullptr;
+  int64_t *d_rmbase = nullptr;
+  bool slv_all_small = false;
+  void *d_xt = nullptr; size_t xt_bytes = 0;
   std::vector<SlvStep> slv_steps;          // ascending (level, round)
   SlvTask *d_slvtask = nullptr; int *d_slv_t2t = nullptr;
   int64_t *d_invoff = nullptr; int64_t inv_elems = 0; int nsubpanels = 0;
@@ -70,6 +77,7 @@ struct pb200_handle_s {
   bool inv_ready = false;
   std::vector<int64_t> h_rmbase;           // per cblk: first entry of its off-diagonal rows in d_rowglob
   int *d_rowglob = nullptr;                // global row of every off-diagonal panel row
+  std::vector<int> inv_lvl_nbmax;          // widest sub-panel of each level (sizes the shared memory of k_tri_inverse)
   std::vector<int> inv_lvl_ptr;            // sub-panels of level l: [inv_lvl_ptr[l], inv_lvl_ptr[l+1])
   cudaStream_t stream_i = nullptr;         // low priority: triangle inversions underneath the factorization
   cudaEvent_t ev_inv = nullptr;
@@ -90,7 +98,6 @@ struct pb200_handle_s {
   std::vector<int> h_gemm_modes;
   std::vector<void *> allocs;
   // ---- small-supernode path of the generic factorization (kernels_small.cuh)
-  struct GStep { int kind; int l0, l1; };   // 0: classic level (diag / trsm / update launches), 1: one fused launch, 2: single-CTA chain of thin levels
   std::vector<GStep> gsteps;
   int *d_lvl_ptr = nullptr;
   int64_t *d_sm_pbase = nullptr, *d_sm_tabL = nullptr, *d_sm_tabU = nullptr;
@@ -139,10 +146,14 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
   std::vector<int64_t> rmbase((size_t)h->cblknbr + 1, 0);
   for (int64_t c = 0; c < h->cblknbr; ++c) rmbase[c + 1] = rmbase[c] + (h->h_stride[c] - h->h_width[c]);
   h->inv_lvl_ptr.assign(h->nlevels + 1, 0);
+  h->inv_lvl_nbmax.assign(h->nlevels, 1);
+  h->slv_lvl_ptr = h->lvl_ptr;
+  h->slv_lvl_step.assign(h->nlevels + 1, 0);
   for (int l = 0; l < h->nlevels; ++l) {
     const int q0 = h->lvl_ptr[l], q1 = h->lvl_ptr[l + 1];
     int rounds = 0;
     h->inv_lvl_ptr[l] = sp;
+    h->slv_lvl_step[l] = (int)h->slv_steps.size();
     for (int q = q0; q < q1; ++q) rounds = std::max(rounds, (h->h_width[lvl_cblk[q]] + NB - 1) / NB);
     for (int r = 0; r < rounds; ++r) {
       int t0 = (int)tasks.size(); long long tiles = 0; long long tt0 = (long long)t2t.size();
@@ -154,6 +165,7 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
         int c0 = r * sw, c1 = std::min(w, c0 + sw);
         int nt = std::max(1, (ld - c1 + PB200_SLV_ROWS - 1) / PB200_SLV_ROWS);
         tasks.push_back({c, (int)tiles, c0, c1, sp, nt, ld, h->h_fcol[c], w, 0, h->h_poff[c], rmbase[c] - w, inv_elems});
+        h->inv_lvl_nbmax[l] = std::max(h->inv_lvl_nbmax[l], c1 - c0);
         for (int i = 0; i < nt; ++i) t2t.push_back((int)tasks.size() - 1 - t0);
         tiles += nt;
         invoff.push_back(inv_elems); inv_elems += (int64_t)(c1 - c0) * (c1 - c0); ++sp;
@@ -163,7 +175,36 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
     }
   }
   h->nsubpanels = sp; h->inv_elems = inv_elems; h->inv_lvl_ptr[h->nlevels] = sp;
+  h->slv_lvl_step[h->nlevels] = (int)h->slv_steps.size();
   h->h_rmbase = rmbase;
+  {
+    // small-cblk levels of the up_down (kernels_small.cuh): same classification as the factorization, over all cblks
+    const int nl = h->nlevels;
+    const int chain_warps = (h->esize >= 16) ? SmChain<cdouble>::WARPS : SmChain<double>::WARPS;
+    const bool off = getenv("PB200_NO_SMALL_PATH") != nullptr;
+    std::vector<char> small(nl, 0);
+    bool all = !off;
+    for (int l = 0; l < nl; ++l) {
+      bool ok = !off;
+      for (int q = h->lvl_ptr[l]; q < h->lvl_ptr[l + 1] && ok; ++q) {
+        const int c = lvl_cblk[q];
+        ok = h->h_width[c] <= PB200_SM_WMAX && h->h_stride[c] - h->h_width[c] <= PB200_SM_RMAX;
+      }
+      small[l] = ok; all = all && ok;
+    }
+    h->slv_all_small = all;
+    for (int l = 0; l < nl;) {
+      const int nc = h->lvl_ptr[l + 1] - h->lvl_ptr[l];
+      if (!small[l]) { h->sgsteps.push_back({0, l, l + 1}); ++l; continue; }
+      if (nc <= 2 * chain_warps) {
+        int e = l + 1;
+        while (e < nl && small[e] && h->lvl_ptr[e + 1] - h->lvl_ptr[e] <= 2 * chain_warps) ++e;
+        h->sgsteps.push_back({2, l, e}); l = e;
+      } else { h->sgsteps.push_back({1, l, l + 1}); ++l; }
+    }
+    { int rc = upload(h, lvl_cblk, &h->d_slv_cblk); if (rc) return rc; }
+    { int rc = upload(h, h->lvl_ptr, &h->d_slv_lvl_ptr); if (rc) return rc; }
+  }
   { int rc = upload(h, tasks, &h->d_slvtask); if (rc) return rc; }
   { int rc = upload(h, t2t, &h->d_slv_t2t); if (rc) return rc; }
   { int rc = upload(h, invoff, &h->d_invoff); if (rc) return rc; }
@@ -610,6 +651,7 @@ extern "C" int pb200_create_dist(pb200_handle_t **out, const pb200_solver_t *s, 
   {
     int64_t *d_rb = nullptr;
     { int rc = upload(h, h->h_rmbase, &d_rb); if (rc) { pb200_destroy(h); return rc; } }
+    h->d_rmbase = d_rb;
     const size_t nrow = (size_t)std::max<int64_t>(h->h_rmbase[C], 1);
     if (cudaMalloc((void **)&h->d_rowglob, nrow * sizeof(int)) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(row map) failed"); }
     h->allocs.push_back(h->d_rowglob); h->device_bytes += nrow * sizeof(int);
@@ -656,7 +698,7 @@ extern "C" int pb200_destroy(pb200_handle_t *h) {
   cudaFree(h->d_flags); cudaFree(h->d_dist_err);
   for (void *p : h->allocs) cudaFree(p);
   cudaFree(h->dL); cudaFree(h->dU); cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals);
-  cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x); cudaFree(h->d_y);
+  cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x); cudaFree(h->d_y); cudaFree(h->d_xt);
   for (auto e : h->sched_ev) cudaEventDestroy(e);
   if (h->stream_u) cudaStreamDestroy(h->stream_u);
   if (h->stream_i) cudaStreamDestroy(h->stream_i);
@@ -893,7 +935,7 @@ static int factorize_tf(pb200_handle_t *h, double crit) {
 }
 
 static int h_gemm_mode(const pb200_handle_t *h, int task) { return h->h_gemm_modes[task]; }
-template <class T> static int invert_range(pb200_handle_t *h, int sp0, int sp1, cudaStream_t sm);
+template <class T> static int invert_range(pb200_handle_t *h, int sp0, int sp1, cudaStream_t sm, int nbmax);
 
 // ------------------------------------------------------------------ factorization (tensor-core path)
 template <class T, int FACTO>
@@ -955,7 +997,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
       const int l = st.rec_ev;
       if (h->inv_lvl_ptr[l + 1] > h->inv_lvl_ptr[l]) {
         CK(cudaStreamWaitEvent(h->stream_i, h->sched_ev[l], 0));
-        int rc = invert_range<T>(h, h->inv_lvl_ptr[l], h->inv_lvl_ptr[l + 1], h->stream_i);
+        int rc = invert_range<T>(h, h->inv_lvl_ptr[l], h->inv_lvl_ptr[l + 1], h->stream_i, h->inv_lvl_nbmax[l]);
         if (rc) return rc;
         launches += lu;
       }
@@ -1071,17 +1113,17 @@ extern "C" int pb200_inertia(pb200_handle_t *h, int64_t *inertia) {
 
 // ------------------------------------------------------------------ solve
 // invert the diagonal triangles of the freshly factored panels (one CTA per sub-panel)
-// sub-panels [sp0, sp1) (tasks are ordered by level, so a level is one contiguous range)
+// sub-panels [sp0, sp1) (tasks are ordered by level, so a level is one contiguous range); nbmax = widest of them
 template <class T>
-static int invert_range(pb200_handle_t *h, int sp0, int sp1, cudaStream_t sm) {
+static int invert_range(pb200_handle_t *h, int sp0, int sp1, cudaStream_t sm, int nbmax = SlvCfg<T>::NB) {
   static bool attr_done[4] = {};
   const int NB = SlvCfg<T>::NB;
-  const size_t smem = (size_t)NB * (NB | 1) * sizeof(T);
   if (!attr_done[h->flt]) {
-    CK(cudaFuncSetAttribute(k_tri_inverse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_tri_inverse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NB * (NB | 1) * sizeof(T))));
     attr_done[h->flt] = true;
   }
   if (sp1 <= sp0) return PB200_SUCCESS;
+  const size_t smem = (size_t)nbmax * (nbmax | 1) * sizeof(T);   // small sub-panels: many CTAs per SM
   const int unit_down = (h->facto != PB200_FACT_LLT);   // LDLt / LDLh / LU-L: unit lower triangle
   k_tri_inverse<T><<<sp1 - sp0, 128, smem, sm>>>((const T *)h->dL, h->d_slvtask + sp0, (T *)h->d_inv, unit_down);
   if (h->facto == PB200_FACT_LU)   // up sweep: lower triangle of ucoeftab's diagonal blok = U^T, non-unit
@@ -1090,8 +1132,16 @@ static int invert_range(pb200_handle_t *h, int sp0, int sp1, cudaStream_t sm) {
 }
 template <class T>
 static int invert_t(pb200_handle_t *h, cudaStream_t sm) {
-  int rc = invert_range<T>(h, 0, h->nsubpanels, sm);
-  if (rc) return rc;
+  // runs of consecutive levels whose widest sub-panel falls in the same size class share a launch
+  auto cls = [](int nb) { return nb <= 16 ? 16 : nb <= 32 ? 32 : nb <= 64 ? 64 : 128; };
+  for (int l = 0; l < h->nlevels;) {
+    const int k = cls(h->inv_lvl_nbmax[l]);
+    int e = l + 1;
+    while (e < h->nlevels && cls(h->inv_lvl_nbmax[e]) == k) ++e;
+    int rc = invert_range<T>(h, h->inv_lvl_ptr[l], h->inv_lvl_ptr[e], sm, std::min(k, (int)SlvCfg<T>::NB));
+    if (rc) return rc;
+    l = e;
+  }
   CK(cudaGetLastError());
   h->inv_ready = true;
   return PB200_SUCCESS;
@@ -1106,16 +1156,70 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
   const T *inv_up = (FACTO == F_LU) ? (const T *)h->d_inv_up : inv;
   T *y = (T *)h->d_y;
   int64_t launches = 0;
-  for (size_t i = 0; i < h->slv_steps.size(); ++i) {
-    const auto &st = h->slv_steps[i];
-    k_fwd<T, FACTO><<<(unsigned)st.ntiles, PB200_SLV_NT, 0, h->stream>>>(L, inv, x, y, ldx, nrhs, h->d_slvtask + st.task0,
-                                                                       h->d_slv_t2t + st.t2t0, h->d_rowglob);
+  static bool sm_attr_done[4][4] = {};
+  const size_t sm_lvl_smem = (size_t)PB200_SM_WARPS * sizeof(SmallSolveWs<T>), sm_chain_smem = (size_t)SmChain<T>::WARPS * sizeof(SmallSolveWs<T>);
+  if (!sm_attr_done[h->flt][FACTO]) {
+    CK(cudaFuncSetAttribute(k_small_solve_level<T, FACTO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_lvl_smem));
+    CK(cudaFuncSetAttribute(k_small_solve_level<T, FACTO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_lvl_smem));
+    CK(cudaFuncSetAttribute(k_small_solve_chain<T, FACTO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chain_smem));
+    CK(cudaFuncSetAttribute(k_small_solve_chain<T, FACTO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chain_smem));
+    sm_attr_done[h->flt][FACTO] = true;
+  }
+  // several right-hand sides through an all-small schedule (ILU): transposed work copies, lanes over right-hand sides
+  const bool tr = h->slv_all_small && nrhs >= 4;
+  T *xs = x, *ys = y;
+  int64_t rs = 1, cs = ldx;
+  const int n = (int)h->n;
+  if (tr) {
+    const size_t need = (size_t)n * nrhs * sizeof(T);
+    if (need > h->xt_bytes) {
+      cudaFree(h->d_xt); h->d_xt = nullptr; h->xt_bytes = 0;
+      if (cudaMalloc(&h->d_xt, need) != cudaSuccess) return fail(PB200_ERR_NOMEM, "cudaMalloc(transposed right-hand sides) failed");
+      h->xt_bytes = need;
+    }
+    xs = (T *)h->d_xt; rs = nrhs; cs = 1;
+    k_rhs_transpose<T><<<dim3((n + 31) / 32, (nrhs + 31) / 32), dim3(32, 8), 0, h->stream>>>(x, xs, n, nrhs, ldx, 1);
     ++launches;
   }
-  for (size_t i = h->slv_steps.size(); i-- > 0;) {
-    const auto &st = h->slv_steps[i];
-    k_bwd<T, FACTO><<<(unsigned)st.ntiles, PB200_BWD_NT, 0, h->stream>>>(Mup, inv_up, x, y, ldx, nrhs, h->d_slvtask + st.task0,
-                                                                       h->d_slv_t2t + st.t2t0, h->d_rowglob, h->d_slv_cnt);
+  for (int dir = 0; dir < 2; ++dir) {
+    const T *M = dir == 0 ? L : Mup;
+    for (size_t gi = 0; gi < h->sgsteps.size(); ++gi) {
+      const auto &gs = h->sgsteps[dir == 0 ? gi : h->sgsteps.size() - 1 - gi];
+      if (gs.kind == 0) {
+        const int s0 = h->slv_lvl_step[gs.l0], s1 = h->slv_lvl_step[gs.l1];
+        for (int k = 0; k < s1 - s0; ++k) {
+          const auto &st = h->slv_steps[dir == 0 ? s0 + k : s1 - 1 - k];
+          if (dir == 0)
+            k_fwd<T, FACTO><<<(unsigned)st.ntiles, PB200_SLV_NT, 0, h->stream>>>(L, inv, xs, ys, ldx, nrhs, h->d_slvtask + st.task0,
+                                                                               h->d_slv_t2t + st.t2t0, h->d_rowglob);
+          else
+            k_bwd<T, FACTO><<<(unsigned)st.ntiles, PB200_BWD_NT, 0, h->stream>>>(Mup, inv_up, xs, ys, ldx, nrhs, h->d_slvtask + st.task0,
+                                                                               h->d_slv_t2t + st.t2t0, h->d_rowglob, h->d_slv_cnt);
+          ++launches;
+        }
+      } else if (gs.kind == 1) {
+        const int q0 = h->slv_lvl_ptr[gs.l0], nc = h->slv_lvl_ptr[gs.l0 + 1] - q0;
+        const unsigned grid = (unsigned)((nc + PB200_SM_WARPS - 1) / PB200_SM_WARPS);
+        if (dir == 0)
+          k_small_solve_level<T, FACTO, 0><<<grid, PB200_SM_WARPS * 32, sm_lvl_smem, h->stream>>>(h->S, M, xs, ys, rs, cs, nrhs, h->d_slv_cblk + q0, nc,
+                                                                                             h->d_rowglob, h->d_rmbase);
+        else
+          k_small_solve_level<T, FACTO, 1><<<grid, PB200_SM_WARPS * 32, sm_lvl_smem, h->stream>>>(h->S, M, xs, ys, rs, cs, nrhs, h->d_slv_cblk + q0, nc,
+                                                                                             h->d_rowglob, h->d_rmbase);
+        ++launches;
+      } else {
+        if (dir == 0)
+          k_small_solve_chain<T, FACTO, 0><<<1, SmChain<T>::WARPS * 32, sm_chain_smem, h->stream>>>(h->S, M, xs, ys, rs, cs, nrhs, h->d_slv_cblk,
+                                                                                               h->d_slv_lvl_ptr + gs.l0, gs.l1 - gs.l0, h->d_rowglob, h->d_rmbase);
+        else
+          k_small_solve_chain<T, FACTO, 1><<<1, SmChain<T>::WARPS * 32, sm_chain_smem, h->stream>>>(h->S, M, xs, ys, rs, cs, nrhs, h->d_slv_cblk,
+                                                                                               h->d_slv_lvl_ptr + gs.l0, gs.l1 - gs.l0, h->d_rowglob, h->d_rmbase);
+        ++launches;
+      }
+    }
+  }
+  if (tr) {
+    k_rhs_transpose<T><<<dim3((n + 31) / 32, (nrhs + 31) / 32), dim3(32, 8), 0, h->stream>>>(xs, x, n, nrhs, ldx, 0);
     ++launches;
   }
   CK(cudaGetLastError());

@@ -221,4 +221,183 @@ k_small_chain(DevSym S, T *L, T *U, const int *__restrict__ cblks, const int *__
   }
 }
 
+// ================================================================ up_down for small cblks
+// Same organisation for the triangular solves: one warp per cblk, levels with many cblks in one launch,
+// runs of thin levels in one CTA.  The right-hand sides are addressed as v[row * rs + rhs * cs]: column-major
+// (rs = 1, cs = ldx, the layout of sm2xtab) or, when every level is small and several right-hand sides are
+// solved together, transposed work copies (rs = nrhs, cs = 1) so that the lanes of a warp — which then run
+// over right-hand sides — touch contiguous memory.
+template <class T>
+struct SmallSolveWs {
+  T W[PB200_SM_WMAX * PB200_SM_LDW];
+  T Xa[PB200_SM_RMAX * PB200_SM_WMAX];
+  T Y[32 * PB200_SM_WMAX];      // per right-hand side of the current chunk: solved block / accumulators
+  int grow[PB200_SM_RMAX];
+};
+
+__device__ __forceinline__ void smem_atomic_add(double *p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void smem_atomic_add(float *p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void smem_atomic_add(cdouble *p, cdouble v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
+__device__ __forceinline__ void smem_atomic_add(cfloat *p, cfloat v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
+
+template <class T>
+__device__ __forceinline__ void small_stage(const DevSym &S, const T *M, int c, const int *__restrict__ rowglob,
+                                            const int64_t *__restrict__ rmbase, SmallSolveWs<T> &ws, int lane, int &w, int &mr, int &fcol) {
+  w = S.width[c]; fcol = S.fcol[c];
+  const int ld = S.stride[c];
+  mr = ld - w;
+  const T *P = M + S.poff[c];
+  for (int e = lane; e < w * w; e += 32) { const int j = e / w, i = e % w; ws.W[j * PB200_SM_LDW + i] = P[(size_t)j * ld + i]; }
+  for (int e = lane; e < mr * w; e += 32) { const int k = e / mr, r = e % mr; ws.Xa[r * PB200_SM_WMAX + k] = P[(size_t)k * ld + w + r]; }
+  const int64_t rb = rmbase[c];
+  for (int r = lane; r < mr; r += 32) ws.grow[r] = rowglob[rb + r];
+}
+
+// down: x_c <- L_cc^-1 x_c (unit unless LLt), y_c = (D^-1) x_c, x[rows] -= L[rows, c] x_c     (updo.c:574-793, 948-984)
+template <class T, int FACTO>
+__device__ void small_fwd(const DevSym &S, const T *L, T *x, T *y, int64_t rs, int64_t cs, int nrhs, int c,
+                          const int *__restrict__ rowglob, const int64_t *__restrict__ rmbase, SmallSolveWs<T> &ws, int lane) {
+  int w, mr, fcol;
+  small_stage<T>(S, L, c, rowglob, rmbase, ws, lane, w, mr, fcol);
+  __syncwarp();
+  for (int r0 = 0; r0 < nrhs; r0 += 32) {
+    const int nrc = min(32, nrhs - r0);
+    if (lane < nrc) {
+      T xv[PB200_SM_WMAX];
+#pragma unroll
+      for (int k = 0; k < PB200_SM_WMAX; ++k) xv[k] = (k < w) ? ld_cg(&x[(int64_t)(fcol + k) * rs + (r0 + lane) * cs]) : ST<T>::zero();
+#pragma unroll
+      for (int j = 0; j < PB200_SM_WMAX; ++j) {
+        if (j < w) {
+          if (FACTO == F_LLT) xv[j] = xv[j] / ws.W[j * PB200_SM_LDW + j];
+#pragma unroll
+          for (int l = j + 1; l < PB200_SM_WMAX; ++l)
+            if (l < w) xv[l] = xv[l] - ws.W[j * PB200_SM_LDW + l] * xv[j];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PB200_SM_WMAX; ++k)
+        if (k < w) {
+          ws.Y[lane * PB200_SM_WMAX + k] = xv[k];
+          y[(int64_t)(fcol + k) * rs + (r0 + lane) * cs] =
+              (FACTO == F_LDLT || FACTO == F_LDLH) ? xv[k] / ws.W[k * PB200_SM_LDW + k] : xv[k];
+        }
+    }
+    __syncwarp();
+    for (int it = lane; it < mr * nrc; it += 32) {
+      const int m = it / nrc, r = it % nrc;
+      T s = ST<T>::zero();
+      for (int k = 0; k < w; ++k) fma_acc(s, ws.Xa[m * PB200_SM_WMAX + k], ws.Y[r * PB200_SM_WMAX + k]);
+      atomic_sub(&x[(int64_t)ws.grow[m] * rs + (r0 + r) * cs], s);
+    }
+    __syncwarp();
+  }
+}
+
+// up: y_c -= op(M[rows, c])^T x[rows], x_c <- op(M_cc)^-T y_c     (updo_sendrecv.c:496-639, updo.c:1309-1342)
+template <class T, int FACTO>
+__device__ void small_bwd(const DevSym &S, const T *M, T *x, T *y, int64_t rs, int64_t cs, int nrhs, int c,
+                          const int *__restrict__ rowglob, const int64_t *__restrict__ rmbase, SmallSolveWs<T> &ws, int lane) {
+  constexpr bool CONJ = (FACTO == F_LDLH);
+  constexpr bool UNIT = (FACTO == F_LDLT || FACTO == F_LDLH);
+  int w, mr, fcol;
+  small_stage<T>(S, M, c, rowglob, rmbase, ws, lane, w, mr, fcol);
+  __syncwarp();
+  for (int r0 = 0; r0 < nrhs; r0 += 32) {
+    const int nrc = min(32, nrhs - r0);
+    for (int e = lane; e < 32 * PB200_SM_WMAX; e += 32) ws.Y[e] = ST<T>::zero();
+    __syncwarp();
+    for (int it = lane; it < mr * nrc; it += 32) {
+      const int m = it / nrc, r = it % nrc;
+      const T xv = ld_cg(&x[(int64_t)ws.grow[m] * rs + (r0 + r) * cs]);
+      for (int k = 0; k < w; ++k) {
+        T a = ws.Xa[m * PB200_SM_WMAX + k];
+        if (CONJ) a = ST<T>::conj(a);
+        smem_atomic_add(&ws.Y[r * PB200_SM_WMAX + k], ST<T>::zero() - a * xv);
+      }
+    }
+    __syncwarp();
+    if (lane < nrc) {
+      T yv[PB200_SM_WMAX];
+#pragma unroll
+      for (int k = 0; k < PB200_SM_WMAX; ++k)
+        yv[k] = (k < w) ? ld_cg(&y[(int64_t)(fcol + k) * rs + (r0 + lane) * cs]) + ws.Y[lane * PB200_SM_WMAX + k] : ST<T>::zero();
+#pragma unroll
+      for (int j = PB200_SM_WMAX - 1; j >= 0; --j) {
+        if (j < w) {
+          T xj = yv[j];
+#pragma unroll
+          for (int l = j + 1; l < PB200_SM_WMAX; ++l)
+            if (l < w) { T a = ws.W[j * PB200_SM_LDW + l]; if (CONJ) a = ST<T>::conj(a); xj = xj - a * yv[l]; }
+          if (!UNIT) xj = xj / ws.W[j * PB200_SM_LDW + j];
+          yv[j] = xj;
+          x[(int64_t)(fcol + j) * rs + (r0 + lane) * cs] = xj;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <class T, int FACTO, int DIR>
+__global__ void __launch_bounds__(PB200_SM_WARPS * 32)
+k_small_solve_level(DevSym S, const T *M, T *x, T *y, int64_t rs, int64_t cs, int nrhs, const int *__restrict__ cblks, int ncblk,
+                    const int *__restrict__ rowglob, const int64_t *__restrict__ rmbase) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmallSolveWs<T> *ws = reinterpret_cast<SmallSolveWs<T> *>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wi = blockIdx.x * PB200_SM_WARPS + warp;
+  if (wi >= ncblk) return;
+  if (DIR == 0) small_fwd<T, FACTO>(S, M, x, y, rs, cs, nrhs, cblks[wi], rowglob, rmbase, ws[warp], lane);
+  else small_bwd<T, FACTO>(S, M, x, y, rs, cs, nrhs, cblks[wi], rowglob, rmbase, ws[warp], lane);
+}
+
+// levels lvl_ptr[0..nlev] walked upwards (DIR 0) or downwards (DIR 1) by one CTA
+template <class T, int FACTO, int DIR>
+__global__ void __launch_bounds__(SmChain<T>::WARPS * 32)
+k_small_solve_chain(DevSym S, const T *M, T *x, T *y, int64_t rs, int64_t cs, int nrhs, const int *__restrict__ cblks,
+                    const int *__restrict__ lvl_ptr, int nlev, const int *__restrict__ rowglob, const int64_t *__restrict__ rmbase) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmallSolveWs<T> *ws = reinterpret_cast<SmallSolveWs<T> *>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int qq = 0; qq < nlev; ++qq) {
+    const int q = (DIR == 0) ? qq : nlev - 1 - qq;
+    const int i0 = lvl_ptr[q], i1 = lvl_ptr[q + 1];
+    for (int wi = i0 + warp; wi < i1; wi += SmChain<T>::WARPS) {
+      if (DIR == 0) small_fwd<T, FACTO>(S, M, x, y, rs, cs, nrhs, cblks[wi], rowglob, rmbase, ws[warp], lane);
+      else small_bwd<T, FACTO>(S, M, x, y, rs, cs, nrhs, cblks[wi], rowglob, rmbase, ws[warp], lane);
+    }
+    __threadfence();
+    __syncthreads();
+  }
+}
+
+// column-major (ld) <-> row-major work copy of the right-hand sides
+template <class T>
+__global__ void k_rhs_transpose(const T *__restrict__ src, T *__restrict__ dst, int n, int nrhs, int64_t ld, int to_rowmajor) {
+  __shared__ T tile[32][33];
+  const int i0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  if (to_rowmajor) {
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+      const int i = i0 + threadIdx.x, r = r0 + rr;
+      if (i < n && r < nrhs) tile[rr][threadIdx.x] = src[(size_t)r * ld + i];
+    }
+    __syncthreads();
+    for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {
+      const int i = i0 + ii, r = r0 + threadIdx.x;
+      if (i < n && r < nrhs) dst[(size_t)i * nrhs + r] = tile[threadIdx.x][ii];
+    }
+  } else {
+    for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {
+      const int i = i0 + ii, r = r0 + threadIdx.x;
+      if (i < n && r < nrhs) tile[ii][threadIdx.x] = src[(size_t)i * nrhs + r];
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+      const int i = i0 + threadIdx.x, r = r0 + rr;
+      if (i < n && r < nrhs) dst[(size_t)r * ld + i] = tile[threadIdx.x][rr];
+    }
+  }
+}
+
 }  // namespace pb200
