@@ -1,9 +1,9 @@
 set -x
 export PYTHONUNBUFFERED=1
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
-tail -12 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --workload c5s --steps 3 --no-cpu-baseline > gpurun_out/bench_c5s.json 2> gpurun_out/bench_c5s.log; echo "rc=$?"
+for wl in c2 c3; do
+n=8
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n bench.py --gpus $n --steps 3 --warmup 3 --workload $wl > gpurun_out/bench_${wl}_n$n.json 2> gpurun_out/bench_${wl}_n$n.log; echo "rc=$?"
 python -c "
-import json; d=json.load(open('gpurun_out/bench_c5s.json')); print('c5s fact_ms', d['fact_ms'], 'solve/rhs', d['solve_ms_per_rhs'], 'launches', d['gpu_launches'], 'e2e numfact', d['e2e']['numfact_call_ms'], 'solve call', d['e2e']['solve_call_ms'], d['backward_error'])"
-timeout 300 python tools/run_case.py 64 7 llt d 2>&1 | grep -E "factorize|solve|backward" | tail -3
-timeout 300 python tools/run_case.py 48 7 llt s 4 2>&1 | grep -E "factorize|solve|backward" | tail -4
+import json; d=json.load(open('gpurun_out/bench_${wl}_n$n.json')); print('$wl n=$n', 'fact_ms', d['fact_ms'], 'GF', d['value'], 'solve', d['solve_ms_per_rhs'], 'berr', d['backward_error'], 'e2e', d['e2e']['value'], d['e2e']['numfact_call_ms'])"
+tail -3 gpurun_out/bench_${wl}_n$n.log
+done
