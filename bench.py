@@ -539,6 +539,7 @@ def main():
         WORKLOADS[args.workload] = (d + " [" + ",".join(args.iparm) + "]", k, N, p, f, nr, over)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per stream (multi-GPU flag waits must not alias)
     # the reference's analysis prints to stdout: keep fd 1 for the single JSON line
     real_out = os.dup(1)
     os.dup2(2, 1)

@@ -109,7 +109,9 @@ struct pb200_handle_s {
   bool attached = false, gathered = true;
   unsigned int *d_flags = nullptr, *d_dist_err = nullptr;   // flags: [0,nlevels) level ready, [nlevels] factorization done, [nlevels+1] barrier
   unsigned int epoch = 0, bar_epoch = 0;
-  struct DistLevel { int sig = 0; unsigned int wait_mask = 0; int task0 = 0, ntasks = 0; long long ntiles = 0; };
+  struct DistLevel { int sig = 0; unsigned int wait_mask = 0, late_mask = 0; int task0 = 0, ntasks = 0; long long ntiles = 0; };
+  cudaStream_t stream_g = nullptr;        // early part of the fan-in gathers (contributors that finished long before the level is due)
+  std::vector<cudaEvent_t> gather_ev;     // per level
   std::vector<DistLevel> dist_lvl;
   FanTask *d_fan = nullptr, *d_pull = nullptr; int npull = 0; long long pull_tiles = 0;
   std::vector<void *> ipc_opened;
@@ -602,6 +604,18 @@ extern "C" int pb200_create_dist(pb200_handle_t **out, const pb200_solver_t *s, 
       D.ntasks = (int)fan.size() - D.task0;
       optr[l + 1] = (int)ocblk.size();
     }
+    // contributors whose last contribution to a level comes from the level just before it (the hand-off on the
+    // critical path); everybody else can be pulled ahead of need
+    for (int64_t k = 0; k < C; ++k) {
+      if (h->plan.owner[k] == rank) continue;
+      for (int b = h->h_fblok[k] + 1; b < h->h_fblok[k + 1]; ++b) {
+        const int fc = h->h_fcblk[b];
+        if (h->plan.owner[fc] == rank && level[fc] == level[k] + 1) h->dist_lvl[level[fc]].late_mask |= 1u << h->plan.owner[k];
+      }
+    }
+    CK(cudaStreamCreateWithFlags(&h->stream_g, cudaStreamNonBlocking));
+    h->gather_ev.resize(nl);
+    for (auto &e : h->gather_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->lvl_ptr = optr; lvl_cblk = ocblk;
     h->npull = (int)pull.size();
     { int rc = upload(h, fan, &h->d_fan); if (rc) { pb200_destroy(h); return rc; } }
@@ -702,6 +716,8 @@ extern "C" int pb200_destroy(pb200_handle_t *h) {
   for (auto e : h->sched_ev) cudaEventDestroy(e);
   if (h->stream_u) cudaStreamDestroy(h->stream_u);
   if (h->stream_i) cudaStreamDestroy(h->stream_i);
+  if (h->stream_g) cudaStreamDestroy(h->stream_g);
+  for (auto e : h->gather_ev) cudaEventDestroy(e);
   if (h->ev_inv) cudaEventDestroy(h->ev_inv);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -773,14 +789,26 @@ static int ensure_gathered(pb200_handle_t *h);
 // ------------------------------------------------------------------ multi-GPU helpers
 static const unsigned long long kDistTimeoutNs = 60ULL * 1000000000ULL;
 template <class T>
-static int64_t launch_fanin(pb200_handle_t *h, int l, cudaStream_t sm) {
+static int64_t launch_fanin(pb200_handle_t *h, int l, cudaStream_t sm, bool split = true) {
   const auto &D = h->dist_lvl[l];
   int64_t n = 0;
   if (D.sig) { k_dist_signal<<<1, 32, 0, sm>>>(h->d_flags, l, h->epoch); ++n; }
   if (D.ntasks) {
-    k_dist_wait<<<1, 32, 0, sm>>>(h->peers, D.wait_mask, l, h->epoch, kDistTimeoutNs, h->d_dist_err);
-    k_fanin_gather<T><<<(unsigned)D.ntiles, 256, 0, sm>>>(h->S, h->peers, (T *)h->dL, (T *)h->dU, h->d_fan + D.task0, D.ntasks);
-    n += 2;
+    const unsigned int late = split ? (D.wait_mask & D.late_mask) : D.wait_mask;
+    const unsigned int early = D.wait_mask & ~late;
+    if (early) {
+      // pulled on the side stream as soon as those GPUs have published the level — usually several levels ahead
+      k_dist_wait<<<1, 32, 0, h->stream_g>>>(h->peers, early, l, h->epoch, kDistTimeoutNs, h->d_dist_err);
+      k_fanin_gather<T><<<(unsigned)D.ntiles, 256, 0, h->stream_g>>>(h->S, h->peers, (T *)h->dL, (T *)h->dU, h->d_fan + D.task0, D.ntasks, early);
+      cudaEventRecord(h->gather_ev[l], h->stream_g);
+      n += 2;
+    }
+    if (late) {
+      k_dist_wait<<<1, 32, 0, sm>>>(h->peers, late, l, h->epoch, kDistTimeoutNs, h->d_dist_err);
+      k_fanin_gather<T><<<(unsigned)D.ntiles, 256, 0, sm>>>(h->S, h->peers, (T *)h->dL, (T *)h->dU, h->d_fan + D.task0, D.ntasks, late);
+      n += 2;
+    }
+    if (early) cudaStreamWaitEvent(sm, h->gather_ev[l], 0);
   }
   return n;
 }
@@ -797,6 +825,7 @@ static int dist_barrier(pb200_handle_t *h) {
   if (!h->attached) return fail(PB200_ERR_STATE, "pb200_ipc_attach has not been called");
   CK(cudaStreamSynchronize(h->stream));
   if (h->stream_u) CK(cudaStreamSynchronize(h->stream_u));
+  if (h->stream_g) CK(cudaStreamSynchronize(h->stream_g));
   ++h->bar_epoch;
   k_dist_signal<<<1, 32, 0, h->stream>>>(h->d_flags, h->nlevels + 1, h->bar_epoch);
   k_dist_wait<<<1, 32, 0, h->stream>>>(h->peers, (1u << h->nranks) - 1u, h->nlevels + 1, h->bar_epoch, kDistTimeoutNs, h->d_dist_err);
@@ -904,7 +933,7 @@ static int factorize_tf(pb200_handle_t *h, double crit) {
     }
     const int l = gs.l0;
     int nc = h->lvl_ptr[l + 1] - h->lvl_ptr[l];
-    if (h->nranks > 1) launches += launch_fanin<T>(h, l, h->stream);
+    if (h->nranks > 1) launches += launch_fanin<T>(h, l, h->stream, getenv("PB200_NO_EARLY_GATHER") == nullptr);
     if (nc == 0) continue;
     if (gs.kind == 1) {   // every cblk of the level is small: diag + trsm + updates fused, one warp per cblk
       const int q0 = h->lvl_ptr[l];
@@ -982,7 +1011,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
           k_diag_transpose<T><<<dim3(4, std::min(st.ntasks, 65535)), dim3(32, 8), 0, sm>>>(h->S, L, U, h->d_lvl_cblk + st.task0, st.ntasks);
         break;
       case 5:
-        launches += launch_fanin<T>(h, st.lvl, sm) - 1;
+        launches += launch_fanin<T>(h, st.lvl, sm, !serial && getenv("PB200_NO_EARLY_GATHER") == nullptr) - 1;
         break;
       case 6:
         if (FACTO == F_LU)

@@ -66,12 +66,16 @@ __global__ void k_dist_wait(Peers P, unsigned int mask, int idx, unsigned int ep
   }
 }
 
-// owner's panel += sum over contributing ranks of their fan-in buffer (same slab offsets everywhere)
+// owner's panel += sum over the contributing ranks selected by `filter` of their fan-in buffer (same slab offsets
+// everywhere).  The sum is ADDED with an L2 reduction: the panel may be receiving local contributions (and the other
+// half of the gather) at the same time.
 template <class T>
 __global__ void __launch_bounds__(256)
-k_fanin_gather(DevSym S, Peers P, T *L, T *U, const FanTask *__restrict__ tasks, int ntasks) {
+k_fanin_gather(DevSym S, Peers P, T *L, T *U, const FanTask *__restrict__ tasks, int ntasks, unsigned int filter) {
   const int t = find_task(tasks, ntasks, (int)blockIdx.x);
   const FanTask tk = tasks[t];
+  const unsigned int mask = tk.mask & filter;
+  if (mask == 0u) return;
   const int c = tk.cblk;
   const int64_t base = S.poff[c], len = S.poff[c + 1] - S.poff[c];
   const int64_t e0 = (int64_t)(blockIdx.x - tk.tile0) * PB200_FAN_ELEMS;
@@ -79,16 +83,14 @@ k_fanin_gather(DevSym S, Peers P, T *L, T *U, const FanTask *__restrict__ tasks,
   for (int q = 0; q < PB200_FAN_ELEMS / 256; ++q) {
     const int64_t e = e0 + q * 256 + threadIdx.x;
     if (e >= len) break;
-    T accL = L[base + e];
-    T accU = ST<T>::zero();
-    if (U != nullptr) accU = U[base + e];
+    T accL = ST<T>::zero(), accU = ST<T>::zero();
     for (int p = 0; p < P.nranks; ++p) {
-      if (!((tk.mask >> p) & 1u)) continue;
+      if (!((mask >> p) & 1u)) continue;
       accL += reinterpret_cast<const T *>(P.L[p])[base + e];
       if (U != nullptr) accU += reinterpret_cast<const T *>(P.U[p])[base + e];
     }
-    L[base + e] = accL;
-    if (U != nullptr) U[base + e] = accU;
+    atomic_sub(&L[base + e], ST<T>::zero() - accL);
+    if (U != nullptr) atomic_sub(&U[base + e], ST<T>::zero() - accU);
   }
 }
 

@@ -86,6 +86,7 @@ def test_plan_agrees_across_ranks_gloo(tmp_path):
 
 GPU_WORKER = r"""
 import os, sys
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
 import numpy as np, torch, torch.distributed as dist
 from conftest import load_golden, lower_mask, relerr, tol
