@@ -48,6 +48,7 @@ struct pb200_handle_s {
   RowTask *d_trsm = nullptr, *d_slv = nullptr;
   UpdTask *d_upd = nullptr;
   void *dL = nullptr, *dU = nullptr;
+  void *dW = nullptr;   // LDLt / LDLh on the tensor path: L*D beside the panels (same layout), written by the TRSM, read by the updates
   // resident CSC
   int64_t nnz = 0;
   int64_t *d_colptr = nullptr;
@@ -692,6 +693,10 @@ extern "C" int pb200_create_dist(pb200_handle_t **out, const pb200_solver_t *s, 
     if (cudaMalloc(&h->dU, slab) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(U slab) failed"); }
     h->device_bytes += slab;
   }
+  if (h->use_mma && (factotype == PB200_FACT_LDLT || factotype == PB200_FACT_LDLH)) {
+    if (cudaMalloc(&h->dW, slab) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(L*D workspace) failed"); }
+    h->device_bytes += slab;
+  }
   CK(cudaMalloc((void **)&h->d_cnt, 4 * sizeof(unsigned long long)));
   CK(cudaMemset(h->d_cnt, 0, 4 * sizeof(unsigned long long)));
   {
@@ -711,7 +716,7 @@ extern "C" int pb200_destroy(pb200_handle_t *h) {
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(h->d_flags); cudaFree(h->d_dist_err);
   for (void *p : h->allocs) cudaFree(p);
-  cudaFree(h->dL); cudaFree(h->dU); cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals);
+  cudaFree(h->dL); cudaFree(h->dU); cudaFree(h->dW); cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals);
   cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x); cudaFree(h->d_y); cudaFree(h->d_xt);
   for (auto e : h->sched_ev) cudaEventDestroy(e);
   if (h->stream_u) cudaStreamDestroy(h->stream_u);
@@ -933,7 +938,7 @@ static int factorize_tf(pb200_handle_t *h, double crit) {
     }
     const int l = gs.l0;
     int nc = h->lvl_ptr[l + 1] - h->lvl_ptr[l];
-    if (h->nranks > 1) launches += launch_fanin<T>(h, l, h->stream, getenv("PB200_NO_EARLY_GATHER") == nullptr);
+    if (h->nranks > 1) launches += launch_fanin<T>(h, l, h->stream, getenv("PB200_EARLY_GATHER") != nullptr);
     if (nc == 0) continue;
     if (gs.kind == 1) {   // every cblk of the level is small: diag + trsm + updates fused, one warp per cblk
       const int q0 = h->lvl_ptr[l];
@@ -1000,18 +1005,18 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
       } break;
       case 1:
         k_trsm_mma<T, FACTO><<<(unsigned)(st.ntiles * lu), 128, trsm_smem_bytes<T>(st.nbmax), sm>>>(
-            h->S, L, U, h->d_sub + st.task0, st.ntasks);
+            h->S, L, U, (T *)h->dW, h->d_sub + st.task0, st.ntasks);
         break;
       case 2:
         k_gemm_scatter<T, FACTO><<<(unsigned)(st.ntiles * lu), UpdCfg<T>::NT, upd_smem_bytes<T>(), sm>>>(
-            h->M, L, U, h->d_desc + st.t2t0);
+            h->M, L, U, (const T *)h->dW, h->d_desc + st.t2t0);
         break;
       case 3:
         if (FACTO == F_LU)
           k_diag_transpose<T><<<dim3(4, std::min(st.ntasks, 65535)), dim3(32, 8), 0, sm>>>(h->S, L, U, h->d_lvl_cblk + st.task0, st.ntasks);
         break;
       case 5:
-        launches += launch_fanin<T>(h, st.lvl, sm, !serial && getenv("PB200_NO_EARLY_GATHER") == nullptr) - 1;
+        launches += launch_fanin<T>(h, st.lvl, sm, !serial && getenv("PB200_EARLY_GATHER") != nullptr) - 1;   // opt-in: measured neutral at N=4 (r01)
         break;
       case 6:
         if (FACTO == F_LU)

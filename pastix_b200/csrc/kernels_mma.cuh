@@ -129,13 +129,15 @@ __device__ __forceinline__ void cp_async_raw(void *smem_dst, const void *gmem_sr
 
 template <class T, int FACTO>
 __global__ void __launch_bounds__(UpdCfg<T>::NT, UpdCfg<T>::CTAS)
-k_gemm_scatter(DevMap M, T *L, T *U, const TileDesc *__restrict__ descs) {
+k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__restrict__ descs) {
   using C = UpdCfg<T>;
   constexpr bool CX = ST<T>::is_complex;
   constexpr int TM = C::TM, TN = C::TN, KC = C::KC, STG = C::STG, NT = C::NT;
   constexpr int LDA = TM + C::PADA, LDB = TN + C::PADB;
   constexpr int MI = TM / C::WM / 16, NI = TN / C::WN / 8;
-  constexpr bool SCALE = (FACTO == F_LDLT || FACTO == F_LDLH);
+  // LDLt / LDLh: the B operand is read from W, the L*D copy the TRSM kernel leaves beside the panels (the
+  // reference's maxbloktab1, compute_trsm.c:86-114; sopalin_compute.c:356-370) — no per-fragment scaling
+  constexpr bool SYM_LDL = (FACTO == F_LDLT || FACTO == F_LDLH);
   constexpr bool CONJB = (FACTO == F_LDLH || FACTO == F_LLT);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sA = reinterpret_cast<T *>(smem_raw);
@@ -157,8 +159,7 @@ k_gemm_scatter(DevMap M, T *L, T *U, const TileDesc *__restrict__ descs) {
   const int wm0 = (warp / C::WN) * (MI * 16), wn0 = (warp % C::WN) * (NI * 8);
 
   const T *Ap = ((FACTO == F_LU && part == 1) ? U : L) + tk.poff;
-  const T *Bp = ((FACTO == F_LU && part == 0) ? U : L) + tk.poff;
-  const T *Dp = L + tk.poff;
+  const T *Bp = (SYM_LDL ? W : ((FACTO == F_LU && part == 0) ? U : L)) + tk.poff;
   const int nchunks = (tk.k1 - tk.k0 + KC - 1) / KC;
 
   auto load_chunk = [&](int c, int stg) {
@@ -174,8 +175,6 @@ k_gemm_scatter(DevMap M, T *L, T *U, const TileDesc *__restrict__ descs) {
       const bool ok = (j < ncols) && (kb + kk < tk.k1);
       cp_async_elem<sizeof(T)>(b + kk * LDB + j, Bp + (size_t)(ok ? kb + kk : tk.k0) * ld + n0 + (ok ? j : 0), ok);
     }
-    if (SCALE && tid < KC)
-      sD[stg * KC + tid] = (kb + tid < tk.k1) ? Dp[(size_t)(kb + tid) * (ld + 1)] : ST<T>::zero();
   };
 
   // ---- scatter maps of this tile: static tables copied asynchronously into shared memory, in the same
@@ -224,7 +223,7 @@ k_gemm_scatter(DevMap M, T *L, T *U, const TileDesc *__restrict__ descs) {
     if (c + STG - 1 < nchunks) load_chunk(c + STG - 1, (c + STG - 1) % STG);
     cp_async_commit();
     const int stg = c % STG;
-    const T *a = sA + stg * KC * LDA, *b = sB + stg * KC * LDB, *d = sD + stg * KC;
+    const T *a = sA + stg * KC * LDA, *b = sB + stg * KC * LDB;
 #pragma unroll
     for (int ks = 0; ks < KC; ks += 8) {
       FragA<CX> fa[MI];
@@ -232,7 +231,7 @@ k_gemm_scatter(DevMap M, T *L, T *U, const TileDesc *__restrict__ descs) {
 #pragma unroll
       for (int x = 0; x < MI; ++x) load_frag_a<T>(fa[x], a, LDA, wm0 + x * 16, ks, lane);
 #pragma unroll
-      for (int y = 0; y < NI; ++y) load_frag_b<T, CONJB, SCALE>(fb[y], b, LDB, wn0 + y * 8, ks, lane, d);
+      for (int y = 0; y < NI; ++y) load_frag_b<T, CONJB, false>(fb[y], b, LDB, wn0 + y * 8, ks, lane, nullptr);
 #pragma unroll
       for (int x = 0; x < MI; ++x)
 #pragma unroll
@@ -328,7 +327,7 @@ inline size_t trsm_smem_bytes(int nb) {
 
 template <class T, int FACTO>
 __global__ void __launch_bounds__(128)
-k_trsm_mma(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, int ntasks) {
+k_trsm_mma(DevSym S, T *L, T *U, T *W, const SubTask *__restrict__ tasks, int ntasks) {
   constexpr bool CX = ST<T>::is_complex;
   constexpr int TM = PB200_TRSM_TM, LDX = TM + SubCfg<T>::PADX;
   constexpr bool UNIT_SYM = (FACTO == F_LDLT || FACTO == F_LDLH);
@@ -459,7 +458,10 @@ k_trsm_mma(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, int ntasks) 
     if (i < mrows)
       for (int kk = tid / TM; kk < nb; kk += 128 / TM) {
         T v = Xs[(size_t)kk * LDX + i];
-        if (UNIT_SYM) v = v / Dp[(size_t)kk * (ld + 1)];
+        if (UNIT_SYM) {
+          W[S.poff[k] + (size_t)(c0 + kk) * ld + r_base + i] = v;   // L*D, the B operand of the updates
+          v = v / Dp[(size_t)kk * (ld + 1)];
+        }
         Xp[(size_t)(c0 + kk) * ld + r_base + i] = v;
       }
   }

@@ -9,6 +9,9 @@ for v, name in enumerate(["DFMA", "DMMA m8n8k4", "DMMA m16n8k8", "DMMA m16n8k16"
     print(f"{name}: {L.pb200_probe_fp64_gflops(0, v):.0f} GFLOP/s")
 for w in (4, 8, 12, 16, 32):
     print(f"DMMA m16n8k8, {w} warps/SM: {L.pb200_probe_fp64_gflops(0, 100 + w):.0f} GFLOP/s")
+for c in (1, 2, 3, 4, 6, 8):
+    print(f"gemm main loop (smem fragments, 32x32 warp tiles), {c} CTAs x 4 warps per SM: no barrier {L.pb200_probe_fp64_gflops(0, 200 + c):.0f}, "
+          f"barrier per 16-k chunk {L.pb200_probe_fp64_gflops(0, 300 + c):.0f} GFLOP/s")
 for dt, nm in ((torch.float64, "DGEMM"), (torch.float32, "SGEMM"), (torch.complex128, "ZGEMM")):
     n = 8192 if dt != torch.complex128 else 4096
     torch.backends.cuda.matmul.allow_tf32 = False
