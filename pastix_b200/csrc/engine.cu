@@ -15,6 +15,7 @@
 #include "../../include/pastix_b200.h"
 #include "kernels_factor.cuh"
 #include "kernels_solve.cuh"
+#include "kernels_solve_dag.cuh"
 #include "kernels_mma.cuh"
 #include "kernels_dist.cuh"
 #include "kernels_small.cuh"
@@ -74,6 +75,11 @@ struct pb200_handle_s {
   int64_t *d_invoff = nullptr; int64_t inv_elems = 0; int nsubpanels = 0;
   void *d_inv = nullptr, *d_inv_up = nullptr;   // inverted diagonal triangles (LU: L and U^T)
   unsigned int *d_slv_cnt = nullptr;
+  // persistent counter-ordered sweeps (kernels_solve_dag.cuh)
+  bool dag_ok = false; int dag_tiles = 0, dag_nbs = 0;
+  DagTick *d_dag_ticks = nullptr; int *d_dag_tgt = nullptr;
+  unsigned int *d_dag_need = nullptr, *d_dag_state = nullptr;   // state: arrived[nsp] ready[nsp] done[nsp] cnt[nsp] ticket[2] err[1]
+  unsigned int *h_dag_err = nullptr;                             // pinned
   void *d_y = nullptr; size_t y_bytes = 0;
   bool inv_ready = false;
   std::vector<int64_t> h_rmbase;           // per cblk: first entry of its off-diagonal rows in d_rowglob
@@ -139,6 +145,83 @@ static size_t elem_size(int flt) {
     case PB200_COMPLEXDOUBLE: return 16;
   }
   return 0;
+}
+
+// ------------------------------------------------------------------ persistent up_down sweeps (kernels_solve_dag.cuh)
+// For every tile (sub-panel x 128 panel rows, ticket order = ascending (level, round)) the distinct sub-panels
+// that own its rows: the counters they bump in the down step (the reference's UPDOWN_CTRBCNT bookkeeping,
+// updo.c:631-793) and the flags they wait on in the up step (flagtab, updo_sendrecv.c:496-639).
+static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks) {
+  h->dag_ok = false;
+  if (getenv("PB200_SOLVE_LEVELS") != nullptr) return PB200_SUCCESS;   // A/B switch: keep the launch-per-level sweeps
+  for (const auto &gs : h->sgsteps) if (gs.kind != 0) return PB200_SUCCESS;   // small-cblk schedules (ILU) keep their fused path
+  const int NB = (h->flt == PB200_COMPLEXDOUBLE) ? SlvCfg<cdouble>::NB : SlvCfg<double>::NB;
+  const int64_t C = h->cblknbr;
+  const int nsp = (int)tasks.size();
+  // (cblk, round) -> sub-panel id, and the sub-panel width of each cblk
+  std::vector<int> sp_ptr(C + 1, 0), sw(C, 1);
+  for (int64_t c = 0; c < C; ++c) {
+    const int w = h->h_width[c], nsub = std::max(1, (w + NB - 1) / NB);
+    sw[c] = (w + nsub - 1) / nsub; sp_ptr[c + 1] = sp_ptr[c] + nsub;
+  }
+  if (sp_ptr[C] != nsp) return PB200_SUCCESS;
+  std::vector<int> spid(nsp, -1);
+  int nbs = 1;
+  long long nticks = nsp;
+  for (int i = 0; i < nsp; ++i) {
+    const SlvTask &tk = tasks[i];
+    spid[sp_ptr[tk.cblk] + tk.c0 / sw[tk.cblk]] = i;
+    nbs = std::max(nbs, tk.c1 - tk.c0);
+    nticks += (tk.ld - tk.c1 + PB200_DAG_ROWS - 1) / PB200_DAG_ROWS;
+  }
+  if (nticks >= (1LL << 30)) return PB200_SUCCESS;
+  std::vector<DagTick> ticks; ticks.reserve((size_t)nticks);
+  std::vector<int> tgt; tgt.reserve((size_t)nticks * 3);
+  std::vector<unsigned int> need(nsp, 0);
+  std::vector<long long> stamp(nsp, -1);
+  for (int i = 0; i < nsp; ++i) {
+    const SlvTask &tk = tasks[i];
+    const int c = tk.cblk, w = tk.w, ld = tk.ld, nb = tk.c1 - tk.c0;
+    const int nt = (ld - tk.c1 + PB200_DAG_ROWS - 1) / PB200_DAG_ROWS;
+    DagTick d{};
+    d.src = tk.invoff; d.aux = tk.poff + (int64_t)tk.c0 * (ld + 1); d.ld = ld; d.nb = nb; d.mrows = -1; d.sp = tk.sp;
+    d.xcol = tk.fcol + tk.c0; d.nsib = nt;
+    ticks.push_back(d);
+    int b = h->h_fblok[c] + 1;                    // first off-diagonal blok
+    const int be = h->h_fblok[c + 1];
+    for (int t = 0; t < nt; ++t) {
+      const long long g = (long long)ticks.size();
+      const int m0 = tk.c1 + t * PB200_DAG_ROWS, m1 = std::min(ld, m0 + PB200_DAG_ROWS);
+      DagTick k{};
+      k.src = tk.poff + (int64_t)tk.c0 * ld + m0; k.aux = tk.rgbase + m0; k.ld = ld; k.nb = nb; k.mrows = m1 - m0; k.sp = tk.sp;
+      k.xcol = tk.fcol + tk.c0; k.grow0 = tk.fcol + m0; k.wrem = w - m0; k.tptr = (int)tgt.size();
+      auto add = [&](int s) { if (stamp[s] != g) { stamp[s] = g; tgt.push_back(s); ++need[s]; } };
+      // rows still inside the diagonal block: later sub-panels of the same cblk
+      for (int m = m0; m < std::min(m1, w); m = (m / sw[c] + 1) * sw[c]) add(spid[sp_ptr[c] + m / sw[c]]);
+      // off-diagonal rows: the bloks crossing [m0, m1)
+      while (b < be && h->h_coefind[b] + h->h_nrow[b] <= m0) ++b;
+      for (int bb = b; bb < be && h->h_coefind[bb] < m1; ++bb) {
+        const int fc = h->h_fcblk[bb];
+        const int lo = std::max(m0, h->h_coefind[bb]), hi = std::min(m1, h->h_coefind[bb] + h->h_nrow[bb]);   // panel rows [lo, hi)
+        const int o0 = h->h_frow[bb] + (lo - h->h_coefind[bb]) - h->h_fcol[fc], o1 = h->h_frow[bb] + (hi - 1 - h->h_coefind[bb]) - h->h_fcol[fc];
+        for (int r = o0 / sw[fc]; r <= o1 / sw[fc]; ++r) add(spid[sp_ptr[fc] + r]);
+      }
+      k.ntgt = (int)tgt.size() - k.tptr;
+      ticks.push_back(k);
+    }
+  }
+  if (tgt.size() >= (size_t)INT32_MAX) return PB200_SUCCESS;
+  for (int s : tgt) if (s < 0) return fail(PB200_ERR_STRUCT, "up_down dependency table: row without an owning sub-panel");
+  { int rc = upload(h, ticks, &h->d_dag_ticks); if (rc) return rc; }
+  { int rc = upload(h, tgt, &h->d_dag_tgt); if (rc) return rc; }
+  { int rc = upload(h, need, &h->d_dag_need); if (rc) return rc; }
+  const size_t sb = ((size_t)4 * nsp + 4) * sizeof(unsigned int);
+  CK(cudaMalloc((void **)&h->d_dag_state, sb));
+  h->allocs.push_back(h->d_dag_state); h->device_bytes += sb;
+  CK(cudaHostAlloc((void **)&h->h_dag_err, sizeof(unsigned int), cudaHostAllocDefault));
+  *h->h_dag_err = 0;
+  h->dag_tiles = (int)ticks.size(); h->dag_nbs = nbs; h->dag_ok = true;
+  return PB200_SUCCESS;
 }
 
 // ------------------------------------------------------------------ schedule of the up_down sweeps
@@ -210,6 +293,7 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
   }
   { int rc = upload(h, tasks, &h->d_slvtask); if (rc) return rc; }
   { int rc = upload(h, t2t, &h->d_slv_t2t); if (rc) return rc; }
+  { int rc = build_solve_dag(h, tasks); if (rc) return rc; }
   { int rc = upload(h, invoff, &h->d_invoff); if (rc) return rc; }
   size_t ib = (size_t)std::max<int64_t>(inv_elems, 1) * h->esize;
   if (cudaMalloc(&h->d_inv, ib) != cudaSuccess) return fail(PB200_ERR_NOMEM, "cudaMalloc(inverse triangles) failed");
@@ -716,6 +800,7 @@ extern "C" int pb200_destroy(pb200_handle_t *h) {
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(h->d_flags); cudaFree(h->d_dist_err);
   for (void *p : h->allocs) cudaFree(p);
+  if (h->h_dag_err) cudaFreeHost(h->h_dag_err);
   cudaFree(h->dL); cudaFree(h->dU); cudaFree(h->dW); cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals);
   cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x); cudaFree(h->d_y); cudaFree(h->d_xt);
   for (auto e : h->sched_ev) cudaEventDestroy(e);
@@ -1215,6 +1300,38 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
     k_rhs_transpose<T><<<dim3((n + 31) / 32, (nrhs + 31) / 32), dim3(32, 8), 0, h->stream>>>(x, xs, n, nrhs, ldx, 1);
     ++launches;
   }
+  if (h->dag_ok) {
+    // one persistent launch per sweep, ordered by device-side contribution counters (kernels_solve_dag.cuh)
+    static bool dag_attr_done[4][4] = {};
+    const size_t smem = DagSmem<T>::bytes(h->dag_nbs), belems = DagSmem<T>::buf_elems(h->dag_nbs);
+    if (!dag_attr_done[h->flt][FACTO]) {
+      CK(cudaFuncSetAttribute(k_fwd_dag<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DagSmem<T>::bytes(SlvCfg<T>::NB)));
+      CK(cudaFuncSetAttribute(k_bwd_dag<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DagSmem<T>::bytes(SlvCfg<T>::NB)));
+      CK(cudaFuncSetAttribute(k_fwd_dag<T, FACTO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CK(cudaFuncSetAttribute(k_bwd_dag<T, FACTO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      dag_attr_done[h->flt][FACTO] = true;
+    }
+    int occ_f = 0, occ_b = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_dag<T, FACTO>, PB200_DAG_NT, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_dag<T, FACTO>, PB200_DAG_NT, smem));
+    if (occ_f < 1 || occ_b < 1) return fail(PB200_ERR_CUDA, "persistent up_down kernels do not fit on this device");
+    const size_t nsp = (size_t)h->nsubpanels;
+    DagArgs A;
+    A.ticks = h->d_dag_ticks; A.tgt = h->d_dag_tgt; A.need = h->d_dag_need;
+    A.arrived = h->d_dag_state; A.ready = A.arrived + nsp; A.done = A.ready + nsp; A.cnt = A.done + nsp;
+    A.ticket = A.cnt + nsp; A.err = A.ticket + 2; A.rowglob = h->d_rowglob;
+    A.G = h->dag_tiles; A.nbs = h->dag_nbs;
+    CK(cudaMemsetAsync(h->d_dag_state, 0, (4 * nsp + 4) * sizeof(unsigned int), h->stream));
+    const unsigned gf = (unsigned)std::min<long long>(A.G, (long long)h->sm_count * occ_f);
+    const unsigned gb = (unsigned)std::min<long long>(A.G, (long long)h->sm_count * occ_b);
+    k_fwd_dag<T, FACTO><<<gf, PB200_DAG_NT, smem, h->stream>>>(L, inv, x, y, ldx, nrhs, A, belems);
+    k_bwd_dag<T, FACTO><<<gb, PB200_DAG_NT, smem, h->stream>>>(Mup, inv_up, x, y, ldx, nrhs, A, belems);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_dag_err, A.err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    if (getenv("PB200_DAG_VERBOSE")) fprintf(stderr, "[pb200 dag] tickets %d, widest sub-panel %d, smem %zu B, CTAs/SM %d/%d\n", A.G, A.nbs, smem, occ_f, occ_b);
+    h->last_launches = 2;
+    return PB200_SUCCESS;
+  }
   for (int dir = 0; dir < 2; ++dir) {
     const T *M = dir == 0 ? L : Mup;
     for (size_t gi = 0; gi < h->sgsteps.size(); ++gi) {
@@ -1296,6 +1413,10 @@ extern "C" int pb200_solve_device(pb200_handle_t *h, void *x_dev, int64_t ldx, i
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   if (seconds) *seconds = ms * 1e-3;
+  if (h->dag_ok && h->h_dag_err && *h->h_dag_err) {
+    *h->h_dag_err = 0;
+    return fail(PB200_ERR_CUDA, "up_down: a contribution counter never reached its target (dependency table / device fault)");
+  }
   return PB200_SUCCESS;
 }
 
