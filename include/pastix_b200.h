@@ -13,6 +13,7 @@
  * Reference interfaces replaced (paths relative to /root/reference/src):
  *   pb200_create        <- sopalin_init / sopalin_init_smp + CoefMatrix_Allocate
  *                          (sopalin/src/sopalin_init.c:99,865; coefinit.c:104)
+ *   pb200_csc_build     <- CscOrdistrib (sopalin/src/csc_intern_build.c:352-570)
  *   pb200_assemble      <- CoefMatrix_Init + Csc2solv_cblk
  *                          (sopalin/src/coefinit.c:237; csc_intern_solve.c:65-125)
  *   pb200_norm1         <- CscNorm1 (sopalin/src/csc_intern_compute.c:120-176),
@@ -145,6 +146,29 @@ int pb200_assemble(pb200_handle_t *h, const int64_t *colptr, const int64_t *rows
                    const void *values, const void *tvalues);
 /* Re-run the device-side zero + scatter from the CSC already resident in HBM. */
 int pb200_reassemble(pb200_handle_t *h);
+
+/* ---- internal CSC built on the device (replaces CscOrdistrib, sopalin/src/csc_intern_build.c:352-570).
+ * From the user's CSC exactly as pastix() receives it — Fortran numbering, colptr[n+1], rows[nnz], values[nnz],
+ * lower triangle for type 'S'/'H' — and Order.permtab (0-based new index of every unknown) it builds the matrix
+ * in the new numbering, symmetrised for 'S'/'H' (mirror entries conjugated for 'H'), every column sorted by row:
+ * the reference's CscMatrix flattened (CSC_COL / CSC_ROWTAB / CSC_VALTAB, blend/src/csc.h).
+ *   type  : Type[1] of the reference call: 'S', 'H' or 'U'
+ *   trans : 0 none; 1 values of A^T on the pattern of A ('U' only: sopar->transcsc); 2 alias of the values
+ *           (forcetrans: LU on a symmetric matrix)
+ * The result stays in HBM (pb200_assemble_csc consumes it without another upload); pb200_csc_fetch copies it to
+ * host arrays of *nnz_out entries (0-based colptr[n+1]; tvalues may be NULL) for the reference's host-side users
+ * of the internal CSC (CscNorm1, the refinement SpMV).  One dof per node only. */
+typedef struct pb200_csc_s pb200_csc_t;
+int pb200_csc_create(pb200_csc_t **out, int flttype, int device);
+int pb200_csc_destroy(pb200_csc_t *c);
+int pb200_csc_build(pb200_csc_t *c, char type, int64_t n, const int64_t *colptr, const int64_t *rows,
+                    const void *values, const int64_t *permtab, int trans, int64_t *nnz_out);
+int pb200_csc_fetch(pb200_csc_t *c, int64_t *colptr, int64_t *rows, void *values, void *tvalues);
+/* CscNorm1 (sopalin/src/csc_intern_compute.c:120-176) of the CSC in HBM: max_j sum_i |a_ij|, each column summed in
+ * storage order like the reference's loop (identical result for real types; complex |.| is the device hypot). */
+int pb200_csc_norm1(pb200_csc_t *c, double *norm);
+/* pb200_assemble from the CSC that pb200_csc_build left in HBM (same device, same order and precision). */
+int pb200_assemble_csc(pb200_handle_t *h, const pb200_csc_t *c);
 
 /* Numeric factorization of the assembled panels.
  *   critere  : static-pivot threshold (|pivot| < critere => pivot := critere)

@@ -15,6 +15,7 @@ SYMBOLS = [
     "pb200_solve_device", "pb200_get_coeftab", "pb200_set_coeftab", "pb200_mark_factorized",
     "pb200_last_launches", "pb200_probe_fp64_gflops", "pb200_set_profile", "pb200_get_profile",
     "pb200_create_dist", "pb200_ipc_size", "pb200_ipc_export", "pb200_ipc_attach", "pb200_dist_barrier", "pb200_dist_plan",
+    "pb200_csc_create", "pb200_csc_destroy", "pb200_csc_build", "pb200_csc_fetch", "pb200_csc_norm1", "pb200_assemble_csc",
 ]
 
 
@@ -57,6 +58,13 @@ def lib() -> C.CDLL:
     L.pb200_norm1.restype = C.c_double
     L.pb200_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pb200_reassemble.argtypes = [C.c_void_p]
+    L.pb200_csc_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
+    L.pb200_csc_destroy.argtypes = [C.c_void_p]
+    L.pb200_csc_build.argtypes = [C.c_void_p, C.c_char, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.POINTER(C.c_int64)]
+    L.pb200_csc_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pb200_assemble_csc.argtypes = [C.c_void_p, C.c_void_p]
+    L.pb200_csc_norm1.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.pb200_factorize.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.pb200_inertia.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.pb200_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_double)]

@@ -20,6 +20,7 @@
 #include "kernels_dist.cuh"
 #include "kernels_small.cuh"
 #include "dist_plan.h"
+#include "csc_build.h"
 
 using namespace pb200;
 
@@ -125,6 +126,7 @@ struct pb200_handle_s {
 };
 
 extern "C" const char *pb200_last_error(void) { return g_err.c_str(); }
+extern "C" void pb200_set_error(const char *msg) { g_err = msg ? msg : ""; }   // csc_build.cu reports through the same channel
 extern "C" const char *pb200_version(void) { return "pastix_b200 0.1 (sm_100a)"; }
 
 template <class V>
@@ -989,6 +991,31 @@ extern "C" int pb200_assemble(pb200_handle_t *h, const int64_t *colptr, const in
   CK(cudaMemcpyAsync(h->d_vals, values, (size_t)nnz * h->esize, cudaMemcpyHostToDevice, h->stream));
   if (h->d_tvals) CK(cudaMemcpyAsync(h->d_tvals, tvalues, (size_t)nnz * h->esize, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return pb200_reassemble(h);
+}
+
+// Assembly from an internal CSC that pb200_csc_build left in HBM (csc_build.cu): no host copy, no second upload.
+extern "C" int pb200_assemble_csc(pb200_handle_t *h, const pb200_csc_t *c) {
+  if (!h || !c) return fail(PB200_ERR_BADARG, "null argument");
+  if (!c->valid) return fail(PB200_ERR_STATE, "no internal CSC built");
+  if (c->flt != h->flt || c->n != h->n) return fail(PB200_ERR_BADARG, "internal CSC does not match this SolverMatrix (precision / order)");
+  if (c->device != h->device) return fail(PB200_ERR_BADARG, "internal CSC lives on another device");
+  if (h->facto == PB200_FACT_LU && !c->has_t) return fail(PB200_ERR_BADARG, "LU needs the transposed values");
+  CK(cudaSetDevice(h->device));
+  const int64_t nnz = c->nnz;
+  if (nnz != h->nnz || !h->d_colptr) {
+    cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals); cudaFree(h->d_tvals);
+    h->d_colptr = nullptr; h->d_rows = nullptr; h->d_vals = nullptr; h->d_tvals = nullptr;
+    CK(cudaMalloc((void **)&h->d_colptr, (size_t)(h->n + 1) * sizeof(int64_t)));
+    CK(cudaMalloc((void **)&h->d_rows, (size_t)std::max<int64_t>(nnz, 1) * sizeof(int)));
+    CK(cudaMalloc(&h->d_vals, (size_t)std::max<int64_t>(nnz, 1) * h->esize));
+    if (h->facto == PB200_FACT_LU) CK(cudaMalloc(&h->d_tvals, (size_t)std::max<int64_t>(nnz, 1) * h->esize));
+    h->nnz = nnz;
+  }
+  CK(cudaMemcpyAsync(h->d_colptr, c->d_colptr, (size_t)(h->n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_rows, c->d_rows, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_vals, c->d_vals, (size_t)nnz * h->esize, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->d_tvals) CK(cudaMemcpyAsync(h->d_tvals, c->d_tvals, (size_t)nnz * h->esize, cudaMemcpyDeviceToDevice, h->stream));
   return pb200_reassemble(h);
 }
 

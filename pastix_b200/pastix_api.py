@@ -183,6 +183,37 @@ class Pastix(PastixLib):
         d = dict(cblknbr=cb, bloknbr=bl); d.update(a); d.update(b)
         return d
 
+    def csc(self) -> dict:
+        """Internal CSC after NUMFACT (CscOrdistrib — built on the device by shim_csc.c unless PB200_HOST_CSC=1):
+        0-based, new numbering, rows sorted in every column."""
+        s = np.zeros(4, dtype=np.int64)
+        self.lib.pb200_shim_csc_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.pb200_shim_csc_sizes(self.pd, s.ctypes.data)
+        if not s[3]:
+            raise RuntimeError("internal CSC not filled (run numfact first)")
+        n, nnz = int(s[0]), int(s[1])
+        colptr = np.zeros(n + 1, dtype=np.int64); rows = np.zeros(nnz, dtype=np.int64)
+        vals = np.zeros(nnz, dtype=self.dtype); tv = np.zeros(nnz, dtype=self.dtype) if s[2] else None
+        self.lib.pb200_shim_csc_get.argtypes = [C.c_void_p] * 5
+        self.lib.pb200_shim_csc_get.restype = C.c_int
+        t = self.lib.pb200_shim_csc_get(self.pd, colptr.ctypes.data, rows.ctypes.data, vals.ctypes.data,
+                                        tv.ctypes.data if tv is not None else None)
+        return dict(colptr=colptr, rows=rows, vals=vals, tvals=tv, type=chr(t))
+
+    def csc_device(self, want_t: bool) -> dict:
+        """The internal CSC as it sits in HBM after the device-side CscOrdistrib (what the assembly kernel read)."""
+        host = self.csc()
+        n, nnz = len(host["colptr"]) - 1, len(host["rows"])
+        colptr = np.zeros(n + 1, dtype=np.int64); rows = np.zeros(nnz, dtype=np.int64)
+        vals = np.zeros(nnz, dtype=self.dtype); tv = np.zeros(nnz, dtype=self.dtype) if want_t else None
+        f = self.lib.pb200_shim_csc_device_get
+        f.argtypes = [C.c_void_p] * 5
+        f.restype = C.c_int64
+        got = f(self.pd, colptr.ctypes.data, rows.ctypes.data, vals.ctypes.data, tv.ctypes.data if want_t else None)
+        if got != nnz:
+            raise RuntimeError(f"device CSC not available / size mismatch ({got} vs {nnz})")
+        return dict(colptr=colptr, rows=rows, vals=vals, tvals=tv)
+
     def sopalin(self):
         """The GPU numeric phase behind this pastix_data as a `Sopalin` (borrowed handle)."""
         from .sopalin import Sopalin

@@ -4,6 +4,8 @@
 # $PASTIX_REFERENCE/src — nothing is copied into this repo) with ONE object replaced:
 # sopalin3d.o (x4 factorization variants) -> pastix_b200/shim/sopalin_b200_shim.c, which routes
 # API_TASK_NUMFACT / API_TASK_SOLVE to the CUDA layer libpastix_b200.so.
+# and ONE symbol: CscOrdistrib (csc_intern_build.c:352) -> pastix_b200/shim/shim_csc.c (internal CSC built on the
+# device); the reference's routine stays linked as CscOrdistrib_hostref (objcopy --redefine-sym).
 # Recipe = SURVEY.md §8c: -DFORCE_NOMPI, no Scotch/METIS (API_ORDER_PERSONAL + KASS), 64-bit
 # PASTIX_INT, -DMULT_SMX (multi-RHS), Fortran-ABI BLAS (only the reference's host-side refinement
 # and analysis use it) = the OpenBLAS shipped inside the opencv_python_headless wheel.
@@ -37,7 +39,7 @@ for P in $PRECS; do
     c) TDEF="-DTYPE_COMPLEX";;
   esac
   LIB="$OUT/libpastix_dropin_$P.so"
-  if [ -f "$LIB" ] && [ "$LIB" -nt "$HERE/sopalin_b200_shim.c" ] && [ "$LIB" -nt "$HERE/shim_hooks.c" ] && [ "$LIB" -nt "$0" ] && [ "$LIB" -nt "$ROOT/include/pastix_b200.h" ]; then
+  if [ -f "$LIB" ] && [ "$LIB" -nt "$HERE/sopalin_b200_shim.c" ] && [ "$LIB" -nt "$HERE/shim_hooks.c" ] && [ "$LIB" -nt "$HERE/shim_csc.c" ] && [ "$LIB" -nt "$HERE/shim_table.h" ] && [ "$LIB" -nt "$0" ] && [ "$LIB" -nt "$ROOT/include/pastix_b200.h" ]; then
     echo "[$P] up to date"; continue
   fi
   DEF="-DFORCE_NOMPI $TDEF -DINTSIZE64 -DMULT_SMX -DX_ARCHi686_pc_linux -DDOF_CONSTANT -DFORCE_NO_CUDA -DVERSION=\"pastix_b200\""
@@ -64,8 +66,14 @@ for P in $PRECS; do
   add "$HERE/sopalin_b200_shim.c" x_shim_sy -DNOEXTRADEF_SY
   add "$HERE/sopalin_b200_shim.c" x_shim_he -DHERMITIAN
   add "$HERE/shim_hooks.c" x_shim_hooks -DCHOL_SOPALIN
+  add "$HERE/shim_csc.c" x_shim_csc -DCHOL_SOPALIN
   xargs -P "$(nproc)" -I{} sh -c '{} 2>>'"$OBJ"'/err.log || echo "FAIL: {}"' < "$JOBS" | tee "$OBJ/fail.log"
   if [ -s "$OBJ/fail.log" ]; then echo "[$P] compile failures (see $OBJ/err.log)"; tail -20 "$OBJ/err.log"; exit 1; fi
+  # the reference's CscOrdistrib stays linked under another name (multi-dof matrices, PB200_HOST_CSC=1); ours takes its place
+  SYM=$(nm "$OBJ/p_csc_intern_build.o" | awk '$2=="T" && $3 ~ /CscOrdistrib$/ {print $3}' | head -1)
+  [ -n "$SYM" ] || { echo "[$P] CscOrdistrib not found in the reference object"; exit 1; }
+  objcopy --redefine-sym "$SYM=CscOrdistrib_hostref" "$OBJ/p_csc_intern_build.o" || exit 1
+  if [ "$SYM" != "CscOrdistrib" ]; then objcopy --redefine-sym "CscOrdistrib=$SYM" "$OBJ/x_shim_csc.o" || exit 1; fi
   gcc -shared -o "$LIB" "$OBJ"/*.o -L"$OUT" -lpastix_b200 "$BLASLIB" -lpthread -lm \
       -Wl,--disable-new-dtags -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$BLASDIR" -Wl,-rpath-link,"$BLASDIR" -Wl,--no-undefined 2> "$OBJ/link.log" \
       || { echo "[$P] link failed"; head -30 "$OBJ/link.log"; exit 1; }

@@ -102,7 +102,47 @@ void pb200_shim_release_data(void *pastix_data)
   pb200_shim_entry_t *e = hook_find(&((pastix_data_t *)pastix_data)->solvmatr);
   if (e == NULL) return;
   if (e->h) pb200_destroy(e->h);
+  if (e->csc) pb200_csc_destroy(e->csc);
   pthread_mutex_lock(&shim_mutex);
-  e->m = NULL; e->h = NULL; e->factorized = 0;
+  memset(e, 0, sizeof(*e));
   pthread_mutex_unlock(&shim_mutex);
+}
+
+/* internal CSC of this pastix_data_t (CscMatrix, blend/src/csc.h) flattened: sizes = {ncol, nnz, has transcsc, filled};
+ * colptr 0-based with ncol+1 entries.  Used by the parity tests of the device-side CscOrdistrib (shim_csc.c). */
+void pb200_shim_csc_sizes(void *pastix_data, int64_t *out)
+{
+  pastix_data_t *pd = (pastix_data_t *)pastix_data;
+  CscMatrix *c = &pd->cscmtx;
+  PASTIX_INT i, ncol = 0, nnz = 0;
+  out[0] = out[1] = out[2] = out[3] = 0;
+  if (!pd->malcsc || CSC_FTAB(c) == NULL) return;
+  for (i = 0; i < CSC_FNBR(c); i++) { ncol += CSC_COLNBR(c, i); nnz = CSC_COL(c, i, CSC_COLNBR(c, i)); }
+  out[0] = ncol; out[1] = nnz; out[2] = (pd->sopar.transcsc != NULL); out[3] = 1;
+}
+int pb200_shim_csc_get(void *pastix_data, int64_t *colptr, int64_t *rows, void *vals, void *tvals)
+{
+  pastix_data_t *pd = (pastix_data_t *)pastix_data;
+  CscMatrix *c = &pd->cscmtx;
+  PASTIX_INT i, j, col = 0, nnz = 0;
+  for (i = 0; i < CSC_FNBR(c); i++) {
+    for (j = 0; j < CSC_COLNBR(c, i); j++) colptr[col++] = CSC_COL(c, i, j);
+    nnz = CSC_COL(c, i, CSC_COLNBR(c, i));
+  }
+  colptr[col] = nnz;
+  for (i = 0; i < nnz; i++) rows[i] = CSC_ROW(c, i);
+  memcpy(vals, CSC_VALTAB(c), (size_t)nnz * sizeof(PASTIX_FLOAT));
+  if (tvals && pd->sopar.transcsc) memcpy(tvals, pd->sopar.transcsc, (size_t)nnz * sizeof(PASTIX_FLOAT));
+  return (int)c->type;
+}
+
+/* the internal CSC as it sits in HBM (what the device assembly read): same layout as pb200_shim_csc_get;
+ * returns nnz, or -1 when CscOrdistrib did not run on the device for this pastix_data_t */
+int64_t pb200_shim_csc_device_get(void *pastix_data, int64_t *colptr, int64_t *rows, void *vals, void *tvals)
+{
+  pastix_data_t *pd = (pastix_data_t *)pastix_data;
+  pb200_shim_entry_t *e = hook_find(&pd->solvmatr);
+  if (e == NULL || e->csc == NULL) return -1;
+  if (pb200_csc_fetch(e->csc, colptr, rows, vals, tvals) != PB200_SUCCESS) return -1;
+  return colptr[pd->n2 > 0 ? pd->n2 : pd->n];
 }

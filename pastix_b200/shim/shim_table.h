@@ -10,6 +10,8 @@ typedef struct pb200_shim_entry_s {
   int                 facto;
   int                 factorized;
   double              critere;
+  pb200_csc_t        *csc;        /* internal CSC built on the device by CscOrdistrib (shim_csc.c) */
+  int                 csc_fresh;  /* set by CscOrdistrib, consumed by the next numeric factorization */
 } pb200_shim_entry_t;
 #define PB200_SHIM_MAX 64
 #define shim_table  PASTIX_PREFIX_F(pb200_shim_table)

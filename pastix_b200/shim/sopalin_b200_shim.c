@@ -114,7 +114,7 @@ static pb200_shim_entry_t *shim_find(const SolverMatrix *m, int create)
     if (shim_table[i].m == m) { e = &shim_table[i]; break; }
   if (e == NULL && create)
     for (i = 0; i < PB200_SHIM_MAX; i++)
-      if (shim_table[i].m == NULL) { e = &shim_table[i]; e->m = m; e->h = NULL; e->factorized = 0; break; }
+      if (shim_table[i].m == NULL) { e = &shim_table[i]; memset(e, 0, sizeof(*e)); e->m = m; break; }
   pthread_mutex_unlock(&shim_mutex);
   return e;
 }
@@ -126,8 +126,9 @@ void pb200_shim_release(const SolverMatrix *m)
   pb200_shim_entry_t *e = shim_find(m, 0);
   if (e == NULL) return;
   if (e->h) pb200_destroy(e->h);
+  if (e->csc) pb200_csc_destroy(e->csc);
   pthread_mutex_lock(&shim_mutex);
-  e->m = NULL; e->h = NULL; e->factorized = 0;
+  memset(e, 0, sizeof(*e));
   pthread_mutex_unlock(&shim_mutex);
 }
 
@@ -176,13 +177,21 @@ static void shim_assemble(pb200_handle_t *h, SolverMatrix *datacode, SopalinPara
 }
 
 /* static-pivot threshold, init_struct_sopalin (sopalin3d.c:586-606) */
-static double shim_critere(SolverMatrix *datacode, SopalinParam *sopar)
+static double shim_critere(SolverMatrix *datacode, SopalinParam *sopar, pb200_csc_t *devcsc)
 {
   double crit = sopar->espilondiag;
   if (crit < 0.0) return -crit;
   if (sopar->usenocsc == 1) return crit;
   if (sopar->fakefact == 1)
     return (double)(UPDOWN_GNODENBR * UPDOWN_GNODENBR + UPDOWN_GNODENBR) * sqrt(sopar->espilondiag);
+#ifndef TYPE_COMPLEX
+  if (devcsc != NULL) {                        /* same sums in the same order on the CSC already in HBM: identical for real types */
+    double nrm = 0.0;
+    if (pb200_csc_norm1(devcsc, &nrm) != PB200_SUCCESS) shim_fatal("pb200_csc_norm1");
+    return nrm * sqrt(sopar->espilondiag);
+  }
+#endif
+  (void)devcsc;
   return CscNorm1(sopar->cscmtx, sopar->pastix_comm) * sqrt(sopar->espilondiag);
 }
 
@@ -212,7 +221,7 @@ static void shim_mirror_coeftab(pb200_handle_t *h, SolverMatrix *datacode)
 static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
 {
   pb200_shim_entry_t *e = shim_find(datacode, 1);
-  int64_t nbpivot = 0; double seconds = 0.0, crit;
+  int64_t nbpivot = 0; double seconds = 0.0, crit; int dev_csc = 0;
   if (e == NULL) { errorPrint("pastix_b200: too many live SolverMatrix instances"); EXIT(MOD_SOPALIN, INTERNAL_ERR); }
   if (sopar->iparm[IPARM_SCHUR] == API_YES || sopar->iparm[IPARM_DISTRIBUTION_LEVEL] != 0 || SOLV_PROCNBR > 1) {
     errorPrint("pastix_b200: Schur / 2D distribution / multi-process SolverMatrix are not handled by this shim");
@@ -224,9 +233,21 @@ static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
   if (e->h == NULL) { e->h = shim_create(datacode); e->facto = PB200_FACTO; }
   e->factorized = 0;
   t1 = clockGet();
-  shim_assemble(e->h, datacode, sopar);
+  if (e->csc != NULL && e->csc_fresh) {        /* CscOrdistrib of this call left the internal CSC in HBM (shim_csc.c) */
+    if (pb200_assemble_csc(e->h, e->csc) != PB200_SUCCESS) shim_fatal("pb200_assemble_csc");
+    dev_csc = 1;
+    e->csc_fresh = 0;
+  } else
+    shim_assemble(e->h, datacode, sopar);
+  /* CoefMatrix_Init releases the transposed values once the panels are filled (coefinit.c:327-341) */
+  if (sopar->transcsc != NULL) {
+    if (PB200_FACTO == PB200_FACT_LU && (sopar->iparm[IPARM_SYM] == API_SYM_YES || sopar->iparm[IPARM_SYM] == API_SYM_HER))
+      sopar->transcsc = NULL;                  /* alias of CSC_VALTAB (forcetrans) */
+    else
+      memFree_null(sopar->transcsc);
+  }
   t2 = clockGet();
-  crit = shim_critere(datacode, sopar);
+  crit = shim_critere(datacode, sopar, dev_csc ? e->csc : NULL);
   t3 = clockGet();
   if (getenv("PB200_SHIM_TIMING") != NULL)
     fprintf(stderr, "[pb200 shim] create %.1f ms, CSC flatten + H2D + device assembly %.1f ms, CscNorm1 %.1f ms\n",
