@@ -184,6 +184,10 @@ int pb200_inertia(pb200_handle_t *h, int64_t *inertia);
  * blend/src/updown.h:69-72). Overwritten by the solution.
  *   seconds : OUT device time of the sweeps, copies excluded (-> DPARM_SOLV_TIME) */
 int pb200_solve(pb200_handle_t *h, void *x, int64_t ldx, int64_t nrhs, double *seconds);
+/* IPARM_TRANSPOSE_SOLVE (api.h): the following pb200_solve / pb200_solve_device calls solve A^T x = b.  Only an LU
+ * factorization is affected (A^T = U^T L^T: the sweeps swap the L and U^T panels, updo.c:165-260, 1553-1600); the
+ * symmetric factorizations ignore it, like the reference. */
+int pb200_set_transpose_solve(pb200_handle_t *h, int transposed);
 /* Same with x already resident in HBM (device pointer). */
 int pb200_solve_device(pb200_handle_t *h, void *x_dev, int64_t ldx, int64_t nrhs, double *seconds);
 

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(_HERE, "lib", "libpastix_
 SYMBOLS = [
     "pb200_last_error", "pb200_version", "pb200_create", "pb200_destroy", "pb200_info", "pb200_panel_offsets",
     "pb200_norm1", "pb200_assemble", "pb200_reassemble", "pb200_factorize", "pb200_inertia", "pb200_solve",
-    "pb200_solve_device", "pb200_get_coeftab", "pb200_set_coeftab", "pb200_mark_factorized",
+    "pb200_solve_device", "pb200_set_transpose_solve", "pb200_get_coeftab", "pb200_set_coeftab", "pb200_mark_factorized",
     "pb200_last_launches", "pb200_probe_fp64_gflops", "pb200_set_profile", "pb200_get_profile",
     "pb200_create_dist", "pb200_ipc_size", "pb200_ipc_export", "pb200_ipc_attach", "pb200_dist_barrier", "pb200_dist_plan",
     "pb200_csc_create", "pb200_csc_destroy", "pb200_csc_build", "pb200_csc_fetch", "pb200_csc_norm1", "pb200_assemble_csc",
@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
     L.pb200_inertia.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.pb200_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_double)]
     L.pb200_solve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_double)]
+    L.pb200_set_transpose_solve.argtypes = [C.c_void_p, C.c_int]
     L.pb200_get_coeftab.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.pb200_set_coeftab.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.pb200_mark_factorized.argtypes = [C.c_void_p]

@@ -83,10 +83,12 @@ struct pb200_handle_s {
   unsigned int *h_dag_err = nullptr;                             // pinned
   void *d_y = nullptr; size_t y_bytes = 0;
   bool inv_ready = false;
+  bool solve_transposed = false;           // IPARM_TRANSPOSE_SOLVE (LU only)
   std::vector<int64_t> h_rmbase;           // per cblk: first entry of its off-diagonal rows in d_rowglob
   int *d_rowglob = nullptr;                // global row of every off-diagonal panel row
   std::vector<int> inv_lvl_nbmax;          // widest sub-panel of each level (sizes the shared memory of k_tri_inverse)
   std::vector<int> inv_lvl_ptr;            // sub-panels of level l: [inv_lvl_ptr[l], inv_lvl_ptr[l+1])
+  std::vector<int> inv_cls_ptr; int *d_inv_order = nullptr;   // sub-panels sorted by size class (k_tri_inverse launches)
   cudaStream_t stream_i = nullptr;         // low priority: triangle inversions underneath the factorization
   cudaEvent_t ev_inv = nullptr;
   // ---- FP64 tensor-core path (double / complex double, direct factorizations)
@@ -292,6 +294,20 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
     }
     { int rc = upload(h, lvl_cblk, &h->d_slv_cblk); if (rc) return rc; }
     { int rc = upload(h, h->lvl_ptr, &h->d_slv_lvl_ptr); if (rc) return rc; }
+  }
+  {
+    // size classes of the triangle inversions (16, 32, 48, 64, 96, 128 columns): widest first is not needed, the
+    // launches are independent
+    const int ncls = 6; const int bound[ncls] = {16, 32, 48, 64, 96, 128};
+    std::vector<std::vector<int>> byc(ncls);
+    for (int i = 0; i < (int)tasks.size(); ++i) {
+      const int nb = tasks[i].c1 - tasks[i].c0;
+      int k = 0; while (k + 1 < ncls && nb > bound[k]) ++k;
+      byc[k].push_back(i);
+    }
+    std::vector<int> order; h->inv_cls_ptr.assign(1, 0);
+    for (int k = 0; k < ncls; ++k) { order.insert(order.end(), byc[k].begin(), byc[k].end()); h->inv_cls_ptr.push_back((int)order.size()); }
+    int rc = upload(h, order, &h->d_inv_order); if (rc) return rc;
   }
   { int rc = upload(h, tasks, &h->d_slvtask); if (rc) return rc; }
   { int rc = upload(h, t2t, &h->d_slv_t2t); if (rc) return rc; }
@@ -1259,34 +1275,43 @@ extern "C" int pb200_inertia(pb200_handle_t *h, int64_t *inertia) {
 
 // ------------------------------------------------------------------ solve
 // invert the diagonal triangles of the freshly factored panels (one CTA per sub-panel)
+static const int kInvClasses[] = {16, 32, 48, 64, 96, 128};
+template <class T>
+static size_t inv_smem(int nbmax) { return (size_t)nbmax * (nbmax + 1) * sizeof(T); }   // two row-packed triangles
+template <class T>
+static int inv_attr(pb200_handle_t *h) {
+  static bool attr_done[4] = {};
+  if (!attr_done[h->flt]) {
+    CK(cudaFuncSetAttribute(k_tri_inverse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem<T>(SlvCfg<T>::NB)));
+    attr_done[h->flt] = true;
+  }
+  return PB200_SUCCESS;
+}
 // sub-panels [sp0, sp1) (tasks are ordered by level, so a level is one contiguous range); nbmax = widest of them
 template <class T>
 static int invert_range(pb200_handle_t *h, int sp0, int sp1, cudaStream_t sm, int nbmax = SlvCfg<T>::NB) {
-  static bool attr_done[4] = {};
-  const int NB = SlvCfg<T>::NB;
-  if (!attr_done[h->flt]) {
-    CK(cudaFuncSetAttribute(k_tri_inverse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NB * (NB | 1) * sizeof(T))));
-    attr_done[h->flt] = true;
-  }
+  { int rc = inv_attr<T>(h); if (rc) return rc; }
   if (sp1 <= sp0) return PB200_SUCCESS;
-  const size_t smem = (size_t)nbmax * (nbmax | 1) * sizeof(T);   // small sub-panels: many CTAs per SM
   const int unit_down = (h->facto != PB200_FACT_LLT);   // LDLt / LDLh / LU-L: unit lower triangle
-  k_tri_inverse<T><<<sp1 - sp0, 128, smem, sm>>>((const T *)h->dL, h->d_slvtask + sp0, (T *)h->d_inv, unit_down);
+  const int ntri = nbmax * (nbmax + 1) / 2;
+  k_tri_inverse<T><<<sp1 - sp0, 128, inv_smem<T>(nbmax), sm>>>((const T *)h->dL, h->d_slvtask + sp0, nullptr, (T *)h->d_inv, unit_down, ntri);
   if (h->facto == PB200_FACT_LU)   // up sweep: lower triangle of ucoeftab's diagonal blok = U^T, non-unit
-    k_tri_inverse<T><<<sp1 - sp0, 128, smem, sm>>>((const T *)h->dU, h->d_slvtask + sp0, (T *)h->d_inv_up, 0);
+    k_tri_inverse<T><<<sp1 - sp0, 128, inv_smem<T>(nbmax), sm>>>((const T *)h->dU, h->d_slvtask + sp0, nullptr, (T *)h->d_inv_up, 0, ntri);
   return PB200_SUCCESS;
 }
+// all sub-panels, one launch per size class (the shared memory of a launch fits its widest triangle)
 template <class T>
 static int invert_t(pb200_handle_t *h, cudaStream_t sm) {
-  // runs of consecutive levels whose widest sub-panel falls in the same size class share a launch
-  auto cls = [](int nb) { return nb <= 16 ? 16 : nb <= 32 ? 32 : nb <= 64 ? 64 : 128; };
-  for (int l = 0; l < h->nlevels;) {
-    const int k = cls(h->inv_lvl_nbmax[l]);
-    int e = l + 1;
-    while (e < h->nlevels && cls(h->inv_lvl_nbmax[e]) == k) ++e;
-    int rc = invert_range<T>(h, h->inv_lvl_ptr[l], h->inv_lvl_ptr[e], sm, std::min(k, (int)SlvCfg<T>::NB));
-    if (rc) return rc;
-    l = e;
+  { int rc = inv_attr<T>(h); if (rc) return rc; }
+  const int unit_down = (h->facto != PB200_FACT_LLT);
+  for (size_t k = 0; k + 1 < h->inv_cls_ptr.size(); ++k) {
+    const int n = h->inv_cls_ptr[k + 1] - h->inv_cls_ptr[k];
+    if (n == 0) continue;
+    const int nbmax = std::min(kInvClasses[k], (int)SlvCfg<T>::NB), ntri = nbmax * (nbmax + 1) / 2;
+    const int *ord = h->d_inv_order + h->inv_cls_ptr[k];
+    k_tri_inverse<T><<<n, 128, inv_smem<T>(nbmax), sm>>>((const T *)h->dL, h->d_slvtask, ord, (T *)h->d_inv, unit_down, ntri);
+    if (h->facto == PB200_FACT_LU)
+      k_tri_inverse<T><<<n, 128, inv_smem<T>(nbmax), sm>>>((const T *)h->dU, h->d_slvtask, ord, (T *)h->d_inv_up, 0, ntri);
   }
   CK(cudaGetLastError());
   h->inv_ready = true;
@@ -1296,10 +1321,14 @@ static int invert_dispatch(pb200_handle_t *h, cudaStream_t sm) { DISPATCH_T(h, i
 
 template <class T, int FACTO>
 static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
-  const T *L = (const T *)h->dL;
-  const T *Mup = (FACTO == F_LU) ? (const T *)h->dU : L;
-  const T *inv = (const T *)h->d_inv;
-  const T *inv_up = (FACTO == F_LU) ? (const T *)h->d_inv_up : inv;
+  // LU with IPARM_TRANSPOSE_SOLVE: A^T = U^T L^T, i.e. the down step runs on the U^T panels (ucoeftab, non-unit
+  // triangle) and the up step on L (unit) — what the reference obtains by rescaling and swapping coeftab/ucoeftab
+  // around its ordinary sweeps (updo.c:165-260, 1553-1600)
+  const bool tsolve = (FACTO == F_LU) && h->solve_transposed;
+  const T *L = (const T *)(tsolve ? h->dU : h->dL);
+  const T *Mup = (FACTO == F_LU) ? (const T *)(tsolve ? h->dL : h->dU) : L;
+  const T *inv = (const T *)(tsolve ? h->d_inv_up : h->d_inv);
+  const T *inv_up = (FACTO == F_LU) ? (const T *)(tsolve ? h->d_inv : h->d_inv_up) : inv;
   T *y = (T *)h->d_y;
   int64_t launches = 0;
   static bool sm_attr_done[4][4] = {};
@@ -1312,7 +1341,7 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
     sm_attr_done[h->flt][FACTO] = true;
   }
   // several right-hand sides through an all-small schedule (ILU): transposed work copies, lanes over right-hand sides
-  const bool tr = h->slv_all_small && nrhs >= 4;
+  const bool tr = h->slv_all_small && nrhs >= 4 && !tsolve;
   T *xs = x, *ys = y;
   int64_t rs = 1, cs = ldx;
   const int n = (int)h->n;
@@ -1363,7 +1392,9 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
     const T *M = dir == 0 ? L : Mup;
     for (size_t gi = 0; gi < h->sgsteps.size(); ++gi) {
       const auto &gs = h->sgsteps[dir == 0 ? gi : h->sgsteps.size() - 1 - gi];
-      if (gs.kind == 0) {
+      // the fused small-cblk kernels read the diagonal block of the panel they sweep (unit L / non-unit U^T fixed by
+      // the direction); a transposed LU solve goes through the general kernels, which take the inverted triangles
+      if (gs.kind == 0 || tsolve) {
         const int s0 = h->slv_lvl_step[gs.l0], s1 = h->slv_lvl_step[gs.l1];
         for (int k = 0; k < s1 - s0; ++k) {
           const auto &st = h->slv_steps[dir == 0 ? s0 + k : s1 - 1 - k];
@@ -1417,6 +1448,12 @@ static int solve_t(pb200_handle_t *h, void *x, int64_t ldx, int nrhs) {
   return fail(PB200_ERR_BADARG, "bad factotype");
 }
 static int solve_dispatch(pb200_handle_t *h, void *x, int64_t ldx, int nrhs) { DISPATCH_T(h, solve_t, h, x, ldx, nrhs) }
+
+extern "C" int pb200_set_transpose_solve(pb200_handle_t *h, int transposed) {
+  if (!h) return fail(PB200_ERR_BADARG, "null handle");
+  h->solve_transposed = transposed != 0;
+  return PB200_SUCCESS;
+}
 
 extern "C" int pb200_solve_device(pb200_handle_t *h, void *x_dev, int64_t ldx, int64_t nrhs, double *seconds) {
   if (!h || !x_dev) return fail(PB200_ERR_BADARG, "null argument");

@@ -55,33 +55,51 @@ __device__ __forceinline__ int panel_row_to_global(const DevSym &S, int c, int m
 }
 
 // ---- inverse of the lower triangle of every diagonal sub-block: X = W^{-1}, W nb x nb (ld), unit or not.
-// One CTA per sub-panel, thread j builds column j by forward substitution into shared memory.
+// One CTA per sub-panel (`order`, when given, lists the sub-panels of one size class so that the launch can be
+// sized for them).  W and X live in shared memory as row-packed lower triangles (row i = columns 0..i);
+// thread j builds column j of X by forward substitution: x_ij = -(sum_{k=j}^{i-1} w_ik x_kj) / w_ii.  The k loop
+// starts at the warp's first column, so the w_ik reads are warp-wide broadcasts and the x_kj reads (own
+// column, written by the same thread) fall on consecutive words: no bank conflicts, no barrier between rows.
+__device__ __forceinline__ int tri_row(int i) { return (i * (i + 1)) >> 1; }
+
 template <class T>
 __global__ void __launch_bounds__(128)
-k_tri_inverse(const T *__restrict__ M, const SlvTask *__restrict__ tasks, T *inv, int unit) {
+k_tri_inverse(const T *__restrict__ M, const SlvTask *__restrict__ tasks, const int *__restrict__ order, T *inv, int unit, int ntri) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *Xs = reinterpret_cast<T *>(smem_raw);
-  const SlvTask tk = tasks[blockIdx.x];
+  T *Ws = reinterpret_cast<T *>(smem_raw);
+  T *Xs = Ws + ntri;
+  const SlvTask tk = tasks[order ? order[blockIdx.x] : blockIdx.x];
   const int ld = tk.ld, nb = tk.c1 - tk.c0;
   const T *W = M + tk.poff + (size_t)tk.c0 * (ld + 1);
-  const int ldx = nb | 1;
-  const int j = threadIdx.x;
   const T one = ST<T>::from_real(1.0), zero = ST<T>::zero();
-  if (j < nb) {
-    T *x = Xs + (size_t)j * ldx;
-    x[j] = unit ? one : one / W[(size_t)j * (ld + 1)];
-    for (int i = j + 1; i < nb; ++i) {
-      T s = zero;
-      for (int k = j; k < i; ++k) fma_acc(s, W[(size_t)k * ld + i], x[k]);
-      s = zero - s;
-      x[i] = unit ? s : s / W[(size_t)i * (ld + 1)];
+  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+    const int k = e / nb, i = e - k * nb;
+    if (i >= k) Ws[tri_row(i) + k] = W[(size_t)k * ld + i];
+  }
+  __syncthreads();
+  const int j = threadIdx.x, j0 = j & ~31;          // j0: first column of this warp
+  if (j0 < nb) {
+    if (j < nb) Xs[tri_row(j) + j] = unit ? one : one / Ws[tri_row(j) + j];
+    for (int i = j0 + 1; i < nb; ++i) {
+      const T *wr = Ws + tri_row(i);
+      T s0 = zero, s1 = zero;
+      int k = j0;
+      for (; k + 1 < i; k += 2) {
+        if (k >= j) fma_acc(s0, wr[k], Xs[tri_row(k) + j]);
+        if (k + 1 >= j) fma_acc(s1, wr[k + 1], Xs[tri_row(k + 1) + j]);
+      }
+      if (k < i && k >= j) fma_acc(s0, wr[k], Xs[tri_row(k) + j]);
+      if (i > j && j < nb) {
+        const T s = zero - (s0 + s1);
+        Xs[tri_row(i) + j] = unit ? s : s / wr[i];
+      }
     }
   }
   __syncthreads();
   T *out = inv + tk.invoff;
   for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
-    const int jj = e / nb, i = e % nb;
-    out[e] = (i >= jj) ? Xs[(size_t)jj * ldx + i] : zero;
+    const int jj = e / nb, i = e - jj * nb;
+    out[e] = (i >= jj) ? Xs[tri_row(i) + jj] : zero;
   }
 }
 

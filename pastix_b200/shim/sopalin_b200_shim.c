@@ -276,10 +276,9 @@ static void shim_updown(SolverMatrix *datacode, SopalinParam *sopar)
     errorPrint("pastix_b200: up_down called before a numeric factorization on this SolverMatrix");
     EXIT(MOD_SOPALIN, BADPARAMETER_ERR);
   }
-  if (sopar->iparm[IPARM_TRANSPOSE_SOLVE] == API_YES) {
-    errorPrint("pastix_b200: IPARM_TRANSPOSE_SOLVE is not handled by this shim");
-    EXIT(MOD_SOPALIN, BADPARAMETER_ERR);
-  }
+  /* IPARM_TRANSPOSE_SOLVE only acts on LU in the reference (updo.c:165, 1553 are under SOPALIN_LU) */
+  if (pb200_set_transpose_solve(e->h, PB200_FACTO == PB200_FACT_LU && sopar->iparm[IPARM_TRANSPOSE_SOLVE] == API_YES) != PB200_SUCCESS)
+    shim_fatal("pb200_set_transpose_solve");
   if (pb200_solve(e->h, UPDOWN_SM2XTAB, (int64_t)UPDOWN_SM2XSZE, (int64_t)UPDOWN_SM2XNBR, &seconds) != PB200_SUCCESS)
     shim_fatal("pb200_solve");
   sopar->dparm[DPARM_SOLV_TIME] = seconds;                       /* updo.c:1495 */

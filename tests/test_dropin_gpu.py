@@ -107,3 +107,31 @@ def test_refinement_runs_on_top_of_gpu_updown():
     assert res <= 1e-8, res
     assert gpu.out()["nbiter"] >= 1
     gpu.release()
+
+
+@pytest.mark.parametrize("prec", ["d", "z"])
+def test_transpose_solve_lu(prec):
+    """IPARM_TRANSPOSE_SOLVE on an LU factorization (updo.c:165-260, 1553-1600): A^T x = b, same answer as the reference."""
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    if not available(prec):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix("cd", 9, DT[prec])
+    b = G.rhs_vector(A.shape[0], 1, DT[prec])
+    ref = RefPastix(prec, threads=1)
+    over = {"IPARM_TRANSPOSE_SOLVE": ref.E["API_YES"]}
+    ref.setup(A, perm0, "lu", sym="no", iparm_over=over).analyze().numfact()
+    xr = ref.solve(b)
+    gpu = Pastix(prec, threads=1).setup(A, perm0, "lu", sym="no", iparm_over=over).analyze().numfact()
+    xg = gpu.solve(b)
+    At = sp.csc_matrix(A).T
+    assert np.linalg.norm(At @ xg - b) / np.linalg.norm(b) <= 1e-12
+    assert np.linalg.norm(A @ xg - b) / np.linalg.norm(b) > 1e-3          # really the transposed system
+    assert relerr(xg, xr) <= 50 * tol(prec)
+    # and back to the plain system on the same factors
+    gpu.iparm[gpu.E["IPARM_TRANSPOSE_SOLVE"]] = gpu.E["API_NO"]
+    x2 = gpu.solve(b)
+    assert np.linalg.norm(A @ x2 - b) / np.linalg.norm(b) <= 1e-12
+    gpu.release()
