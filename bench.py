@@ -149,16 +149,28 @@ def measure_fp64_peak(device: int) -> dict:
     return out
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant k_gemm_scatter launch, from the committed
-    `ncu --set full` capture (profiles/r01/ncu_gemm_scatter_c3_summary.json); None when absent."""
-    p = os.path.join(ROOT, "profiles", "r01", "ncu_gemm_scatter_c3_summary.json")
+def ncu_traffic(workload: str = "c2"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (k_gemm_scatter: the largest
+    captured launch) and of the two up_down sweeps, from the committed `ncu --set full` captures
+    (profiles/r01/r01b_full_*_summary.json, written by tools/gpu_profile.sh + tools/ncu_summary.py); None when absent."""
+    wl = workload if workload in ("c2", "c3") else "c2"
+    out = None
     try:
-        d = json.load(open(p))["dominant"]
-        return {"dram_bytes": d["dram_bytes_read"] + d["dram_bytes_write"], "launch_tiles": d["grid_tiles"],
-                "launch_ms": d["duration_s"] * 1e3, "capture": "c3, one launch (ncu --set full)"}
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01", f"r01b_full_gemm_scatter_{wl}_summary.json")))
+        k = max(d, key=lambda x: x.get("grid", 0))
+        out = {"dram_bytes": k["dram_read_bytes"] + k["dram_write_bytes"], "launch_tiles": int(k["grid"]),
+               "launch_ms": k["duration_us"] * 1e-3, "dmma_pipe_active_pct": k.get("dmma_pipe_pct"),
+               "l2_hit_pct": k.get("l2_hit_pct"), "capture": f"{wl}, largest captured launch (ncu --set full, cold cache)"}
     except Exception:
-        return None
+        pass
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01", "r01b_full_updown_c2_summary.json")))
+        if out is not None and wl == "c2":
+            out["updown_sweeps"] = [{"kernel": k["kernel"].replace("void ", "").split("<")[0], "dram_bytes": k["dram_read_bytes"] + k["dram_write_bytes"],
+                                     "launch_ms": k["duration_us"] * 1e-3} for k in d]
+    except Exception:
+        pass
+    return out
 
 
 def measured_peaks() -> dict:
@@ -315,7 +327,7 @@ def our_arm(args):
         asm_s.append(time.perf_counter() - ta)
         s.factorize(crit)
         fact_s.append(s.fact_time)
-        launches += s.last_launches() + 1 + 2   # + assembly + triangle inversions
+        launches += s.last_launches() + 1       # factorization (incl. the triangle inversions) + assembly
         x_dev.copy_(x_src); torch.cuda.synchronize(local)
         s.solve_device(x_dev.data_ptr(), n, nrhs)
         solve_s.append(s.solv_time)
@@ -346,7 +358,7 @@ def our_arm(args):
         ach = prof["gemm_flops"] / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         roof = {"kernel": "k_gemm_scatter (fused DMMA GEMM + scatter-add into facing cblks)", "bound": "tensor",
                 "achieved": ach, "peak": peak["peak_tflops"], "unit": "TFLOP/s", "frac": ach / peak["peak_tflops"],
-                "traffic": ncu_traffic(), "peak_source": peak["source"], "fp64_peaks": {k: v for k, v in peak.items() if k.endswith("tflops")},
+                "traffic": ncu_traffic(args.workload), "peak_source": peak["source"], "fp64_peaks": {k: v for k, v in peak.items() if k.endswith("tflops")},
                 "kernel_share_of_step": gms / tot if tot > 0 else None,
                 "kind_ms_serialised": prof["ms"], "kind_launches": prof["launches"],
                 "algorithmic_flops_per_factorization": prof["gemm_flops"]}

@@ -1312,6 +1312,7 @@ static int invert_t(pb200_handle_t *h, cudaStream_t sm) {
     k_tri_inverse<T><<<n, 128, inv_smem<T>(nbmax), sm>>>((const T *)h->dL, h->d_slvtask, ord, (T *)h->d_inv, unit_down, ntri);
     if (h->facto == PB200_FACT_LU)
       k_tri_inverse<T><<<n, 128, inv_smem<T>(nbmax), sm>>>((const T *)h->dU, h->d_slvtask, ord, (T *)h->d_inv_up, 0, ntri);
+    h->last_launches += (h->facto == PB200_FACT_LU) ? 2 : 1;
   }
   CK(cudaGetLastError());
   h->inv_ready = true;

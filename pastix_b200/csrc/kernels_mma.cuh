@@ -108,8 +108,10 @@ constexpr size_t upd_smem_bytes() {
 
 // fire-and-forget reductions (RED.ADD.F64 at L2): the reference serialises these adds with
 // mutex_blok (sopalin_compute.c:563-580)
-__device__ __forceinline__ void red_sub(double *p, double v) { atomicAdd(p, -v); }
-__device__ __forceinline__ void red_sub(cdouble *p, cdouble v) { atomicAdd(&p->x, -v.x); atomicAdd(&p->y, -v.y); }
+// (the sign is flipped on the integer pipe: a DADD would compete with the DMMAs for the FP64 pipe)
+__device__ __forceinline__ double neg_bits(double v) { return __longlong_as_double(__double_as_longlong(v) ^ (long long)0x8000000000000000ULL); }
+__device__ __forceinline__ void red_sub(double *p, double v) { atomicAdd(p, neg_bits(v)); }
+__device__ __forceinline__ void red_sub(cdouble *p, cdouble v) { atomicAdd(&p->x, neg_bits(v.x)); atomicAdd(&p->y, neg_bits(v.y)); }
 
 // last index i in [0, n) with key[i] <= v (keys ascending, key[0] <= v assumed)
 __device__ __forceinline__ int upper_le_s(const int *key, int n, int v) {
@@ -162,18 +164,25 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
   const T *Bp = (SYM_LDL ? W : ((FACTO == F_LU && part == 0) ? U : L)) + tk.poff;
   const int nchunks = (tk.k1 - tk.k0 + KC - 1) / KC;
 
+  // operand staging: thread (lk0, li) = (tid / TM, tid % TM) copies element li of the columns k = lk0, lk0 + KSTEP, ...
+  // of a chunk; everything that does not change from chunk to chunk (row predicate, column-k0 addresses) is
+  // resolved once per tile, so that a chunk costs one 64-bit add and one predicate per cp.async
+  static_assert(TM == TN && NT % TM == 0 && KC % (NT / TM) == 0, "operand staging assumes square tiles");
+  constexpr int KSTEP = NT / TM;
+  const int li = tid % TM, lk0 = tid / TM;
+  const bool a_ok = li < mrows, b_ok = li < ncols;
+  const T *pA = Ap + (size_t)tk.k0 * ld + m0 + (a_ok ? li : 0);
+  const T *pB = Bp + (size_t)tk.k0 * ld + n0 + (b_ok ? li : 0);
+  const int ktot = tk.k1 - tk.k0;
   auto load_chunk = [&](int c, int stg) {
-    const int kb = tk.k0 + c * KC;
-    T *a = sA + stg * KC * LDA, *b = sB + stg * KC * LDB;
-    for (int e = tid; e < KC * TM; e += NT) {
-      const int kk = e / TM, i = e % TM;
-      const bool ok = (i < mrows) && (kb + kk < tk.k1);
-      cp_async_elem<sizeof(T)>(a + kk * LDA + i, Ap + (size_t)(ok ? kb + kk : tk.k0) * ld + m0 + (ok ? i : 0), ok);
-    }
-    for (int e = tid; e < KC * TN; e += NT) {
-      const int kk = e / TN, j = e % TN;
-      const bool ok = (j < ncols) && (kb + kk < tk.k1);
-      cp_async_elem<sizeof(T)>(b + kk * LDB + j, Bp + (size_t)(ok ? kb + kk : tk.k0) * ld + n0 + (ok ? j : 0), ok);
+    const int kb = c * KC + lk0;                       // first column of this thread, relative to k0
+    T *a = sA + stg * KC * LDA + lk0 * LDA + li, *b = sB + stg * KC * LDB + lk0 * LDB + li;
+    const T *ga = pA + (size_t)kb * ld, *gb = pB + (size_t)kb * ld;
+#pragma unroll
+    for (int q = 0; q < KC / KSTEP; ++q) {
+      const bool kin = kb + q * KSTEP < ktot;
+      cp_async_elem<sizeof(T)>(a + q * KSTEP * LDA, (a_ok && kin) ? ga + (size_t)(q * KSTEP) * ld : pA, a_ok && kin);
+      cp_async_elem<sizeof(T)>(b + q * KSTEP * LDB, (b_ok && kin) ? gb + (size_t)(q * KSTEP) * ld : pB, b_ok && kin);
     }
   };
 
@@ -260,42 +269,64 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
       c_tw[y][e] = cmv.tw;
       c_tgt[y][e] = cmv.ctgt;
     }
+  auto value = [&](int x, int y, int hh, int e) -> T {
+    if constexpr (CX) return cdouble(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
+    else return acc[x][y].re[hh * 2 + e];
+  };
+  if (tk.mode == 1) {
+    // own panel: symmetric variants only keep the lower triangle of the diagonal blok
 #pragma unroll
-  for (int x = 0; x < MI; ++x)
+    for (int x = 0; x < MI; ++x)
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int i = wm0 + x * 16 + g + hh * 8;
-      if (i >= mrows) continue;
-      const int rb = s_rm[i].rb, roff = s_rm[i].roff;
-      const int trow = (rb - rb_lo) * ncb - cb_lo;
+      for (int hh = 0; hh < 2; ++hh) {
+        const int i = wm0 + x * 16 + g + hh * 8;
+        if (i >= mrows) continue;
+        const int roff = s_rm[i].roff;
 #pragma unroll
-      for (int y = 0; y < NI; ++y)
+        for (int y = 0; y < NI; ++y)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          T v;
-          if constexpr (CX) v = cdouble(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
-          else v = acc[x][y].re[hh * 2 + e];
-          if (tk.mode == 1) {
-            // own panel: symmetric variants only keep the lower triangle of the diagonal blok
-            if (c_cj[y][e] != 0x7fffffff && (FACTO == F_LU || roff >= c_cj[y][e])) red_sub(TA + c_tgt[y][e] + roff, v);
-            continue;
+          for (int e = 0; e < 2; ++e)
+            if (c_cj[y][e] != 0x7fffffff && (FACTO == F_LU || roff >= c_cj[y][e])) red_sub(TA + c_tgt[y][e] + roff, value(x, y, hh, e));
+      }
+    return;
+  }
+  // facing cblks: (row blok rb, column blok cb) -> row offset of rb inside the cblk facing cb (-1: no such pair);
+  // one lookup + one test per element, the column sentinel (cb = INT_MAX) fails rb >= cb
+  auto scatter = [&](auto lookup) {
+#pragma unroll
+    for (int x = 0; x < MI; ++x)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int i = wm0 + x * 16 + g + hh * 8;
+        if (i >= mrows) continue;
+        const int rb = s_rm[i].rb, roff = s_rm[i].roff;
+#pragma unroll
+        for (int y = 0; y < NI; ++y)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int cb = c_cb[y][e];
+            int ro = (rb >= cb) ? lookup(rb, cb) : -1;
+            if (ro < 0) continue;
+            ro += roff;
+            const T v = value(x, y, hh, e);
+            if (FACTO != F_LU || part == 0 || ro >= c_tw[y][e]) {
+              red_sub(TA + c_tgt[y][e] + ro, v);
+            } else if (rb != cb) {
+              // U contribution to a diagonal target: stored transposed into coeftab
+              // (sopalin_compute.c:431-435, 572-575); the b1 == b2 square is skipped
+              const int j = wn0 + y * 8 + t4 * 2 + e;
+              const int tld = s_cm[j].tld;
+              red_sub(L + (c_tgt[y][e] - (int64_t)c_cj[y][e] * tld) + (int64_t)ro * tld + c_cj[y][e], v);
+            }
           }
-          const int cb = c_cb[y][e];
-          if (rb < cb) continue;
-          int ro = tab_in_smem ? s_tab[trow + cb] : M.pairoff[tk.pbase + (int64_t)rb * (rb + 1) / 2 + cb];
-          if (ro < 0) continue;
-          ro += roff;
-          if (FACTO != F_LU || part == 0 || ro >= c_tw[y][e]) {
-            red_sub(TA + c_tgt[y][e] + ro, v);
-          } else if (rb != cb) {
-            // U contribution to a diagonal target: stored transposed into coeftab
-            // (sopalin_compute.c:431-435, 572-575); the b1 == b2 square is skipped
-            const int j = wn0 + y * 8 + t4 * 2 + e;
-            const int tld = s_cm[j].tld;
-            red_sub(L + (c_tgt[y][e] - (int64_t)c_cj[y][e] * tld) + (int64_t)ro * tld + c_cj[y][e], v);
-          }
-        }
-    }
+      }
+  };
+  if (tab_in_smem) {
+    const int tbase = -rb_lo * ncb - cb_lo;
+    scatter([&](int rb, int cb) { return s_tab[tbase + rb * ncb + cb]; });
+  } else {
+    scatter([&](int rb, int cb) { return M.pairoff[tk.pbase + (int64_t)rb * (rb + 1) / 2 + cb]; });
+  }
 }
 
 // ---------------------------------------------------------------- panel TRSM on DMMA
