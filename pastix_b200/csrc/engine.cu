@@ -158,7 +158,7 @@ static size_t elem_size(int flt) {
 static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks) {
   h->dag_ok = false;
   if (getenv("PB200_SOLVE_LEVELS") != nullptr) return PB200_SUCCESS;   // A/B switch: keep the launch-per-level sweeps
-  for (const auto &gs : h->sgsteps) if (gs.kind != 0) return PB200_SUCCESS;   // small-cblk schedules (ILU) keep their fused path
+  if (h->slv_all_small) return PB200_SUCCESS;   // all-small schedules (incomplete factorizations) keep their fused warp-per-cblk path
   const int NB = (h->flt == PB200_COMPLEXDOUBLE) ? SlvCfg<cdouble>::NB : SlvCfg<double>::NB;
   const int64_t C = h->cblknbr;
   const int nsp = (int)tasks.size();
@@ -178,7 +178,7 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
     nbs = std::max(nbs, tk.c1 - tk.c0);
     nticks += (tk.ld - tk.c1 + PB200_DAG_ROWS - 1) / PB200_DAG_ROWS;
   }
-  if (nticks >= (1LL << 30)) return PB200_SUCCESS;
+  if (nticks >= (1LL << 24)) return PB200_SUCCESS;   // millions of tiny tickets: the level sweeps batch them better
   std::vector<DagTick> ticks; ticks.reserve((size_t)nticks);
   std::vector<int> tgt; tgt.reserve((size_t)nticks * 3);
   std::vector<unsigned int> need(nsp, 0);

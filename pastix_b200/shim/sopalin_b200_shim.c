@@ -184,14 +184,12 @@ static double shim_critere(SolverMatrix *datacode, SopalinParam *sopar, pb200_cs
   if (sopar->usenocsc == 1) return crit;
   if (sopar->fakefact == 1)
     return (double)(UPDOWN_GNODENBR * UPDOWN_GNODENBR + UPDOWN_GNODENBR) * sqrt(sopar->espilondiag);
-#ifndef TYPE_COMPLEX
-  if (devcsc != NULL) {                        /* same sums in the same order on the CSC already in HBM: identical for real types */
+  if (devcsc != NULL) {                        /* same sums in the same order on the CSC already in HBM: identical for real
+                                                  types; complex: |z| is the device hypot (within an ulp of cabs) */
     double nrm = 0.0;
     if (pb200_csc_norm1(devcsc, &nrm) != PB200_SUCCESS) shim_fatal("pb200_csc_norm1");
     return nrm * sqrt(sopar->espilondiag);
   }
-#endif
-  (void)devcsc;
   return CscNorm1(sopar->cscmtx, sopar->pastix_comm) * sqrt(sopar->espilondiag);
 }
 

@@ -135,3 +135,20 @@ def test_transpose_solve_lu(prec):
     x2 = gpu.solve(b)
     assert np.linalg.norm(A @ x2 - b) / np.linalg.norm(b) <= 1e-12
     gpu.release()
+
+
+@pytest.mark.parametrize("prec,kind,facto,sym", [("z", "cd", "lu", "no"), ("c", "cd", "lu", "no"), ("s", "lap7", "llt", "yes")])
+def test_static_pivot_threshold_from_device_norm(prec, kind, facto, sym):
+    """critere = ||A||_1 * sqrt(DPARM_EPSILON_MAGN_CTRL) (sopalin3d.c:586-606) with the 1-norm taken on the internal
+    CSC in HBM: identical sums for real types, within an ulp of cabs() per entry for complex ones."""
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    if not available(prec):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix(kind, 8, DT[prec])
+    ref = RefPastix(prec, threads=1).setup(A, perm0, facto, sym=sym).analyze().numfact()
+    gpu = Pastix(prec, threads=1).setup(A, perm0, facto, sym=sym).analyze().numfact()
+    want = ref.norm1() * np.sqrt(ref.out()["epsilon_magn_ctrl"])
+    assert abs(gpu.critere() - want) <= 4e-16 * want * (1 if prec in ("s", "d") else 8)
+    gpu.release()

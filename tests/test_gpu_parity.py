@@ -100,3 +100,30 @@ def test_multi_rhs_solve_matches_single_rhs(name):
     for k in range(9):
         assert relerr(X[:, k], cols[k]) <= 50 * tol(g["prec"]), (name, k)
     s.close()
+
+
+@pytest.mark.parametrize("name", ["lap7_8_llt_d", "lap27_6_ldlt_d", "cd_8_lu_d", "cd_6_lu_c", "lap7_10_llt_d_bs16"])
+def test_persistent_updown_equals_level_sweeps(name, monkeypatch):
+    """The counter-ordered persistent sweeps (kernels_solve_dag.cuh, two launches per solve) against the
+    launch-per-level sweeps (kernels_solve.cuh, PB200_SOLVE_LEVELS=1) on the same factors, 5 right-hand sides
+    (one full group of 4 + a partial one)."""
+    from pastix_b200 import Sopalin
+    from pastix_b200.csc import permute_rhs
+    g = load_golden(name)
+    b1 = permute_rhs(g["b"], g["permtab"]).reshape(-1, 1)
+    out = []
+    for levels in (False, True):
+        if levels:
+            monkeypatch.setenv("PB200_SOLVE_LEVELS", "1")
+        s = Sopalin(g, g["prec"], g["facto"])
+        s.assemble(g["colptr"], g["rows"], g["values"], g["tvalues"])
+        s.factorize(g["critere"])
+        X = np.asfortranarray(b1 * (1.0 + 0.5 * np.arange(5))[None, :]).astype(s.dtype, order="F")
+        s.solve(X)
+        if levels:
+            assert s.last_launches() > 2
+        else:
+            assert s.last_launches() == 2, "persistent path not taken"
+        out.append(X)
+        s.close()
+    assert relerr(out[0], out[1]) <= 50 * tol(g["prec"])
