@@ -147,6 +147,29 @@ int pb200_assemble(pb200_handle_t *h, const int64_t *colptr, const int64_t *rows
 /* Re-run the device-side zero + scatter from the CSC already resident in HBM. */
 int pb200_reassemble(pb200_handle_t *h);
 
+/* ---- vector back end of the refinement drivers (replaces the host `struct solver` operations of
+ * sopalin/src/raff_functions.c:100-650 under the reference's unchanged raff_gmres.c / raff_grad.c / raff_bicgstab.c).
+ * Vectors are n-element arrays of the handle's precision allocated by pb200_vec_alloc (managed memory: kernels use them
+ * in HBM, the scalars and pointer tables the drivers allocate through the same call stay host-dereferenceable).
+ * Scalars (`alpha`, `result`) are HOST pointers to one element.  Every call is synchronous. */
+int pb200_vec_alloc(pb200_handle_t *h, void **p, int64_t bytes);                 /* Pastix_Malloc  */
+int pb200_vec_free(pb200_handle_t *h, void *p);                                  /* Pastix_Free    */
+int pb200_vec_set(pb200_handle_t *h, void *dst, const void *src_host, int64_t nelem);   /* host -> vector (Pastix_B, Pastix_X) */
+int pb200_vec_get(pb200_handle_t *h, void *dst_host, const void *src, int64_t nelem);   /* vector -> host (Pastix_End)         */
+int pb200_vec_zero(pb200_handle_t *h, void *dst, int64_t nelem);
+int pb200_vec_copy(pb200_handle_t *h, void *dst, const void *src, int64_t nelem);       /* CscCopy  */
+int pb200_vec_scal(pb200_handle_t *h, const void *alpha, void *x, int64_t nelem);       /* CscScal: x <- alpha x */
+int pb200_vec_axpy(pb200_handle_t *h, const void *alpha, const void *x, void *y, int64_t nelem);   /* CscAXPY: y <- y + alpha x */
+/* result = sum_i x_i * (conj_y ? conj(y_i) : y_i)   (CscGradBeta / CscGmresBeta / CscNormFro^2, csc_intern_compute.c:1041-1560);
+ * fixed reduction tree: reproducible from run to run */
+int pb200_vec_dot(pb200_handle_t *h, int conj_y, const void *x, const void *y, int64_t nelem, void *result);
+/* r = A x (b == NULL) or r = b - A x, A = the internal CSC resident in HBM (CscAx / CscbMAx, csc_intern_compute.c:448, 1146);
+ * type = CscMatrix.type ('S', 'H', 'U'); trans != 0: A^T x (IPARM_TRANSPOSE_SOLVE).  Gathered row by row: no atomics, the
+ * same additions in the same order as the reference's sequential product. */
+int pb200_csc_ax(pb200_handle_t *h, char type, int trans, const void *b, const void *x, void *r);
+/* d = up_down(s) with the factors in HBM (Pastix_Precond); d may alias s */
+int pb200_precond(pb200_handle_t *h, const void *s, void *d);
+
 /* ---- internal CSC built on the device (replaces CscOrdistrib, sopalin/src/csc_intern_build.c:352-570).
  * From the user's CSC exactly as pastix() receives it — Fortran numbering, colptr[n+1], rows[nnz], values[nnz],
  * lower triangle for type 'S'/'H' — and Order.permtab (0-based new index of every unknown) it builds the matrix

@@ -15,6 +15,8 @@ SYMBOLS = [
     "pb200_solve_device", "pb200_set_transpose_solve", "pb200_get_coeftab", "pb200_set_coeftab", "pb200_mark_factorized",
     "pb200_last_launches", "pb200_probe_fp64_gflops", "pb200_set_profile", "pb200_get_profile",
     "pb200_create_dist", "pb200_ipc_size", "pb200_ipc_export", "pb200_ipc_attach", "pb200_dist_barrier", "pb200_dist_plan",
+    "pb200_vec_alloc", "pb200_vec_free", "pb200_vec_set", "pb200_vec_get", "pb200_vec_zero", "pb200_vec_copy", "pb200_vec_scal",
+    "pb200_vec_axpy", "pb200_vec_dot", "pb200_csc_ax", "pb200_precond",
     "pb200_csc_create", "pb200_csc_destroy", "pb200_csc_build", "pb200_csc_fetch", "pb200_csc_norm1", "pb200_assemble_csc",
 ]
 

@@ -19,6 +19,7 @@
 #include "kernels_mma.cuh"
 #include "kernels_dist.cuh"
 #include "kernels_small.cuh"
+#include "kernels_raff.cuh"
 #include "dist_plan.h"
 #include "csc_build.h"
 
@@ -84,6 +85,7 @@ struct pb200_handle_s {
   void *d_y = nullptr; size_t y_bytes = 0;
   bool inv_ready = false;
   bool solve_transposed = false;           // IPARM_TRANSPOSE_SOLVE (LU only)
+  void *d_raff_partial = nullptr, *h_raff_partial = nullptr;   // dot-product partial sums (device / pinned host)
   std::vector<int64_t> h_rmbase;           // per cblk: first entry of its off-diagonal rows in d_rowglob
   int *d_rowglob = nullptr;                // global row of every off-diagonal panel row
   std::vector<int> inv_lvl_nbmax;          // widest sub-panel of each level (sizes the shared memory of k_tri_inverse)
@@ -819,6 +821,8 @@ extern "C" int pb200_destroy(pb200_handle_t *h) {
   cudaFree(h->d_flags); cudaFree(h->d_dist_err);
   for (void *p : h->allocs) cudaFree(p);
   if (h->h_dag_err) cudaFreeHost(h->h_dag_err);
+  if (h->h_raff_partial) cudaFreeHost(h->h_raff_partial);
+  cudaFree(h->d_raff_partial);
   cudaFree(h->dL); cudaFree(h->dU); cudaFree(h->dW); cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals);
   cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x); cudaFree(h->d_y); cudaFree(h->d_xt);
   for (auto e : h->sched_ev) cudaEventDestroy(e);
@@ -1502,6 +1506,136 @@ extern "C" int pb200_solve(pb200_handle_t *h, void *x, int64_t ldx, int64_t nrhs
   CK(cudaMemcpyAsync(x, h->d_x, bytes, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return PB200_SUCCESS;
+}
+
+// ------------------------------------------------------------------ refinement back end (kernels_raff.cuh)
+// Vectors are managed allocations: kernels work on them in HBM, and the handful of scalars / pointer tables the
+// reference's drivers allocate through the same call stay host-dereferenceable.
+extern "C" int pb200_vec_alloc(pb200_handle_t *h, void **p, int64_t bytes) {
+  if (!h || !p || bytes < 0) return fail(PB200_ERR_BADARG, "bad argument");
+  CK(cudaSetDevice(h->device));
+  *p = nullptr;
+  const size_t nb = (size_t)std::max<int64_t>(bytes, 8);
+  if (cudaMallocManaged(p, nb) != cudaSuccess) return fail(PB200_ERR_NOMEM, "cudaMallocManaged(refinement vector) failed");
+  if (nb >= (size_t)(1 << 16)) {   // a vector: make HBM its home before the first kernel touches it
+    CK(cudaMemsetAsync(*p, 0, nb, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  } else {
+    memset(*p, 0, nb);
+  }
+  return PB200_SUCCESS;
+}
+extern "C" int pb200_vec_free(pb200_handle_t *h, void *p) {
+  if (!h) return fail(PB200_ERR_BADARG, "null handle");
+  CK(cudaSetDevice(h->device));
+  if (p) CK(cudaFree(p));
+  return PB200_SUCCESS;
+}
+extern "C" int pb200_vec_set(pb200_handle_t *h, void *dst, const void *src_host, int64_t nelem) {
+  if (!h || !dst || (!src_host && nelem > 0)) return fail(PB200_ERR_BADARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  if (src_host) CK(cudaMemcpyAsync(dst, src_host, (size_t)nelem * h->esize, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PB200_SUCCESS;
+}
+extern "C" int pb200_vec_zero(pb200_handle_t *h, void *dst, int64_t nelem) {
+  if (!h || !dst) return fail(PB200_ERR_BADARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(dst, 0, (size_t)nelem * h->esize, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PB200_SUCCESS;
+}
+extern "C" int pb200_vec_get(pb200_handle_t *h, void *dst_host, const void *src, int64_t nelem) {
+  if (!h || !dst_host || !src) return fail(PB200_ERR_BADARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(dst_host, src, (size_t)nelem * h->esize, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PB200_SUCCESS;
+}
+extern "C" int pb200_vec_copy(pb200_handle_t *h, void *dst, const void *src, int64_t nelem) {
+  if (!h || !dst || !src) return fail(PB200_ERR_BADARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(dst, src, (size_t)nelem * h->esize, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PB200_SUCCESS;
+}
+template <class T>
+static int vec_axpy_t(pb200_handle_t *h, const void *alpha, const void *x, void *y, int64_t n) {
+  T a; memcpy(&a, alpha, sizeof(T));   // the caller's scalar is a C99 complex: 8-byte aligned, not alignof(T)
+  k_raff_axpy<T><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, a, (const T *)x, (T *)y);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return PB200_SUCCESS;
+}
+template <class T>
+static int vec_scal_t(pb200_handle_t *h, const void *alpha, void *x, int64_t n) {
+  T a; memcpy(&a, alpha, sizeof(T));
+  k_raff_scal<T><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, a, (T *)x);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return PB200_SUCCESS;
+}
+template <class T>
+static int vec_dot_t(pb200_handle_t *h, int conjy, const void *x, const void *y, int64_t n, void *result) {
+  if (!h->d_raff_partial) {
+    CK(cudaMalloc(&h->d_raff_partial, PB200_RAFF_BLOCKS * 16));
+    CK(cudaHostAlloc(&h->h_raff_partial, PB200_RAFF_BLOCKS * 16, cudaHostAllocDefault));
+  }
+  k_raff_dot<T><<<PB200_RAFF_BLOCKS, 256, 0, h->stream>>>(n, (const T *)x, (const T *)y, conjy, (T *)h->d_raff_partial);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_raff_partial, h->d_raff_partial, PB200_RAFF_BLOCKS * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  T s = ST<T>::zero();
+  const T *p = (const T *)h->h_raff_partial;
+  for (int i = 0; i < PB200_RAFF_BLOCKS; ++i) s = s + p[i];
+  memcpy(result, &s, sizeof(T));
+  return PB200_SUCCESS;
+}
+template <class T>
+static int csc_ax_t(pb200_handle_t *h, int type, int trans, const void *b, const void *x, void *r) {
+  // row c of A read off column c of the symmetric-pattern CSC (see kernels_raff.cuh); A^T x is the column itself
+  const T *vals = (const T *)h->d_vals; int conjv = 0;
+  if (!trans) {
+    if (type == 'H') conjv = 1;
+    else if (type == 'U') {
+      if (!h->d_tvals) return fail(PB200_ERR_STATE, "unsymmetric matrix without the transposed values in HBM");
+      vals = (const T *)h->d_tvals;
+    }
+  }
+  k_raff_spmv<T><<<(unsigned)((h->n + 127) / 128), 128, 0, h->stream>>>(h->n, h->d_colptr, h->d_rows, vals, conjv, (const T *)x, (const T *)b, (T *)r);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return PB200_SUCCESS;
+}
+static int vec_check(pb200_handle_t *h, const void *a, const void *b) {
+  if (!h || !a || !b) return fail(PB200_ERR_BADARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  return PB200_SUCCESS;
+}
+extern "C" int pb200_vec_axpy(pb200_handle_t *h, const void *alpha, const void *x, void *y, int64_t nelem) {
+  { int rc = vec_check(h, x, y); if (rc) return rc; }
+  if (!alpha) return fail(PB200_ERR_BADARG, "null argument");
+  DISPATCH_T(h, vec_axpy_t, h, alpha, x, y, nelem)
+}
+extern "C" int pb200_vec_scal(pb200_handle_t *h, const void *alpha, void *x, int64_t nelem) {
+  { int rc = vec_check(h, alpha, x); if (rc) return rc; }
+  DISPATCH_T(h, vec_scal_t, h, alpha, x, nelem)
+}
+extern "C" int pb200_vec_dot(pb200_handle_t *h, int conj_y, const void *x, const void *y, int64_t nelem, void *result) {
+  { int rc = vec_check(h, x, y); if (rc) return rc; }
+  if (!result) return fail(PB200_ERR_BADARG, "null argument");
+  DISPATCH_T(h, vec_dot_t, h, conj_y, x, y, nelem, result)
+}
+extern "C" int pb200_csc_ax(pb200_handle_t *h, char type, int trans, const void *b, const void *x, void *r) {
+  { int rc = vec_check(h, x, r); if (rc) return rc; }
+  if (!h->d_colptr || !h->assembled) return fail(PB200_ERR_STATE, "no internal CSC resident in HBM");
+  if (type != 'S' && type != 'H' && type != 'U') return fail(PB200_ERR_BADARG, "matrix type must be S, H or U");
+  DISPATCH_T(h, csc_ax_t, h, (int)type, trans, b, x, r)
+}
+extern "C" int pb200_precond(pb200_handle_t *h, const void *s, void *d) {
+  { int rc = vec_check(h, s, d); if (rc) return rc; }
+  if (d != s) CK(cudaMemcpyAsync(d, s, (size_t)h->n * h->esize, cudaMemcpyDeviceToDevice, h->stream));
+  return pb200_solve_device(h, d, h->n, 1, nullptr);
 }
 
 // ------------------------------------------------------------------ factor slabs <-> host

@@ -39,7 +39,7 @@ for P in $PRECS; do
     c) TDEF="-DTYPE_COMPLEX";;
   esac
   LIB="$OUT/libpastix_dropin_$P.so"
-  if [ -f "$LIB" ] && [ "$LIB" -nt "$HERE/sopalin_b200_shim.c" ] && [ "$LIB" -nt "$HERE/shim_hooks.c" ] && [ "$LIB" -nt "$HERE/shim_csc.c" ] && [ "$LIB" -nt "$HERE/shim_table.h" ] && [ "$LIB" -nt "$0" ] && [ "$LIB" -nt "$ROOT/include/pastix_b200.h" ]; then
+  if [ -f "$LIB" ] && [ "$LIB" -nt "$HERE/sopalin_b200_shim.c" ] && [ "$LIB" -nt "$HERE/shim_hooks.c" ] && [ "$LIB" -nt "$HERE/shim_csc.c" ] && [ "$LIB" -nt "$HERE/shim_raff.c" ] && [ "$LIB" -nt "$HERE/shim_table.h" ] && [ "$LIB" -nt "$0" ] && [ "$LIB" -nt "$ROOT/include/pastix_b200.h" ]; then
     echo "[$P] up to date"; continue
   fi
   DEF="-DFORCE_NOMPI $TDEF -DINTSIZE64 -DMULT_SMX -DX_ARCHi686_pc_linux -DDOF_CONSTANT -DFORCE_NO_CUDA -DVERSION=\"pastix_b200\""
@@ -55,7 +55,8 @@ for P in $PRECS; do
   add $R/sparse-matrix/src/pastix_sparse_matrix.c sm_psm -DCHOL_SOPALIN
   for f in bordi sopalin_thread compute_context_nbr coefinit csc_intern_build csc_intern_io csc_intern_solve csc_intern_updown csc_utils cscd_utils cscd_utils_fortran debug_dump ooc pastix pastix_fortran sopalin_init sopalin_option sparse_gemm_cpu tools; do add $R/sopalin/src/$f.c p_$f -DCHOL_SOPALIN; done
   # the reference compiles these four times (src/CMakeLists.txt:40-62); sopalin3d.c is the one we replace
-  for f in starpu_submit_tasks csc_intern_compute raff_functions starpu_updo; do
+  # raff_functions.c (the host `struct solver` back end of the refinement drivers) is replaced by shim_raff.c
+  for f in starpu_submit_tasks csc_intern_compute starpu_updo; do
     add $R/sopalin/src/$f.c p_${f}_po -DCHOL_SOPALIN
     add $R/sopalin/src/$f.c p_${f}_ge -DSOPALIN_LU
     add $R/sopalin/src/$f.c p_${f}_sy -DNOEXTRADEF_SY
@@ -65,6 +66,10 @@ for P in $PRECS; do
   add "$HERE/sopalin_b200_shim.c" x_shim_ge -DSOPALIN_LU
   add "$HERE/sopalin_b200_shim.c" x_shim_sy -DNOEXTRADEF_SY
   add "$HERE/sopalin_b200_shim.c" x_shim_he -DHERMITIAN
+  add "$HERE/shim_raff.c" x_raff_po -DCHOL_SOPALIN
+  add "$HERE/shim_raff.c" x_raff_ge -DSOPALIN_LU
+  add "$HERE/shim_raff.c" x_raff_sy -DNOEXTRADEF_SY
+  add "$HERE/shim_raff.c" x_raff_he -DHERMITIAN
   add "$HERE/shim_hooks.c" x_shim_hooks -DCHOL_SOPALIN
   add "$HERE/shim_csc.c" x_shim_csc -DCHOL_SOPALIN
   xargs -P "$(nproc)" -I{} sh -c '{} 2>>'"$OBJ"'/err.log || echo "FAIL: {}"' < "$JOBS" | tee "$OBJ/fail.log"

@@ -152,3 +152,51 @@ def test_static_pivot_threshold_from_device_norm(prec, kind, facto, sym):
     want = ref.norm1() * np.sqrt(ref.out()["epsilon_magn_ctrl"])
     assert abs(gpu.critere() - want) <= 4e-16 * want * (1 if prec in ("s", "d") else 8)
     gpu.release()
+
+
+REFINE_CASES = [
+    # kind, N, prec, facto, sym, refinement, incomplete level (None: complete factorization)
+    ("lap7", 10, "d", "llt", "yes", "API_RAF_GMRES", 1),
+    ("lap7", 10, "d", "llt", "yes", "API_RAF_GRAD", 1),
+    ("lap7", 10, "d", "ldlt", "yes", "API_RAF_GRAD", 1),
+    ("cd", 9, "d", "lu", "no", "API_RAF_BICGSTAB", 1),
+    ("cd", 9, "d", "lu", "no", "API_RAF_GMRES", 1),
+    ("cd", 8, "z", "lu", "no", "API_RAF_GMRES", 1),
+    ("lap7her", 8, "z", "ldlh", "her", "API_RAF_GMRES", 1),
+    ("lap7", 8, "s", "llt", "yes", "API_RAF_GRAD", 1),
+    ("cd", 9, "d", "lu", "no", "API_RAF_PIVOT", None),      # static-pivot refinement: host vectors around the GPU up_down
+]
+
+
+@pytest.mark.parametrize("kind,N,prec,facto,sym,raf,ilu", REFINE_CASES)
+def test_refinement_on_device_vectors_matches_reference(kind, N, prec, facto, sym, raf, ilu):
+    """API_TASK_REFINE: the reference's unchanged drivers (raff_gmres.c, raff_grad.c, raff_bicgstab.c) over the device
+    vector back end (shim_raff.c + kernels_raff.cuh) against the same drivers over the reference's host back end
+    (raff_functions.c): same iteration count (+-1: the dot products are summed in a different order), same solution."""
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    if not available(prec):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix(kind, N, DT[prec])
+    b = G.rhs_vector(A.shape[0], 1, DT[prec])[:, 0].copy()
+    eps = 1e-10 if prec in ("d", "z") else 1e-5
+    out = []
+    for cls in (RefPastix, Pastix):
+        p = cls(prec, threads=1)
+        over = {"IPARM_REFINEMENT": p.E[raf], "IPARM_ITERMAX": 60, "IPARM_GMRES_IM": 25}
+        if ilu is not None:
+            over.update({"IPARM_INCOMPLETE": 1, "IPARM_LEVEL_OF_FILL": ilu})
+        p.setup(A, perm0, facto, sym=sym, iparm_over=over, dparm_over={"DPARM_EPSILON_REFINEMENT": eps}).analyze().numfact()
+        x = p.solve(b)
+        x = p.refine(b, x)
+        out.append((x, p.out()["nbiter"], p.out()["relative_error"]))
+        if cls is Pastix:
+            p.release()
+    (xr, itr, errr), (xg, itg, errg) = out
+    Af = full_matrix(A, sym)
+    res = np.linalg.norm(Af @ xg - b) / np.linalg.norm(b)
+    assert res <= 50 * eps, res
+    assert abs(itg - itr) <= 1 and (ilu is None or itg >= 1), (itg, itr)
+    assert relerr(xg, xr) <= 1e3 * eps
