@@ -4,6 +4,7 @@
 # $PASTIX_REFERENCE/src — nothing is copied into this repo) with ONE object replaced:
 # sopalin3d.o (x4 factorization variants) -> pastix_b200/shim/sopalin_b200_shim.c, which routes
 # API_TASK_NUMFACT / API_TASK_SOLVE to the CUDA layer libpastix_b200.so.
+# one more object: raff_functions.o (x4) -> pastix_b200/shim/shim_raff.c (refinement vector back end on the device),
 # and ONE symbol: CscOrdistrib (csc_intern_build.c:352) -> pastix_b200/shim/shim_csc.c (internal CSC built on the
 # device); the reference's routine stays linked as CscOrdistrib_hostref (objcopy --redefine-sym).
 # Recipe = SURVEY.md §8c: -DFORCE_NOMPI, no Scotch/METIS (API_ORDER_PERSONAL + KASS), 64-bit
