@@ -154,6 +154,7 @@ extern "C" int pb200_csc_destroy(pb200_csc_t *c) {
   cudaFree(c->d_ucolptr); cudaFree(c->d_urows); cudaFree(c->d_uvals); cudaFree(c->d_perm);
   cudaFree(c->d_keys0); cudaFree(c->d_keys1); cudaFree(c->d_pay0); cudaFree(c->d_pay1); cudaFree(c->d_tmp);
   cudaFree(c->d_colptr); cudaFree(c->d_rows); cudaFree(c->d_vals); cudaFree(c->d_tvals); cudaFree(c->d_extra);
+  for (int i = 0; i < PB200_CSC_NPIN; ++i) { if (c->pin[i]) cudaFreeHost(c->pin[i]); if (c->pstream[i]) cudaStreamDestroy(c->pstream[i]); }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return PB200_SUCCESS;
@@ -234,14 +235,20 @@ extern "C" int pb200_csc_build(pb200_csc_t *c, char type, int64_t n, const int64
 // frees and re-allocates its CscMatrix on every NUMFACT), so a plain cudaMemcpy is bound by first-touch page faults of
 // ONE thread (C3: 424 MB in ~200 ms).  Here several host threads each pull their slice through a small pinned
 // buffer on their own stream, so that the DMA, the faults and the memcpy of different slices overlap.
-static int parallel_d2h(int device, void *dst, const void *src, size_t bytes) {
-  const size_t PIECE = (size_t)8 << 20;
-  unsigned nt = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
-  nt = (unsigned)std::min<size_t>(nt, (bytes + PIECE - 1) / PIECE);
+static const size_t kPiece = (size_t)8 << 20;
+static int parallel_d2h(pb200_csc_t *c, void *dst, const void *src, size_t bytes) {
+  unsigned nt = std::min<unsigned>(PB200_CSC_NPIN, std::max(1u, std::thread::hardware_concurrency()));
+  nt = (unsigned)std::min<size_t>(nt, (bytes + kPiece - 1) / kPiece);
   if (bytes < ((size_t)16 << 20) || nt < 2) {
     if (cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
     return 0;
   }
+  // pinned pieces and streams are created once per pb200_csc_t (cudaHostAlloc costs milliseconds)
+  for (unsigned i = 0; i < nt; ++i)
+    if (!c->pin[i]) {
+      if (cudaHostAlloc(&c->pin[i], kPiece, cudaHostAllocDefault) != cudaSuccess) { c->pin[i] = nullptr; return 1; }
+      if (cudaStreamCreateWithFlags(&c->pstream[i], cudaStreamNonBlocking) != cudaSuccess) return 1;
+    }
   {
     // first touch with 2 MB pages where the kernel allows it (transparent huge pages in madvise/always mode):
     // ~500x fewer page faults on a fresh malloc'ed destination; a refusal is harmless
@@ -251,20 +258,18 @@ static int parallel_d2h(int device, void *dst, const void *src, size_t bytes) {
   std::vector<std::thread> th;
   std::vector<int> rc(nt, 0);
   const size_t slice = ((bytes / nt) + 4095) & ~(size_t)4095;
+  const int device = c->device;
   for (unsigned i = 0; i < nt; ++i)
     th.emplace_back([&, i]() {
       const size_t lo = std::min(bytes, (size_t)i * slice), hi = (i + 1 == nt) ? bytes : std::min(bytes, lo + slice);
       if (hi <= lo) return;
-      void *pin = nullptr; cudaStream_t st = nullptr;
-      if (cudaSetDevice(device) != cudaSuccess || cudaHostAlloc(&pin, PIECE, cudaHostAllocDefault) != cudaSuccess ||
-          cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { rc[i] = 1; if (pin) cudaFreeHost(pin); return; }
-      for (size_t off = lo; off < hi && !rc[i]; off += PIECE) {
-        const size_t n = std::min(PIECE, hi - off);
-        if (cudaMemcpyAsync(pin, (const char *)src + off, n, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaStreamSynchronize(st) != cudaSuccess) { rc[i] = 1; break; }
-        memcpy((char *)dst + off, pin, n);
+      if (cudaSetDevice(device) != cudaSuccess) { rc[i] = 1; return; }
+      for (size_t off = lo; off < hi; off += kPiece) {
+        const size_t n = std::min(kPiece, hi - off);
+        if (cudaMemcpyAsync(c->pin[i], (const char *)src + off, n, cudaMemcpyDeviceToHost, c->pstream[i]) != cudaSuccess ||
+            cudaStreamSynchronize(c->pstream[i]) != cudaSuccess) { rc[i] = 1; break; }
+        memcpy((char *)dst + off, c->pin[i], n);
       }
-      cudaStreamDestroy(st); cudaFreeHost(pin);
     });
   for (auto &t : th) t.join();
   for (int r : rc) if (r) return 1;
@@ -281,8 +286,8 @@ extern "C" int pb200_csc_fetch(pb200_csc_t *c, int64_t *colptr, int64_t *rows, v
     int64_t *wide = reinterpret_cast<int64_t *>(c->d_keys0);   // 2*unz*8 bytes >= nnz*8
     k_csc_widen<<<(unsigned)((c->nnz + 255) / 256), 256, 0, c->stream>>>(c->nnz, c->d_rows, wide);
     CCK(cudaStreamSynchronize(c->stream));
-    if (parallel_d2h(c->device, rows, wide, (size_t)c->nnz * 8) || parallel_d2h(c->device, values, c->d_vals, (size_t)c->nnz * c->esize) ||
-        (tvalues && parallel_d2h(c->device, tvalues, c->d_tvals, (size_t)c->nnz * c->esize)))
+    if (parallel_d2h(c, rows, wide, (size_t)c->nnz * 8) || parallel_d2h(c, values, c->d_vals, (size_t)c->nnz * c->esize) ||
+        (tvalues && parallel_d2h(c, tvalues, c->d_tvals, (size_t)c->nnz * c->esize)))
       return cfail(PB200_ERR_CUDA, "device -> host copy of the internal CSC failed");
   }
   CCK(cudaStreamSynchronize(c->stream));

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define PB200_CSC_NPIN 8
 struct pb200_csc_s {
   int flt = 0, device = 0;
   size_t esize = 0;
@@ -18,4 +19,6 @@ struct pb200_csc_s {
   size_t cap_colptr = 0, cap_rows = 0, cap_vals = 0, cap_tvals = 0, cap_extra = 0;
   int64_t n = 0, nnz = 0;
   bool has_t = false, valid = false;
+  // pinned staging pieces of the parallel device -> host fetch (one per worker thread, created on first use)
+  void *pin[PB200_CSC_NPIN] = {}; cudaStream_t pstream[PB200_CSC_NPIN] = {};
 };

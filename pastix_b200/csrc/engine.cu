@@ -1281,7 +1281,7 @@ extern "C" int pb200_inertia(pb200_handle_t *h, int64_t *inertia) {
 // invert the diagonal triangles of the freshly factored panels (one CTA per sub-panel)
 static const int kInvClasses[] = {16, 32, 48, 64, 96, 128};
 template <class T>
-static size_t inv_smem(int nbmax) { return (size_t)nbmax * (nbmax + 1) * sizeof(T); }   // two row-packed triangles
+static size_t inv_smem(int nbmax) { return ((size_t)nbmax * (nbmax + 1) / 2 + (size_t)tri_xelems(nbmax)) * sizeof(T); }   // packed W + per-warp X rectangles
 template <class T>
 static int inv_attr(pb200_handle_t *h) {
   static bool attr_done[4] = {};

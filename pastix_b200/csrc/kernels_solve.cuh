@@ -56,11 +56,16 @@ __device__ __forceinline__ int panel_row_to_global(const DevSym &S, int c, int m
 
 // ---- inverse of the lower triangle of every diagonal sub-block: X = W^{-1}, W nb x nb (ld), unit or not.
 // One CTA per sub-panel (`order`, when given, lists the sub-panels of one size class so that the launch can be
-// sized for them).  W and X live in shared memory as row-packed lower triangles (row i = columns 0..i);
-// thread j builds column j of X by forward substitution: x_ij = -(sum_{k=j}^{i-1} w_ik x_kj) / w_ii.  The k loop
-// starts at the warp's first column, so the w_ik reads are warp-wide broadcasts and the x_kj reads (own
-// column, written by the same thread) fall on consecutive words: no bank conflicts, no barrier between rows.
-__device__ __forceinline__ int tri_row(int i) { return (i * (i + 1)) >> 1; }
+// sized for them).  Thread j builds column j of X by forward substitution, x_ij = -(sum_{k<i} w_ik x_kj) / w_ii.
+// W sits in shared memory as a row-packed triangle (row i = columns 0..i).  X is stored per warp: the 32 columns
+// [j0, j0+32) of warp j0/32 as a rectangle of rows j0..nb-1, zero above the diagonal — so the k loop of a row runs
+// from the warp's first column without predicates: w_ik is a warp-wide broadcast, x_kj (own column, written by the
+// same thread) falls on consecutive words, the loop unrolls into independent FMA chains, and no barrier separates
+// the rows.
+__device__ __host__ __forceinline__ int tri_row(int i) { return (i * (i + 1)) >> 1; }
+// elements of the per-warp X rectangles of an nb-wide triangle, and the offset of warp block wb
+__device__ __host__ __forceinline__ int tri_xbase(int wb, int nb) { return 32 * (wb * nb - 16 * wb * (wb - 1)); }
+__device__ __host__ __forceinline__ int tri_xelems(int nb) { return tri_xbase((nb + 31) / 32, nb); }
 
 template <class T>
 __global__ void __launch_bounds__(128)
@@ -76,30 +81,35 @@ k_tri_inverse(const T *__restrict__ M, const SlvTask *__restrict__ tasks, const 
     const int k = e / nb, i = e - k * nb;
     if (i >= k) Ws[tri_row(i) + k] = W[(size_t)k * ld + i];
   }
+  for (int e = threadIdx.x; e < tri_xelems(nb); e += blockDim.x) Xs[e] = zero;
   __syncthreads();
-  const int j = threadIdx.x, j0 = j & ~31;          // j0: first column of this warp
+  const int j = threadIdx.x, j0 = j & ~31, lj = j & 31;          // j0: first column of this warp
   if (j0 < nb) {
-    if (j < nb) Xs[tri_row(j) + j] = unit ? one : one / Ws[tri_row(j) + j];
+    T *xc = Xs + tri_xbase(j0 >> 5, nb) + lj;                      // X(j0 + t, j) = xc[32 t]
+    if (j < nb) xc[32 * (j - j0)] = unit ? one : one / Ws[tri_row(j) + j];
     for (int i = j0 + 1; i < nb; ++i) {
-      const T *wr = Ws + tri_row(i);
-      T s0 = zero, s1 = zero;
-      int k = j0;
-      for (; k + 1 < i; k += 2) {
-        if (k >= j) fma_acc(s0, wr[k], Xs[tri_row(k) + j]);
-        if (k + 1 >= j) fma_acc(s1, wr[k + 1], Xs[tri_row(k + 1) + j]);
+      const T *wr = Ws + tri_row(i) + j0;                          // W(i, j0 + t) = wr[t]
+      const int cnt = i - j0;
+      T s0 = zero, s1 = zero, s2 = zero, s3 = zero;
+      int t = 0;
+      for (; t + 3 < cnt; t += 4) {
+        fma_acc(s0, wr[t], xc[32 * t]);
+        fma_acc(s1, wr[t + 1], xc[32 * (t + 1)]);
+        fma_acc(s2, wr[t + 2], xc[32 * (t + 2)]);
+        fma_acc(s3, wr[t + 3], xc[32 * (t + 3)]);
       }
-      if (k < i && k >= j) fma_acc(s0, wr[k], Xs[tri_row(k) + j]);
+      for (; t < cnt; ++t) fma_acc(s0, wr[t], xc[32 * t]);
       if (i > j && j < nb) {
-        const T s = zero - (s0 + s1);
-        Xs[tri_row(i) + j] = unit ? s : s / wr[i];
+        const T sm = zero - ((s0 + s1) + (s2 + s3));
+        xc[32 * cnt] = unit ? sm : sm / wr[cnt];
       }
     }
   }
   __syncthreads();
   T *out = inv + tk.invoff;
   for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
-    const int jj = e / nb, i = e - jj * nb;
-    out[e] = (i >= jj) ? Xs[tri_row(i) + jj] : zero;
+    const int jj = e / nb, i = e - jj * nb, b0 = jj & ~31;
+    out[e] = (i >= jj) ? Xs[tri_xbase(b0 >> 5, nb) + 32 * (i - b0) + (jj & 31)] : zero;
   }
 }
 
