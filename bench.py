@@ -356,9 +356,12 @@ def our_arm(args):
         gms = prof["ms"]["gemm_scatter"]
         tot = sum(prof["ms"].values())
         ach = prof["gemm_flops"] / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        traf = ncu_traffic(args.workload)
         roof = {"kernel": "k_gemm_scatter (fused DMMA GEMM + scatter-add into facing cblks)", "bound": "tensor",
                 "achieved": ach, "peak": peak["peak_tflops"], "unit": "TFLOP/s", "frac": ach / peak["peak_tflops"],
-                "traffic": ncu_traffic(args.workload), "peak_source": peak["source"], "fp64_peaks": {k: v for k, v in peak.items() if k.endswith("tflops")},
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (the largest one captured by ncu --set full;
+                # which launch, its duration and pipe utilisation are in traffic_capture)
+                "traffic": traf["dram_bytes"] if traf else None, "traffic_capture": traf, "peak_source": peak["source"], "fp64_peaks": {k: v for k, v in peak.items() if k.endswith("tflops")},
                 "kernel_share_of_step": gms / tot if tot > 0 else None,
                 "kind_ms_serialised": prof["ms"], "kind_launches": prof["launches"],
                 "algorithmic_flops_per_factorization": prof["gemm_flops"]}

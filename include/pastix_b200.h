@@ -107,6 +107,22 @@ int pb200_create(pb200_handle_t **h, const pb200_solver_t *solver,
                  int flttype, int factotype, int device);
 int pb200_destroy(pb200_handle_t *h);
 
+/* Options of pb200_create_opts (zero-initialise; NULL = all defaults).
+ *   schur : IPARM_SCHUR == API_YES (api.h).  The reference never factors the column block that holds the last
+ *           column (compute_1d returns at once, sopalin/src/sopalin_compute.c:767-772; blend keeps it unsplit,
+ *           blend/src/splitpart.c:573-584): it only receives contributions, so after pb200_factorize its panel IS the
+ *           Schur complement — what pastix_getSchur copies out of SOLV_COEFTAB (sopalin/src/pastix.c:6434-6475;
+ *           read it with pb200_get_cblk(h, cblknbr-1, ...)).  up_down ignores that cblk and every blok facing it in
+ *           the down, diagonal and up steps (updo.c:425-428, 639-646, 951-954, 1154-1180; updo_sendrecv.c:518-523):
+ *           the interior system is solved and the Schur unknowns keep their right-hand side. */
+typedef struct pb200_options_s {
+  int32_t schur;
+  int32_t reserved[7];
+} pb200_options_t;
+/* pb200_create / pb200_create_dist with options (rank 0 of 1 for a single GPU). */
+int pb200_create_opts(pb200_handle_t **h, const pb200_solver_t *solver, int flttype, int factotype,
+                      int device, int rank, int nranks, const pb200_options_t *opts);
+
 /* ---- multi-GPU: one process per GPU of one box, `nranks` <= 8 (the reference's distributed mode:
  * dpastix + MPI, one SolverMatrix per process with fan-in targets, blend/src/ftgt.h:68-127).
  * Every process builds the SAME single-process SolverMatrix (the analysis is deterministic) and passes
@@ -217,6 +233,9 @@ int pb200_solve_device(pb200_handle_t *h, void *x_dev, int64_t ldx, int64_t nrhs
 /* Copy the factor slab(s) device -> host / host -> device. U may be NULL unless LU. */
 int pb200_get_coeftab(pb200_handle_t *h, void *L, void *U);
 int pb200_set_coeftab(pb200_handle_t *h, const void *L, const void *U);
+/* One column block's panel(s), device -> host: stride*width elements laid out like SolverCblk.coeftab / .ucoeftab
+ * (blend/src/solver.h:94-117).  U may be NULL. */
+int pb200_get_cblk(pb200_handle_t *h, int64_t cblk, void *L, void *U);
 
 /* Declare panels uploaded with pb200_set_coeftab to be already factorized
  * (solve-only use: factors computed elsewhere, e.g. by the reference). */

@@ -45,6 +45,8 @@ class Oracle:
         self._norm1 = f("norm1"); self._norm1.restype = C.c_double
         self._assemble = f("assemble"); self._assemble.restype = C.c_int64
         self._factorize = f("factorize"); self._factorize.restype = C.c_int
+        self._factorize_schur = f("factorize_schur"); self._factorize_schur.restype = C.c_int
+        self._solve_schur = f("solve_schur"); self._solve_schur.restype = None
         self._inertia = f("inertia"); self._inertia.restype = C.c_int64
         self._solve = f("solve"); self._solve.restype = None
 
@@ -64,9 +66,10 @@ class Oracle:
                                           C.c_void_p(U.ctypes.data) if U is not None else None))
         return L, U
 
-    def factorize(self, facto: str, L, U, crit: float) -> int:
+    def factorize(self, facto: str, L, U, crit: float, schur: bool = False) -> int:
+        """schur: IPARM_SCHUR semantics — the last cblk is left unfactored (it holds the Schur complement)."""
         nb = C.c_int64(0)
-        rc = self._factorize(C.byref(self.os), C.c_int(FACTO[facto]), C.c_void_p(L.ctypes.data),
+        rc = (self._factorize_schur if schur else self._factorize)(C.byref(self.os), C.c_int(FACTO[facto]), C.c_void_p(L.ctypes.data),
                              C.c_void_p(U.ctypes.data) if U is not None else None, C.c_double(crit), C.byref(nb))
         if rc:
             raise RuntimeError("oracle: negative diagonal term")
@@ -75,11 +78,12 @@ class Oracle:
     def inertia(self, L) -> int:
         return int(self._inertia(C.byref(self.os), C.c_void_p(L.ctypes.data)))
 
-    def solve(self, facto: str, L, U, x):
-        """x: (n,) or (n,nrhs) Fortran-ordered, permuted ordering; solved in place."""
+    def solve(self, facto: str, L, U, x, schur: bool = False):
+        """x: (n,) or (n,nrhs) Fortran-ordered, permuted ordering; solved in place.
+        schur: the last cblk and the bloks facing it are ignored (interior solve, x_S = b_S)."""
         assert x.dtype == self.dtype and (x.ndim == 1 or x.flags.f_contiguous)
         nrhs = 1 if x.ndim == 1 else x.shape[1]
-        self._solve(C.byref(self.os), C.c_int(FACTO[facto]), C.c_void_p(L.ctypes.data),
+        (self._solve_schur if schur else self._solve)(C.byref(self.os), C.c_int(FACTO[facto]), C.c_void_p(L.ctypes.data),
                     C.c_void_p(U.ctypes.data) if U is not None else None, C.c_void_p(x.ctypes.data),
                     C.c_int64(x.shape[0]), C.c_int64(nrhs))
         return x

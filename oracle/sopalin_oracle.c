@@ -246,7 +246,7 @@ static int64_t find_blok(const osolver *s, int64_t c, int64_t r)
  * contributor of c has a smaller index), each as compute_1d does.
  * Returns 0, or 1 on a negative pivot in real LLt.
  */
-int PFX(oracle_factorize)(const osolver *s, int facto, T *L, T *U, double crit, int64_t *nbpivot)
+static int factorize_impl(const osolver *s, int facto, T *L, T *U, double crit, int64_t *nbpivot, int schur)
 {
   int64_t c, b1, b2, i, j, l;
   int herm = (facto == FACT_LDLH);
@@ -265,6 +265,9 @@ int PFX(oracle_factorize)(const osolver *s, int facto, T *L, T *U, double crit, 
     int64_t w = s->lcol[c] - s->fcol[c] + 1, ld = s->stride[c], m = ld - w;
     int64_t fb = s->bloknum[c], lb = s->bloknum[c + 1];
     T *A = L + s->poff[c];            /* diag blok has coefind 0 */
+    /* IPARM_SCHUR: the cblk holding the last column is left as assembled + updated = the Schur complement
+       (compute_1d returns at once, sopalin_compute.c:767-772) */
+    if (schur && c == s->cblknbr - 1) continue;
     T *P = A + w;                     /* off-diagonal panel */
     T *UA = U ? U + s->poff[c] : NULL, *UP = UA ? UA + w : NULL;
     /* factor_diag */
@@ -349,6 +352,15 @@ int PFX(oracle_factorize)(const osolver *s, int facto, T *L, T *U, double crit, 
   return 0;
 }
 
+int PFX(oracle_factorize)(const osolver *s, int facto, T *L, T *U, double crit, int64_t *nbpivot)
+{
+  return factorize_impl(s, facto, L, U, crit, nbpivot, 0);
+}
+int PFX(oracle_factorize_schur)(const osolver *s, int facto, T *L, T *U, double crit, int64_t *nbpivot)
+{
+  return factorize_impl(s, facto, L, U, crit, nbpivot, 1);
+}
+
 /* number of positive diagonal terms of D (sopalin3d.c:1145-1161) */
 int64_t PFX(oracle_inertia)(const osolver *s, const T *L)
 {
@@ -367,15 +379,18 @@ int64_t PFX(oracle_inertia)(const osolver *s, const T *L)
 }
 
 /* up_down on x (n x nrhs, column-major, leading dimension ldx, permuted order) */
-void PFX(oracle_solve)(const osolver *s, int facto, const T *L, const T *U, T *x, int64_t ldx, int64_t nrhs)
+static void solve_impl(const osolver *s, int facto, const T *L, const T *U, T *x, int64_t ldx, int64_t nrhs, int schur)
 {
+  /* IPARM_SCHUR: the last cblk and every blok facing it are ignored by all three steps (updo.c:425-428, 639-646,
+     1154-1180; updo_sendrecv.c:518-523): the interior system is solved, the Schur unknowns keep their right-hand side */
+  const int64_t ncb = schur ? s->cblknbr - 1 : s->cblknbr, skip = schur ? s->cblknbr - 1 : -1;
   int64_t c, b, i, j, k;
   int herm = (facto == FACT_LDLH);
   int unit = (facto != FACT_LLT); /* updo.c:582-594: non-unit only for LLt */
   for (k = 0; k < nrhs; k++) {
     T *xk = x + k * ldx;
     /* DOWN */
-    for (c = 0; c < s->cblknbr; c++) {
+    for (c = 0; c < ncb; c++) {
       int64_t w = s->lcol[c] - s->fcol[c] + 1, ld = s->stride[c];
       const T *A = L + s->poff[c];
       T *xc = xk + s->fcol[c];
@@ -387,17 +402,18 @@ void PFX(oracle_solve)(const osolver *s, int facto, const T *L, const T *U, T *x
         int64_t nr = s->lrow[b] - s->frow[b] + 1;
         const T *B = A + s->coefind[b];
         T *xt = xk + s->frow[b];
+        if (s->fcblk[b] == skip) continue;
         for (j = 0; j < w; j++) for (i = 0; i < nr; i++) xt[i] -= B[j * ld + i] * xc[j];
       }
     }
     /* DIAG (LDLt / LDLh) */
     if (facto == FACT_LDLT || facto == FACT_LDLH)
-      for (c = 0; c < s->cblknbr; c++) {
+      for (c = 0; c < ncb; c++) {
         int64_t w = s->lcol[c] - s->fcol[c] + 1, ld = s->stride[c];
         for (j = 0; j < w; j++) xk[s->fcol[c] + j] /= L[s->poff[c] + j * (ld + 1)];
       }
     /* UP */
-    for (c = s->cblknbr - 1; c >= 0; c--) {
+    for (c = ncb - 1; c >= 0; c--) {
       int64_t w = s->lcol[c] - s->fcol[c] + 1, ld = s->stride[c];
       const T *A = ((facto == FACT_LU) ? U : L) + s->poff[c];
       T *xc = xk + s->fcol[c];
@@ -405,6 +421,7 @@ void PFX(oracle_solve)(const osolver *s, int facto, const T *L, const T *U, T *x
         int64_t nr = s->lrow[b] - s->frow[b] + 1;
         const T *B = A + s->coefind[b];
         const T *xt = xk + s->frow[b];
+        if (s->fcblk[b] == skip) continue;
         for (j = 0; j < w; j++) {
           T acc = 0;
           for (i = 0; i < nr; i++) acc += (herm ? CONJ(B[j * ld + i]) : B[j * ld + i]) * xt[i];
@@ -420,4 +437,13 @@ void PFX(oracle_solve)(const osolver *s, int facto, const T *L, const T *U, T *x
       }
     }
   }
+}
+
+void PFX(oracle_solve)(const osolver *s, int facto, const T *L, const T *U, T *x, int64_t ldx, int64_t nrhs)
+{
+  solve_impl(s, facto, L, U, x, ldx, nrhs, 0);
+}
+void PFX(oracle_solve_schur)(const osolver *s, int facto, const T *L, const T *U, T *x, int64_t ldx, int64_t nrhs)
+{
+  solve_impl(s, facto, L, U, x, ldx, nrhs, 1);
 }

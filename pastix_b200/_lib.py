@@ -18,6 +18,7 @@ SYMBOLS = [
     "pb200_vec_alloc", "pb200_vec_free", "pb200_vec_set", "pb200_vec_get", "pb200_vec_zero", "pb200_vec_copy", "pb200_vec_scal",
     "pb200_vec_axpy", "pb200_vec_dot", "pb200_csc_ax", "pb200_precond",
     "pb200_csc_create", "pb200_csc_destroy", "pb200_csc_build", "pb200_csc_fetch", "pb200_csc_norm1", "pb200_assemble_csc",
+    "pb200_create_opts", "pb200_get_cblk",
 ]
 
 
@@ -31,6 +32,11 @@ class Info(C.Structure):
     """pb200_info_t"""
     _fields_ = [("n", C.c_int64), ("coefnbr", C.c_int64), ("nlevels", C.c_int64), ("device_bytes", C.c_int64),
                 ("device", C.c_int32), ("sm_count", C.c_int32), ("cc_major", C.c_int32), ("cc_minor", C.c_int32)]
+
+
+class Options(C.Structure):
+    """pb200_options_t"""
+    _fields_ = [("schur", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 _lib = None
@@ -49,6 +55,9 @@ def lib() -> C.CDLL:
     L.pb200_version.restype = C.c_char_p
     L.pb200_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(SolverDesc), C.c_int, C.c_int, C.c_int]
     L.pb200_create_dist.argtypes = [C.POINTER(C.c_void_p), C.POINTER(SolverDesc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.pb200_create_opts.argtypes = [C.POINTER(C.c_void_p), C.POINTER(SolverDesc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(Options)]
+    L.pb200_get_cblk.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.pb200_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
     L.pb200_ipc_attach.argtypes = [C.c_void_p, C.c_void_p]
     L.pb200_dist_barrier.argtypes = [C.c_void_p]

@@ -85,6 +85,8 @@ struct pb200_handle_s {
   void *d_y = nullptr; size_t y_bytes = 0;
   bool inv_ready = false;
   bool solve_transposed = false;           // IPARM_TRANSPOSE_SOLVE (LU only)
+  bool schur = false;                      // IPARM_SCHUR: the last cblk is never factored (it ends up holding the Schur complement) and
+                                           // up_down ignores it and every blok facing it (sopalin_compute.c:767-772, updo.c:425-428)
   void *d_raff_partial = nullptr, *h_raff_partial = nullptr;   // dot-product partial sums (device / pinned host)
   std::vector<int64_t> h_rmbase;           // per cblk: first entry of its off-diagonal rows in d_rowglob
   int *d_rowglob = nullptr;                // global row of every off-diagonal panel row
@@ -174,11 +176,23 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
   std::vector<int> spid(nsp, -1);
   int nbs = 1;
   long long nticks = nsp;
+  // Schur mode: the last cblk gets no ticket at all and every panel ends where its rows start facing it (those bloks
+  // are the last ones of a panel: the Schur cblk holds the highest rows) — the reference's "ignore schur" tests in
+  // the down, diagonal and up loops (updo.c:425-428, 639-646, 711-714, 951-954, 1154-1180; updo_sendrecv.c:518-523)
+  const int sc = h->schur ? (int)C - 1 : -1;
+  std::vector<int> mend(C);
+  for (int64_t c = 0; c < C; ++c) {
+    mend[c] = h->h_stride[c];
+    if (sc >= 0)
+      for (int b = h->h_fblok[c] + 1; b < h->h_fblok[c + 1]; ++b)
+        if (h->h_fcblk[b] == sc) { mend[c] = h->h_coefind[b]; break; }
+  }
   for (int i = 0; i < nsp; ++i) {
     const SlvTask &tk = tasks[i];
     spid[sp_ptr[tk.cblk] + tk.c0 / sw[tk.cblk]] = i;
+    if (tk.cblk == sc) continue;
     nbs = std::max(nbs, tk.c1 - tk.c0);
-    nticks += (tk.ld - tk.c1 + PB200_DAG_ROWS - 1) / PB200_DAG_ROWS;
+    nticks += (std::max(mend[tk.cblk], tk.c1) - tk.c1 + PB200_DAG_ROWS - 1) / PB200_DAG_ROWS;
   }
   if (nticks >= (1LL << 24)) return PB200_SUCCESS;   // millions of tiny tickets: the level sweeps batch them better
   std::vector<DagTick> ticks; ticks.reserve((size_t)nticks);
@@ -187,8 +201,10 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
   std::vector<long long> stamp(nsp, -1);
   for (int i = 0; i < nsp; ++i) {
     const SlvTask &tk = tasks[i];
+    if (tk.cblk == sc) continue;
     const int c = tk.cblk, w = tk.w, ld = tk.ld, nb = tk.c1 - tk.c0;
-    const int nt = (ld - tk.c1 + PB200_DAG_ROWS - 1) / PB200_DAG_ROWS;
+    const int me = std::max(mend[c], tk.c1);   // rows [c1, me) of the panel take part
+    const int nt = (me - tk.c1 + PB200_DAG_ROWS - 1) / PB200_DAG_ROWS;
     DagTick d{};
     d.src = tk.invoff; d.aux = tk.poff + (int64_t)tk.c0 * (ld + 1); d.ld = ld; d.nb = nb; d.mrows = -1; d.sp = tk.sp;
     d.xcol = tk.fcol + tk.c0; d.nsib = nt;
@@ -197,7 +213,7 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
     const int be = h->h_fblok[c + 1];
     for (int t = 0; t < nt; ++t) {
       const long long g = (long long)ticks.size();
-      const int m0 = tk.c1 + t * PB200_DAG_ROWS, m1 = std::min(ld, m0 + PB200_DAG_ROWS);
+      const int m0 = tk.c1 + t * PB200_DAG_ROWS, m1 = std::min(me, m0 + PB200_DAG_ROWS);
       DagTick k{};
       k.src = tk.poff + (int64_t)tk.c0 * ld + m0; k.aux = tk.rgbase + m0; k.ld = ld; k.nb = nb; k.mrows = m1 - m0; k.sp = tk.sp;
       k.xcol = tk.fcol + tk.c0; k.grow0 = tk.fcol + m0; k.wrem = w - m0; k.tptr = (int)tgt.size();
@@ -303,6 +319,7 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
     const int ncls = 6; const int bound[ncls] = {16, 32, 48, 64, 96, 128};
     std::vector<std::vector<int>> byc(ncls);
     for (int i = 0; i < (int)tasks.size(); ++i) {
+      if (h->schur && tasks[i].cblk == (int)h->cblknbr - 1) continue;   // never factored: nothing to invert
       const int nb = tasks[i].c1 - tasks[i].c0;
       int k = 0; while (k + 1 < ncls && nb > bound[k]) ++k;
       byc[k].push_back(i);
@@ -589,7 +606,14 @@ extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int f
 
 extern "C" int pb200_create_dist(pb200_handle_t **out, const pb200_solver_t *s, int flttype, int factotype, int device,
                                  int rank, int nranks) {
+  return pb200_create_opts(out, s, flttype, factotype, device, rank, nranks, nullptr);
+}
+
+extern "C" int pb200_create_opts(pb200_handle_t **out, const pb200_solver_t *s, int flttype, int factotype, int device,
+                                 int rank, int nranks, const pb200_options_t *opts) {
   if (!out || !s) return fail(PB200_ERR_BADARG, "null argument");
+  const bool schur = opts && opts->schur != 0;
+  if (schur && nranks > 1) return fail(PB200_ERR_BADARG, "Schur mode is single-GPU (the reference's Schur cblk lives on one process too)");
   if (nranks < 1 || nranks > PB200_MAXRANKS || rank < 0 || rank >= nranks) return fail(PB200_ERR_BADARG, "bad rank / nranks");
   if (elem_size(flttype) == 0) return fail(PB200_ERR_BADARG, "bad flttype");
   if (factotype < 0 || factotype > 3) return fail(PB200_ERR_BADARG, "bad factotype");
@@ -607,6 +631,7 @@ extern "C" int pb200_create_dist(pb200_handle_t **out, const pb200_solver_t *s, 
   h->flt = flttype; h->facto = factotype; h->device = device; h->esize = elem_size(flttype);
   h->sm_count = prop.multiProcessorCount; h->cc_major = prop.major; h->cc_minor = prop.minor;
   h->rank = rank; h->nranks = nranks; h->gathered = (nranks == 1);
+  h->schur = schur;
   const int64_t C = s->cblknbr, B = s->bloknbr;
   h->cblknbr = C; h->bloknbr = B;
   h->h_fcol.resize(C); h->h_width.resize(C); h->h_stride.resize(C); h->h_fblok.resize(C + 1);
@@ -629,6 +654,7 @@ extern "C" int pb200_create_dist(pb200_handle_t **out, const pb200_solver_t *s, 
   if (h->h_fblok[C] != B) return bad("bloknum sentinel != bloknbr");
   h->n = s->lcolnum[C - 1] + 1;
   h->coefnbr = h->h_poff[C];
+  if (h->schur && s->bloknum[C] - s->bloknum[C - 1] != 1) return bad("Schur mode: the last cblk has off-diagonal bloks");
   for (int64_t c = 0; c < C; ++c) {
     int b0 = h->h_fblok[c], b1 = h->h_fblok[c + 1];
     if (b1 <= b0) return bad("cblk without diagonal blok");
@@ -730,6 +756,17 @@ extern "C" int pb200_create_dist(pb200_handle_t **out, const pb200_solver_t *s, 
     CK(cudaMemset(h->d_flags, 0, (size_t)(nl + 2) * sizeof(unsigned int)));
     CK(cudaMalloc((void **)&h->d_dist_err, sizeof(unsigned int)));
     CK(cudaMemset(h->d_dist_err, 0, sizeof(unsigned int)));
+  }
+
+  if (h->schur) {
+    // IPARM_SCHUR: compute_1d returns at once for the cblk holding the last column (sopalin_compute.c:767-772) — it
+    // keeps receiving contributions and is never factored.  The factorization schedule simply does not list it.
+    std::vector<int> optr(nl + 1, 0), ocblk;
+    for (int l = 0; l < nl; ++l) {
+      for (int q = h->lvl_ptr[l]; q < h->lvl_ptr[l + 1]; ++q) if (lvl_cblk[q] != (int)C - 1) ocblk.push_back(lvl_cblk[q]);
+      optr[l + 1] = (int)ocblk.size();
+    }
+    h->lvl_ptr = optr; lvl_cblk = ocblk;
   }
 
   // ---- per-level task lists
@@ -1330,6 +1367,8 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
   // triangle) and the up step on L (unit) — what the reference obtains by rescaling and swapping coeftab/ucoeftab
   // around its ordinary sweeps (updo.c:165-260, 1553-1600)
   const bool tsolve = (FACTO == F_LU) && h->solve_transposed;
+  if (h->schur && !h->dag_ok)
+    return fail(PB200_ERR_STATE, "Schur mode: up_down needs the persistent sweeps (not an all-small / PB200_SOLVE_LEVELS schedule)");
   const T *L = (const T *)(tsolve ? h->dU : h->dL);
   const T *Mup = (FACTO == F_LU) ? (const T *)(tsolve ? h->dL : h->dU) : L;
   const T *inv = (const T *)(tsolve ? h->d_inv_up : h->d_inv);
@@ -1648,6 +1687,21 @@ extern "C" int pb200_get_coeftab(pb200_handle_t *h, void *L, void *U) {
   if (U) {
     if (!h->dU) return fail(PB200_ERR_STATE, "no U slab (not an LU factorization)");
     CK(cudaMemcpy(U, h->dU, slab, cudaMemcpyDeviceToHost));
+  }
+  return PB200_SUCCESS;
+}
+
+// one panel: coeftab[c] / ucoeftab[c] as the reference lays them out (stride x width, column-major)
+extern "C" int pb200_get_cblk(pb200_handle_t *h, int64_t c, void *L, void *U) {
+  if (!h || !L) return fail(PB200_ERR_BADARG, "null argument");
+  if (c < 0 || c >= h->cblknbr) return fail(PB200_ERR_BADARG, "cblk index out of range");
+  CK(cudaSetDevice(h->device));
+  if (h->factorized) { int rc = ensure_gathered(h); if (rc) return rc; }
+  const size_t off = (size_t)h->h_poff[c] * h->esize, bytes = (size_t)(h->h_poff[c + 1] - h->h_poff[c]) * h->esize;
+  CK(cudaMemcpy(L, (const char *)h->dL + off, bytes, cudaMemcpyDeviceToHost));
+  if (U) {
+    if (!h->dU) return fail(PB200_ERR_STATE, "no U slab (not an LU factorization)");
+    CK(cudaMemcpy(U, (const char *)h->dU + off, bytes, cudaMemcpyDeviceToHost));
   }
   return PB200_SUCCESS;
 }

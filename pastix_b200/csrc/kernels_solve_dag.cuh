@@ -31,7 +31,7 @@ namespace pb200 {
 #define PB200_DAG_NT 256
 #define PB200_DAG_ROWS 64                 // panel rows per T ticket
 #define PB200_DAG_LDT (PB200_DAG_ROWS + 1) // shared-memory leading dimension of a tile (both products conflict-free)
-#define PB200_DAG_TIMEOUT 6000000000LL    // cycles (~3 s): a dependency that never arrives is an error, not a hang
+#define PB200_DAG_TIMEOUT 20000000000LL   // cycles (~10 s): a dependency that never arrives is an error, not a hang
 
 struct DagTick {
   int64_t src;     // T: slab offset of the tile's first element (first row, column c0);  D: offset of the inverted triangle

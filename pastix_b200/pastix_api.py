@@ -120,6 +120,14 @@ class PastixLib:
         self._call(E["API_TASK_REFINE"], E["API_TASK_REFINE"], b=x, nrhs=1)
         return x
 
+    def get_schur(self, w: int) -> np.ndarray:
+        """pastix_getSchur (pastix.c:6434-6475) after a NUMFACT with IPARM_SCHUR = API_YES: the w x w panel of the last,
+        never-factored column block (w = its width; lower triangle meaningful for symmetric factorizations)."""
+        S = np.zeros(w * w, dtype=self.dtype)
+        self.lib.pastix_getSchur.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.pastix_getSchur(self.pd, S.ctypes.data)
+        return S.reshape(w, w, order="F")
+
     def clean(self):
         E = self.E
         if self.pd:

@@ -8,6 +8,7 @@ typedef struct pb200_shim_entry_s {
   const SolverMatrix *m;
   pb200_handle_t     *h;
   int                 facto;
+  int                 schur;      /* handle built for IPARM_SCHUR == API_YES */
   int                 factorized;
   double              critere;
   pb200_csc_t        *csc;        /* internal CSC built on the device by CscOrdistrib (shim_csc.c) */

@@ -24,7 +24,8 @@
  * back sopar->diagchange, DPARM_FACT_TIME, DPARM_SOLV_TIME, IPARM_INERTIA and the solution in
  * updovct.sm2xtab.  Factors stay resident in HBM, keyed by SolverMatrix*; set PB200_HOST_COEFTAB=1
  * to also mirror them into cblktab[].coeftab/ucoeftab (malloc'ed like CoefMatrix_Allocate,
- * coefinit.c:104, so CoefMatrix_Free keeps working) for Schur/dump consumers.
+ * coefinit.c:104, so CoefMatrix_Free keeps working) for dump consumers.  With IPARM_SCHUR the last
+ * cblk's panel (= the Schur complement) is always copied back, for pastix_getSchur.
  * No CPU fallback: a CUDA failure is a fatal error (errorPrint + EXIT, like the reference's own
  * fatal paths, common/src/errors.h:161-165).
  */
@@ -133,9 +134,9 @@ void pb200_shim_release(const SolverMatrix *m)
 }
 
 /* SolverMatrix -> flat arrays -> device handle */
-static pb200_handle_t *shim_create(SolverMatrix *datacode)
+static pb200_handle_t *shim_create(SolverMatrix *datacode, int schur)
 {
-  pb200_solver_t s; pb200_handle_t *h = NULL;
+  pb200_solver_t s; pb200_handle_t *h = NULL; pb200_options_t opts;
   int64_t *buf, *fcol, *lcol, *bnum, *strd, *frow, *lrow, *fcb, *cind;
   PASTIX_INT i, C = SYMB_CBLKNBR, B = SYMB_BLOKNBR;
   buf = (int64_t *)malloc(sizeof(int64_t) * (size_t)(4 * (C + 1) + 4 * B + 8));
@@ -152,7 +153,9 @@ static pb200_handle_t *shim_create(SolverMatrix *datacode)
   s.cblknbr = C; s.bloknbr = B;
   s.fcolnum = fcol; s.lcolnum = lcol; s.bloknum = bnum; s.stride = strd;
   s.frownum = frow; s.lrownum = lrow; s.cblknum = fcb; s.coefind = cind;
-  if (pb200_create(&h, &s, PB200_FLT, PB200_FACTO, -1) != PB200_SUCCESS) shim_fatal("pb200_create");
+  memset(&opts, 0, sizeof(opts));
+  opts.schur = schur;
+  if (pb200_create_opts(&h, &s, PB200_FLT, PB200_FACTO, -1, 0, 1, &opts) != PB200_SUCCESS) shim_fatal("pb200_create_opts");
   free(buf);
   return h;
 }
@@ -216,19 +219,31 @@ static void shim_mirror_coeftab(pb200_handle_t *h, SolverMatrix *datacode)
   free(L); if (U) free(U);
 }
 
+/* IPARM_SCHUR: the Schur complement is what the never-factored last cblk holds after the factorization.  The reference
+ * leaves it in SOLV_COEFTAB(last cblk) — user memory when pastix_setSchurArray was called (pastix.c:3400-3412), else
+ * allocated like every panel (coefinit.c:141-150) — where pastix_getSchur reads it (pastix.c:6434-6475). */
+static void shim_fetch_schur(pb200_handle_t *h, SolverMatrix *datacode)
+{
+  PASTIX_INT c = SYMB_CBLKNBR - 1;
+  size_t sz = (size_t)SOLV_STRIDE(c) * (size_t)(SYMB_LCOLNUM(c) - SYMB_FCOLNUM(c) + 1);
+  if (SOLV_COEFTAB(c) == NULL) { MALLOC_INTERN(SOLV_COEFTAB(c), sz, PASTIX_FLOAT); }
+  if (pb200_get_cblk(h, (int64_t)c, SOLV_COEFTAB(c), NULL) != PB200_SUCCESS) shim_fatal("pb200_get_cblk");
+}
+
 static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
 {
   pb200_shim_entry_t *e = shim_find(datacode, 1);
   int64_t nbpivot = 0; double seconds = 0.0, crit; int dev_csc = 0;
   if (e == NULL) { errorPrint("pastix_b200: too many live SolverMatrix instances"); EXIT(MOD_SOPALIN, INTERNAL_ERR); }
-  if (sopar->iparm[IPARM_SCHUR] == API_YES || sopar->iparm[IPARM_DISTRIBUTION_LEVEL] != 0 || SOLV_PROCNBR > 1) {
-    errorPrint("pastix_b200: Schur / 2D distribution / multi-process SolverMatrix are not handled by this shim");
+  const int schur = (sopar->schur == API_YES);
+  if (sopar->iparm[IPARM_DISTRIBUTION_LEVEL] != 0 || SOLV_PROCNBR > 1) {
+    errorPrint("pastix_b200: 2D distribution / multi-process SolverMatrix are not handled by this shim");
     EXIT(MOD_SOPALIN, BADPARAMETER_ERR);
   }
   {
   double t0 = clockGet(), t1, t2, t3;
-  if (e->h != NULL && e->facto != PB200_FACTO) { pb200_destroy(e->h); e->h = NULL; }
-  if (e->h == NULL) { e->h = shim_create(datacode); e->facto = PB200_FACTO; }
+  if (e->h != NULL && (e->facto != PB200_FACTO || e->schur != schur)) { pb200_destroy(e->h); e->h = NULL; }
+  if (e->h == NULL) { e->h = shim_create(datacode, schur); e->facto = PB200_FACTO; e->schur = schur; }
   e->factorized = 0;
   t1 = clockGet();
   if (e->csc != NULL && e->csc_fresh) {        /* CscOrdistrib of this call left the internal CSC in HBM (shim_csc.c) */
@@ -264,6 +279,7 @@ static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
     sopar->iparm[IPARM_INERTIA] = (PASTIX_INT)inertia; }
 #endif
   if (getenv("PB200_HOST_COEFTAB") != NULL) shim_mirror_coeftab(e->h, datacode);
+  else if (schur) shim_fetch_schur(e->h, datacode);
 }
 
 static void shim_updown(SolverMatrix *datacode, SopalinParam *sopar)

@@ -107,9 +107,12 @@ class Sopalin:
         return {"ms": dict(zip(names, list(ms))), "launches": dict(zip(names, [int(v) for v in n])), "gemm_flops": float(fl.value)}
 
     def __init__(self, solver: SolverMatrix | dict, prec: str = "d", facto: str = "llt", device: int = -1,
-                 rank: int = 0, nranks: int = 1):
-        """rank/nranks > 1: one process per GPU; call `attach()` (collective) before assembling."""
+                 rank: int = 0, nranks: int = 1, schur: bool = False):
+        """rank/nranks > 1: one process per GPU; call `attach()` (collective) before assembling.
+        schur: IPARM_SCHUR semantics — the last cblk is never factored (after `factorize` its panel is the Schur
+        complement, `get_schur()`), and `solve` ignores it (sopalin_compute.c:767-772, updo.c:425-428)."""
         self._borrowed = False
+        self.schur = bool(schur)
         self.rank, self.nranks = rank, nranks
         if isinstance(solver, dict):
             solver = SolverMatrix.from_dict(solver)
@@ -121,8 +124,9 @@ class Sopalin:
                                      p(solver.bloknum), p(solver.stride), p(solver.frownum), p(solver.lrownum),
                                      p(solver.cblknum), p(solver.coefind))
         self.h = C.c_void_p(None)
-        _check(self.L.pb200_create_dist(C.byref(self.h), C.byref(self._desc), FLTTYPE[prec], FACTO[facto], device,
-                                        rank, nranks))
+        opts = _lib.Options(int(self.schur))
+        _check(self.L.pb200_create_opts(C.byref(self.h), C.byref(self._desc), FLTTYPE[prec], FACTO[facto], device,
+                                        rank, nranks, C.byref(opts)))
         self._read_info()
 
     # -- multi-GPU plumbing ----------------------------------------------------
@@ -227,6 +231,21 @@ class Sopalin:
         Uh = np.empty(self.coefnbr, dtype=self.dtype) if self.facto == "lu" else None
         _check(self.L.pb200_get_coeftab(self.h, Lh.ctypes.data, Uh.ctypes.data if Uh is not None else None))
         return Lh, Uh
+
+    def get_cblk(self, c: int, with_u: bool = False):
+        """coeftab[c] (and ucoeftab[c]) as stride x width column-major arrays."""
+        off = self.solver.panel_offsets()
+        w = int(self.solver.lcolnum[c] - self.solver.fcolnum[c] + 1); ld = int(self.solver.stride[c])
+        Lh = np.empty(int(off[c + 1] - off[c]), dtype=self.dtype)
+        Uh = np.empty_like(Lh) if with_u else None
+        _check(self.L.pb200_get_cblk(self.h, c, Lh.ctypes.data, Uh.ctypes.data if with_u else None))
+        Lh = Lh.reshape(ld, w, order="F")
+        return (Lh, Uh.reshape(ld, w, order="F")) if with_u else Lh
+
+    def get_schur(self) -> np.ndarray:
+        """The Schur complement left in the last cblk by a `schur=True` factorization (what pastix_getSchur copies,
+        pastix.c:6434-6475): w x w, lower triangle meaningful for the symmetric factorizations, full for LU."""
+        return self.get_cblk(self.solver.cblknbr - 1)
 
     def set_coeftab(self, Lh, Uh=None, factorized: bool = False):
         Lh = np.ascontiguousarray(Lh, dtype=self.dtype)

@@ -30,6 +30,7 @@ def load_golden(name):
         d[k] = float(d[k])
     for k in ("fcol", "lcol", "bloknum", "stride", "frow", "lrow", "fcblk", "coefind", "permtab", "colptr", "rows"):
         d[k] = d[k].astype(np.int64)
+    d["schur"] = bool(int(d["schur"])) if "schur" in d else False
     d.setdefault("tvalues", None)
     d.setdefault("U", None)
     return d

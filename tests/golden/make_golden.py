@@ -64,7 +64,30 @@ CASES = [
     ("lap7_8_ilu2_llt_d", "lap7", 8, "d", "llt", {"IPARM_INCOMPLETE": 1, "IPARM_LEVEL_OF_FILL": 2}, 1),
     ("lap7sing_6_ldlt_d", "lap7sing", 6, "d", "ldlt", {}, 1),
     ("lap7_10_llt_d_bs16", "lap7", 10, "d", "llt", {"IPARM_MIN_BLOCKSIZE": 8, "IPARM_MAX_BLOCKSIZE": 16}, 1),
+    # IPARM_SCHUR: the last cblk (top separator, numbered last by the nested dissection) is left unfactored = Schur
+    # complement; the solve is the interior solve (sopalin_compute.c:767-772, updo.c:425-428)
+    ("lap7_8_llt_d_schur", "lap7", 8, "d", "llt", {"IPARM_SCHUR": 1}, 2),
+    ("lap27_6_ldlt_d_schur", "lap27", 6, "d", "ldlt", {"IPARM_SCHUR": 1}, 1),
+    ("cd_8_lu_d_schur", "cd", 8, "d", "lu", {"IPARM_SCHUR": 1}, 2),
+    ("cd_6_lu_z_schur", "cd", 6, "z", "lu", {"IPARM_SCHUR": 1}, 1),
+    ("lap7_12_llt_d_schur_bs", "lap7", 12, "d", "llt", {"IPARM_SCHUR": 1, "IPARM_MIN_BLOCKSIZE": 20, "IPARM_MAX_BLOCKSIZE": 40}, 1),
 ]
+
+
+def check_schur(name, A, sym, peritab, S, x, b, w):
+    """The reference's Schur mode against dense linear algebra: S = A_SS - A_SI A_II^-1 A_IS on the last w unknowns
+    of the final ordering, and the solve = interior solve with the Schur unknowns left at their right-hand side."""
+    Af = A if sym == "no" else (A + (sp.tril(A, -1).T.conj() if sym == "her" else sp.tril(A, -1).T))
+    P = sp.csc_matrix(Af)[peritab][:, peritab].toarray()
+    n = P.shape[0]; k = n - w
+    St = P[k:, k:] - P[k:, :k] @ np.linalg.solve(P[:k, :k], P[:k, k:])
+    e = np.abs((S if sym == "no" else np.tril(S)) - (St if sym == "no" else np.tril(St))).max() / np.abs(St).max()
+    bp = b.reshape(n, -1)[peritab]
+    xp = bp.copy(); xp[:k] = np.linalg.solve(P[:k, :k], bp[:k])
+    ex = np.abs(x.reshape(n, -1)[peritab] - xp).max() / np.abs(xp).max()
+    tolv = 1e-12 if P.dtype in (np.float64, np.complex128) else 1e-4
+    assert e < tolv and ex < tolv, (name, e, ex)
+    print(f"  schur: width {w}, |S - dense Schur| {e:.1e}, |x - interior solve| {ex:.1e}")
 
 
 def make(name, kind, N, prec, facto, over, nrhs):
@@ -91,7 +114,12 @@ def make(name, kind, N, prec, facto, over, nrhs):
              permtab=permtab, colptr=csc["colptr"], rows=csc["rows"], values=csc["vals"],
              critere=crit, norm1=r.norm1(), L=L, nbpivot=out["static_pivoting"], inertia=out["inertia"],
              nnzeros=out["nnzeros"], fact_flops=out["fact_flops"], b=b, x=x,
-             prec=prec, facto=facto, sym=sym, kind=kind, N=N)
+             prec=prec, facto=facto, sym=sym, kind=kind, N=N, schur=int(over.get("IPARM_SCHUR", 0)))
+    if d["schur"]:
+        cb = s["cblknbr"]; w = int(s["lcol"][cb - 1] - s["fcol"][cb - 1] + 1)
+        S = r.get_schur(w)                       # pastix_getSchur = the last cblk's coeftab
+        assert np.array_equal(S.ravel(order="F"), L[-w * w:]), name
+        check_schur(name, A, sym, peritab, S, x, b, w)
     if mine["tvalues"] is not None:
         d["tvalues"] = mine["tvalues"]
     if U is not None:

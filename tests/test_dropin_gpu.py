@@ -137,6 +137,70 @@ def test_transpose_solve_lu(prec):
     gpu.release()
 
 
+SCHUR_CASES = [
+    # kind, N, prec, facto, iparm overrides, user-provided Schur array (pastix_setSchurArray)
+    ("lap7", 10, "d", "llt", {}, False),
+    ("lap7", 10, "d", "ldlt", {}, True),
+    ("cd", 8, "d", "lu", {}, False),
+    ("cd", 6, "z", "lu", {}, True),
+    ("lap7", 14, "d", "llt", {"IPARM_MIN_BLOCKSIZE": 20, "IPARM_MAX_BLOCKSIZE": 40}, False),   # Schur cblk wider than a sub-panel
+    ("lap7", 8, "s", "llt", {}, False),                                                          # generic (SIMT) factorization path
+]
+
+
+@pytest.mark.parametrize("kind,N,prec,facto,over,user_array", SCHUR_CASES)
+def test_schur_complement_matches_reference(kind, N, prec, facto, over, user_array):
+    """IPARM_SCHUR = API_YES through pastix(): the last column block is never factored (sopalin_compute.c:767-772),
+    pastix_getSchur (pastix.c:6434-6475) returns the same Schur complement from the drop-in as from the reference —
+    and the one dense linear algebra gives —, API_TASK_SOLVE is the interior solve that leaves the Schur unknowns at
+    their right-hand side (updo.c:425-428, 1154-1180)."""
+    import ctypes as C
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    if not available(prec):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix(kind, N, DT[prec])
+    n = A.shape[0]
+    sym = {"llt": "yes", "ldlt": "yes", "lu": "no", "ldlh": "her"}[facto]
+    over = dict(over, IPARM_SCHUR=1)
+    b = G.rhs_vector(n, 2, DT[prec])
+    ref = RefPastix(prec, threads=1).setup(A, perm0, facto, sym=sym, iparm_over=over).analyze()
+    sr = ref.solver()
+    w = int(sr["lcol"][sr["cblknbr"] - 1] - sr["fcol"][sr["cblknbr"] - 1] + 1)
+    ref.numfact()
+    Sr = ref.get_schur(w)
+    xr = ref.solve(b)
+    gpu = Pastix(prec, threads=1).setup(A, perm0, facto, sym=sym, iparm_over=over).analyze()
+    mine = None
+    if user_array:                                   # the Schur complement lands in user memory (pastix.c:3400-3412)
+        mine = np.zeros(w * w, dtype=DT[prec])
+        gpu.lib.pastix_setSchurArray.argtypes = [C.c_void_p, C.c_void_p]
+        gpu.lib.pastix_setSchurArray(gpu.pd, mine.ctypes.data)
+    gpu.numfact()
+    Sg = gpu.get_schur(w)
+    if mine is not None:
+        assert np.array_equal(mine.reshape(w, w, order="F"), Sg)
+    xg = gpu.solve(b)
+    t = tol(prec)
+    lo = (lambda M: M) if facto == "lu" else np.tril
+    assert relerr(lo(Sg), lo(Sr)) <= t, "Schur complement differs from the reference's"
+    # dense check, independent of both
+    _, peritab = gpu.order()
+    P = full_matrix(A, sym)[peritab][:, peritab].toarray()
+    k = n - w
+    St = P[k:, k:] - P[k:, :k] @ np.linalg.solve(P[:k, :k], P[:k, k:])
+    assert relerr(lo(Sg), lo(St)) <= (1e-12 if prec in ("d", "z") else 1e-4)
+    assert relerr(xg, xr) <= 50 * t
+    assert np.array_equal(xg[peritab][k:], b[peritab][k:]), "Schur unknowns must keep their right-hand side"
+    # a second NUMFACT + SOLVE on the same analysis gives the same answer (handle reuse, re-assembly)
+    gpu.numfact()
+    assert relerr(lo(gpu.get_schur(w)), lo(Sg)) <= t
+    assert relerr(gpu.solve(b), xg) <= 50 * t
+    gpu.release()
+
+
 @pytest.mark.parametrize("prec,kind,facto,sym", [("z", "cd", "lu", "no"), ("c", "cd", "lu", "no"), ("s", "lap7", "llt", "yes")])
 def test_static_pivot_threshold_from_device_norm(prec, kind, facto, sym):
     """critere = ||A||_1 * sqrt(DPARM_EPSILON_MAGN_CTRL) (sopalin3d.c:586-606) with the 1-norm taken on the internal

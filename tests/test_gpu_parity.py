@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 def run_cuda(g, nrhs_b=None):
     from pastix_b200 import Sopalin
-    s = Sopalin(g, g["prec"], g["facto"])
+    s = Sopalin(g, g["prec"], g["facto"], schur=g["schur"])
     s.assemble(g["colptr"], g["rows"], g["values"], g["tvalues"])
     assert abs(s.norm1(g["colptr"], g["values"]) - g["norm1"]) <= 1e-12 * g["norm1"]
     L0, U0 = s.get_coeftab()
@@ -47,6 +47,16 @@ def test_factor_and_solve_match_reference(name):
     xs = unpermute_solution(x, g["permtab"])
     # a replaced pivot is ~1e-15: the solution of that (numerically singular) system is not a parity quantity
     assert relerr(xs, g["x"]) <= (50 * t if g["nbpivot"] == 0 else 1e-1)
+    if g["schur"]:
+        # IPARM_SCHUR: the never-factored last cblk is the Schur complement pastix_getSchur hands out, and the
+        # Schur unknowns keep their right-hand side bit for bit
+        cb = g["cblknbr"]; w = int(g["lcol"][cb - 1] - g["fcol"][cb - 1] + 1)
+        S, Sr = s.get_schur(), g["L"][-w * w:].reshape(w, w, order="F")
+        if g["facto"] != "lu":
+            S, Sr = np.tril(S), np.tril(Sr)
+        assert relerr(S, Sr) <= t
+        xp, bp = x.reshape(s.n, -1), permute_rhs(g["b"], g["permtab"]).reshape(s.n, -1)
+        assert np.array_equal(xp[s.n - w:], bp[s.n - w:])
     s.close()
 
 
@@ -61,6 +71,20 @@ def test_solve_only_with_reference_factors(name):
     x = permute_rhs(g["b"], g["permtab"])
     s.solve(x)
     assert relerr(unpermute_solution(x, g["permtab"]), g["x"]) <= 50 * tol(g["prec"])
+    s.close()
+
+
+def test_schur_mode_refuses_the_level_sweeps(monkeypatch):
+    """Schur mode is implemented on the persistent up_down only; the A/B switch must fail loudly, not solve wrongly."""
+    from pastix_b200 import Sopalin, PastixB200Error
+    from pastix_b200.csc import permute_rhs
+    g = load_golden("lap7_8_llt_d_schur")
+    monkeypatch.setenv("PB200_SOLVE_LEVELS", "1")
+    s = Sopalin(g, "d", "llt", schur=True)
+    s.assemble(g["colptr"], g["rows"], g["values"])
+    s.factorize(g["critere"])
+    with pytest.raises(PastixB200Error):
+        s.solve(permute_rhs(g["b"], g["permtab"]))
     s.close()
 
 

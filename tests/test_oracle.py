@@ -20,7 +20,7 @@ def test_oracle_matches_golden(name):
     n1 = o.norm1(g["colptr"], g["values"])
     assert abs(n1 - g["norm1"]) <= 1e-13 * g["norm1"]
     L, U = o.assemble(g["colptr"], g["rows"], g["values"], g["tvalues"], herm=False, lu=lu)
-    nb = o.factorize(g["facto"], L, U, g["critere"])
+    nb = o.factorize(g["facto"], L, U, g["critere"], schur=g["schur"])
     assert nb == g["nbpivot"]
     m = lower_mask(g) if not lu else slice(None)
     t = tol(g["prec"])
@@ -31,7 +31,7 @@ def test_oracle_matches_golden(name):
         assert o.inertia(L) == g["inertia"]
     from pastix_b200.csc import permute_rhs, unpermute_solution
     x = permute_rhs(g["b"], g["permtab"])
-    o.solve(g["facto"], L, U, x)
+    o.solve(g["facto"], L, U, x, schur=g["schur"])
     # a replaced pivot is ~1e-15: the solution of that (numerically singular) system is not a parity quantity
     st = 50 * t if g["nbpivot"] == 0 else 1e-1
     assert relerr(unpermute_solution(x, g["permtab"]), g["x"]) <= st
@@ -46,6 +46,30 @@ def test_oracle_solve_with_reference_factors(name):
     x = permute_rhs(g["b"], g["permtab"])
     o.solve(g["facto"], g["L"], g["U"], x)
     assert relerr(unpermute_solution(x, g["permtab"]), g["x"]) <= 50 * tol(g["prec"])
+
+
+def test_schur_goldens_hold_the_dense_schur_complement():
+    """IPARM_SCHUR fixtures: the last cblk of the reference's coeftab is A_SS - A_SI A_II^-1 A_IS of the internal CSC
+    (dense linear algebra, independent of both the reference and the oracle), and x_S == b_S in its solution."""
+    import scipy.sparse as sp
+    names = [n for n in golden_names() if load_golden(n)["schur"]]
+    assert names, "no Schur fixtures"
+    for name in names:
+        g = load_golden(name)
+        n = len(g["colptr"]) - 1
+        A = sp.csc_matrix((g["values"], g["rows"], g["colptr"]), shape=(n, n)).toarray()   # permuted ordering
+        if g["sym"] != "no":                       # the internal CSC of a symmetric matrix holds the lower triangle
+            A = np.tril(A) + np.tril(A, -1).T
+        cb = g["cblknbr"]; w = int(g["lcol"][cb - 1] - g["fcol"][cb - 1] + 1); k = n - w
+        S = g["L"][-w * w:].reshape(w, w, order="F")
+        St = A[k:, k:] - A[k:, :k] @ np.linalg.solve(A[:k, :k], A[:k, k:])
+        if g["sym"] != "no":
+            S, St = np.tril(S), np.tril(St)
+        assert relerr(S, St) <= 1e-12, name
+        xp = g["x"].reshape(n, -1)[np.argsort(g["permtab"])]      # permuted solution
+        bp = g["b"].reshape(n, -1)[np.argsort(g["permtab"])]
+        assert np.array_equal(xp[k:], bp[k:]), name
+        assert relerr(xp[:k], np.linalg.solve(A[:k, :k], bp[:k])) <= 1e-12, name
 
 
 def test_golden_structures_are_consistent():
