@@ -11,10 +11,18 @@
 //   parent(c)  = facing cblk of c's first off-diagonal blok
 //   cost(c)    = PaStiX's flop model of the cblk (blend_symbol_cost.c:52-88, 382-430)
 //   candidates = contiguous rank interval, split among the children in proportion to subtree cost
-//   owner(c)   = the only candidate, or (shared cblk) round-robin over the interval along the chain.
+//   owner(c)   = the only candidate, or (shared cblk) dealt over the interval.
+// Two ways of dealing the shared column blocks (PB200_DIST_CHAIN, read by every rank):
+//   "deal"  (default) every shared cblk on its own, heaviest first to the least-loaded GPU of its interval: best flop
+//           balance, but consecutive cblks of one separator alternate between GPUs, so every level of the top chains is
+//           a hand-off (flag + fan-in pull) between two GPUs;
+//   "group" the chain of shared cblks of one separator (same candidate interval, linked by parent) stays on ONE GPU:
+//           hand-offs only where the elimination tree branches, at the price of a coarser flop balance.
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace pb200 {
@@ -97,8 +105,7 @@ inline DistPlan dist_plan(int64_t C, const int *fblok, const int *fcblk, const i
     }
     std::vector<double> L(nranks, 0.0);
     auto least = [&](int a2, int b2) { int best = a2; for (int p = a2 + 1; p < b2; ++p) if (L[p] < L[best]) best = p; return best; };
-    std::sort(subtrees.begin(), subtrees.end(), [&](const Item &x, const Item &y) { return sub[x.c] != sub[y.c] ? sub[x.c] > sub[y.c] : x.c < y.c; });
-    for (const Item &it : subtrees) {
+    auto place_subtree = [&](const Item &it) {
       const int p = least(it.a, it.b);
       L[p] += sub[it.c];
       std::vector<int> st2{it.c};
@@ -107,7 +114,38 @@ inline DistPlan dist_plan(int64_t C, const int *fblok, const int *fcblk, const i
         P.owner[c] = p;
         for (int q = cptr[c]; q < cptr[c + 1]; ++q) st2.push_back(child[q]);
       }
+    };
+    const char *mode = getenv("PB200_DIST_CHAIN");
+    if (mode && !strcmp(mode, "group")) {
+      // the subtrees that have no choice (one candidate) first, then the chains (the big indivisible items, heaviest
+      // first to the least-loaded GPU of their interval), then the free subtrees level what is left uneven
+      {
+        std::vector<Item> rest;
+        for (const Item &it : subtrees) { if (it.b - it.a == 1) place_subtree(it); else rest.push_back(it); }
+        subtrees.swap(rest);
+      }
+      std::vector<int> sa(C, -1), sb(C, -1), gid(C, -1);
+      for (const Item &it : shared) { sa[it.c] = it.a; sb[it.c] = it.b; }
+      std::sort(shared.begin(), shared.end(), [](const Item &x, const Item &y) { return x.c > y.c; });   // parents first
+      struct Group { double cost; int a, b, first; };
+      std::vector<Group> groups;
+      for (const Item &it : shared) {
+        const int p = parent[it.c];
+        if (p >= 0 && gid[p] >= 0 && sa[p] == it.a && sb[p] == it.b) gid[it.c] = gid[p];
+        else { gid[it.c] = (int)groups.size(); groups.push_back({0.0, it.a, it.b, it.c}); }
+        groups[gid[it.c]].cost += cost[it.c];
+      }
+      std::vector<int> order(groups.size());
+      for (size_t k = 0; k < order.size(); ++k) order[k] = (int)k;
+      std::sort(order.begin(), order.end(), [&](int x, int y) {
+        return groups[x].cost != groups[y].cost ? groups[x].cost > groups[y].cost : groups[x].first < groups[y].first; });
+      std::vector<int> gowner(groups.size(), 0);
+      for (int k : order) { const int p = least(groups[k].a, groups[k].b); L[p] += groups[k].cost; gowner[k] = p; }
+      for (const Item &it : shared) P.owner[it.c] = gowner[gid[it.c]];
+      shared.clear();
     }
+    std::sort(subtrees.begin(), subtrees.end(), [&](const Item &x, const Item &y) { return sub[x.c] != sub[y.c] ? sub[x.c] > sub[y.c] : x.c < y.c; });
+    for (const Item &it : subtrees) place_subtree(it);
     std::sort(shared.begin(), shared.end(), [&](const Item &x, const Item &y) { return cost[x.c] != cost[y.c] ? cost[x.c] > cost[y.c] : x.c < y.c; });
     for (const Item &it : shared) {
       const int p = least(it.a, it.b);

@@ -1,6 +1,6 @@
 """Dev tool: run one synthetic case end to end on the GPU (analysis by the
 reference in oracle/_ref, numeric phase by pastix_b200) and print timings and
-the backward error.  usage: python tools/run_case.py N stencil facto prec [nrhs] [--ref]"""
+the backward error.  usage: python tools/run_case.py N stencil facto prec [nrhs] [--ref] [--reps=K] [--json=path]"""
 import os
 import sys
 import time
@@ -43,21 +43,32 @@ def main():
     print(f"levels={eng.nlevels} device_bytes={eng.device_bytes / 1e9:.2f} GB")
     eng.assemble(csc["colptr"], csc["rows"], csc["values"], csc["tvalues"])
     crit = critere_from_norm(eng.norm1(csc["colptr"], csc["values"]))
-    for it in range(3):
+    reps = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--reps=")), 3)
+    rec = {"N": N, "stencil": stencil, "facto": facto, "prec": prec, "n": int(A.shape[0]), "cblknbr": int(s["cblknbr"]),
+           "coefnbr": int(s["coefnbr"]), "fact_flops": float(out["fact_flops"]), "analysis_s": t1 - t0,
+           "device_bytes": int(eng.device_bytes), "levels": int(eng.nlevels), "fact_ms": [], "solve_ms_per_rhs": []}
+    for it in range(reps):
         if it:
             eng.reassemble()
         nb = eng.factorize(crit)
         print(f"factorize: {eng.fact_time * 1e3:.2f} ms  {out['fact_flops'] / eng.fact_time / 1e9:.1f} GFLOP/s "
-              f"nbpivot={nb} launches={eng.last_launches()}")
+              f"nbpivot={nb} launches={eng.last_launches()}", flush=True)
+        rec["fact_ms"].append(eng.fact_time * 1e3)
     b = G.rhs_vector(A.shape[0], nrhs, dt)
     for it in range(2):
         x = permute_rhs(b, permtab)
         eng.solve(x)
-        print(f"solve: {eng.solv_time * 1e3:.2f} ms ({eng.solv_time * 1e3 / nrhs:.3f} ms/rhs) launches={eng.last_launches()}")
+        print(f"solve: {eng.solv_time * 1e3:.2f} ms ({eng.solv_time * 1e3 / nrhs:.3f} ms/rhs) launches={eng.last_launches()}", flush=True)
+        rec["solve_ms_per_rhs"].append(eng.solv_time * 1e3 / nrhs)
     xs = unpermute_solution(x, permtab)
     Af = A if sym == "no" else (A + sp.tril(A, -1).T if sym == "yes" else A + sp.tril(A, -1).conj().T)
     res = np.linalg.norm(Af @ xs - b) / np.linalg.norm(b)
     print(f"backward error ||b-Ax||/||b|| = {res:.3e}")
+    rec.update(backward_error=float(res), nbpivot=int(nb), gflops=float(out["fact_flops"] / (min(rec["fact_ms"]) * 1e-3) / 1e9))
+    jp = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--json=")), None)
+    if jp:
+        import json
+        json.dump(rec, open(jp, "w"))
     if "--ref" in sys.argv:
         r = RefPastix(prec, threads=os.cpu_count()).setup(A, perm0, facto, sym=sym).analyze()
         t = time.time(); r.numfact(); xr = r.solve(b)
