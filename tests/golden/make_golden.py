@@ -40,6 +40,8 @@ def case_matrix(kind, N, dt):
         v = A.data.copy(); off = A.row != A.col
         v[off] = v[off] + 0.3j * np.where((A.row[off] - A.col[off]) % 2 == 0, 1, -1)
         return sp.csc_matrix((v, (A.row, A.col)), shape=A.shape), G.nested_dissection_perm(N)
+    if kind == "diag":        # no coupling at all: every cblk is a root without off-diagonal bloks
+        return sp.diags(np.arange(1, N + 1).astype(dt)).tocsc(), np.arange(N)[::-1].copy()
     if kind == "lap7sing":    # zero pivots: forces the static-pivoting rule
         A = G.laplacian_3d(N, 7, dt).tolil()
         n = N ** 3
@@ -64,6 +66,14 @@ CASES = [
     ("lap7_8_ilu2_llt_d", "lap7", 8, "d", "llt", {"IPARM_INCOMPLETE": 1, "IPARM_LEVEL_OF_FILL": 2}, 1),
     ("lap7sing_6_ldlt_d", "lap7sing", 6, "d", "ldlt", {}, 1),
     ("lap7_10_llt_d_bs16", "lap7", 10, "d", "llt", {"IPARM_MIN_BLOCKSIZE": 8, "IPARM_MAX_BLOCKSIZE": 16}, 1),
+    # edge cases: one unknown, one cblk, no off-diagonal blok anywhere
+    ("lap1d1_llt_d", "lap1d", 1, "d", "llt", {}, 1),
+    ("lap1d3_ldlt_d", "lap1d", 3, "d", "ldlt", {}, 2),
+    ("diag20_lu_d", "diag", 20, "d", "lu", {}, 1),
+    # remaining precision x factorization combinations of the generic (SIMT) path
+    ("lap7_6_ldlt_s", "lap7", 6, "s", "ldlt", {}, 1),
+    ("cd_6_lu_s", "cd", 6, "s", "lu", {}, 2),
+    ("lap7her_6_ldlh_c", "lap7her", 6, "c", "ldlh", {}, 1),
     # IPARM_SCHUR: the last cblk (top separator, numbered last by the nested dissection) is left unfactored = Schur
     # complement; the solve is the interior solve (sopalin_compute.c:767-772, updo.c:425-428)
     ("lap7_8_llt_d_schur", "lap7", 8, "d", "llt", {"IPARM_SCHUR": 1}, 2),
