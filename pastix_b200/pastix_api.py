@@ -19,8 +19,9 @@ LIBDIR = os.path.join(_HERE, "lib")
 DTYPES = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
 
 
-def dropin_path(prec: str) -> str:
-    return os.path.join(LIBDIR, f"libpastix_dropin_{prec}.so")
+def dropin_path(prec: str, int_bits: int = 64) -> str:
+    """int_bits=32: the build with the reference's default 32-bit PASTIX_INT (libpastix_dropin_<p>_i32.so)."""
+    return os.path.join(LIBDIR, f"libpastix_dropin_{prec}{'_i32' if int_bits == 32 else ''}.so")
 
 
 def load_enums(path: str = None) -> dict:
@@ -31,8 +32,11 @@ class PastixLib:
     """One pastix_data_t instance driven through pastix(); `libpath` decides which build of
     libpastix serves it."""
 
-    def __init__(self, prec: str, libpath: str, enums: dict, threads: int = 1, verbose: int = 0):
+    def __init__(self, prec: str, libpath: str, enums: dict, threads: int = 1, verbose: int = 0, int_bits: int = 64):
+        """int_bits: width of PASTIX_INT in that build (INTSIZE64 / INTSIZE32, common_pastix.h:331-347)."""
         os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")  # PaStiX threads itself (SURVEY §8c)
+        self.idt = np.int64 if int_bits == 64 else np.int32
+        self.cint = C.c_int64 if int_bits == 64 else C.c_int32
         if not os.path.exists(libpath):
             raise RuntimeError(f"{libpath} is missing: run __graft_entry__.build() where the reference tree is available")
         self.prec = prec
@@ -40,7 +44,7 @@ class PastixLib:
         self.lib = C.CDLL(libpath, mode=C.RTLD_LOCAL)
         self.E = enums
         self.pd = C.c_void_p(None)
-        self.iparm = np.zeros(self.E["IPARM_SIZE"], dtype=np.int64)
+        self.iparm = np.zeros(self.E["IPARM_SIZE"], dtype=self.idt)
         self.dparm = np.zeros(self.E["DPARM_SIZE"], dtype=np.float64)
         self.threads = threads
         self.verbose = verbose
@@ -51,10 +55,10 @@ class PastixLib:
         self.iparm[E["IPARM_START_TASK"]] = start
         self.iparm[E["IPARM_END_TASK"]] = end
         bp = b.ctypes.data_as(C.c_void_p) if b is not None else None
-        self.lib.pastix(C.byref(self.pd), C.c_int(0), C.c_int64(self.n),
+        self.lib.pastix(C.byref(self.pd), C.c_int(0), self.cint(self.n),
                         self.colptr.ctypes.data_as(C.c_void_p), self.rows.ctypes.data_as(C.c_void_p),
                         self.vals.ctypes.data_as(C.c_void_p), self.perm.ctypes.data_as(C.c_void_p),
-                        self.invp.ctypes.data_as(C.c_void_p), bp, C.c_int64(nrhs),
+                        self.invp.ctypes.data_as(C.c_void_p), bp, self.cint(nrhs),
                         self.iparm.ctypes.data_as(C.c_void_p), self.dparm.ctypes.data_as(C.c_void_p))
         err = int(self.iparm[E["IPARM_ERROR_NUMBER"]])
         if err != 0:
@@ -68,12 +72,12 @@ class PastixLib:
         A = sp.csc_matrix(A)
         A.sort_indices()
         self.n = A.shape[0]
-        self.colptr = (A.indptr.astype(np.int64) + 1)
-        self.rows = (A.indices.astype(np.int64) + 1)
+        self.colptr = (A.indptr.astype(self.idt) + 1)
+        self.rows = (A.indices.astype(self.idt) + 1)
         self.vals = np.ascontiguousarray(A.data.astype(self.dtype))
-        self.perm = perm0.astype(np.int64) + 1
+        self.perm = perm0.astype(self.idt) + 1
         self.invp = np.empty_like(self.perm)
-        self.invp[self.perm - 1] = np.arange(1, self.n + 1)
+        self.invp[self.perm - 1] = np.arange(1, self.n + 1, dtype=self.idt)
         self.iparm[E["IPARM_MODIFY_PARAMETER"]] = E["API_NO"]      # defaults: pastix.c:334-456
         self._call(E["API_TASK_INIT"], E["API_TASK_INIT"])
         fact = {"llt": "API_FACT_LLT", "ldlt": "API_FACT_LDLT", "lu": "API_FACT_LU", "ldlh": "API_FACT_LDLH"}[facto]
@@ -152,8 +156,8 @@ class PastixLib:
 class Pastix(PastixLib):
     """pastix() served by the drop-in library: reference host code + B200 numeric phase."""
 
-    def __init__(self, prec: str = "d", threads: int = 1, verbose: int = 0):
-        super().__init__(prec, dropin_path(prec), load_enums(), threads=threads, verbose=verbose)
+    def __init__(self, prec: str = "d", threads: int = 1, verbose: int = 0, int_bits: int = 64):
+        super().__init__(prec, dropin_path(prec, int_bits), load_enums(), threads=threads, verbose=verbose, int_bits=int_bits)
 
     # -- hooks of the drop-in (pastix_b200/shim/shim_hooks.c) ----------------------------------
     def handle(self) -> int:

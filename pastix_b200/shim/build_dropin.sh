@@ -11,7 +11,10 @@
 # PASTIX_INT, -DMULT_SMX (multi-RHS), Fortran-ABI BLAS (only the reference's host-side refinement
 # and analysis use it) = the OpenBLAS shipped inside the opencv_python_headless wheel.
 # Without the reference tree (GPU box) the prebuilt .so files are kept.
-# usage: pastix_b200/shim/build_dropin.sh [precisions...]      (default: d z s c)
+# A precision followed by "32" (d32, z32, ...) builds with the reference's DEFAULT 32-bit PASTIX_INT (-DINTSIZE32,
+# common_pastix.h:331-347) into libpastix_dropin_<p>_i32.so: the shim widens the SolverMatrix into the int64 C ABI and
+# the internal CSC takes the reference's host CscOrdistrib (shim_csc.c), everything else is identical.
+# usage: pastix_b200/shim/build_dropin.sh [precisions...]      (default: d z s c d32)
 set -u
 HERE="$(cd "$(dirname "$0")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
@@ -19,7 +22,7 @@ R=${PASTIX_REFERENCE:-/root/reference}/src
 OUT="$ROOT/pastix_b200/lib"
 [ -d "$R" ] || { echo "reference sources not found at $R — keeping prebuilt drop-in libraries"; exit 0; }
 [ -f "$OUT/libpastix_b200.so" ] || { echo "build libpastix_b200.so first (python -m pastix_b200.build)"; exit 1; }
-PRECS="${*:-d z s c}"
+PRECS="${*:-d z s c d32}"
 BLASDIR=$(python - <<'PY'
 import glob, os, sysconfig
 sp = sysconfig.get_paths()["purelib"]
@@ -32,19 +35,23 @@ BLASLIB=$(ls "$BLASDIR"/libopenblas*.so | head -1)
 INC="-I$HERE -I$R/common/src -I$R/symbol/src -I$R/order/src -I$R/sopalin/src -I$R/blend/src -I$R/fax/src -I$R/kass/src -I$R/perf/src -I$R/sparse-matrix/src -I$ROOT/include"
 CC="gcc -O2 -w -std=gnu99 -fcommon -fPIC"
 
-for P in $PRECS; do
+for PP in $PRECS; do
+  P=${PP%32}
+  INTDEF="-DINTSIZE64"; SUF=""
+  if [ "$PP" != "$P" ]; then INTDEF="-DINTSIZE32"; SUF="_i32"; fi
   case $P in
     d) TDEF="-DPREC_DOUBLE";;
     z) TDEF="-DPREC_DOUBLE -DTYPE_COMPLEX";;
     s) TDEF="";;
     c) TDEF="-DTYPE_COMPLEX";;
+    *) echo "unknown precision $PP"; exit 1;;
   esac
-  LIB="$OUT/libpastix_dropin_$P.so"
+  LIB="$OUT/libpastix_dropin_$P$SUF.so"
   if [ -f "$LIB" ] && [ "$LIB" -nt "$HERE/sopalin_b200_shim.c" ] && [ "$LIB" -nt "$HERE/shim_hooks.c" ] && [ "$LIB" -nt "$HERE/shim_csc.c" ] && [ "$LIB" -nt "$HERE/shim_raff.c" ] && [ "$LIB" -nt "$HERE/shim_table.h" ] && [ "$LIB" -nt "$0" ] && [ "$LIB" -nt "$ROOT/include/pastix_b200.h" ]; then
-    echo "[$P] up to date"; continue
+    echo "[$PP] up to date"; continue
   fi
-  DEF="-DFORCE_NOMPI $TDEF -DINTSIZE64 -DMULT_SMX -DX_ARCHi686_pc_linux -DDOF_CONSTANT -DFORCE_NO_CUDA -DVERSION=\"pastix_b200\""
-  OBJ="$OUT/_dropin_obj_$P"; mkdir -p "$OBJ"
+  DEF="-DFORCE_NOMPI $TDEF $INTDEF -DMULT_SMX -DX_ARCHi686_pc_linux -DDOF_CONSTANT -DFORCE_NO_CUDA -DVERSION=\"pastix_b200\""
+  OBJ="$OUT/_dropin_obj_$P$SUF"; mkdir -p "$OBJ"
   JOBS="$OBJ/jobs.txt"; : > "$JOBS"
   add() { echo "$CC $INC $DEF $3 -c $1 -o $OBJ/$2.o" >> "$JOBS"; }
   for f in common_integer common_error common_memory trace common; do add $R/common/src/$f.c c_$f -DCHOL_SOPALIN; done
@@ -84,5 +91,5 @@ for P in $PRECS; do
       -Wl,--disable-new-dtags -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$BLASDIR" -Wl,-rpath-link,"$BLASDIR" -Wl,--no-undefined 2> "$OBJ/link.log" \
       || { echo "[$P] link failed"; head -30 "$OBJ/link.log"; exit 1; }
   rm -rf "$OBJ"
-  echo "[$P] built $LIB"
+  echo "[$PP] built $LIB"
 done

@@ -75,3 +75,27 @@ def test_flop_model_matches_reference_count():
                 gemm += 2.0 * mk * nk * n
             tot += potrf + trsm + gemm
         assert abs(tot - g["fact_flops"]) <= 1e-9 * g["fact_flops"], (name, tot, g["fact_flops"])
+
+
+@pytest.mark.parametrize("name,kind,N", [("lap7_8_llt_d", "lap7", 8), ("cd_8_lu_d", "cd", 8)])
+def test_int32_dropin_analysis_gives_the_golden_structures(name, kind, N):
+    """The drop-in built with the reference's DEFAULT 32-bit PASTIX_INT (libpastix_dropin_d_i32.so): pastix() runs
+    ordering -> blend on the CPU (no GPU needed before NUMFACT) and the SolverMatrix the shim hands to the C ABI,
+    widened to int64, is bit-identical to the one the 64-bit reference produced for the golden fixture."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from conftest import load_golden
+    from make_golden import case_matrix, DT
+    from pastix_b200.pastix_api import Pastix, dropin_path
+    if not os.path.exists(dropin_path("d", 32)):
+        pytest.skip("int32 drop-in not built (needs the reference tree at build time)")
+    g = load_golden(name)
+    A, perm0 = case_matrix(kind, N, DT["d"])
+    p = Pastix("d", int_bits=32).setup(A, perm0, g["facto"], sym=g["sym"]).analyze()
+    s = p.solver(); permtab, _ = p.order()
+    assert s["cblknbr"] == g["cblknbr"] and s["bloknbr"] == g["bloknbr"]
+    for k, k2 in (("fcolnum", "fcol"), ("lcolnum", "lcol"), ("bloknum", "bloknum"), ("stride", "stride"),
+                  ("frownum", "frow"), ("lrownum", "lrow"), ("cblknum", "fcblk"), ("coefind", "coefind")):
+        assert np.array_equal(s[k][:len(g[k2])], g[k2]), k
+    assert np.array_equal(permtab, g["permtab"])
+    assert p.out()["fact_flops"] == g["fact_flops"] and p.out()["nnzeros"] == g["nnzeros"]

@@ -70,6 +70,35 @@ def test_pastix_dropin_matches_reference(kind, N, prec, facto, over, nrhs):
     gpu.release()
 
 
+@pytest.mark.parametrize("kind,N,facto,nrhs", [("lap7", 12, "llt", 2), ("cd", 10, "lu", 1), ("lap27", 14, "ldlt", 1)])
+def test_int32_dropin_matches_reference(kind, N, facto, nrhs):
+    """The drop-in built with the reference's default 32-bit PASTIX_INT (libpastix_dropin_d_i32.so; the shim widens the
+    SolverMatrix into the int64 C ABI, the internal CSC takes the reference's host CscOrdistrib) against the 64-bit
+    reference: same pastix() calls, same outputs."""
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix, dropin_path
+    from pastix_b200 import generators as G
+    if not available("d") or not os.path.exists(dropin_path("d", 32)):
+        pytest.skip("oracle/_ref or the int32 drop-in not built")
+    A, perm0 = case_matrix(kind, N, DT["d"])
+    sym = {"llt": "yes", "ldlt": "yes", "lu": "no"}[facto]
+    b = G.rhs_vector(A.shape[0], nrhs, DT["d"])
+    ref = RefPastix("d", threads=1).setup(A, perm0, facto, sym=sym).analyze().numfact()
+    xr = ref.solve(b)
+    gpu = Pastix("d", threads=1, int_bits=32).setup(A, perm0, facto, sym=sym).analyze().numfact()
+    xg = gpu.solve(b)
+    og, orf = gpu.out(), ref.out()
+    assert og["nnzeros"] == orf["nnzeros"] and og["fact_flops"] == orf["fact_flops"]
+    assert og["static_pivoting"] == orf["static_pivoting"]
+    if facto == "ldlt":
+        assert og["inertia"] == orf["inertia"]
+    assert relerr(xg, xr) <= 50 * tol("d")
+    Af = full_matrix(A, sym)
+    assert np.linalg.norm(Af @ xg - b) / np.linalg.norm(b) <= 1e-12
+    gpu.release()
+
+
 def test_factors_match_reference_through_handle():
     """coeftab read back from HBM through the handle the shim keeps == the reference's panels."""
     from make_golden import case_matrix, DT
