@@ -637,7 +637,7 @@ extern "C" int pb200_create_opts(pb200_handle_t **out, const pb200_solver_t *s, 
   h->h_fcol.resize(C); h->h_width.resize(C); h->h_stride.resize(C); h->h_fblok.resize(C + 1);
   h->h_frow.resize(B); h->h_nrow.resize(B); h->h_fcblk.resize(B); h->h_coefind.resize(B);
   h->h_poff.resize(C + 1);
-  auto bad = [&](const std::string &m) { delete h; return fail(PB200_ERR_STRUCT, m); };
+  auto bad = [&](const std::string &m) { pb200_destroy(h); return fail(PB200_ERR_STRUCT, m); };   // also frees what was uploaded so far
   h->h_poff[0] = 0;
   for (int64_t c = 0; c < C; ++c) {
     int64_t w = s->lcolnum[c] - s->fcolnum[c] + 1;
