@@ -99,6 +99,56 @@ def test_int32_dropin_matches_reference(kind, N, facto, nrhs):
     gpu.release()
 
 
+def test_two_live_instances_and_refactorization_with_new_values():
+    """Step-by-step use of pastix() (src/example/src/step-by-step.c, reentrant.c): two pastix_data alive at once, their
+    NUMFACT / SOLVE calls interleaved (one device handle per SolverMatrix in the shim's side table), then a second
+    NUMFACT on the SAME analysis with new matrix values — the internal CSC is rebuilt from the user's avals on every
+    NUMFACT (pastix.c:3486-3489) and the resident factors must follow."""
+    from make_golden import case_matrix, DT
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    A1, p1 = case_matrix("lap7", 10, DT["d"])
+    A2, p2 = case_matrix("cd", 8, DT["d"])
+    b1 = G.rhs_vector(A1.shape[0], 1, DT["d"])[:, 0].copy()
+    b2 = G.rhs_vector(A2.shape[0], 2, DT["d"])
+    g1 = Pastix("d", threads=1).setup(A1, p1, "ldlt").analyze()
+    g2 = Pastix("d", threads=1).setup(A2, p2, "lu", sym="no").analyze()
+    g1.numfact(); g2.numfact()
+    assert g1.handle() != g2.handle() and g1.handle() and g2.handle()
+    x2 = g2.solve(b2); x1 = g1.solve(b1)
+    F1 = full_matrix(A1, "yes")
+    assert np.linalg.norm(F1 @ x1 - b1) / np.linalg.norm(b1) <= 1e-12
+    assert np.linalg.norm(A2 @ x2 - b2) / np.linalg.norm(b2) <= 1e-12
+    h1 = g1.handle()
+    g1.vals *= 2.0                                   # same pattern, new values: A1 <- 2 A1
+    g1.numfact()
+    assert g1.handle() == h1, "the analysis did not change: the device handle (schedule, slabs) must be reused"
+    y1 = g1.solve(b1)
+    assert np.linalg.norm(2.0 * (F1 @ y1) - b1) / np.linalg.norm(b1) <= 1e-12
+    assert relerr(2.0 * y1, x1) <= 50 * tol("d")
+    assert relerr(g2.solve(b2), x2) <= 1e-14         # the other instance's factors are untouched
+    g1.release(); g2.release()
+
+
+def test_analysis_with_several_blend_threads():
+    """IPARM_THREAD_NBR > 1 only shapes blend's task vectors (ttsktab); the numeric phase on the GPU ignores them and
+    must give the same answer as the reference run with the same iparm."""
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    if not available("d"):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix("lap7", 12, DT["d"])
+    b = G.rhs_vector(A.shape[0], 1, DT["d"])[:, 0].copy()
+    xr = RefPastix("d", threads=4).setup(A, perm0, "llt").analyze().numfact().solve(b)
+    gpu = Pastix("d", threads=4).setup(A, perm0, "llt").analyze().numfact()
+    xg = gpu.solve(b)
+    assert relerr(xg, xr) <= 50 * tol("d")
+    assert np.linalg.norm(full_matrix(A, "yes") @ xg - b) / np.linalg.norm(b) <= 1e-12
+    gpu.release()
+
+
 def test_factors_match_reference_through_handle():
     """coeftab read back from HBM through the handle the shim keeps == the reference's panels."""
     from make_golden import case_matrix, DT
