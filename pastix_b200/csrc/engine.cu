@@ -85,6 +85,8 @@ struct pb200_handle_s {
   void *d_y = nullptr; size_t y_bytes = 0;
   bool inv_ready = false;
   bool solve_transposed = false;           // IPARM_TRANSPOSE_SOLVE (LU only)
+  unsigned attr_mask = 0;                  // which cudaFuncSetAttribute groups this handle has applied on ITS device (the
+                                           // attributes are per device: a process-wide flag would skip the second GPU)
   bool schur = false;                      // IPARM_SCHUR: the last cblk is never factored (it ends up holding the Schur complement) and
                                            // up_down ignores it and every blok facing it (sopalin_compute.c:767-772, updo.c:425-428)
   void *d_raff_partial = nullptr, *h_raff_partial = nullptr;   // dot-product partial sums (device / pinned host)
@@ -1083,17 +1085,15 @@ static int factorize_tf(pb200_handle_t *h, double crit) {
   const int lu = (FACTO == F_LU) ? 2 : 1;
   // dynamic shared memory for the diagonal block: as much as fits
   int smem_max = 200 * 1024;
-  static bool attr_done[4][4] = {};
-  if (!attr_done[h->flt][FACTO]) {
+  if (!(h->attr_mask & 1u)) {   // once per handle
     CK(cudaFuncSetAttribute(k_diag_factor<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    attr_done[h->flt][FACTO] = true;
+    h->attr_mask |= 1u;
   }
-  static bool sm_attr_done[4][4] = {};
   const size_t sm_lvl_smem = (size_t)PB200_SM_WARPS * sizeof(SmallWs<T>), sm_chain_smem = (size_t)SmChain<T>::WARPS * sizeof(SmallWs<T>);
-  if (!sm_attr_done[h->flt][FACTO]) {
+  if (!(h->attr_mask & 2u)) {
     CK(cudaFuncSetAttribute(k_small_level<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_lvl_smem));
     CK(cudaFuncSetAttribute(k_small_chain<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chain_smem));
-    sm_attr_done[h->flt][FACTO] = true;
+    h->attr_mask |= 2u;
   }
   int64_t launches = 0;
   for (const auto &gs : h->gsteps) {
@@ -1145,12 +1145,11 @@ template <class T, int FACTO>
 static int factorize_mma(pb200_handle_t *h, double crit) {
   T *L = (T *)h->dL, *U = (T *)h->dU;
   const int lu = (FACTO == F_LU) ? 2 : 1;
-  static bool attr_done[4][4] = {};
-  if (!attr_done[h->flt][FACTO]) {
+  if (!(h->attr_mask & 4u)) {   // once per handle
     CK(cudaFuncSetAttribute(k_gemm_scatter<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem_bytes<T>()));
     CK(cudaFuncSetAttribute(k_trsm_mma<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)trsm_smem_bytes<T>(SubCfg<T>::NBMAX)));
-    attr_done[h->flt][FACTO] = true;
+    h->attr_mask |= 4u;
   }
   int64_t launches = 0;
   const bool prof = h->prof_on || getenv("PB200_PROFILE") != nullptr;
@@ -1321,10 +1320,9 @@ template <class T>
 static size_t inv_smem(int nbmax) { return ((size_t)nbmax * (nbmax + 1) / 2 + (size_t)tri_xelems(nbmax)) * sizeof(T); }   // packed W + per-warp X rectangles
 template <class T>
 static int inv_attr(pb200_handle_t *h) {
-  static bool attr_done[4] = {};
-  if (!attr_done[h->flt]) {
+  if (!(h->attr_mask & 8u)) {   // once per handle
     CK(cudaFuncSetAttribute(k_tri_inverse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem<T>(SlvCfg<T>::NB)));
-    attr_done[h->flt] = true;
+    h->attr_mask |= 8u;
   }
   return PB200_SUCCESS;
 }
@@ -1375,14 +1373,13 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
   const T *inv_up = (FACTO == F_LU) ? (const T *)(tsolve ? h->d_inv : h->d_inv_up) : inv;
   T *y = (T *)h->d_y;
   int64_t launches = 0;
-  static bool sm_attr_done[4][4] = {};
   const size_t sm_lvl_smem = (size_t)PB200_SM_WARPS * sizeof(SmallSolveWs<T>), sm_chain_smem = (size_t)SmChain<T>::WARPS * sizeof(SmallSolveWs<T>);
-  if (!sm_attr_done[h->flt][FACTO]) {
+  if (!(h->attr_mask & 16u)) {
     CK(cudaFuncSetAttribute(k_small_solve_level<T, FACTO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_lvl_smem));
     CK(cudaFuncSetAttribute(k_small_solve_level<T, FACTO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_lvl_smem));
     CK(cudaFuncSetAttribute(k_small_solve_chain<T, FACTO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chain_smem));
     CK(cudaFuncSetAttribute(k_small_solve_chain<T, FACTO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chain_smem));
-    sm_attr_done[h->flt][FACTO] = true;
+    h->attr_mask |= 16u;
   }
   // several right-hand sides through an all-small schedule (ILU): transposed work copies, lanes over right-hand sides
   const bool tr = h->slv_all_small && nrhs >= 4 && !tsolve;
@@ -1402,14 +1399,13 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
   }
   if (h->dag_ok) {
     // one persistent launch per sweep, ordered by device-side contribution counters (kernels_solve_dag.cuh)
-    static bool dag_attr_done[4][4] = {};
     const size_t smem = DagSmem<T>::bytes(h->dag_nbs), belems = DagSmem<T>::buf_elems(h->dag_nbs);
-    if (!dag_attr_done[h->flt][FACTO]) {
+    if (!(h->attr_mask & 32u)) {
       CK(cudaFuncSetAttribute(k_fwd_dag<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DagSmem<T>::bytes(SlvCfg<T>::NB)));
       CK(cudaFuncSetAttribute(k_bwd_dag<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DagSmem<T>::bytes(SlvCfg<T>::NB)));
       CK(cudaFuncSetAttribute(k_fwd_dag<T, FACTO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       CK(cudaFuncSetAttribute(k_bwd_dag<T, FACTO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      dag_attr_done[h->flt][FACTO] = true;
+      h->attr_mask |= 32u;
     }
     int occ_f = 0, occ_b = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_dag<T, FACTO>, PB200_DAG_NT, smem));

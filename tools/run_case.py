@@ -1,5 +1,5 @@
-"""Dev tool: run one synthetic case end to end on the GPU (analysis by the
-reference in oracle/_ref, numeric phase by pastix_b200) and print timings and
+"""Dev tool: run one synthetic case end to end on the GPU (analysis = the reference's unchanged host code inside
+the drop-in library, numeric phase by pastix_b200 through the C ABI) and print timings and
 the backward error.  usage: python tools/run_case.py N stencil facto prec [nrhs] [--ref] [--reps=K] [--json=path]"""
 import os
 import sys
@@ -10,7 +10,7 @@ import scipy.sparse as sp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.refpastix import RefPastix  # noqa: E402
+from pastix_b200.pastix_api import Pastix  # noqa: E402
 from pastix_b200 import Sopalin, critere_from_norm, generators as G  # noqa: E402
 from pastix_b200.csc import internal_csc, permute_rhs, unpermute_solution  # noqa: E402
 
@@ -31,10 +31,12 @@ def main():
     sym = {"llt": "yes", "ldlt": "yes", "lu": "no", "ldlh": "her"}[facto]
     devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)
     try:
-        r = RefPastix(prec, threads=1).setup(A, perm0, facto, sym=sym).analyze()
+        r = Pastix(prec, threads=1).setup(A, perm0, facto, sym=sym).analyze()
     finally:
         os.dup2(saved, 1)
     s = r.solver(); permtab, _ = r.order(); out = r.out()
+    cb = s["cblknbr"]
+    s["coefnbr"] = int(np.sum(s["stride"][:cb] * (s["lcolnum"][:cb] - s["fcolnum"][:cb] + 1)))
     t1 = time.time()
     print(f"analysis {t1 - t0:.2f}s: n={A.shape[0]} cblk={s['cblknbr']} blok={s['bloknbr']} coefnbr={s['coefnbr']} "
           f"flops={out['fact_flops']:.4g} nnzL={out['nnzeros']}")
@@ -69,7 +71,8 @@ def main():
     if jp:
         import json
         json.dump(rec, open(jp, "w"))
-    if "--ref" in sys.argv:
+    if "--ref" in sys.argv:      # comparison leg only: the unmodified reference on the host cores (test infrastructure)
+        from oracle.refpastix import RefPastix
         r = RefPastix(prec, threads=os.cpu_count()).setup(A, perm0, facto, sym=sym).analyze()
         t = time.time(); r.numfact(); xr = r.solve(b)
         o = r.out()
