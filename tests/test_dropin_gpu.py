@@ -297,6 +297,25 @@ def test_static_pivot_threshold_from_device_norm(prec, kind, facto, sym):
     gpu.release()
 
 
+@pytest.mark.parametrize("eps", [-1e-6, -0.25])
+def test_absolute_static_pivot_threshold(eps):
+    """DPARM_EPSILON_MAGN_CTRL < 0 is an ABSOLUTE static-pivot threshold (sopalin3d.c:586-590).  On a matrix with zero
+    diagonal entries the replaced-pivot count (IPARM_STATIC_PIVOTING) and the inertia must equal the reference's."""
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    if not available("d"):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix("lap7sing", 8, DT["d"])
+    dp = {"DPARM_EPSILON_MAGN_CTRL": eps}
+    ref = RefPastix("d", threads=1).setup(A, perm0, "ldlt", dparm_over=dp).analyze().numfact()
+    gpu = Pastix("d", threads=1).setup(A, perm0, "ldlt", dparm_over=dp).analyze().numfact()
+    assert gpu.critere() == -eps
+    assert gpu.out()["static_pivoting"] == ref.out()["static_pivoting"] >= 1
+    assert gpu.out()["inertia"] == ref.out()["inertia"]
+    gpu.release()
+
+
 REFINE_CASES = [
     # kind, N, prec, facto, sym, refinement, incomplete level (None: complete factorization)
     ("lap7", 10, "d", "llt", "yes", "API_RAF_GMRES", 1),
