@@ -55,6 +55,19 @@ def test_no_cpu_fallback_without_gpu():
         Sopalin(g, "s", "llt")
 
 
+def test_argument_errors_are_reported_before_any_device_work():
+    """Bad arguments come back as PB200_ERR_BADARG with a message (no GPU needed to reach these checks)."""
+    from conftest import load_golden
+    from pastix_b200 import Sopalin, PastixB200Error
+    g = load_golden("lap7_8_llt_d_schur")
+    with pytest.raises(PastixB200Error, match="Schur mode is single-GPU"):
+        Sopalin(g, "d", "llt", rank=0, nranks=2, schur=True)
+    with pytest.raises(PastixB200Error, match="bad rank"):
+        Sopalin(g, "d", "llt", rank=3, nranks=2)
+    with pytest.raises(PastixB200Error, match="bad rank"):
+        Sopalin(g, "d", "llt", rank=0, nranks=99)
+
+
 def test_flop_model_matches_reference_count():
     """DPARM_FACT_FLOPS of the golden fixtures (the metric's numerator, blend_symbol_cost.c:52-88)
     re-derived from the SolverMatrix arrays with the formulas of flops.h:74-117."""

@@ -74,6 +74,23 @@ def test_solve_only_with_reference_factors(name):
     s.close()
 
 
+@pytest.mark.parametrize("name", ["cd_8_lu_d", "lap7_10_llt_d_bs16"])
+def test_get_cblk_equals_slab_slices(name):
+    """pb200_get_cblk (one panel, the layout of SolverCblk.coeftab / .ucoeftab) against pb200_get_coeftab."""
+    g = load_golden(name)
+    s, _, (L, U), _ = run_cuda(g)
+    off = s.solver.panel_offsets()
+    for c in (0, g["cblknbr"] // 2, g["cblknbr"] - 1):
+        w = int(g["lcol"][c] - g["fcol"][c] + 1); ld = int(g["stride"][c])
+        if U is not None:
+            Lc, Uc = s.get_cblk(c, with_u=True)
+            assert np.array_equal(Uc, U[off[c]:off[c + 1]].reshape(ld, w, order="F"))
+        else:
+            Lc = s.get_cblk(c)
+        assert np.array_equal(Lc, L[off[c]:off[c + 1]].reshape(ld, w, order="F"))
+    s.close()
+
+
 def test_schur_mode_refuses_the_level_sweeps(monkeypatch):
     """Schur mode is implemented on the persistent up_down only; the A/B switch must fail loudly, not solve wrongly."""
     from pastix_b200 import Sopalin, PastixB200Error
