@@ -240,6 +240,10 @@ static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
     errorPrint("pastix_b200: 2D distribution / multi-process SolverMatrix are not handled by this shim");
     EXIT(MOD_SOPALIN, BADPARAMETER_ERR);
   }
+  if (sopar->fakefact == API_YES) {             /* IPARM_FILL_MATRIX: synthetic coefficients (coefinit.c:343-437) */
+    errorPrint("pastix_b200: IPARM_FILL_MATRIX (fake factorization) is not handled by this shim");
+    EXIT(MOD_SOPALIN, BADPARAMETER_ERR);
+  }
   {
   double t0 = clockGet(), t1, t2, t3;
   if (e->h != NULL && (e->facto != PB200_FACTO || e->schur != schur)) { pb200_destroy(e->h); e->h = NULL; }
