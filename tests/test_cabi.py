@@ -68,6 +68,43 @@ def test_argument_errors_are_reported_before_any_device_work():
         Sopalin(g, "d", "llt", rank=0, nranks=99)
 
 
+_REFUSAL = r"""
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests/golden")
+from make_golden import case_matrix, DT
+from pastix_b200.pastix_api import Pastix
+A, perm0 = case_matrix("lap7", 6, DT["d"])
+p = Pastix("d").setup(A, perm0, "llt", iparm_over={over!r}).analyze()
+p.numfact()
+print("NUMFACT RETURNED")
+"""
+
+
+@pytest.mark.parametrize("over,msg", [({"IPARM_FILL_MATRIX": 1}, "IPARM_FILL_MATRIX"),
+                                      ({"IPARM_DISTRIBUTION_LEVEL": 2}, "2D distribution"),
+                                      ({}, "no CUDA device")])
+def test_dropin_refuses_loudly(over, msg, tmp_path):
+    """What the shim does not handle ends the way the reference's own fatal paths do (errorPrint + EXIT -> abort,
+    common/src/errors.h:161-165) with a message naming the reason — never a silent different computation.  The last
+    case: pastix(API_TASK_NUMFACT) on a machine without a GPU (skipped where one is present)."""
+    import subprocess
+    import sys
+    import torch
+    from pastix_b200.pastix_api import dropin_path
+    if not os.path.exists(dropin_path("d")):
+        pytest.skip("drop-in library not built")
+    if not over and torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    script = tmp_path / "refuse.py"
+    script.write_text(_REFUSAL.format(root=ROOT, over=over))
+    # PB200_HOST_CSC=1: the internal CSC through the reference's host routine, so that on a machine without a GPU the
+    # first device contact is the numeric phase itself (otherwise the device-side CscOrdistrib already reports "no CUDA")
+    env = dict(os.environ, PB200_HOST_CSC="1") if over else dict(os.environ)
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode != 0 and "NUMFACT RETURNED" not in out.stdout
+    assert msg in out.stdout + out.stderr, (out.stdout[-500:], out.stderr[-500:])
+
+
 def test_flop_model_matches_reference_count():
     """DPARM_FACT_FLOPS of the golden fixtures (the metric's numerator, blend_symbol_cost.c:52-88)
     re-derived from the SolverMatrix arrays with the formulas of flops.h:74-117."""
