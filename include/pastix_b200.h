@@ -26,10 +26,13 @@
  *   pb200_inertia       <- inertia count (sopalin/src/sopalin3d.c:1145-1161)
  *   pb200_solve         <- {po,sy,he,ge}_updo_thread -> up_down_smp
  *                          (sopalin/src/updo.c:67,114-1664; updo_sendrecv.c:496-639)
- *   pb200_get_coeftab / pb200_set_coeftab
+ *   pb200_get_coeftab / pb200_set_coeftab / pb200_get_cblk
  *                       <- SolverCblk.coeftab / .ucoeftab contents
  *                          (blend/src/solver.h:94-117), so host consumers
- *                          (Schur, dumps, refinement) keep working
+ *                          (pastix_getSchur, dumps) keep working
+ *   pb200_create_opts   <- the same with SopalinParam.schur (IPARM_SCHUR: the last
+ *                          column block is left unfactored, sopalin_compute.c:767-772,
+ *                          and ignored by up_down, updo.c:425-428)
  *   pb200_destroy       <- CoefMatrix_Free + sopalin_clean (coefinit.c:479)
  *
  * Error behaviour: every call returns PB200_SUCCESS (0) or a negative code;
