@@ -85,6 +85,9 @@ struct pb200_handle_s {
   void *d_y = nullptr; size_t y_bytes = 0;
   bool inv_ready = false;
   bool solve_transposed = false;           // IPARM_TRANSPOSE_SOLVE (LU only)
+  // round-2 experiment (PB200_GRAPH=1, not measured yet): the launch sequence of one factorization captured once per
+  // pivot threshold and replayed as a CUDA graph
+  cudaGraphExec_t fact_graph = nullptr; double fact_graph_crit = 0.0; int64_t fact_graph_launches = 0;
   unsigned attr_mask = 0;                  // which cudaFuncSetAttribute groups this handle has applied on ITS device (the
                                            // attributes are per device: a process-wide flag would skip the second GPU)
   bool schur = false;                      // IPARM_SCHUR: the last cblk is never factored (it ends up holding the Schur complement) and
@@ -864,6 +867,7 @@ extern "C" int pb200_destroy(pb200_handle_t *h) {
   cudaFree(h->d_raff_partial);
   cudaFree(h->dL); cudaFree(h->dU); cudaFree(h->dW); cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals);
   cudaFree(h->d_tvals); cudaFree(h->d_cnt); cudaFree(h->d_x); cudaFree(h->d_y); cudaFree(h->d_xt);
+  if (h->fact_graph) cudaGraphExecDestroy(h->fact_graph);
   for (auto e : h->sched_ev) cudaEventDestroy(e);
   if (h->stream_u) cudaStreamDestroy(h->stream_u);
   if (h->stream_i) cudaStreamDestroy(h->stream_i);
@@ -1159,6 +1163,19 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
   const bool serial = prof || getenv("PB200_SERIAL") != nullptr;
   const bool overlap_inv = !serial && h->nranks == 1 && getenv("PB200_INV_OVERLAP") != nullptr;   // opt-in: measured slower (r01)
+  // The schedule is a fixed sequence of launches on two streams joined by events: capture it once (per threshold value,
+  // which is a by-value kernel argument) and replay it — kernel-to-kernel dependencies then resolve on the device
+  // without the stream scheduler in between.  Multi-GPU schedules carry an epoch argument and stay on streams.
+  const bool use_graph = !serial && !overlap_inv && h->nranks == 1 && h->nlevels > 0 && getenv("PB200_GRAPH") != nullptr;
+  if (use_graph && h->fact_graph && h->fact_graph_crit == crit) {
+    CK(cudaGraphLaunch(h->fact_graph, h->stream));
+    h->last_launches = h->fact_graph_launches;
+    return PB200_SUCCESS;
+  }
+  if (use_graph) {
+    if (h->fact_graph) { cudaGraphExecDestroy(h->fact_graph); h->fact_graph = nullptr; }
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  }
   for (const auto &st : h->steps) {
     cudaStream_t sm = (serial || st.strm == 0) ? h->stream : h->stream_u;
     if (!serial && st.wait_ev >= 0) CK(cudaStreamWaitEvent(sm, h->sched_ev[st.wait_ev], 0));
@@ -1234,6 +1251,15 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   }
   CK(cudaGetLastError());
   h->last_launches = launches;
+  if (use_graph) {
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamEndCapture(h->stream, &g));
+    cudaError_t e = cudaGraphInstantiate(&h->fact_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { h->fact_graph = nullptr; return fail(PB200_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    h->fact_graph_crit = crit; h->fact_graph_launches = launches;
+    CK(cudaGraphLaunch(h->fact_graph, h->stream));
+  }
   return PB200_SUCCESS;
 }
 

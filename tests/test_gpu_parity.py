@@ -91,6 +91,27 @@ def test_get_cblk_equals_slab_slices(name):
     s.close()
 
 
+@pytest.mark.parametrize("name", ["lap7_8_llt_d", "lap27_6_ldlt_d", "cd_8_lu_d", "cd_6_lu_z", "lap7_10_llt_d_bs16"])
+def test_graph_replay_equals_stream_launches(name, monkeypatch):
+    """PB200_GRAPH=1 (round-2 experiment): the captured launch sequence, first run (capture + launch) and replay, gives
+    the factors of the stream-launched schedule."""
+    g = load_golden(name)
+    s0, _, (L0, U0), nb0 = run_cuda(g)
+    s0.close()
+    monkeypatch.setenv("PB200_GRAPH", "1")
+    from pastix_b200 import Sopalin
+    s = Sopalin(g, g["prec"], g["facto"])
+    m = lower_mask(g) if g["facto"] != "lu" else slice(None)
+    for it in range(3):
+        s.assemble(g["colptr"], g["rows"], g["values"], g["tvalues"])
+        assert s.factorize(g["critere"]) == nb0
+        L, U = s.get_coeftab()
+        assert relerr(L[m], L0[m]) <= tol(g["prec"]), (name, it)
+        if U0 is not None:
+            assert relerr(U, U0) <= tol(g["prec"]), (name, it)
+    s.close()
+
+
 def test_schur_mode_refuses_the_level_sweeps(monkeypatch):
     """Schur mode is implemented on the persistent up_down only; the A/B switch must fail loudly, not solve wrongly."""
     from pastix_b200 import Sopalin, PastixB200Error
