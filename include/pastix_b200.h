@@ -230,6 +230,10 @@ int pb200_solve(pb200_handle_t *h, void *x, int64_t ldx, int64_t nrhs, double *s
  * factorization is affected (A^T = U^T L^T: the sweeps swap the L and U^T panels, updo.c:165-260, 1553-1600); the
  * symmetric factorizations ignore it, like the reference. */
 int pb200_set_transpose_solve(pb200_handle_t *h, int transposed);
+/* Internal CSC of type 'H' (IPARM_SYM = API_SYM_HER): the next pb200_assemble fills ucoeftab with the conjugate of
+ * `tvalues`, as Csc2solv_cblk does for cscmtx->type == 'H' (csc_intern_solve.c:110-116).  pb200_assemble_csc takes the
+ * type from the device CSC itself. */
+int pb200_set_hermitian(pb200_handle_t *h, int hermitian);
 /* Same with x already resident in HBM (device pointer). */
 int pb200_solve_device(pb200_handle_t *h, void *x_dev, int64_t ldx, int64_t nrhs, double *seconds);
 

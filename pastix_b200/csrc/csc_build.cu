@@ -82,7 +82,7 @@ __global__ void k_csc_colptr(int64_t n, int rb, const unsigned long long *__rest
 
 template <class T>
 __global__ void k_csc_gather(int64_t nnz, int rb, const unsigned long long *__restrict__ keys, const unsigned *__restrict__ pay,
-                             const T *__restrict__ uvals, int *rows, T *vals, T *tvals, int64_t toff) {
+                             const T *__restrict__ uvals, int *rows, T *vals, T *tvals, int64_t toff, int *bad) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nnz) return;
   rows[k] = (int)(keys[k] & ((1ull << rb) - 1));
@@ -90,7 +90,13 @@ __global__ void k_csc_gather(int64_t nnz, int rb, const unsigned long long *__re
   T v = uvals[p & ~CONJ_FLAG];
   if (p & CONJ_FLAG) v = ST<T>::conj(v);
   vals[k] = v;
-  if (tvals) tvals[k] = uvals[pay[toff + k]];
+  if (tvals) {
+    // the k-th transposed key must sit at the very (column, row) of the k-th main key: a pattern that is not
+    // symmetric would pair values by sorted position only (the reference requires a symmetric pattern for LU too)
+    const unsigned long long pos = (1ull << (2 * rb)) - 1;
+    if ((keys[toff + k] & pos) != (keys[k] & pos)) *bad = 2;
+    tvals[k] = uvals[pay[toff + k]];
+  }
 }
 
 // CscNorm1 (csc_intern_compute.c:120-176): max over columns of the sum of |a_ij|, summed in storage order by one
@@ -163,7 +169,8 @@ extern "C" int pb200_csc_destroy(pb200_csc_t *c) {
 template <class T>
 static void launch_gather(pb200_csc_t *c, int64_t nnz, int rb, bool want_t) {
   k_csc_gather<T><<<(unsigned)((nnz + 255) / 256), 256, 0, c->stream>>>(nnz, rb, c->d_keys1, c->d_pay1, (const T *)c->d_uvals, c->d_rows,
-                                                                       (T *)c->d_vals, want_t ? (T *)c->d_tvals : nullptr, nnz);
+                                                                       (T *)c->d_vals, want_t ? (T *)c->d_tvals : nullptr, nnz,
+                                                                       reinterpret_cast<int *>(c->d_extra + 2));
 }
 
 extern "C" int pb200_csc_build(pb200_csc_t *c, char type, int64_t n, const int64_t *colptr, const int64_t *rows, const void *values,
@@ -225,8 +232,14 @@ extern "C" int pb200_csc_build(pb200_csc_t *c, char type, int64_t n, const int64
     if (trans == 2) CCK(cudaMemcpyAsync(c->d_tvals, c->d_vals, (size_t)nnz * c->esize, cudaMemcpyDeviceToDevice, c->stream));
   }
   CCK(cudaGetLastError());
+  if (trans == 1) {
+    int bad = 0;
+    CCK(cudaMemcpyAsync(&bad, c->d_extra + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CCK(cudaStreamSynchronize(c->stream));
+    if (bad) return cfail(PB200_ERR_STRUCT, "unsymmetric pattern: the transposed copy does not fit the pattern of A");
+  }
   CCK(cudaStreamSynchronize(c->stream));
-  c->n = n; c->nnz = nnz; c->has_t = (trans != 0); c->valid = true;
+  c->n = n; c->nnz = nnz; c->has_t = (trans != 0); c->valid = true; c->type = type;
   *nnz_out = nnz;
   return PB200_SUCCESS;
 }

@@ -19,6 +19,7 @@ struct pb200_csc_s {
   size_t cap_colptr = 0, cap_rows = 0, cap_vals = 0, cap_tvals = 0, cap_extra = 0;
   int64_t n = 0, nnz = 0;
   bool has_t = false, valid = false;
+  char type = 'S';   // 'S' / 'H' / 'U' as given to pb200_csc_build (CscMatrix.type, blend/src/csc.h)
   // pinned staging pieces of the parallel device -> host fetch (one per worker thread, created on first use)
   void *pin[PB200_CSC_NPIN] = {}; cudaStream_t pstream[PB200_CSC_NPIN] = {};
 };

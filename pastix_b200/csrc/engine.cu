@@ -25,6 +25,8 @@
 
 using namespace pb200;
 
+#define PB200_SLAB_PAD 4096
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #define CK(call)                                                                        \
@@ -85,6 +87,7 @@ struct pb200_handle_s {
   void *d_y = nullptr; size_t y_bytes = 0;
   bool inv_ready = false;
   bool solve_transposed = false;           // IPARM_TRANSPOSE_SOLVE (LU only)
+  bool herm = false;                       // internal CSC of type 'H': ucoeftab takes conj(transposed values) (csc_intern_solve.c:112-115)
   // round-2 experiment (PB200_GRAPH=1, not measured yet): the launch sequence of one factorization captured once per
   // pivot threshold and replayed as a CUDA graph
   cudaGraphExec_t fact_graph = nullptr; double fact_graph_crit = 0.0; int64_t fact_graph_launches = 0;
@@ -423,26 +426,33 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
     if (lu) h->steps.push_back({3, q0, q1 - q0, 0, 0, l});
     if (rounds == 0) h->steps.push_back({4, 0, 0, 0, 0, l});   // multi-GPU: no cblk of this level lives here; keeps the level's events
     for (int r = 0; r < rounds; ++r) {
-      // diag
-      int t0 = (int)sub.size(), nbmax = 0;
-      for (int q = q0; q < q1; ++q) {
-        int c = lvl_cblk[q], w = h->h_width[c];
-        if ((w + NBMAX - 1) / NBMAX <= r) continue;
-        int c0, c1; subpanel(w, r, c0, c1);
-        sub.push_back({c, 0, c0, c1}); nbmax = std::max(nbmax, c1 - c0);
+      // diag and trsm, each as (at most) two launches: sub-panels of at most 64 columns and wider ones — the narrow
+      // kernels hold a quarter of the registers / shared memory and keep several CTAs per SM on the fat bottom levels
+      int t0 = 0; long long tiles = 0;
+      for (int cls = 0; cls < 2; ++cls) {
+        int nbmax = 0; t0 = (int)sub.size();
+        for (int q = q0; q < q1; ++q) {
+          int c = lvl_cblk[q], w = h->h_width[c];
+          if ((w + NBMAX - 1) / NBMAX <= r) continue;
+          int c0, c1; subpanel(w, r, c0, c1);
+          if ((c1 - c0 > 64) != (cls == 1)) continue;
+          sub.push_back({c, 0, c0, c1}); nbmax = std::max(nbmax, c1 - c0);
+        }
+        if ((int)sub.size() > t0)
+          h->steps.push_back({0, t0, (int)sub.size() - t0, (long long)sub.size() - t0, nbmax, l});
       }
-      h->steps.push_back({0, t0, (int)sub.size() - t0, (long long)sub.size() - t0, nbmax, l});
-      // trsm
-      t0 = (int)sub.size(); long long tiles = 0; nbmax = 0;
-      for (int q = q0; q < q1; ++q) {
-        int c = lvl_cblk[q], w = h->h_width[c], ld = h->h_stride[c];
-        if ((w + NBMAX - 1) / NBMAX <= r) continue;
-        int c0, c1; subpanel(w, r, c0, c1);
-        if (ld - c1 <= 0) continue;
-        sub.push_back({c, (int)tiles, c0, c1}); tiles += (ld - c1 + PB200_TRSM_TM - 1) / PB200_TRSM_TM;
-        nbmax = std::max(nbmax, c1 - c0);
+      for (int cls = 0; cls < 2; ++cls) {
+        int nbmax = 0; t0 = (int)sub.size(); tiles = 0;
+        for (int q = q0; q < q1; ++q) {
+          int c = lvl_cblk[q], w = h->h_width[c], ld = h->h_stride[c];
+          if ((w + NBMAX - 1) / NBMAX <= r) continue;
+          int c0, c1; subpanel(w, r, c0, c1);
+          if (ld - c1 <= 0 || (c1 - c0 > 64) != (cls == 1)) continue;
+          sub.push_back({c, (int)tiles, c0, c1}); tiles += (ld - c1 + PB200_TRSM_TM - 1) / PB200_TRSM_TM;
+          nbmax = std::max(nbmax, c1 - c0);
+        }
+        if (tiles > 0) h->steps.push_back({1, t0, (int)sub.size() - t0, tiles, nbmax, l});
       }
-      if (tiles > 0) h->steps.push_back({1, t0, (int)sub.size() - t0, tiles, nbmax, l});
       // internal update
       t0 = (int)gemm.size(); tiles = 0;
       for (int q = q0; q < q1; ++q) {
@@ -832,16 +842,21 @@ extern "C" int pb200_create_opts(pb200_handle_t **out, const pb200_solver_t *s, 
     if (rc) { pb200_destroy(h); return rc; }
   }
 
-  size_t slab = (size_t)h->coefnbr * h->esize;
-  if (cudaMalloc(&h->dL, slab) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(L slab) failed"); }
-  h->device_bytes += slab;
+  // the TMA-staged tiles of k_gemm_scatter copy whole 64-row column segments: the last tile of the last panel reads
+  // (and discards) up to one segment past the slab
+  const size_t slab = (size_t)h->coefnbr * h->esize, slab_alloc = slab + PB200_SLAB_PAD;
+  if (cudaMalloc(&h->dL, slab_alloc) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(L slab) failed"); }
+  h->device_bytes += slab_alloc;
+  CK(cudaMemset((char *)h->dL + slab, 0, PB200_SLAB_PAD));
   if (factotype == PB200_FACT_LU) {
-    if (cudaMalloc(&h->dU, slab) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(U slab) failed"); }
-    h->device_bytes += slab;
+    if (cudaMalloc(&h->dU, slab_alloc) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(U slab) failed"); }
+    h->device_bytes += slab_alloc;
+    CK(cudaMemset((char *)h->dU + slab, 0, PB200_SLAB_PAD));
   }
   if (h->use_mma && (factotype == PB200_FACT_LDLT || factotype == PB200_FACT_LDLH)) {
-    if (cudaMalloc(&h->dW, slab) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(L*D workspace) failed"); }
-    h->device_bytes += slab;
+    if (cudaMalloc(&h->dW, slab_alloc) != cudaSuccess) { pb200_destroy(h); return fail(PB200_ERR_NOMEM, "cudaMalloc(L*D workspace) failed"); }
+    h->device_bytes += slab_alloc;
+    CK(cudaMemset(h->dW, 0, slab_alloc));
   }
   CK(cudaMalloc((void **)&h->d_cnt, 4 * sizeof(unsigned long long)));
   CK(cudaMemset(h->d_cnt, 0, 4 * sizeof(unsigned long long)));
@@ -1016,7 +1031,7 @@ static int reassemble_t(pb200_handle_t *h) {
   CK(cudaMemsetAsync(h->d_cnt + 1, 0, sizeof(unsigned long long), h->stream));
   int n = (int)h->n;
   k_assemble<T><<<(n + 255) / 256, 256, 0, h->stream>>>(h->S, n, h->d_colptr, h->d_rows, (const T *)h->d_vals,
-                                                        (const T *)h->d_tvals, 0, (T *)h->dL, (T *)h->dU, h->d_cnt + 1,
+                                                        (const T *)h->d_tvals, h->herm ? 1 : 0, (T *)h->dL, (T *)h->dU, h->d_cnt + 1,
                                                         h->d_owner, h->rank);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
@@ -1065,6 +1080,7 @@ extern "C" int pb200_assemble_csc(pb200_handle_t *h, const pb200_csc_t *c) {
   if (c->device != h->device) return fail(PB200_ERR_BADARG, "internal CSC lives on another device");
   if (h->facto == PB200_FACT_LU && !c->has_t) return fail(PB200_ERR_BADARG, "LU needs the transposed values");
   CK(cudaSetDevice(h->device));
+  h->herm = (c->type == 'H');
   const int64_t nnz = c->nnz;
   if (nnz != h->nnz || !h->d_colptr) {
     cudaFree(h->d_colptr); cudaFree(h->d_rows); cudaFree(h->d_vals); cudaFree(h->d_tvals);
@@ -1162,6 +1178,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
   const bool serial = prof || getenv("PB200_SERIAL") != nullptr;
+  const bool diag_old = getenv("PB200_DIAG_OLD") != nullptr;   // A/B switch: the one-barrier-per-pivot kernel of round 1
   const bool overlap_inv = !serial && h->nranks == 1 && getenv("PB200_INV_OVERLAP") != nullptr;   // opt-in: measured slower (r01)
   // The schedule is a fixed sequence of launches on two streams joined by events: capture it once (per threshold value,
   // which is a by-value kernel argument) and replay it — kernel-to-kernel dependencies then resolve on the device
@@ -1186,7 +1203,12 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
     if (prof) cudaEventRecord(pe0, h->stream);
     switch (st.kind) {
       case 0: {
-        k_diag_sub<T, FACTO><<<st.ntasks, 256, 0, sm>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
+        if (diag_old)
+          k_diag_sub<T, FACTO><<<st.ntasks, 256, 0, sm>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
+        else if (st.nbmax <= 64)
+          k_diag_blk<T, FACTO, 4><<<st.ntasks, 256, 0, sm>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
+        else if constexpr (SubCfg<T>::NBMAX > 64)
+          k_diag_blk<T, FACTO, SubCfg<T>::NBMAX / 16><<<st.ntasks, 256, 0, sm>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
       } break;
       case 1:
         k_trsm_mma<T, FACTO><<<(unsigned)(st.ntiles * lu), 128, trsm_smem_bytes<T>(st.nbmax), sm>>>(
@@ -1514,6 +1536,14 @@ static int solve_t(pb200_handle_t *h, void *x, int64_t ldx, int nrhs) {
   return fail(PB200_ERR_BADARG, "bad factotype");
 }
 static int solve_dispatch(pb200_handle_t *h, void *x, int64_t ldx, int nrhs) { DISPATCH_T(h, solve_t, h, x, ldx, nrhs) }
+
+// Hermitian-typed internal CSC ('H'): the U^T panels of an LU factorization are filled with the CONJUGATE of the
+// transposed values (csc_intern_solve.c:110-116).  pb200_assemble_csc sets it from the device CSC's type.
+extern "C" int pb200_set_hermitian(pb200_handle_t *h, int hermitian) {
+  if (!h) return fail(PB200_ERR_BADARG, "null handle");
+  h->herm = hermitian != 0;
+  return PB200_SUCCESS;
+}
 
 extern "C" int pb200_set_transpose_solve(pb200_handle_t *h, int transposed) {
   if (!h) return fail(PB200_ERR_BADARG, "null handle");

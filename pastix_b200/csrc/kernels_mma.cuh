@@ -85,14 +85,25 @@ template <class T> struct UpdCfg;
 #define PB200_UPD_D_WN 2
 #define PB200_UPD_D_CTAS 4
 #endif
+// operand staging of k_gemm_scatter: 1 = TMA bulk copies (cp.async.bulk, one per panel-column segment, completion on an
+// mbarrier; no LSU work and no address arithmetic in the compute warps), 0 = 8-byte cp.async (LDGSTS) by every thread
+#ifndef PB200_UPD_TMA
+#define PB200_UPD_TMA 1
+#endif
 template <> struct UpdCfg<double> {
   static constexpr int TM = PB200_UPD_D_TM, TN = PB200_UPD_D_TN, KC = PB200_UPD_D_KC, STG = PB200_UPD_D_STG,
                        WM = PB200_UPD_D_WM, WN = PB200_UPD_D_WN, PADA = 4, PADB = 4;
   static constexpr int NT = WM * WN * 32, CTAS = PB200_UPD_D_CTAS;
+  static constexpr bool TMA = PB200_UPD_TMA != 0;
+  // a column segment is copied from the 16-byte aligned address at or just below its first element (panel columns are
+  // only 8-byte aligned when the stride is odd): TM + 2 elements, the consumer shifts its row index by the parity
+  static constexpr int CPY = TM + 2;
 };
 template <> struct UpdCfg<cdouble> {
   static constexpr int TM = 64, TN = 64, KC = 16, STG = 3, WM = 4, WN = 2, PADA = 2, PADB = 2;
   static constexpr int NT = WM * WN * 32, CTAS = 2;
+  static constexpr bool TMA = PB200_UPD_TMA != 0;
+  static constexpr int CPY = TM;   // 16-byte elements: always aligned
 };
 #ifndef PB200_TABMAX
 #define PB200_TABMAX 1536
@@ -103,7 +114,7 @@ template <class T>
 constexpr size_t upd_smem_bytes() {
   using C = UpdCfg<T>;
   return (size_t)C::STG * C::KC * ((C::TM + C::PADA) + (C::TN + C::PADB) + 1) * sizeof(T) +
-         (size_t)C::TN * sizeof(ColMap) + (size_t)C::TM * sizeof(RowMap) + (size_t)PB200_TABMAX * 4;
+         (size_t)C::TN * sizeof(ColMap) + (size_t)C::TM * sizeof(RowMap) + (size_t)PB200_TABMAX * 4 + (size_t)C::STG * 8;
 }
 
 // fire-and-forget reductions (RED.ADD.F64 at L2): the reference serialises these adds with
@@ -147,8 +158,6 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
   T *sD = sB + STG * KC * LDB;
   ColMap *s_cm = reinterpret_cast<ColMap *>(sD + STG * KC);
   RowMap *s_rm = reinterpret_cast<RowMap *>(s_cm + TN);
-  int *s_tab = reinterpret_cast<int *>(s_rm + TM);
-
   int tile = blockIdx.x, part = 0;
   if (FACTO == F_LU) { part = tile & 1; tile >>= 1; }
   // the whole tile description in one (broadcast) load: no dependent index chasing before the first
@@ -164,31 +173,16 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
   const T *Bp = (SYM_LDL ? W : ((FACTO == F_LU && part == 0) ? U : L)) + tk.poff;
   const int nchunks = (tk.k1 - tk.k0 + KC - 1) / KC;
 
-  // operand staging: thread (lk0, li) = (tid / TM, tid % TM) copies element li of the columns k = lk0, lk0 + KSTEP, ...
-  // of a chunk; everything that does not change from chunk to chunk (row predicate, column-k0 addresses) is
-  // resolved once per tile, so that a chunk costs one 64-bit add and one predicate per cp.async
-  static_assert(TM == TN && NT % TM == 0 && KC % (NT / TM) == 0, "operand staging assumes square tiles");
-  constexpr int KSTEP = NT / TM;
-  const int li = tid % TM, lk0 = tid / TM;
-  const bool a_ok = li < mrows, b_ok = li < ncols;
-  const T *pA = Ap + (size_t)tk.k0 * ld + m0 + (a_ok ? li : 0);
-  const T *pB = Bp + (size_t)tk.k0 * ld + n0 + (b_ok ? li : 0);
+  int *s_tab = reinterpret_cast<int *>(s_rm + TM);
   const int ktot = tk.k1 - tk.k0;
-  auto load_chunk = [&](int c, int stg) {
-    const int kb = c * KC + lk0;                       // first column of this thread, relative to k0
-    T *a = sA + stg * KC * LDA + lk0 * LDA + li, *b = sB + stg * KC * LDB + lk0 * LDB + li;
-    const T *ga = pA + (size_t)kb * ld, *gb = pB + (size_t)kb * ld;
+  Acc<CX> acc[MI][NI];
 #pragma unroll
-    for (int q = 0; q < KC / KSTEP; ++q) {
-      const bool kin = kb + q * KSTEP < ktot;
-      cp_async_elem<sizeof(T)>(a + q * KSTEP * LDA, (a_ok && kin) ? ga + (size_t)(q * KSTEP) * ld : pA, a_ok && kin);
-      cp_async_elem<sizeof(T)>(b + q * KSTEP * LDB, (b_ok && kin) ? gb + (size_t)(q * KSTEP) * ld : pB, b_ok && kin);
-    }
-  };
+  for (int a = 0; a < MI; ++a)
+#pragma unroll
+    for (int b = 0; b < NI; ++b) acc[a][b].zero();
 
-  // ---- scatter maps of this tile: static tables copied asynchronously into shared memory, in the same
-  // cp.async group as the first operand chunk (they land while the pipeline fills; the first barrier of
-  // the main loop publishes them)
+  // ---- scatter maps of this tile: static tables copied asynchronously into shared memory (cp.async group 0; they
+  // land while the operand pipeline fills and are published by the main loop's first barrier)
   const int rb_lo = tk.rb_lo, cb_lo = tk.cb_lo, ncb = tk.ncb;
   const bool tab_in_smem = (tk.mode == 0) && (tk.nrb * ncb <= PB200_TABMAX);
   if (tk.mode == 0) {
@@ -213,6 +207,102 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
     }
   }
 
+  if constexpr (C::TMA) {
+    // ---- TMA-staged operands.  One bulk copy per (operand, panel column) of a chunk (columns 0..KC-1 of A, then of
+    // B), completing on the stage's mbarrier.  Rows past the
+    // tile's extent are whatever follows in the slab: they only reach accumulator rows / columns that are never
+    // written.  Columns past k1 are not copied; the partial 8-column step is zero-filled once.
+    static_assert(STG >= 2 && (2 * KC) % (NT / 32) == 0, "two stages at least; the column copies divide evenly among the warps");
+    static_assert((LDA * sizeof(T)) % 16 == 0 && (LDB * sizeof(T)) % 16 == 0 && LDA >= C::CPY && LDB >= C::CPY, "bulk copy alignment");
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_tab + PB200_TABMAX);
+    constexpr unsigned CPYB = C::CPY * sizeof(T);
+    // parity (0/1 element) of the first element of column k0 of each operand, and of the stride
+    const int ldpar = (sizeof(T) == 8) ? (ld & 1) : 0;
+    const int64_t eA = tk.poff + (int64_t)tk.k0 * ld + m0, eB = tk.poff + (int64_t)tk.k0 * ld + n0;
+    const int parA = (sizeof(T) == 8) ? (int)(eA & 1) : 0, parB = (sizeof(T) == 8) ? (int)(eB & 1) : 0;
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < STG; ++s) mbar_init(bar + s, 1);
+      mbar_fence_init();
+    }
+    // columns [ktot, roundup8(ktot)) of the last chunk are zero-filled (generic stores by every thread) when its
+    // stage is free: before the pipeline starts if the chunk is part of the prologue, else right before its copies
+    // are issued — at least one CTA barrier separates the stores from the fragment loads either way
+    const int cl = nchunks - 1, kz0 = ktot - cl * KC, kz1 = (kz0 + 7) & ~7;
+    auto zero_tail = [&]() {
+      T *a = sA + (cl % STG) * KC * LDA + kz0 * LDA, *b = sB + (cl % STG) * KC * LDB + kz0 * LDB;
+      for (int e = tid; e < (kz1 - kz0) * LDA; e += NT) a[e] = ST<T>::zero();
+      for (int e = tid; e < (kz1 - kz0) * LDB; e += NT) b[e] = ST<T>::zero();
+    };
+    if (kz1 > kz0 && cl < STG) zero_tail();
+    cp_async_commit();
+    __syncthreads();
+    // every warp issues its share of the chunk's 2*KC column copies (lanes 0 .. CPW-1, one copy each: the uniform-datapath
+    // UBLKCP is issued once per active lane); thread 0 posts the byte count (the mbarrier's tx-count is signed, copies
+    // completing before the expect_tx are fine)
+    constexpr int CPW = 2 * KC / (NT / 32);
+    auto issue = [&](int c) {
+      const int stg = c % STG, nk = min(KC, ktot - c * KC);
+      if (tid == 0) mbar_arrive_expect_tx(bar + stg, 2u * (unsigned)nk * CPYB);
+      const int q = warp * CPW + lane, kk = q & (KC - 1), isb = q / KC;
+      if (lane < CPW && kk < nk) {
+        const int k = c * KC + kk;
+        const int par = ((isb ? parB : parA) + k * ldpar) & 1;
+        const T *src = (isb ? Bp : Ap) + (size_t)(tk.k0 + k) * ld + (isb ? n0 : m0) - par;
+        T *dst = (isb ? sB + stg * KC * LDB + kk * LDB : sA + stg * KC * LDA + kk * LDA);
+        bulk_g2s(dst, src, CPYB, bar + stg);
+      }
+    };
+    for (int c = 0; c < STG && c < nchunks; ++c) issue(c);
+    // this thread's fragment columns are k = (even) + t4 (+4): one parity per operand for the whole tile
+    const int t4f = lane & 3;
+    const int pa = (parA + t4f * ldpar) & 1, pb = (parB + t4f * ldpar) & 1;
+    cp_async_wait<0>();
+    for (int c = 0; c < nchunks; ++c) {
+      const int stg = c % STG;
+      mbar_wait(bar + stg, (unsigned)((c / STG) & 1));
+      const T *a = sA + stg * KC * LDA + pa, *b = sB + stg * KC * LDB + pb;
+      const int nk8 = min(KC, (ktot - c * KC + 7) & ~7);
+#pragma unroll
+      for (int ks = 0; ks < KC; ks += 8) {
+        if (ks < nk8) {
+          FragA<CX> fa[MI];
+          FragB<CX> fb[NI];
+#pragma unroll
+          for (int x = 0; x < MI; ++x) load_frag_a<T>(fa[x], a, LDA, wm0 + x * 16, ks, lane);
+#pragma unroll
+          for (int y = 0; y < NI; ++y) load_frag_b<T, CONJB, false>(fb[y], b, LDB, wn0 + y * 8, ks, lane, nullptr);
+#pragma unroll
+          for (int x = 0; x < MI; ++x)
+#pragma unroll
+            for (int y = 0; y < NI; ++y) mma_acc(acc[x][y], fa[x], fb[y]);
+        }
+      }
+      __syncthreads();   // stage free again (and, first time round, the scatter maps are published)
+      if (c + STG == cl && kz1 > kz0) zero_tail();
+      if (c + STG < nchunks) issue(c + STG);
+    }
+  } else {
+  // operand staging: thread (lk0, li) = (tid / TM, tid % TM) copies element li of the columns k = lk0, lk0 + KSTEP, ...
+  // of a chunk; everything that does not change from chunk to chunk (row predicate, column-k0 addresses) is
+  // resolved once per tile, so that a chunk costs one 64-bit add and one predicate per cp.async
+  static_assert(TM == TN && NT % TM == 0 && KC % (NT / TM) == 0, "operand staging assumes square tiles");
+  constexpr int KSTEP = NT / TM;
+  const int li = tid % TM, lk0 = tid / TM;
+  const bool a_ok = li < mrows, b_ok = li < ncols;
+  const T *pA = Ap + (size_t)tk.k0 * ld + m0 + (a_ok ? li : 0);
+  const T *pB = Bp + (size_t)tk.k0 * ld + n0 + (b_ok ? li : 0);
+  auto load_chunk = [&](int c, int stg) {
+    const int kb = c * KC + lk0;                       // first column of this thread, relative to k0
+    T *a = sA + stg * KC * LDA + lk0 * LDA + li, *b = sB + stg * KC * LDB + lk0 * LDB + li;
+    const T *ga = pA + (size_t)kb * ld, *gb = pB + (size_t)kb * ld;
+#pragma unroll
+    for (int q = 0; q < KC / KSTEP; ++q) {
+      const bool kin = kb + q * KSTEP < ktot;
+      cp_async_elem<sizeof(T)>(a + q * KSTEP * LDA, (a_ok && kin) ? ga + (size_t)(q * KSTEP) * ld : pA, a_ok && kin);
+      cp_async_elem<sizeof(T)>(b + q * KSTEP * LDB, (b_ok && kin) ? gb + (size_t)(q * KSTEP) * ld : pB, b_ok && kin);
+    }
+  };
 #pragma unroll
   for (int s = 0; s < STG - 1; ++s) {
     if (s < nchunks) load_chunk(s, s);
@@ -220,12 +310,6 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
   }
 
   // ---- main loop: C(TM x TN) = A(TM x K) * B(TN x K)^T on DMMA
-  Acc<CX> acc[MI][NI];
-#pragma unroll
-  for (int a = 0; a < MI; ++a)
-#pragma unroll
-    for (int b = 0; b < NI; ++b) acc[a][b].zero();
-
   for (int c = 0; c < nchunks; ++c) {
     cp_async_wait<STG - 2>();
     __syncthreads();
@@ -249,6 +333,7 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
   }
   cp_async_wait<0>();
   if (nchunks == 0) __syncthreads();   // (never: K >= 1) maps are published by the main loop's first barrier
+  }
 
   // ---- epilogue: subtract the tile from its targets straight from the accumulators with
   // fire-and-forget L2 reductions: nothing is read back, so no latency is exposed here.
@@ -339,6 +424,10 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
 // left to right: T = X_jb - sum_{kb<jb} Y_kb W[jb,kb]^T, Y_jb = T inv(W[jb,jb])^T, both on DMMA.
 #define PB200_TRSM_TM 64
 template <class T> struct SubCfg;
+// widest sub-panel factored in one diag -> TRSM round.  Measured in round 2 (profiles/r02/README.md): with the blocked
+// diagonal kernel a whole 121-column cblk in ONE round (128) costs diag 46 us + TRSM 23 us against 2 x (21 + 13) + 13 us
+// for two rounds of 64 — no gain on the chain, and the 214 KB / one-CTA-per-SM TRSM of 128 columns loses on the fat
+// levels (C3: 302 ms vs 286 ms).  64 stays the default; -DPB200_NBMAX_D=128 builds the single-round variant.
 #ifndef PB200_NBMAX_D
 #define PB200_NBMAX_D 64
 #endif
@@ -634,6 +723,215 @@ k_diag_sub(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, double crit,
       if (i < nb && j < nb && (FACTO == F_LU || i >= j)) A[(size_t)j * ld + i] = a[ia][jb];
     }
   if (FACTO == F_LU) {
+    // mirror (LU)^T into ucoeftab's diagonal blok through a 16 x 16 shared-memory transpose per register tile
+    __shared__ T tr[16][17];
+    T *UA = U + S.poff[c] + (size_t)tk.c0 * (ld + 1);
+#pragma unroll
+    for (int ia = 0; ia < R; ++ia)
+#pragma unroll
+      for (int jb = 0; jb < R; ++jb) {
+        __syncthreads();
+        tr[ty][tx] = a[ia][jb];                     // element (16ia+tx, 16jb+ty)
+        __syncthreads();
+        const int i = ty + 16 * ia, j = tx + 16 * jb;   // element (i,j) sits in tr[tx][ty]
+        if (i < nb && j < nb) UA[(size_t)i * ld + j] = tr[tx][ty];
+      }
+  }
+}
+
+// ---------------------------------------------------------------- blocked diagonal sub-block (round 2)
+// Same job and same register layout as k_diag_sub (16 x 16 thread grid, 2-D cyclic, the block never leaves the
+// registers), but the pivots are taken BS at a time: per step the BS block columns (and, LU, block rows) go through
+// shared memory once, EVERY thread factors the BS x BS diagonal block redundantly in registers (no barrier, no
+// shuffle between pivots), one thread per row solves its row of the block column against it, and the trailing matrix
+// receives one rank-BS update — 2 CTA barriers per BS pivots instead of one per pivot, which is what lets a whole
+// 120-column cblk go through ONE diag -> TRSM round.  Blocking as PASTIX_potrf_block / sytrf_block / getrf_block
+// (compute_diag.c:171-203, 262-307, 486-518); pivot rule of the unblocked kernels (:133-137, 232-236, 444-448).
+template <class T, int FACTO> struct DiagBS { static constexpr int BS = (FACTO == F_LU || ST<T>::is_complex) ? 4 : 8; };
+
+template <class T, int FACTO, int R, int S>
+__device__ __forceinline__ void diag_blk_step(T (&a)[R][R], int nb, int tid, int tx, int ty, double crit,
+                                              unsigned long long *nbpivot, T (*P)[16 * R], T (*Q)[16 * R],
+                                              T (*X)[16 * R], T (*Y)[16 * R], T (*Dout)[DiagBS<T, FACTO>::BS]) {
+  constexpr int BS = DiagBS<T, FACTO>::BS, NBP = 16 * R, J0 = S * BS, JB = J0 / 16, O = J0 % 16, J1 = J0 + BS, IA0 = J1 / 16;
+  constexpr bool LU = (FACTO == F_LU), LDL = (FACTO == F_LDLT || FACTO == F_LDLH);
+  if (J0 >= nb) return;   // uniform
+  const T zero = ST<T>::zero();
+  // 1. the owners publish the raw block columns (rows >= J0) and, LU, the raw block rows (columns >= J1)
+  if (ty >= O && ty < O + BS) {
+#pragma unroll
+    for (int ia = JB; ia < R; ++ia) {
+      const int r = tx + 16 * ia;
+      if (r >= J0) P[ty - O][r] = a[ia][JB];
+    }
+  }
+  if (LU && tx >= O && tx < O + BS) {
+#pragma unroll
+    for (int jb = IA0; jb < R; ++jb) {
+      const int c = ty + 16 * jb;
+      if (c >= J1) Q[tx - O][c] = a[JB][jb];
+    }
+  }
+  __syncthreads();
+  // 2. every thread factors the BS x BS diagonal block (d[r][q] = element (J0 + r, J0 + q))
+  T d[BS][BS], invd[BS], piv[BS];
+#pragma unroll
+  for (int q = 0; q < BS; ++q)
+#pragma unroll
+    for (int r = 0; r < BS; ++r)
+      if (LU || r >= q) d[r][q] = P[q][J0 + r];
+#pragma unroll
+  for (int k = 0; k < BS; ++k) {
+    T pv = d[k][k];
+    if (below_crit<T>(pv, crit)) {
+      pv = ST<T>::from_real(crit);
+      if (tid == 0 && J0 + k < nb) atomicAdd(nbpivot, 1ULL);
+    }
+    T inv;
+    pivot_inv<FACTO>(pv, inv);
+    d[k][k] = pv; invd[k] = inv; piv[k] = pv;
+    T wk[BS];   // row factor of pivot k inside the block
+#pragma unroll
+    for (int r = k + 1; r < BS; ++r) {
+      const T l = d[r][k] * inv;
+      d[r][k] = l;
+      if (FACTO == F_LLT) wk[r] = l;
+      else if (FACTO == F_LDLT) wk[r] = pv * l;
+      else if (FACTO == F_LDLH) wk[r] = pv * ST<T>::conj(l);
+    }
+#pragma unroll
+    for (int c = k + 1; c < BS; ++c)
+#pragma unroll
+      for (int r = (LU ? k + 1 : c); r < BS; ++r) d[r][c] = d[r][c] - d[r][k] * (LU ? d[k][c] : wk[c]);
+  }
+  // 3. one thread publishes the factored block
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < BS; ++q)
+#pragma unroll
+      for (int r = 0; r < BS; ++r)
+        if (LU || r >= q) Dout[q][r] = d[r][q];
+  }
+  // 4. one thread per row below the block (LU: and one per column right of it) solves against the block
+  if (J1 < NBP) {
+    constexpr int M = NBP - J1;                        // rows (columns) still to come, padding included
+    constexpr int G = (2 * M <= 256) ? M : 128;        // LU: first thread of the column group
+    if (tid < M) {
+      const int r = J1 + tid;
+      T x[BS];
+#pragma unroll
+      for (int q = 0; q < BS; ++q) {
+        T acc = P[q][r];
+#pragma unroll
+        for (int qq = 0; qq < q; ++qq) {
+          // LLt: x L11^T = p (symmetric, no conjugate: compute_diag.c:140); LDLt/LDLh: w conj?(L11)^T = p, w = l d;
+          // LU: x U11 = p
+          const T f = LU ? d[qq][q] : (FACTO == F_LDLH ? ST<T>::conj(d[q][qq]) : d[q][qq]);
+          acc = acc - x[qq] * f;
+        }
+        if (LDL) {
+          x[q] = acc;                                  // w = l * d
+          const T l = acc * invd[q];
+          X[q][r] = l;
+          Y[q][r] = (FACTO == F_LDLH) ? piv[q] * ST<T>::conj(l) : piv[q] * l;
+        } else {
+          x[q] = acc * invd[q];
+          X[q][r] = x[q];
+        }
+      }
+    }
+    if (LU && tid >= G && tid < G + M) {
+      const int c = J1 + (tid - G);
+      T u[BS];
+#pragma unroll
+      for (int q = 0; q < BS; ++q) {
+        T acc = Q[q][c];
+#pragma unroll
+        for (int qq = 0; qq < q; ++qq) acc = acc - d[q][qq] * u[qq];   // L11 unit lower
+        u[q] = acc;
+        Y[q][c] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  // 5. the owners take the finished block columns (and rows) back
+  if (ty >= O && ty < O + BS) {
+#pragma unroll
+    for (int ia = JB; ia < R; ++ia) {
+      const int r = tx + 16 * ia;
+      if (r >= J1) a[ia][JB] = X[ty - O][r];
+      else if (r >= J0 && (LU || r - J0 >= ty - O)) a[ia][JB] = Dout[ty - O][r - J0];
+    }
+  }
+  if (LU && tx >= O && tx < O + BS) {
+#pragma unroll
+    for (int jb = IA0; jb < R; ++jb) {
+      const int c = ty + 16 * jb;
+      if (c >= J1) a[JB][jb] = Y[tx - O][c];
+    }
+  }
+  // 6. rank-BS update of the trailing matrix, in registers
+  if (IA0 < R) {
+#pragma unroll
+    for (int q = 0; q < BS; ++q) {
+      T xv[R], yv[R];
+#pragma unroll
+      for (int i = IA0; i < R; ++i) {
+        const int r = tx + 16 * i, c = ty + 16 * i;
+        xv[i] = (r >= J1) ? X[q][r] : zero;
+        yv[i] = (c >= J1) ? ((LU || LDL) ? Y[q][c] : X[q][c]) : zero;
+      }
+#pragma unroll
+      for (int ia = IA0; ia < R; ++ia)
+#pragma unroll
+        for (int jb = IA0; jb < R; ++jb) {
+          if (!LU && jb > ia) continue;   // symmetric variants: lower triangle of 16 x 16 register tiles only
+          a[ia][jb] = a[ia][jb] - xv[ia] * yv[jb];
+        }
+    }
+  }
+}
+
+template <class T, int FACTO, int R>
+__global__ void __launch_bounds__(256)
+k_diag_blk(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, double crit, unsigned long long *nbpivot) {
+  constexpr int BS = DiagBS<T, FACTO>::BS, NBP = 16 * R;
+  constexpr bool LU = (FACTO == F_LU), LDL = (FACTO == F_LDLT || FACTO == F_LDLH);
+  __shared__ T P[BS][NBP];
+  __shared__ T Q[LU ? BS : 1][LU ? NBP : 1];
+  __shared__ T X[BS][NBP];
+  __shared__ T Y[(LU || LDL) ? BS : 1][(LU || LDL) ? NBP : 1];
+  __shared__ T Dout[BS][BS];
+  const SubTask tk = tasks[blockIdx.x];
+  const int c = tk.cblk, ld = S.stride[c], nb = tk.c1 - tk.c0;
+  T *A = L + S.poff[c] + (size_t)tk.c0 * (ld + 1);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  T a[R][R];
+#pragma unroll
+  for (int ia = 0; ia < R; ++ia)
+#pragma unroll
+    for (int jb = 0; jb < R; ++jb) {
+      if (!LU && jb > ia) continue;
+      const int i = tx + 16 * ia, j = ty + 16 * jb;
+      // padding: identity, so that the blocked steps need no edge cases
+      a[ia][jb] = (i < nb && j < nb) ? A[(size_t)j * ld + i] : ((i == j) ? ST<T>::from_real(1.0) : ST<T>::zero());
+    }
+  typedef T (*Row)[NBP];
+#define PB200_DB(SS) if constexpr (SS * BS < NBP) diag_blk_step<T, FACTO, R, SS>(a, nb, tid, tx, ty, crit, nbpivot, P, (Row)Q, X, (Row)Y, Dout);
+  PB200_DB(0) PB200_DB(1) PB200_DB(2) PB200_DB(3) PB200_DB(4) PB200_DB(5) PB200_DB(6) PB200_DB(7)
+  PB200_DB(8) PB200_DB(9) PB200_DB(10) PB200_DB(11) PB200_DB(12) PB200_DB(13) PB200_DB(14) PB200_DB(15)
+  PB200_DB(16) PB200_DB(17) PB200_DB(18) PB200_DB(19) PB200_DB(20) PB200_DB(21) PB200_DB(22) PB200_DB(23)
+  PB200_DB(24) PB200_DB(25) PB200_DB(26) PB200_DB(27) PB200_DB(28) PB200_DB(29) PB200_DB(30) PB200_DB(31)
+#undef PB200_DB
+#pragma unroll
+  for (int ia = 0; ia < R; ++ia)
+#pragma unroll
+    for (int jb = 0; jb < R; ++jb) {
+      if (!LU && jb > ia) continue;
+      const int i = tx + 16 * ia, j = ty + 16 * jb;
+      if (i < nb && j < nb && (LU || i >= j)) A[(size_t)j * ld + i] = a[ia][jb];
+    }
+  if constexpr (LU) {
     // mirror (LU)^T into ucoeftab's diagonal blok through a 16 x 16 shared-memory transpose per register tile
     __shared__ T tr[16][17];
     T *UA = U + S.poff[c] + (size_t)tk.c0 * (ld + 1);

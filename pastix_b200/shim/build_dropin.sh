@@ -87,6 +87,15 @@ for PP in $PRECS; do
   [ -n "$SYM" ] || { echo "[$P] CscOrdistrib not found in the reference object"; exit 1; }
   objcopy --redefine-sym "$SYM=CscOrdistrib_hostref" "$OBJ/p_csc_intern_build.o" || exit 1
   if [ "$SYM" != "CscOrdistrib" ]; then objcopy --redefine-sym "CscOrdistrib=$SYM" "$OBJ/x_shim_csc.o" || exit 1; fi
+  # the reference's release points (coefinit.c:479 CoefMatrix_Free, solverRealloc.c:217 solverExit) stay linked as
+  # *_hostref; shim_hooks.c defines the public names, drops the device state of that SolverMatrix and calls them
+  for FN in CoefMatrix_Free:p_coefinit solverExit:b_solverRealloc; do
+    F=${FN%%:*}; O=${FN##*:}
+    SYM=$(nm "$OBJ/$O.o" | awk -v f="$F" '$2=="T" && $3 ~ (f "$") {print $3}' | head -1)
+    [ -n "$SYM" ] || { echo "[$P] $F not found in the reference object $O.o"; exit 1; }
+    objcopy --redefine-sym "$SYM=${F}_hostref" "$OBJ/$O.o" || exit 1
+    if [ "$SYM" != "$F" ]; then objcopy --redefine-sym "$F=$SYM" "$OBJ/x_shim_hooks.o" || exit 1; fi
+  done
   gcc -shared -o "$LIB" "$OBJ"/*.o -L"$OUT" -lpastix_b200 "$BLASLIB" -lpthread -lm \
       -Wl,--disable-new-dtags -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$BLASDIR" -Wl,-rpath-link,"$BLASDIR" -Wl,--no-undefined 2> "$OBJ/link.log" \
       || { echo "[$P] link failed"; head -30 "$OBJ/link.log"; exit 1; }

@@ -47,18 +47,7 @@ void CscOrdistrib_hostref(CscMatrix *thecsc, char *Type, PASTIX_FLOAT **transcsc
                           PASTIX_INT Nrow, PASTIX_INT Ncol, PASTIX_INT Nnzero, PASTIX_INT *colptr, PASTIX_INT *rowind,
                           PASTIX_FLOAT *val, PASTIX_INT forcetrans, const SolverMatrix *solvmtx, PASTIX_INT procnum, PASTIX_INT dof);
 
-static pb200_shim_entry_t *csc_entry(const SolverMatrix *m)
-{
-  int i; pb200_shim_entry_t *e = NULL;
-  pthread_mutex_lock(&shim_mutex);
-  for (i = 0; i < PB200_SHIM_MAX; i++)
-    if (shim_table[i].m == m) { e = &shim_table[i]; break; }
-  if (e == NULL)
-    for (i = 0; i < PB200_SHIM_MAX; i++)
-      if (shim_table[i].m == NULL) { e = &shim_table[i]; memset(e, 0, sizeof(*e)); e->m = m; break; }
-  pthread_mutex_unlock(&shim_mutex);
-  return e;
-}
+static pb200_shim_entry_t *csc_entry(const SolverMatrix *m) { return pb200_shim_entry(m, 1); }
 
 void CscOrdistrib(CscMatrix *thecsc, char *Type, PASTIX_FLOAT **transcsc, const Order *ord,
                   PASTIX_INT Nrow, PASTIX_INT Ncol, PASTIX_INT Nnzero, PASTIX_INT *colptr, PASTIX_INT *rowind,

@@ -41,15 +41,98 @@
 #include "pastixstr.h"
 #include "shim_table.h"
 
-static pb200_shim_entry_t *hook_find(const SolverMatrix *m)
+/* ---- the side table: a growing array of pointers to heap entries (an entry never moves once handed out) */
+static pb200_shim_entry_t **shim_tab = NULL;
+static int                  shim_cap = 0;
+static pthread_mutex_t      shim_mutex = PTHREAD_MUTEX_INITIALIZER;
+
+pb200_shim_entry_t *pb200_shim_entry(const SolverMatrix *m, int create)
 {
-  int i; pb200_shim_entry_t *e = NULL;
+  int i, slot = -1; pb200_shim_entry_t *e = NULL;
   pthread_mutex_lock(&shim_mutex);
-  for (i = 0; i < PB200_SHIM_MAX; i++)
-    if (shim_table[i].m == m) { e = &shim_table[i]; break; }
+  for (i = 0; i < shim_cap; i++) {
+    if (shim_tab[i] != NULL && shim_tab[i]->m == m) { e = shim_tab[i]; break; }
+    if (shim_tab[i] == NULL && slot < 0) slot = i;
+  }
+  if (e == NULL && create) {
+    if (slot < 0) {
+      int ncap = shim_cap ? 2 * shim_cap : 16;
+      pb200_shim_entry_t **nt = (pb200_shim_entry_t **)realloc(shim_tab, sizeof(*nt) * (size_t)ncap);
+      if (nt != NULL) {
+        for (i = shim_cap; i < ncap; i++) nt[i] = NULL;
+        slot = shim_cap; shim_tab = nt; shim_cap = ncap;
+      }
+    }
+    if (slot >= 0 && (e = (pb200_shim_entry_t *)calloc(1, sizeof(*e))) != NULL) { e->m = m; shim_tab[slot] = e; }
+  }
   pthread_mutex_unlock(&shim_mutex);
   return e;
 }
+
+void pb200_shim_entry_drop(const SolverMatrix *m)
+{
+  int i; pb200_shim_entry_t *e = NULL;
+  pthread_mutex_lock(&shim_mutex);
+  for (i = 0; i < shim_cap; i++)
+    if (shim_tab[i] != NULL && shim_tab[i]->m == m) { e = shim_tab[i]; shim_tab[i] = NULL; break; }
+  pthread_mutex_unlock(&shim_mutex);
+  if (e == NULL) return;
+  if (e->h) pb200_destroy(e->h);
+  if (e->csc) pb200_csc_destroy(e->csc);
+  free(e);
+}
+
+int pb200_shim_live_entries(void)
+{
+  int i, n = 0;
+  pthread_mutex_lock(&shim_mutex);
+  for (i = 0; i < shim_cap; i++) if (shim_tab[i] != NULL) n++;
+  pthread_mutex_unlock(&shim_mutex);
+  return n;
+}
+
+/* FNV-1a over the fields shim_create flattens (sopalin_b200_shim.c): what the device schedule, the panel layout and the
+ * scatter maps are derived from */
+void pb200_shim_fingerprint(const SolverMatrix *m, uint64_t fp[2])
+{
+  uint64_t h = 1469598103934665603ULL; PASTIX_INT i; uint64_t coefnbr = 0;
+#define FP_MIX(v) do { h ^= (uint64_t)(v); h *= 1099511628211ULL; } while (0)
+  for (i = 0; i < m->cblknbr; i++) {
+    FP_MIX(m->cblktab[i].fcolnum); FP_MIX(m->cblktab[i].lcolnum); FP_MIX(m->cblktab[i].bloknum); FP_MIX(m->cblktab[i].stride);
+    coefnbr += (uint64_t)m->cblktab[i].stride * (uint64_t)(m->cblktab[i].lcolnum - m->cblktab[i].fcolnum + 1);
+  }
+  for (i = 0; i < m->bloknbr; i++) {
+    FP_MIX(m->bloktab[i].frownum); FP_MIX(m->bloktab[i].lrownum); FP_MIX(m->bloktab[i].cblknum); FP_MIX(m->bloktab[i].coefind);
+  }
+#undef FP_MIX
+  fp[0] = h;
+  fp[1] = ((uint64_t)m->cblknbr << 40) ^ ((uint64_t)m->bloknbr << 16) ^ coefnbr;
+}
+
+/* ---- the reference's release points.  The reference objects keep their own routines under *_hostref names. */
+void CoefMatrix_Free_hostref(SopalinParam *sopar, SolverMatrix *datacode, PASTIX_INT factotype);
+void solverExit_hostref(SolverMatrix *solvmtx);
+
+/* CoefMatrix_Free (coefinit.c:479): the host panels go away — before a new blend on the same pastix_data
+ * (pastix.c:2716) and before every re-fill of the coefficients (pastix.c:3391).  The factors on the device are void
+ * from here on; the handle itself is kept (a re-factorization on the same analysis reuses schedule and slabs) and
+ * is checked against the structure's fingerprint at the next numeric factorization. */
+void CoefMatrix_Free(SopalinParam *sopar, SolverMatrix *datacode, PASTIX_INT factotype)
+{
+  pb200_shim_entry_t *e = pb200_shim_entry(datacode, 0);
+  if (e != NULL) e->factorized = 0;
+  CoefMatrix_Free_hostref(sopar, datacode, factotype);
+}
+
+/* solverExit (solverRealloc.c:217): the SolverMatrix is destroyed (API_TASK_CLEAN, pastix.c:4539) — all HBM held for
+ * it is released here.  Temporaries of the analysis never have an entry. */
+void solverExit(SolverMatrix *solvmtx)
+{
+  pb200_shim_entry_drop(solvmtx);
+  solverExit_hostref(solvmtx);
+}
+
+static pb200_shim_entry_t *hook_find(const SolverMatrix *m) { return pb200_shim_entry(m, 0); }
 
 /* pb200_handle_t* behind a pastix_data_t (NULL before the first API_TASK_NUMFACT) */
 void *pb200_shim_get_handle(void *pastix_data)
@@ -96,17 +179,12 @@ void pb200_shim_solver_get(void *pastix_data, int64_t *fcolnum, int64_t *lcolnum
   }
 }
 
-/* release the HBM held for this pastix_data_t (call before API_TASK_CLEAN) */
+/* release the HBM held for this pastix_data_t explicitly (API_TASK_CLEAN does it too, through solverExit) */
 void pb200_shim_release_data(void *pastix_data)
 {
-  pb200_shim_entry_t *e = hook_find(&((pastix_data_t *)pastix_data)->solvmatr);
-  if (e == NULL) return;
-  if (e->h) pb200_destroy(e->h);
-  if (e->csc) pb200_csc_destroy(e->csc);
-  pthread_mutex_lock(&shim_mutex);
-  memset(e, 0, sizeof(*e));
-  pthread_mutex_unlock(&shim_mutex);
+  pb200_shim_entry_drop(&((pastix_data_t *)pastix_data)->solvmatr);
 }
+int pb200_shim_live(void) { return pb200_shim_live_entries(); }
 
 /* internal CSC of this pastix_data_t (CscMatrix, blend/src/csc.h) flattened: sizes = {ncol, nnz, has transcsc, filled};
  * colptr 0-based with ncol+1 entries.  Used by the parity tests of the device-side CscOrdistrib (shim_csc.c). */

@@ -77,11 +77,8 @@ void *sopalin_updo_comm(void *arg);
 
 static pb200_handle_t *raff_handle(const SolverMatrix *m)
 {
-  int i; pb200_handle_t *h = NULL;
-  pthread_mutex_lock(&shim_mutex);
-  for (i = 0; i < PB200_SHIM_MAX; i++)
-    if (shim_table[i].m == m) { h = shim_table[i].h; break; }
-  pthread_mutex_unlock(&shim_mutex);
+  pb200_shim_entry_t *e = pb200_shim_entry(m, 0);
+  pb200_handle_t *h = e ? e->h : NULL;
   if (h == NULL) {
     errorPrint("pastix_b200: refinement called before a numeric factorization on this SolverMatrix");
     EXIT(MOD_SOPALIN, BADPARAMETER_ERR);

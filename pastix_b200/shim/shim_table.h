@@ -1,8 +1,15 @@
 /* shim_table.h — side table SolverMatrix* -> device handle, shared by the four factorization
- * variants of one precision build and by shim_hooks.c */
+ * variants of one precision build, shim_csc.c, shim_raff.c and shim_hooks.c (which owns it).
+ * An entry is keyed by the ADDRESS of the SolverMatrix (&pastix_data->solvmatr, pastixstr.h:48), which survives a
+ * re-run of API_TASK_ANALYSE and may be handed out again by malloc after API_TASK_CLEAN: the entry therefore also
+ * carries a structural fingerprint of the SolverMatrix its handle was built for (checked at every numeric
+ * factorization), and the reference's own release points — CoefMatrix_Free (coefinit.c:479, called from
+ * pastix_task_blend pastix.c:2716 and pastix_fillin_csc :3391) and solverExit (solverRealloc.c:217, called from
+ * pastix_task_clean pastix.c:4539) — are intercepted (build_dropin.sh, objcopy --redefine-sym) to drop it. */
 #ifndef PB200_SHIM_TABLE_H
 #define PB200_SHIM_TABLE_H
 #include <pthread.h>
+#include <stdint.h>
 #include "pastix_b200.h"
 typedef struct pb200_shim_entry_s {
   const SolverMatrix *m;
@@ -13,10 +20,18 @@ typedef struct pb200_shim_entry_s {
   double              critere;
   pb200_csc_t        *csc;        /* internal CSC built on the device by CscOrdistrib (shim_csc.c) */
   int                 csc_fresh;  /* set by CscOrdistrib, consumed by the next numeric factorization */
+  uint64_t            fp[2];      /* fingerprint of the SolverMatrix the handle was built for */
+  int                 herm;       /* internal CSC type 'H' (conjugated transposed values) */
 } pb200_shim_entry_t;
-#define PB200_SHIM_MAX 64
-#define shim_table  PASTIX_PREFIX_F(pb200_shim_table)
-#define shim_mutex  PASTIX_PREFIX_F(pb200_shim_mutex)
-extern pb200_shim_entry_t shim_table[PB200_SHIM_MAX];
-extern pthread_mutex_t    shim_mutex;
+#define pb200_shim_entry        PASTIX_PREFIX_F(pb200_shim_entry)
+#define pb200_shim_entry_drop   PASTIX_PREFIX_F(pb200_shim_entry_drop)
+#define pb200_shim_fingerprint  PASTIX_PREFIX_F(pb200_shim_fingerprint)
+#define pb200_shim_live_entries PASTIX_PREFIX_F(pb200_shim_live_entries)
+/* entry of SolverMatrix m (created empty when absent and `create` is set); entries never move */
+pb200_shim_entry_t *pb200_shim_entry(const SolverMatrix *m, int create);
+/* destroy the handle / device CSC of m's entry and forget it */
+void pb200_shim_entry_drop(const SolverMatrix *m);
+/* cblknbr, bloknbr, coefnbr and a hash of every cblktab / bloktab field the device schedule is derived from */
+void pb200_shim_fingerprint(const SolverMatrix *m, uint64_t fp[2]);
+int  pb200_shim_live_entries(void);
 #endif

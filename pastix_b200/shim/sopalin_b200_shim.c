@@ -90,16 +90,8 @@
 #define PB200_FACTO PB200_FACT_LDLT
 #endif
 
-/* ---- side table: SolverMatrix* -> device handle (shared by the four variants of one precision) */
+/* ---- side table: SolverMatrix* -> device handle (owned by shim_hooks.c) */
 #include "shim_table.h"
-#ifdef CHOL_SOPALIN
-#ifndef SOPALIN_LU
-pb200_shim_entry_t shim_table[PB200_SHIM_MAX];
-pthread_mutex_t    shim_mutex = PTHREAD_MUTEX_INITIALIZER;
-#endif
-#endif
-extern pb200_shim_entry_t shim_table[PB200_SHIM_MAX];
-extern pthread_mutex_t    shim_mutex;
 
 static void shim_fatal(const char *what)
 {
@@ -107,31 +99,11 @@ static void shim_fatal(const char *what)
   EXIT(MOD_SOPALIN, INTERNAL_ERR);
 }
 
-static pb200_shim_entry_t *shim_find(const SolverMatrix *m, int create)
-{
-  int i; pb200_shim_entry_t *e = NULL;
-  pthread_mutex_lock(&shim_mutex);
-  for (i = 0; i < PB200_SHIM_MAX; i++)
-    if (shim_table[i].m == m) { e = &shim_table[i]; break; }
-  if (e == NULL && create)
-    for (i = 0; i < PB200_SHIM_MAX; i++)
-      if (shim_table[i].m == NULL) { e = &shim_table[i]; memset(e, 0, sizeof(*e)); e->m = m; break; }
-  pthread_mutex_unlock(&shim_mutex);
-  return e;
-}
+static pb200_shim_entry_t *shim_find(const SolverMatrix *m, int create) { return pb200_shim_entry(m, create); }
 
-/* release the HBM held for one SolverMatrix (call before freeing it; also run on re-analysis) */
+/* release the HBM held for one SolverMatrix (the reference's own release points call it: shim_hooks.c) */
 #define pb200_shim_release PASTIX_PREFIX_F(API_CALL(pb200_shim_release))
-void pb200_shim_release(const SolverMatrix *m)
-{
-  pb200_shim_entry_t *e = shim_find(m, 0);
-  if (e == NULL) return;
-  if (e->h) pb200_destroy(e->h);
-  if (e->csc) pb200_csc_destroy(e->csc);
-  pthread_mutex_lock(&shim_mutex);
-  memset(e, 0, sizeof(*e));
-  pthread_mutex_unlock(&shim_mutex);
-}
+void pb200_shim_release(const SolverMatrix *m) { pb200_shim_entry_drop(m); }
 
 /* SolverMatrix -> flat arrays -> device handle */
 static pb200_handle_t *shim_create(SolverMatrix *datacode, int schur)
@@ -174,6 +146,7 @@ static void shim_assemble(pb200_handle_t *h, SolverMatrix *datacode, SopalinPara
     for (j = 0; j < CSC_COLNBR(csc, i); j++) colptr[col++] = CSC_COL(csc, i, j);
   colptr[col] = nnz;
   for (i = 0; i < nnz; i++) rows[i] = CSC_ROW(csc, i);
+  if (pb200_set_hermitian(h, csc->type == 'H') != PB200_SUCCESS) shim_fatal("pb200_set_hermitian");
   if (pb200_assemble(h, colptr, rows, CSC_VALTAB(csc), sopar->transcsc) != PB200_SUCCESS) shim_fatal("pb200_assemble");
   free(colptr); free(rows);
   (void)datacode;
@@ -246,8 +219,14 @@ static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
   }
   {
   double t0 = clockGet(), t1, t2, t3;
-  if (e->h != NULL && (e->facto != PB200_FACTO || e->schur != schur)) { pb200_destroy(e->h); e->h = NULL; }
-  if (e->h == NULL) { e->h = shim_create(datacode, schur); e->facto = PB200_FACTO; e->schur = schur; }
+  /* the handle must have been built for THIS structure: the key (the SolverMatrix address) survives a new
+   * API_TASK_ANALYSE on the same pastix_data and can be reused by malloc after API_TASK_CLEAN */
+  { uint64_t fp[2];
+    pb200_shim_fingerprint(datacode, fp);
+    if (e->h != NULL && (e->facto != PB200_FACTO || e->schur != schur || e->fp[0] != fp[0] || e->fp[1] != fp[1])) {
+      pb200_destroy(e->h); e->h = NULL;
+    }
+    if (e->h == NULL) { e->h = shim_create(datacode, schur); e->facto = PB200_FACTO; e->schur = schur; e->fp[0] = fp[0]; e->fp[1] = fp[1]; } }
   e->factorized = 0;
   t1 = clockGet();
   if (e->csc != NULL && e->csc_fresh) {        /* CscOrdistrib of this call left the internal CSC in HBM (shim_csc.c) */
