@@ -170,7 +170,9 @@ static size_t elem_size(int flt) {
 static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks) {
   h->dag_ok = false;
   if (getenv("PB200_SOLVE_LEVELS") != nullptr) return PB200_SUCCESS;   // A/B switch: keep the launch-per-level sweeps
-  if (h->slv_all_small) return PB200_SUCCESS;   // all-small schedules (incomplete factorizations) keep their fused warp-per-cblk path
+  // all-small schedules (incomplete factorizations) keep their fused warp-per-cblk path — except in Schur mode, which
+  // only the persistent sweeps implement (the reference ignores the Schur cblk on every path, updo.c:425-428)
+  if (h->slv_all_small && !h->schur) return PB200_SUCCESS;
   const int NB = (h->flt == PB200_COMPLEXDOUBLE) ? SlvCfg<cdouble>::NB : SlvCfg<double>::NB;
   const int64_t C = h->cblknbr;
   const int nsp = (int)tasks.size();
@@ -1430,7 +1432,7 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
     h->attr_mask |= 16u;
   }
   // several right-hand sides through an all-small schedule (ILU): transposed work copies, lanes over right-hand sides
-  const bool tr = h->slv_all_small && nrhs >= 4 && !tsolve;
+  const bool tr = h->slv_all_small && nrhs >= 4 && !tsolve && !h->dag_ok;
   T *xs = x, *ys = y;
   int64_t rs = 1, cs = ldx;
   const int n = (int)h->n;

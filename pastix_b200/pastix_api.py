@@ -99,6 +99,24 @@ class PastixLib:
             self.dparm[E[k]] = v
         return self
 
+    def rebind(self, A: sp.spmatrix):
+        """Another user matrix of the same order on the SAME pastix_data (the ordering handed over at setup is kept):
+        the caller re-runs analyze() / numfact()."""
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        assert A.shape[0] == self.n
+        self.colptr = (A.indptr.astype(self.idt) + 1)
+        self.rows = (A.indices.astype(self.idt) + 1)
+        self.vals = np.ascontiguousarray(A.data.astype(self.dtype))
+        return self
+
+    def set_perm(self, perm0: np.ndarray):
+        """Another API_ORDER_PERSONAL permutation for the next analyze() on the same pastix_data."""
+        self.perm = perm0.astype(self.idt) + 1
+        self.invp = np.empty_like(self.perm)
+        self.invp[self.perm - 1] = np.arange(1, self.n + 1, dtype=self.idt)
+        return self
+
     def analyze(self):
         E = self.E
         self._call(E["API_TASK_ORDERING"], E["API_TASK_ANALYSE"])
@@ -233,6 +251,11 @@ class Pastix(PastixLib):
         if not h:
             raise RuntimeError("no device handle yet: run numfact() first")
         return Sopalin.from_handle(h, self.prec, self.facto)
+
+    def live_entries(self) -> int:
+        """Number of SolverMatrix entries the shim's side table holds (this precision's library)."""
+        self.lib.pb200_shim_live.restype = C.c_int
+        return int(self.lib.pb200_shim_live())
 
     def release(self):
         """Free the HBM held for this pastix_data (before clean())."""

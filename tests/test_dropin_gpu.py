@@ -130,6 +130,93 @@ def test_two_live_instances_and_refactorization_with_new_values():
     g1.release(); g2.release()
 
 
+def test_new_analysis_with_another_structure_on_the_same_pastix_data():
+    """The shim keys its device state by &pastix_data->solvmatr, an address that survives a second API_TASK_ANALYSE on
+    the same pastix_data (pastix_task_blend only calls CoefMatrix_Free, pastix.c:2714-2718).  A new ordering (hence a
+    different SolverMatrix at the same address, same n) and new values must get a NEW schedule / slab — the structural
+    fingerprint in the side table — not the stale one.  (A new ordering is the re-analysis the unmodified reference
+    itself survives; it corrupts its heap when the PATTERN changes on a live pastix_data.)"""
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    A1, p1 = case_matrix("lap7", 10, DT["d"])
+    n = A1.shape[0]
+    b = G.rhs_vector(n, 1, DT["d"])[:, 0].copy()
+    g = Pastix("d", threads=1).setup(A1, p1, "ldlt").analyze().numfact()
+    x1 = g.solve(b)
+    F1 = full_matrix(A1, "yes")
+    assert np.linalg.norm(F1 @ x1 - b) / np.linalg.norm(b) <= 1e-12
+    c1 = g.sopalin().coefnbr
+    p2 = (n - 1 - p1).astype(p1.dtype)                 # the mirrored elimination order: another symbol structure
+    g.set_perm(p2)
+    g.vals *= 3.0
+    g.analyze().numfact()
+    assert g.sopalin().coefnbr != c1, "the handle was not rebuilt for the new structure"
+    x2 = g.solve(b)
+    assert np.linalg.norm(3.0 * (F1 @ x2) - b) / np.linalg.norm(b) <= 1e-12
+    ref = RefPastix("d", threads=1).setup(3.0 * A1, p2, "ldlt").analyze().numfact()
+    assert relerr(x2, ref.solve(b)) <= 50 * tol("d")
+    assert g.live_entries() == 1
+    g.clean()
+    assert g.live_entries() == 0
+
+
+def test_clean_releases_the_device_and_a_recycled_address_gets_a_fresh_handle():
+    """API_TASK_CLEAN (pastix_task_clean -> solverExit, pastix.c:4539) must free the HBM held for that pastix_data
+    without any non-reference call, and a later pastix_data that malloc places at the same address must not inherit
+    anything: several init..clean cycles with different matrices, no explicit release."""
+    import torch
+    from make_golden import case_matrix, DT
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    cases = [("lap7", 10, "llt", "yes"), ("cd", 8, "lu", "no"), ("lap27", 8, "ldlt", "yes"), ("lap7", 9, "ldlt", "yes")]
+    free0 = None
+    for it, (kind, N, facto, sym) in enumerate(cases * 2):
+        A, p0 = case_matrix(kind, N, DT["d"])
+        b = G.rhs_vector(A.shape[0], 1, DT["d"])[:, 0].copy()
+        g = Pastix("d", threads=1).setup(A, p0, facto, sym=sym).analyze().numfact()
+        x = g.solve(b)
+        assert np.linalg.norm(full_matrix(A, sym) @ x - b) / np.linalg.norm(b) <= 1e-12, (it, kind)
+        assert g.live_entries() == 1
+        g.clean()
+        assert g.live_entries() == 0
+        torch.cuda.synchronize()
+        free = torch.cuda.mem_get_info()[0]
+        if free0 is None:
+            free0 = free                               # after the first cycle: context, module and pools are loaded
+        assert free >= free0 - (8 << 20), f"cycle {it}: {free0 - free} bytes of HBM not returned by API_TASK_CLEAN"
+
+
+@pytest.mark.parametrize("prec,sym,kind", [("d", "yes", "lap7"), ("z", "yes", "lap7shift"), ("z", "her", "lap7her"), ("c", "her", "lap7her")])
+def test_lu_on_a_symmetric_or_hermitian_typed_matrix(prec, sym, kind):
+    """IPARM_FACTORIZATION = LU with IPARM_SYM = YES / HER: the reference builds the internal CSC of type 'S' / 'H' with
+    forcetrans (pastix.c:3294-3310) and fills ucoeftab with the transposed values — CONJUGATED for 'H'
+    (csc_intern_solve.c:110-116).  Same calls on both libraries."""
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    if not available(prec):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix(kind, 8, DT[prec])
+    b = G.rhs_vector(A.shape[0], 2, DT[prec])
+    ref = RefPastix(prec, threads=1).setup(A, perm0, "lu", sym=sym).analyze().numfact()
+    xr = ref.solve(b)
+    for host_csc in (False, True):                     # device-built internal CSC and the reference's host CscOrdistrib
+        if host_csc:
+            os.environ["PB200_HOST_CSC"] = "1"
+        try:
+            gpu = Pastix(prec, threads=1).setup(A, perm0, "lu", sym=sym).analyze().numfact()
+            xg = gpu.solve(b)
+        finally:
+            os.environ.pop("PB200_HOST_CSC", None)
+        res = np.linalg.norm(full_matrix(A, sym) @ xg - b) / np.linalg.norm(b)
+        assert res <= (1e-12 if prec in ("d", "z") else 1e-4), (res, host_csc)
+        assert relerr(xg, xr) <= 50 * tol(prec), host_csc
+        gpu.clean()
+
+
 def test_analysis_with_several_blend_threads():
     """IPARM_THREAD_NBR > 1 only shapes blend's task vectors (ttsktab); the numeric phase on the GPU ignores them and
     must give the same answer as the reference run with the same iparm."""
@@ -224,6 +311,7 @@ SCHUR_CASES = [
     ("cd", 6, "z", "lu", {}, True),
     ("lap7", 14, "d", "llt", {"IPARM_MIN_BLOCKSIZE": 20, "IPARM_MAX_BLOCKSIZE": 40}, False),   # Schur cblk wider than a sub-panel
     ("lap7", 8, "s", "llt", {}, False),                                                          # generic (SIMT) factorization path
+    ("lap1d", 100, "d", "llt", {}, False),                                                       # every cblk small: the solve must still take the Schur-aware sweeps
 ]
 
 
