@@ -145,6 +145,13 @@ int pb200_ipc_size(void);
 int pb200_ipc_export(pb200_handle_t *h, void *blob);
 int pb200_ipc_attach(pb200_handle_t *h, const void *all_blobs);
 int pb200_dist_barrier(pb200_handle_t *h);
+/* ONE host process driving the n GPUs of the box — what pastix() does with iparm[IPARM_CUDA_NBR] = n (api.h:115-120;
+ * the reference's own multi-GPU knob, read by its StarPU back end).  hs[r] = pb200_create_dist(..., device r, rank r,
+ * n); peer access is enabled pairwise and the peers' slabs are addressed directly, no IPC blob.  The collective calls
+ * (pb200_assemble*, pb200_reassemble, pb200_factorize) block until every rank has reached them: drive each handle
+ * from its own host thread (shim/sopalin_b200_shim.c does).  pb200_destroy_group frees all of them at once. */
+int pb200_attach_local(pb200_handle_t **hs, int n);
+int pb200_destroy_group(pb200_handle_t **hs, int n);
 /* The mapping alone (host only, no GPU): owner[cblknbr] = rank of each column block; optional
  * contrib[cblknbr] = bit mask of the other ranks that contribute to it, load[nranks] = flops mapped. */
 int pb200_dist_plan(const pb200_solver_t *solver, int factotype, int nranks,

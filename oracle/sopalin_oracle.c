@@ -182,6 +182,11 @@ static int potrf_block(T *A, int64_t n, int64_t ld, int64_t *nbpivot, double cri
     /* SYRK 'L' (complex: zherk, sopalin_compute.h:178-179): S -= P P^H, lower only */
     for (j = 0; j < ms; j++) for (l = 0; l < bs; l++) for (i = j; i < ms; i++)
       S[j * ld + i] -= P[l * ld + i] * CONJ(P[l * ld + j]);
+#ifdef CPLX
+    /* zherk treats S as Hermitian: with beta = 1 it starts from DBLE(S(j,j)) and adds real products only, so the
+     * imaginary part of every trailing diagonal entry is dropped (reference BLAS zherk.f, "C(J,J) = DBLE(C(J,J))") */
+    for (j = 0; j < ms; j++) S[j * ld + j] = (T)(__real__ S[j * ld + j]);
+#endif
   }
   return 0;
 }

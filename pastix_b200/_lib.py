@@ -18,7 +18,7 @@ SYMBOLS = [
     "pb200_vec_alloc", "pb200_vec_free", "pb200_vec_set", "pb200_vec_get", "pb200_vec_zero", "pb200_vec_copy", "pb200_vec_scal",
     "pb200_vec_axpy", "pb200_vec_dot", "pb200_csc_ax", "pb200_precond",
     "pb200_csc_create", "pb200_csc_destroy", "pb200_csc_build", "pb200_csc_fetch", "pb200_csc_norm1", "pb200_assemble_csc",
-    "pb200_create_opts", "pb200_get_cblk", "pb200_set_hermitian",
+    "pb200_create_opts", "pb200_get_cblk", "pb200_set_hermitian", "pb200_attach_local", "pb200_destroy_group",
 ]
 
 

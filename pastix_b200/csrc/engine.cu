@@ -129,6 +129,7 @@ struct pb200_handle_s {
   int *d_owner = nullptr;
   Peers peers{};
   bool attached = false, gathered = true;
+  bool local_group = false;               // pb200_attach_local: the peers are handles of THIS process (no IPC mappings, no collective in destroy)
   unsigned int *d_flags = nullptr, *d_dist_err = nullptr;   // flags: [0,nlevels) level ready, [nlevels] factorization done, [nlevels+1] barrier
   unsigned int epoch = 0, bar_epoch = 0;
   struct DistLevel { int sig = 0; unsigned int wait_mask = 0, late_mask = 0; int task0 = 0, ntasks = 0; long long ntiles = 0; };
@@ -413,9 +414,13 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
 
   std::vector<SubTask> sub;
   std::vector<GemmTask> gemm;
+  // complex LLt: the reference factors the 64-column blocks of PASTIX_potrf_block with a SYMMETRIC unblocked kernel
+  // (csqrt + geru, compute_diag.c:140) but updates the trailing block with zherk (sopalin_compute.h:178-179), so its
+  // result depends on where the block boundaries are: keep them at multiples of MAXSIZEOFBLOCKS = 64 (compute_diag.c:46)
+  const bool ref_blocking = cx && h->facto == PB200_FACT_LLT;
   auto subpanel = [&](int w, int r, int &c0, int &c1) {
     int nsub = (w + NBMAX - 1) / NBMAX;
-    int sw = (((w + nsub - 1) / nsub) + 7) & ~7;
+    int sw = ref_blocking ? NBMAX : ((((w + nsub - 1) / nsub) + 7) & ~7);
     c0 = r * sw; c1 = std::min(w, c0 + sw);
   };
   for (int l = 0; l < h->nlevels; ++l) {
@@ -875,7 +880,7 @@ extern "C" int pb200_create_opts(pb200_handle_t **out, const pb200_solver_t *s, 
 extern "C" int pb200_destroy(pb200_handle_t *h) {
   if (!h) return PB200_SUCCESS;
   cudaSetDevice(h->device);
-  if (h->attached) dist_barrier(h);   // collective: no peer is still reading our slab
+  if (h->attached && !h->local_group) dist_barrier(h);   // collective: no peer is still reading our slab
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(h->d_flags); cudaFree(h->d_dist_err);
   for (void *p : h->allocs) cudaFree(p);
@@ -1079,7 +1084,6 @@ extern "C" int pb200_assemble_csc(pb200_handle_t *h, const pb200_csc_t *c) {
   if (!h || !c) return fail(PB200_ERR_BADARG, "null argument");
   if (!c->valid) return fail(PB200_ERR_STATE, "no internal CSC built");
   if (c->flt != h->flt || c->n != h->n) return fail(PB200_ERR_BADARG, "internal CSC does not match this SolverMatrix (precision / order)");
-  if (c->device != h->device) return fail(PB200_ERR_BADARG, "internal CSC lives on another device");
   if (h->facto == PB200_FACT_LU && !c->has_t) return fail(PB200_ERR_BADARG, "LU needs the transposed values");
   CK(cudaSetDevice(h->device));
   h->herm = (c->type == 'H');
@@ -1093,10 +1097,12 @@ extern "C" int pb200_assemble_csc(pb200_handle_t *h, const pb200_csc_t *c) {
     if (h->facto == PB200_FACT_LU) CK(cudaMalloc(&h->d_tvals, (size_t)std::max<int64_t>(nnz, 1) * h->esize));
     h->nnz = nnz;
   }
-  CK(cudaMemcpyAsync(h->d_colptr, c->d_colptr, (size_t)(h->n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_rows, c->d_rows, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_vals, c->d_vals, (size_t)nnz * h->esize, cudaMemcpyDeviceToDevice, h->stream));
-  if (h->d_tvals) CK(cudaMemcpyAsync(h->d_tvals, c->d_tvals, (size_t)nnz * h->esize, cudaMemcpyDeviceToDevice, h->stream));
+  // the device CSC may live on another GPU of the box (one pb200_csc_build, several handles): peer copies
+  CK(cudaMemcpyPeerAsync(h->d_colptr, h->device, c->d_colptr, c->device, (size_t)(h->n + 1) * sizeof(int64_t), h->stream));
+  CK(cudaMemcpyPeerAsync(h->d_rows, h->device, c->d_rows, c->device, (size_t)nnz * sizeof(int), h->stream));
+  CK(cudaMemcpyPeerAsync(h->d_vals, h->device, c->d_vals, c->device, (size_t)nnz * h->esize, h->stream));
+  if (h->d_tvals) CK(cudaMemcpyPeerAsync(h->d_tvals, h->device, c->d_tvals, c->device, (size_t)nnz * h->esize, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return pb200_reassemble(h);
 }
 
@@ -1817,6 +1823,49 @@ extern "C" int pb200_ipc_attach(pb200_handle_t *h, const void *all_handles) {
     h->peers.flags[p] = (unsigned int *)q;
   }
   h->attached = true;
+  return PB200_SUCCESS;
+}
+
+// All `n` handles of one distributed factorization live in THIS process (one host process driving the GPUs of the
+// box, e.g. pastix() with iparm[IPARM_CUDA_NBR] = n): peer access is enabled pairwise and the peers' slabs / flags
+// are addressed directly — no IPC blobs.  hs[r] must have been created with rank r of n.  The blocking calls
+// (pb200_reassemble, pb200_factorize, ...) are collective: the caller drives every handle from its own host thread.
+extern "C" int pb200_attach_local(pb200_handle_t **hs, int n) {
+  if (!hs || n < 2 || n > PB200_MAXRANKS) return fail(PB200_ERR_BADARG, "bad handle group");
+  for (int r = 0; r < n; ++r) {
+    if (!hs[r] || hs[r]->nranks != n || hs[r]->rank != r) return fail(PB200_ERR_BADARG, "handle r must be rank r of n");
+    if (hs[r]->attached) return fail(PB200_ERR_STATE, "handle already attached");
+    for (int q = 0; q < r; ++q)
+      if (hs[q]->device == hs[r]->device) return fail(PB200_ERR_BADARG, "two ranks on one device");
+  }
+  for (int r = 0; r < n; ++r) {
+    CK(cudaSetDevice(hs[r]->device));
+    for (int q = 0; q < n; ++q) {
+      if (q == r) continue;
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, hs[r]->device, hs[q]->device));
+      if (!can) return fail(PB200_ERR_CUDA, "no peer access between the devices of the group");
+      cudaError_t e = cudaDeviceEnablePeerAccess(hs[q]->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+      else if (e != cudaSuccess) return fail(PB200_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    }
+  }
+  for (int r = 0; r < n; ++r) {
+    pb200_handle_t *h = hs[r];
+    h->peers.rank = r; h->peers.nranks = n;
+    for (int q = 0; q < n; ++q) { h->peers.L[q] = hs[q]->dL; h->peers.U[q] = hs[q]->dU; h->peers.flags[q] = hs[q]->d_flags; }
+    h->attached = true; h->local_group = true;
+  }
+  return PB200_SUCCESS;
+}
+
+// destroy the handles of a pb200_attach_local group (all of them, in one call: no peer may outlive the others)
+extern "C" int pb200_destroy_group(pb200_handle_t **hs, int n) {
+  if (!hs) return PB200_SUCCESS;
+  for (int r = 0; r < n; ++r)
+    if (hs[r]) { cudaSetDevice(hs[r]->device); cudaDeviceSynchronize(); }
+  for (int r = 0; r < n; ++r)
+    if (hs[r]) { hs[r]->local_group = true; pb200_destroy(hs[r]); hs[r] = nullptr; }
   return PB200_SUCCESS;
 }
 

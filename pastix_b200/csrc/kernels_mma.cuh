@@ -371,7 +371,20 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
         for (int y = 0; y < NI; ++y)
 #pragma unroll
           for (int e = 0; e < 2; ++e)
-            if (c_cj[y][e] != 0x7fffffff && (FACTO == F_LU || roff >= c_cj[y][e])) red_sub(TA + c_tgt[y][e] + roff, value(x, y, hh, e));
+            if (c_cj[y][e] != 0x7fffffff && (FACTO == F_LU || roff >= c_cj[y][e])) {
+              if constexpr (CX && FACTO == F_LLT) {
+                // the reference's trailing update of a complex LLt block is zherk (sopalin_compute.h:178-179): the
+                // diagonal entry becomes Re(c_jj) - sum |a_jl|^2, its imaginary part is dropped.  Each diagonal
+                // entry belongs to one tile of the launch and nothing else touches it meanwhile: plain store.
+                if (roff == c_cj[y][e]) {
+                  T *p = TA + c_tgt[y][e] + roff;
+                  atomicAdd(&p->x, neg_bits(value(x, y, hh, e).x));
+                  p->y = 0.0;
+                  continue;
+                }
+              }
+              red_sub(TA + c_tgt[y][e] + roff, value(x, y, hh, e));
+            }
       }
     return;
   }

@@ -77,7 +77,8 @@ void pb200_shim_entry_drop(const SolverMatrix *m)
     if (shim_tab[i] != NULL && shim_tab[i]->m == m) { e = shim_tab[i]; shim_tab[i] = NULL; break; }
   pthread_mutex_unlock(&shim_mutex);
   if (e == NULL) return;
-  if (e->h) pb200_destroy(e->h);
+  if (e->ngpu > 1) pb200_destroy_group(e->hs, e->ngpu);
+  else if (e->h) pb200_destroy(e->h);
   if (e->csc) pb200_csc_destroy(e->csc);
   free(e);
 }
@@ -185,6 +186,29 @@ void pb200_shim_release_data(void *pastix_data)
   pb200_shim_entry_drop(&((pastix_data_t *)pastix_data)->solvmatr);
 }
 int pb200_shim_live(void) { return pb200_shim_live_entries(); }
+
+/* The factors where the reference leaves them: cblktab[].coeftab / .ucoeftab (solver.h:94-117) filled from HBM on
+ * demand, allocated like CoefMatrix_Allocate does (coefinit.c:104-160) so that CoefMatrix_Free / solverExit release
+ * them.  For consumers that read the panels directly (dump_all / PASTIX_DUMP_FACTO, user code walking the
+ * SolverMatrix); up_down and refinement never need it.  Returns 0, or -1 when nothing is factorized. */
+int pb200_shim_fetch_coeftab(void *pastix_data)
+{
+  SolverMatrix *m = &((pastix_data_t *)pastix_data)->solvmatr;
+  pb200_shim_entry_t *e = hook_find(m);
+  PASTIX_INT c;
+  if (e == NULL || e->h == NULL || !e->factorized) return -1;
+  for (c = 0; c < m->cblknbr; c++) {
+    size_t sz = (size_t)m->cblktab[c].stride * (size_t)(m->cblktab[c].lcolnum - m->cblktab[c].fcolnum + 1);
+    const int lu = (e->facto == PB200_FACT_LU);
+    if (m->cblktab[c].coeftab == NULL) { MALLOC_INTERN(m->cblktab[c].coeftab, sz, PASTIX_FLOAT); }
+    if (lu && m->cblktab[c].ucoeftab == NULL) { MALLOC_INTERN(m->cblktab[c].ucoeftab, sz, PASTIX_FLOAT); }
+    if (pb200_get_cblk(e->h, (int64_t)c, m->cblktab[c].coeftab, lu ? m->cblktab[c].ucoeftab : NULL) != PB200_SUCCESS) {
+      errorPrint("pastix_b200: pb200_get_cblk: %s", pb200_last_error());
+      return -1;
+    }
+  }
+  return 0;
+}
 
 /* internal CSC of this pastix_data_t (CscMatrix, blend/src/csc.h) flattened: sizes = {ncol, nnz, has transcsc, filled};
  * colptr 0-based with ncol+1 entries.  Used by the parity tests of the device-side CscOrdistrib (shim_csc.c). */

@@ -13,7 +13,9 @@
 #include "pastix_b200.h"
 typedef struct pb200_shim_entry_s {
   const SolverMatrix *m;
-  pb200_handle_t     *h;
+  pb200_handle_t     *h;          /* the handle up_down / refinement / read-backs go through (= hs[0]) */
+  pb200_handle_t     *hs[8];      /* iparm[IPARM_CUDA_NBR] = ngpu > 1: one handle per device (pb200_attach_local group) */
+  int                 ngpu;
   int                 facto;
   int                 schur;      /* handle built for IPARM_SCHUR == API_YES */
   int                 factorized;

@@ -106,7 +106,7 @@ static pb200_shim_entry_t *shim_find(const SolverMatrix *m, int create) { return
 void pb200_shim_release(const SolverMatrix *m) { pb200_shim_entry_drop(m); }
 
 /* SolverMatrix -> flat arrays -> device handle */
-static pb200_handle_t *shim_create(SolverMatrix *datacode, int schur)
+static pb200_handle_t *shim_create(SolverMatrix *datacode, int schur, int rank, int nranks)
 {
   pb200_solver_t s; pb200_handle_t *h = NULL; pb200_options_t opts;
   int64_t *buf, *fcol, *lcol, *bnum, *strd, *frow, *lrow, *fcb, *cind;
@@ -127,13 +127,15 @@ static pb200_handle_t *shim_create(SolverMatrix *datacode, int schur)
   s.frownum = frow; s.lrownum = lrow; s.cblknum = fcb; s.coefind = cind;
   memset(&opts, 0, sizeof(opts));
   opts.schur = schur;
-  if (pb200_create_opts(&h, &s, PB200_FLT, PB200_FACTO, -1, 0, 1, &opts) != PB200_SUCCESS) shim_fatal("pb200_create_opts");
+  /* one GPU: the current device; a group: devices 0 .. nranks-1 of the box */
+  if (pb200_create_opts(&h, &s, PB200_FLT, PB200_FACTO, nranks > 1 ? rank : -1, rank, nranks, &opts) != PB200_SUCCESS)
+    shim_fatal("pb200_create_opts");
   free(buf);
   return h;
 }
 
-/* internal block-CSC (CscOrdistrib, csc_intern_build.c:352) -> flat colptr/rows/values -> panels in HBM */
-static void shim_assemble(pb200_handle_t *h, SolverMatrix *datacode, SopalinParam *sopar)
+/* internal block-CSC (CscOrdistrib, csc_intern_build.c:352) -> flat 0-based colptr / rows (host) */
+static void shim_flatten_csc(SopalinParam *sopar, int64_t **colptr_out, int64_t **rows_out)
 {
   const CscMatrix *csc = sopar->cscmtx;
   PASTIX_INT i, j, ncol = 0, nnz = 0, col = 0;
@@ -146,10 +148,37 @@ static void shim_assemble(pb200_handle_t *h, SolverMatrix *datacode, SopalinPara
     for (j = 0; j < CSC_COLNBR(csc, i); j++) colptr[col++] = CSC_COL(csc, i, j);
   colptr[col] = nnz;
   for (i = 0; i < nnz; i++) rows[i] = CSC_ROW(csc, i);
-  if (pb200_set_hermitian(h, csc->type == 'H') != PB200_SUCCESS) shim_fatal("pb200_set_hermitian");
-  if (pb200_assemble(h, colptr, rows, CSC_VALTAB(csc), sopar->transcsc) != PB200_SUCCESS) shim_fatal("pb200_assemble");
-  free(colptr); free(rows);
-  (void)datacode;
+  *colptr_out = colptr; *rows_out = rows;
+}
+
+/* one rank's share of a numeric factorization: panels filled from the internal CSC (device copy when CscOrdistrib
+ * left one in HBM, host arrays otherwise), then the factorization.  With several GPUs every rank runs this in its
+ * own host thread: pb200_reassemble / pb200_factorize are collective (include/pastix_b200.h, pb200_attach_local). */
+typedef struct shim_job_s {
+  pb200_handle_t *h;
+  pb200_csc_t    *devcsc;           /* NULL: host arrays below */
+  const int64_t  *colptr, *rows;
+  const void     *vals, *tvals;
+  int             herm;
+  double          crit;
+  int64_t         nbpivot;
+  double          seconds;
+  int             rc;
+  char            err[256];
+} shim_job_t;
+
+static void *shim_job_run(void *arg)
+{
+  shim_job_t *j = (shim_job_t *)arg;
+  j->rc = PB200_SUCCESS; j->err[0] = 0;
+  if (j->devcsc != NULL) j->rc = pb200_assemble_csc(j->h, j->devcsc);
+  else {
+    j->rc = pb200_set_hermitian(j->h, j->herm);
+    if (j->rc == PB200_SUCCESS) j->rc = pb200_assemble(j->h, j->colptr, j->rows, j->vals, j->tvals);
+  }
+  if (j->rc == PB200_SUCCESS) j->rc = pb200_factorize(j->h, j->crit, &j->nbpivot, &j->seconds);
+  if (j->rc != PB200_SUCCESS) { strncpy(j->err, pb200_last_error(), sizeof(j->err) - 1); j->err[sizeof(j->err) - 1] = 0; }
+  return NULL;
 }
 
 /* static-pivot threshold, init_struct_sopalin (sopalin3d.c:586-606) */
@@ -206,8 +235,9 @@ static void shim_fetch_schur(pb200_handle_t *h, SolverMatrix *datacode)
 static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
 {
   pb200_shim_entry_t *e = shim_find(datacode, 1);
-  int64_t nbpivot = 0; double seconds = 0.0, crit; int dev_csc = 0;
-  if (e == NULL) { errorPrint("pastix_b200: too many live SolverMatrix instances"); EXIT(MOD_SOPALIN, INTERNAL_ERR); }
+  int64_t nbpivot = 0, *colptr = NULL, *rows = NULL; double seconds = 0.0, crit; int dev_csc = 0, r, G;
+  shim_job_t jobs[8]; pthread_t thr[8];
+  if (e == NULL) { errorPrint("pastix_b200: out of memory (side table)"); EXIT(MOD_SOPALIN, OUTOFMEMORY_ERR); }
   const int schur = (sopar->schur == API_YES);
   if (sopar->iparm[IPARM_DISTRIBUTION_LEVEL] != 0 || SOLV_PROCNBR > 1) {
     errorPrint("pastix_b200: 2D distribution / multi-process SolverMatrix are not handled by this shim");
@@ -217,24 +247,60 @@ static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
     errorPrint("pastix_b200: IPARM_FILL_MATRIX (fake factorization) is not handled by this shim");
     EXIT(MOD_SOPALIN, BADPARAMETER_ERR);
   }
+  /* iparm[IPARM_CUDA_NBR] (api.h:115-120, "number of cuda devices", default 0): the GPUs of the box this
+   * factorization is spread over.  The Schur cblk lives on one process in the reference too: one GPU. */
+  G = (int)sopar->iparm[IPARM_CUDA_NBR];
+  if (G < 1 || schur) G = 1;
+  if (G > 8) G = 8;
   {
   double t0 = clockGet(), t1, t2, t3;
   /* the handle must have been built for THIS structure: the key (the SolverMatrix address) survives a new
    * API_TASK_ANALYSE on the same pastix_data and can be reused by malloc after API_TASK_CLEAN */
   { uint64_t fp[2];
     pb200_shim_fingerprint(datacode, fp);
-    if (e->h != NULL && (e->facto != PB200_FACTO || e->schur != schur || e->fp[0] != fp[0] || e->fp[1] != fp[1])) {
-      pb200_destroy(e->h); e->h = NULL;
+    if (e->h != NULL && (e->facto != PB200_FACTO || e->schur != schur || e->ngpu != G || e->fp[0] != fp[0] || e->fp[1] != fp[1])) {
+      if (e->ngpu > 1) pb200_destroy_group(e->hs, e->ngpu); else pb200_destroy(e->h);
+      e->h = NULL; memset(e->hs, 0, sizeof(e->hs)); e->ngpu = 0;
     }
-    if (e->h == NULL) { e->h = shim_create(datacode, schur); e->facto = PB200_FACTO; e->schur = schur; e->fp[0] = fp[0]; e->fp[1] = fp[1]; } }
+    if (e->h == NULL) {
+      for (r = 0; r < G; r++) e->hs[r] = shim_create(datacode, schur, r, G);
+      if (G > 1 && pb200_attach_local(e->hs, G) != PB200_SUCCESS) shim_fatal("pb200_attach_local");
+      e->h = e->hs[0]; e->ngpu = G;
+      e->facto = PB200_FACTO; e->schur = schur; e->fp[0] = fp[0]; e->fp[1] = fp[1];
+    } }
   e->factorized = 0;
   t1 = clockGet();
   if (e->csc != NULL && e->csc_fresh) {        /* CscOrdistrib of this call left the internal CSC in HBM (shim_csc.c) */
-    if (pb200_assemble_csc(e->h, e->csc) != PB200_SUCCESS) shim_fatal("pb200_assemble_csc");
     dev_csc = 1;
     e->csc_fresh = 0;
   } else
-    shim_assemble(e->h, datacode, sopar);
+    shim_flatten_csc(sopar, &colptr, &rows);
+  t2 = clockGet();
+  crit = shim_critere(datacode, sopar, dev_csc ? e->csc : NULL);
+  t3 = clockGet();
+  e->critere = crit;
+  if (sopar->iparm[IPARM_VERBOSE] > API_VERBOSE_YES)
+    fprintf(stdout, "Pivoting criterium (||A||*sqrt(epsilon)) = %g\n", crit);
+  for (r = 0; r < G; r++) {
+    memset(&jobs[r], 0, sizeof(jobs[r]));
+    jobs[r].h = e->hs[r]; jobs[r].devcsc = dev_csc ? e->csc : NULL;
+    jobs[r].colptr = colptr; jobs[r].rows = rows; jobs[r].vals = CSC_VALTAB(sopar->cscmtx); jobs[r].tvals = sopar->transcsc;
+    jobs[r].herm = (sopar->cscmtx->type == 'H'); jobs[r].crit = crit;
+  }
+  for (r = 1; r < G; r++)
+    if (pthread_create(&thr[r], NULL, shim_job_run, &jobs[r]) != 0) { errorPrint("pastix_b200: pthread_create failed"); EXIT(MOD_SOPALIN, INTERNAL_ERR); }
+  shim_job_run(&jobs[0]);
+  for (r = 1; r < G; r++) pthread_join(thr[r], NULL);
+  for (r = 0; r < G; r++) {
+    if (jobs[r].rc != PB200_SUCCESS) {
+      errorPrint("pastix_b200: numeric factorization (GPU %d of %d): %s", r, G, jobs[r].err);
+      EXIT(MOD_SOPALIN, INTERNAL_ERR);
+    }
+    nbpivot += jobs[r].nbpivot;                                  /* the reference's MPI_Allreduce, sopalin3d.c:1138 */
+    if (jobs[r].seconds > seconds) seconds = jobs[r].seconds;
+  }
+  if (colptr) free(colptr);
+  if (rows) free(rows);
   /* CoefMatrix_Init releases the transposed values once the panels are filled (coefinit.c:327-341) */
   if (sopar->transcsc != NULL) {
     if (PB200_FACTO == PB200_FACT_LU && (sopar->iparm[IPARM_SYM] == API_SYM_YES || sopar->iparm[IPARM_SYM] == API_SYM_HER))
@@ -242,17 +308,10 @@ static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
     else
       memFree_null(sopar->transcsc);
   }
-  t2 = clockGet();
-  crit = shim_critere(datacode, sopar, dev_csc ? e->csc : NULL);
-  t3 = clockGet();
   if (getenv("PB200_SHIM_TIMING") != NULL)
-    fprintf(stderr, "[pb200 shim] create %.1f ms, CSC flatten + H2D + device assembly %.1f ms, CscNorm1 %.1f ms\n",
-            (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3);
+    fprintf(stderr, "[pb200 shim] create %.1f ms, CSC flatten %.1f ms, CscNorm1 %.1f ms, assembly + factorization on %d GPU(s) %.1f ms\n",
+            (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, G, (clockGet() - t3) * 1e3);
   }
-  e->critere = crit;
-  if (sopar->iparm[IPARM_VERBOSE] > API_VERBOSE_YES)
-    fprintf(stdout, "Pivoting criterium (||A||*sqrt(epsilon)) = %g\n", crit);
-  if (pb200_factorize(e->h, crit, &nbpivot, &seconds) != PB200_SUCCESS) shim_fatal("pb200_factorize");
   e->factorized = 1;
   sopar->diagchange = (PASTIX_INT)nbpivot;                       /* -> IPARM_STATIC_PIVOTING (pastix.c:3853) */
   sopar->dparm[DPARM_FACT_TIME] = seconds;                       /* sopalin3d.c:1125-1132 */

@@ -81,6 +81,10 @@ CASES = [
     ("cd_8_lu_d_schur", "cd", 8, "d", "lu", {"IPARM_SCHUR": 1}, 2),
     ("cd_6_lu_z_schur", "cd", 6, "z", "lu", {"IPARM_SCHUR": 1}, 1),
     ("lap7_12_llt_d_schur_bs", "lap7", 12, "d", "llt", {"IPARM_SCHUR": 1, "IPARM_MIN_BLOCKSIZE": 20, "IPARM_MAX_BLOCKSIZE": 40}, 1),
+    # complex LLt with a cblk wider than MAXSIZEOFBLOCKS = 64: the reference's unblocked kernel is symmetric (csqrt + geru,
+    # compute_diag.c:140) but its blocked trailing update is zherk (sopalin_compute.h:178-179) — whatever that computes
+    # on a complex SYMMETRIC matrix is the reference's result, block boundaries at multiples of 64 included
+    ("lap7shift_8_llt_z_wide", "lap7shift", 8, "z", "llt", {"IPARM_MIN_BLOCKSIZE": 100, "IPARM_MAX_BLOCKSIZE": 200}, 1),
 ]
 
 

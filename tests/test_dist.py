@@ -143,3 +143,65 @@ def test_multi_gpu_factorization_matches_reference(tmp_path, nranks):
                           "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+CUDA_NBR_CASES = [
+    # kind, N, prec, facto, nrhs
+    ("lap7", 16, "d", "llt", 2),
+    ("lap27", 14, "d", "ldlt", 1),
+    ("cd", 12, "d", "lu", 2),
+    ("cd", 10, "z", "lu", 1),
+    ("lap7her", 10, "z", "ldlh", 1),
+    ("lap7", 10, "s", "llt", 1),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ngpu", [2, 4])
+@pytest.mark.parametrize("kind,N,prec,facto,nrhs", CUDA_NBR_CASES)
+def test_pastix_with_iparm_cuda_nbr_matches_reference(kind, N, prec, facto, nrhs, ngpu):
+    """Multi-GPU through the reference API: iparm[IPARM_CUDA_NBR] = G (api.h:115-120) on the drop-in — ONE process,
+    G devices, the same pastix() calls — against the unmodified reference and against the drop-in on one GPU:
+    solution, pivot count, inertia and the full factor panels."""
+    import numpy as np
+    import scipy.sparse as sp
+    import torch
+    if torch.cuda.device_count() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from conftest import lower_mask, relerr, tol
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    if not available(prec):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix(kind, N, DT[prec])
+    sym = {"llt": "yes", "ldlt": "yes", "lu": "no", "ldlh": "her"}[facto]
+    b = G.rhs_vector(A.shape[0], nrhs, DT[prec])
+    ref = RefPastix(prec, threads=1).setup(A, perm0, facto, sym=sym).analyze().numfact()
+    xr = ref.solve(b)
+    one = Pastix(prec, threads=1).setup(A, perm0, facto, sym=sym).analyze().numfact()
+    L1, U1 = one.sopalin().get_coeftab()
+    multi = Pastix(prec, threads=1).setup(A, perm0, facto, sym=sym, iparm_over={"IPARM_CUDA_NBR": ngpu}).analyze()
+    t = tol(prec)
+    m = lower_mask(ref.solver()) if facto != "lu" else slice(None)   # the strict upper triangles of the diagonal bloks are never defined
+    for it in range(2):                                   # second pass: re-factorization on the same handles
+        multi.numfact()
+        xg = multi.solve(b)
+        assert multi.out()["static_pivoting"] == ref.out()["static_pivoting"]
+        if facto == "ldlt" and prec in ("s", "d"):
+            assert multi.out()["inertia"] == ref.out()["inertia"]
+        assert relerr(xg, xr) <= 50 * t, (it, "x")
+        Lg, Ug = multi.sopalin().get_coeftab()            # rank 0's slab after the gather
+        assert relerr(Lg[m], L1[m]) <= t, (it, "L")
+        if U1 is not None:
+            assert relerr(Ug, U1) <= t, (it, "U")
+    lo = sp.tril(A, -1)
+    Af = A if sym == "no" else (A + (lo.conj().T if sym == "her" else lo.T)).tocsc()
+    res = np.linalg.norm(Af @ xg - b) / np.linalg.norm(b)
+    assert res <= (1e-12 if prec in ("d", "z") else 1e-4), res
+    assert multi.live_entries() == 2
+    multi.clean(); one.clean()
+    assert multi.live_entries() == 0
+    ref.clean()

@@ -61,11 +61,12 @@ def test_full_factor_panels_match_the_reference_at_scale(kind, N, prec, facto):
     A, perm0 = case_matrix(kind, N, DT[prec])
     sym = SYM[facto]
     b = G.rhs_vector(A.shape[0], 2, DT[prec])
-    ref = RefPastix(prec, threads=min(8, os.cpu_count() or 1)).setup(A, perm0, facto, sym=sym).analyze().numfact()
+    nthr = min(4, os.cpu_count() or 1)                  # IPARM_THREAD_NBR shapes blend's splitting: same value on both sides
+    ref = RefPastix(prec, threads=nthr).setup(A, perm0, facto, sym=sym).analyze().numfact()
     Lr, Ur = ref.coef()
     xr = ref.solve(b)
     sol = ref.solver()
-    gpu = Pastix(prec, threads=1).setup(A, perm0, facto, sym=sym).analyze().numfact()
+    gpu = Pastix(prec, threads=nthr).setup(A, perm0, facto, sym=sym).analyze().numfact()
     s = gpu.sopalin()
     Lg, Ug = s.get_coeftab()
     xg = gpu.solve(b)
