@@ -184,6 +184,61 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "_which": "fallback"}
 
 
+def bench_config(args) -> dict:
+    """`config` of the JSON line: identical in both arms (ours / --impl reference) for the same command line."""
+    desc = WORKLOADS[args.workload][0]
+    over = WORKLOADS[args.workload][6]
+    return {"workload": f"{args.workload}: {desc}",
+            "ordering": "geometric nested dissection passed as API_ORDER_PERSONAL (Scotch is not in the image)",
+            "iparm": {k: int(v) for k, v in sorted(over.items())},
+            "l2": "inputs larger than L2: the factor slab is rewritten by the assembly at the start of every step",
+            "gpus": int(args.gpus),
+            "multi_gpu": ("single GPU" if args.gpus == 1 else
+                          "ONE factorization spread over the GPUs (strong scaling): proportional subtree mapping + fan-in over NVLink peer memory")}
+
+
+def sample_cblks(cblknbr: int, k: int = 64):
+    """Evenly spaced column blocks plus the last ones (the top of the elimination tree, where every update has landed)."""
+    idx = set(np.linspace(0, cblknbr - 1, num=min(k, cblknbr)).astype(int).tolist())
+    idx.update(range(max(0, cblknbr - 8), cblknbr))
+    return sorted(idx)
+
+
+def _sol_view(sol: dict) -> dict:
+    """The two flat SolverMatrix dicts (Pastix.solver() / RefPastix.solver()) under one naming."""
+    g = lambda a, b: sol[a] if a in sol else sol[b]
+    return dict(cblknbr=int(sol["cblknbr"]), fcol=g("fcolnum", "fcol"), lcol=g("lcolnum", "lcol"), bloknum=sol["bloknum"],
+                stride=sol["stride"], frow=g("frownum", "frow"), lrow=g("lrownum", "lrow"))
+
+
+def factor_columns(sol: dict, get_panel, cols) -> dict:
+    """Columns of the factor as {global column: (global rows, values)} read through `get_panel(c)` (stride x width).
+    Independent of how blend split the column blocks: IPARM_THREAD_NBR changes the split, not L."""
+    v = _sol_view(sol)
+    out = {}
+    fcol = np.asarray(v["fcol"][:v["cblknbr"]])
+    for j in cols:
+        c = int(np.searchsorted(fcol, j, side="right") - 1)
+        P = get_panel(c)
+        rows = np.concatenate([np.arange(v["frow"][b], v["lrow"][b] + 1) for b in range(int(v["bloknum"][c]), int(v["bloknum"][c + 1]))])
+        col = P[:, j - int(fcol[c])]
+        keep = rows >= j                                   # lower part: the strict upper triangle of a diagonal blok is undefined
+        out[j] = (rows[keep], col[keep])
+    return out
+
+
+def columns_relerr(a: dict, b: dict) -> float:
+    """max |a - b| / max |b| over the sampled columns (rows matched by global index; a row absent on one side counts
+    as a structural zero)."""
+    num, den = 0.0, 1e-300
+    for j in a:
+        ra, va = a[j]; rb, vb = b[j]
+        da = dict(zip(ra.tolist(), va.tolist())); db = dict(zip(rb.tolist(), vb.tolist()))
+        for r in set(da) | set(db):
+            num = max(num, abs(da.get(r, 0.0) - db.get(r, 0.0))); den = max(den, abs(db.get(r, 0.0)))
+    return float(num / den)
+
+
 # ----------------------------------------------------------------------------- reference (CPU) arm
 def run_reference_fact(wl: str, threads: int, steps: int, warmup: int, budget_s: float, N_override: int | None = None):
     """The UNMODIFIED reference (oracle/_ref) through its own pastix(): analysis once, then NUMFACT + SOLVE
@@ -214,7 +269,8 @@ def run_reference_fact(wl: str, threads: int, steps: int, warmup: int, budget_s:
             break
     Af = A if SYM[facto] == "no" else None
     return {"flops": flops, "fact_s": float(np.mean(ft)), "solve_s": float(np.mean(st)), "wall_s": float(np.mean(wall)),
-            "steps_run": done, "N": N, "n": A.shape[0], "nrhs": nrhs, "x": x, "A": A, "b": b, "threads": threads}
+            "steps_run": done, "N": N, "n": A.shape[0], "nrhs": nrhs, "x": x, "A": A, "b": b, "threads": threads,
+            "ref": r, "nbpivot": r.out()["static_pivoting"]}
 
 
 def reference_arm(args):
@@ -232,9 +288,9 @@ def reference_arm(args):
     return {
         "impl": "reference", "metric": "numeric factorization throughput (PaStiX flop count)", "value": gf, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "steps_run": r["steps_run"], "warmup": args.warmup,
-        "ms_per_step": r["wall_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": r["wall_s"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": {"d": "f64", "z": "c128", "s": "f32", "c": "c64"}[prec], "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "threads": cores},
+        "config": bench_config(args), "threads": cores,
         "fact_ms": r["fact_s"] * 1e3, "solve_ms_per_rhs": r["solve_s"] * 1e3 / r["nrhs"],
         "cpu_baseline": {"value": gf, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": gf, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -243,7 +299,7 @@ def reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- our arm
-def our_arm(args):
+def our_arm(args, with_cpu_baseline: bool = False):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -376,13 +432,11 @@ def our_arm(args):
         line = {
             "metric": "numeric factorization throughput (PaStiX flop count)", "value": gf_total, "unit": "GFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_region / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": {"d": "f64", "z": "c128", "s": "f32", "c": "c64"}[prec], "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "n": n, "nnzL": nnzL, "fact_flops": flops, "nrhs": nrhs,
-                       "ordering": "geometric nested dissection passed as API_ORDER_PERSONAL (Scotch is not in the image)",
-                       "l2": "inputs larger than L2: the factor slab (%.2f GB) is rewritten by the device-side assembly every step"
-                             % (s.coefnbr * ESIZE[prec] * (2 if facto == "lu" else 1) / 1e9),
-                       "multi_gpu": "replicas" if world > 1 else "single"},
+            "config": bench_config(args),
+            "problem": {"n": n, "nnzL": nnzL, "fact_flops": flops, "nrhs": nrhs, "cblknbr": int(s.solver.cblknbr),
+                        "factor_slab_GB": s.coefnbr * ESIZE[prec] * (2 if facto == "lu" else 1) / 1e9},
             "fact_ms": fact_mean * 1e3, "assemble_ms": float(np.mean(asm_s)) * 1e3,
             "solve_ms_per_rhs": solve_mean * 1e3 / nrhs,
             "pct_fp64_peak": 100.0 * (flops / fact_mean / 1e12) / roof["peak"],
@@ -394,7 +448,9 @@ def our_arm(args):
             "gpu_launches": int(launches),
             "roofline": roof, "clocks": clocks, "analysis_s": t_analysis,
         }
-    gpu.release()
+    if line is not None and with_cpu_baseline:
+        line["cpu_baseline"], line["parity"] = cpu_baseline_for(args, gpu=gpu, x_gpu=x)
+    gpu.clean()                                            # API_TASK_CLEAN: releases the HBM through the intercepted solverExit
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -404,8 +460,11 @@ def our_arm(args):
 def our_arm_dist(args):
     """N > 1: ONE factorization spread over the N GPUs of the box (strong scaling): proportional subtree
     mapping of the column blocks, fan-in contributions pulled by the owner over NVLink peer memory
-    (DESIGN.md §6).  Every rank runs the same deterministic host analysis; `value` = the whole job's
-    DPARM_FACT_FLOPS / max over ranks of the device-timed factorization."""
+    (DESIGN.md §6).  Launched as one process per GPU (torch.distributed.run): every rank runs the same deterministic
+    host analysis and drives its own GPU through the C ABI (pb200_create_dist + CUDA IPC); `value` = the whole job's
+    DPARM_FACT_FLOPS / max over ranks of the device-timed factorization.  `e2e` is the call a PaStiX user makes:
+    pastix(API_TASK_NUMFACT) with iparm[IPARM_CUDA_NBR] = N on the drop-in, ONE process (rank 0) driving the N devices
+    with host buffers, while the other ranks wait on a CPU-side barrier."""
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -414,6 +473,28 @@ def our_arm_dist(args):
         raise SystemExit("bench.py: no CUDA device — pastix_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    cpu_group = dist.new_group(backend="gloo")       # waits that must not occupy a GPU
+    ctx = dict(torch=torch, dist=dist, rank=rank, world=world, local=local, cpu_group=cpu_group)
+    line = dist_case(args, args.workload, args.steps, args.warmup, ctx)
+    if args.workload == "c2" and not args.iparm and os.environ.get("PB200_ALSO", "1") != "0":
+        # the north_star target config beside the headline one, at the same N
+        try:
+            l3 = dist_case(args, "c3", min(args.steps, 3), 3, ctx)
+            if line is not None and l3 is not None:
+                line["also"] = {"c3": {k: l3[k] for k in ("value", "unit", "fact_ms", "solve_ms_per_rhs", "backward_error", "ms_per_step",
+                                                         "gpu_launches", "e2e", "factor_relerr_vs_n1", "load_share", "device_bytes_per_gpu")}}
+                line["also"]["c3"]["workload"] = l3["config"]["workload"]
+        except Exception as e:
+            if line is not None:
+                line["also"] = {"c3": {"error": repr(e)}}
+    dist.barrier(group=cpu_group)
+    dist.destroy_process_group()
+    return line
+
+
+def dist_case(args, workload, steps, warmup, ctx):
+    torch, dist = ctx["torch"], ctx["dist"]
+    rank, world, local, cpu_group = ctx["rank"], ctx["world"], ctx["local"], ctx["cpu_group"]
 
     def barrier():
         dist.barrier(); torch.cuda.synchronize(local)
@@ -427,7 +508,7 @@ def our_arm_dist(args):
     from pastix_b200 import Sopalin, critere_from_norm, generators as G
     from pastix_b200.csc import internal_csc, permute_rhs, unpermute_solution
     import scipy.sparse as sp
-    desc, kind, N, prec, facto, nrhs, over = WORKLOADS[args.workload]
+    desc, kind, N, prec, facto, nrhs, over = WORKLOADS[workload]
     dt = DT[prec]
     A, perm0 = case_matrix(kind, N, dt)
     n = A.shape[0]
@@ -443,76 +524,103 @@ def our_arm_dist(args):
     crit = critere_from_norm(s.norm1(csc["colptr"], csc["values"]))
     xp = permute_rhs(b, permtab)
     Af = A if SYM[facto] == "no" else (A + (sp.tril(A, -1).conj().T if SYM[facto] == "her" else sp.tril(A, -1).T)).tocsc()
-    log(f"[rank {rank}] {args.workload}: n={n} nnzL={nnzL} flops={flops:.4g} analysis {t_analysis:.1f}s "
+    log(f"[rank {rank}] {workload}: n={n} nnzL={nnzL} flops={flops:.4g} analysis {t_analysis:.1f}s "
         f"load share {load[rank] / load.sum():.3f} device_bytes {s.device_bytes / 1e9:.2f} GB")
-    # ---- e2e: host CSC -> HBM, factorization, host rhs -> solution (public API of this package)
-    e2e_fact, e2e_solve = [], []
-    for it in range(args.warmup + args.steps):
-        barrier()
-        t0 = time.perf_counter()
-        s.assemble(csc["colptr"], csc["rows"], csc["values"], csc["tvalues"])
-        s.factorize(crit)
-        barrier()
-        t1 = time.perf_counter()
-        x = xp.copy(order="F"); s.solve(x)
-        t2 = time.perf_counter()
-        if it >= args.warmup:
-            e2e_fact.append(t1 - t0); e2e_solve.append(t2 - t1)
-    berr = float(np.linalg.norm(Af @ unpermute_solution(x, permtab) - b) / np.linalg.norm(b))
-    e2e_fact_s = maxr(float(np.mean(e2e_fact))); e2e_solve_s = maxr(float(np.mean(e2e_solve)))
-    nnzA = Af.nnz
-    h2d = (n + 1) * 8 + nnzA * 8 + nnzA * ESIZE[prec] * (2 if facto == "lu" else 1) + n * nrhs * ESIZE[prec]
-    d2h = n * nrhs * ESIZE[prec] + 8
-    # ---- device-resident steps
+    s.assemble(csc["colptr"], csc["rows"], csc["values"], csc["tvalues"])
+    # ---- device-resident steps: inputs already in HBM
     x_src = torch.from_numpy(np.ascontiguousarray(xp.T)).to(f"cuda:{local}"); x_dev = torch.empty_like(x_src)
     fact_s, solve_s, launches = [], [], 0
     sampler = ClockSampler(local)
-    for it in range(args.warmup):
+    for it in range(warmup):
         s.reassemble(); s.factorize(crit)
     barrier()
     if rank == 0:
         sampler.start()
     t_begin = time.perf_counter()
-    for it in range(args.steps):
+    for it in range(steps):
         s.reassemble()
         s.factorize(crit)
         fact_s.append(s.fact_time); launches += s.last_launches() + 1
         x_dev.copy_(x_src); torch.cuda.synchronize(local)
         s.solve_device(x_dev.data_ptr(), n, nrhs)      # first solve after a factorization pulls the peers' panels
         solve_s.append(s.solv_time); launches += s.last_launches() + 3
-    barrier()
+        barrier()                                      # nobody re-assembles while a peer still pulls panels
     t_region = maxr(time.perf_counter() - t_begin)
     clocks = sampler.stop() if rank == 0 else None
     fact_mean = maxr(float(np.mean(fact_s))); solve_mean = maxr(float(np.mean(solve_s)))
     xh = x_dev.cpu().numpy()
     xs = unpermute_solution(xh.T if xh.ndim == 2 else xh.reshape(n, 1), permtab)
     berr_dev = float(np.linalg.norm(Af @ xs.reshape(n, -1) - b) / np.linalg.norm(b))
+    # ---- the same factors as one GPU computes: sampled cblks of this run against a single-GPU factorization
+    rel_n1 = None
+    if rank == 0:
+        try:
+            s1 = Sopalin(solver, prec, facto, device=local)
+            s1.assemble(csc["colptr"], csc["rows"], csc["values"], csc["tvalues"]); s1.factorize(crit)
+            num, den = 0.0, 1e-300
+            for c in sample_cblks(solver["cblknbr"]):
+                w = int(solver["lcolnum"][c] - solver["fcolnum"][c] + 1)
+                Pn = s.get_cblk(c); P1 = s1.get_cblk(c)
+                if facto != "lu":                      # the strict upper triangle of the diagonal blok is undefined
+                    iu = np.triu_indices(w, 1); Pn[:w][iu] = 0; P1[:w][iu] = 0
+                num = max(num, float(np.max(np.abs(Pn - P1)))); den = max(den, float(np.max(np.abs(P1))))
+            rel_n1 = num / den
+            s1.close()
+        except Exception as e:
+            rel_n1 = repr(e)
+    dev_bytes = maxr(float(s.device_bytes))
+    barrier()
+    s.close()                                          # collective
+    an.clean()
+    # ---- e2e: pastix() with iparm[IPARM_CUDA_NBR] = N, one process, host buffers
+    dist.barrier(group=cpu_group)
+    e2e = None
+    if rank == 0:
+        try:
+            g = Pastix(prec, threads=1).setup(A, perm0, facto, sym=SYM[facto],
+                                              iparm_over=dict(over, IPARM_CUDA_NBR=world)).analyze()
+            tf, ts = [], []
+            for it in range(warmup + steps):
+                t0 = time.perf_counter(); g.numfact(); t1 = time.perf_counter(); x = g.solve(b); t2 = time.perf_counter()
+                if it >= warmup:
+                    tf.append(t1 - t0); ts.append(t2 - t1)
+            berr = float(np.linalg.norm(Af @ x - b) / np.linalg.norm(b))
+            nnzA = Af.nnz
+            e2e = {"value": flops / float(np.mean(tf)) / 1e9, "unit": "GFLOP/s",
+                   "h2d_bytes_per_step": int((n + 1) * 8 + nnzA * 8 + nnzA * ESIZE[prec] + n * nrhs * ESIZE[prec]),
+                   "d2h_bytes_per_step": int(n * nrhs * ESIZE[prec] + 8),
+                   "numfact_call_ms": float(np.mean(tf)) * 1e3, "solve_call_ms": float(np.mean(ts)) * 1e3, "backward_error": berr,
+                   "fact_ms_dparm": g.out()["fact_time"] * 1e3,
+                   "host_memory": "pageable (the reference's own CSC/RHS buffers)",
+                   "call": "pastix(API_TASK_NUMFACT) + pastix(API_TASK_SOLVE) on libpastix_dropin with iparm[IPARM_CUDA_NBR] = %d "
+                           "(one process driving the %d GPUs)" % (world, world)}
+            g.clean()
+        except Exception as e:
+            e2e = {"value": None, "error": repr(e)}
+    dist.barrier(group=cpu_group)
     line = None
     if rank == 0:
+        a2 = argparse.Namespace(**vars(args)); a2.workload = workload
         line = {
             "metric": "numeric factorization throughput (PaStiX flop count)", "value": flops / fact_mean / 1e9, "unit": "GFLOP/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_region / args.steps * 1e3,
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": t_region / steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": {"d": "f64", "z": "c128", "s": "f32", "c": "c64"}[prec], "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "n": n, "nnzL": nnzL, "fact_flops": flops, "nrhs": nrhs,
-                       "ordering": "geometric nested dissection passed as API_ORDER_PERSONAL (Scotch is not in the image)",
-                       "l2": "inputs larger than L2: the factor slab is rewritten by the device-side assembly every step",
-                       "multi_gpu": "one factorization over %d GPUs: proportional subtree mapping + fan-in over NVLink peer memory" % world,
-                       "load_share": [float(v) for v in load / load.sum()]},
+            "config": bench_config(a2),
+            "problem": {"n": n, "nnzL": nnzL, "fact_flops": flops, "nrhs": nrhs, "cblknbr": int(solver["cblknbr"])},
+            "load_share": [float(v) for v in load / load.sum()], "device_bytes_per_gpu": dev_bytes,
             "fact_ms": fact_mean * 1e3, "solve_ms_per_rhs": solve_mean * 1e3 / nrhs, "backward_error": berr_dev,
-            "e2e": {"value": flops / e2e_fact_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "numfact_call_ms": e2e_fact_s * 1e3, "solve_call_ms": e2e_solve_s * 1e3, "backward_error": berr,
-                    "call": "Sopalin.assemble(host CSC) + factorize + solve(host rhs) on every rank (pb200_create_dist path)"},
-            "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None, "clocks": clocks, "analysis_s": t_analysis,
+            "fact_ms_covers": "numeric factorization + inversion of the diagonal triangles of the owned cblks (what N = 1 times)",
+            "factor_relerr_vs_n1": rel_n1,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None, "clocks": clocks, "analysis_s": t_analysis,
         }
-    s.close()
-    dist.barrier()
-    dist.destroy_process_group()
     return line
 
 
-def cpu_baseline_for(args) -> dict:
-    """Reference CPU sopalin on the host cores, bounded sample (rank 0, N=1 only)."""
+def cpu_baseline_for(args, gpu=None, x_gpu=None):
+    """Reference CPU sopalin on the host cores, bounded sample (rank 0, N=1 only).  When the sample IS the workload
+    (c2, c4s, c5s) the reference's results are also compared with the drop-in's: solution, pivot count and sampled
+    columns of the factor (structure-independent: the two analyses run blend with different IPARM_THREAD_NBR)."""
     cores = os.cpu_count() or 1
     desc, kind, N, prec, facto, nrhs, over = WORKLOADS[args.workload]
     # bounded sample: the full workload when it is <= ~1e12 flop, else the same stencil on a smaller grid
@@ -527,11 +635,37 @@ def cpu_baseline_for(args) -> dict:
     try:
         r = run_reference_fact(args.workload, cores, 1, 0, 120.0, N_override=Ns)
     except Exception as e:  # pragma: no cover
-        return {"value": None, "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+        return {"value": None, "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}, None
     if r is None:
-        return {"value": None, "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref not present"}
-    return {"value": r["flops"] / r["fact_s"] / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "reference",
-            "sample": sample, "fact_s": r["fact_s"], "solve_ms_per_rhs": r["solve_s"] * 1e3 / r["nrhs"]}
+        return {"value": None, "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref not present"}, None
+    cb = {"value": r["flops"] / r["fact_s"] / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "reference",
+          "sample": sample, "fact_s": r["fact_s"], "solve_ms_per_rhs": r["solve_s"] * 1e3 / r["nrhs"]}
+    parity = None
+    if Ns is None and gpu is not None and not over.get("IPARM_INCOMPLETE"):
+        try:
+            ref = r["ref"]
+            xr = np.asarray(r["x"]).reshape(r["n"], -1); xg = np.asarray(x_gpu).reshape(r["n"], -1)
+            parity = {"against": "the unmodified reference (oracle/_ref) on the same pastix() calls, %d threads" % cores,
+                      "x_relerr": float(np.max(np.abs(xg - xr)) / np.max(np.abs(xr))),
+                      "nbpivot_equal": bool(gpu.out()["static_pivoting"] == r["nbpivot"])}
+            s = gpu.sopalin()
+            sol_g, sol_r = gpu.solver(), ref.solver()
+            cbl = sample_cblks(sol_g["cblknbr"])
+            cols = sorted({int(sol_g["fcolnum"][c]) for c in cbl} | {int(sol_g["lcolnum"][c]) for c in cbl})
+            Lr, Ur = ref.coef()
+            vr = _sol_view(sol_r)
+            wr = np.asarray(vr["lcol"][:vr["cblknbr"]]) - np.asarray(vr["fcol"][:vr["cblknbr"]]) + 1
+            poff = np.concatenate([[0], np.cumsum(np.asarray(vr["stride"][:vr["cblknbr"]]) * wr)]).astype(np.int64)
+            ref_panel = lambda M: (lambda c: M[poff[c]:poff[c + 1]].reshape(int(vr["stride"][c]), int(wr[c]), order="F"))
+            parity["L_relerr_sampled_cblks"] = columns_relerr(factor_columns(sol_g, lambda c: s.get_cblk(c), cols),
+                                                              factor_columns(sol_r, ref_panel(Lr), cols))
+            if facto == "lu":
+                parity["U_relerr_sampled_cblks"] = columns_relerr(
+                    factor_columns(sol_g, lambda c: s.get_cblk(c, with_u=True)[1], cols), factor_columns(sol_r, ref_panel(Ur), cols))
+            parity["sampled_columns"] = len(cols)
+        except Exception as e:  # the headline line must survive
+            parity = {"error": repr(e)}
+    return cb, parity
 
 
 def main():
@@ -563,11 +697,12 @@ def main():
         line = reference_arm(args)
     else:
         world = int(os.environ.get("WORLD_SIZE", "1"))
-        line = our_arm_dist(args) if (world > 1 and not os.environ.get("PB200_REPLICAS")) else our_arm(args)
-        if line is not None and args.gpus == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_for(args)
-        elif line is not None:
-            line["cpu_baseline"] = None
+        if world > 1 and not os.environ.get("PB200_REPLICAS"):
+            line = our_arm_dist(args)
+        else:
+            line = our_arm(args, with_cpu_baseline=(args.gpus == 1 and not args.no_cpu_baseline))
+        if line is not None:
+            line.setdefault("cpu_baseline", None)
     # the north_star target config beside the headline one (N=1 default run only): C3 = 100^3 27-point LDLt
     if (args.impl == "ours" and line is not None and args.gpus == 1 and args.workload == "c2" and not args.iparm
             and os.environ.get("PB200_ALSO", "1") != "0"):

@@ -100,7 +100,7 @@ struct pb200_handle_s {
   int *d_rowglob = nullptr;                // global row of every off-diagonal panel row
   std::vector<int> inv_lvl_nbmax;          // widest sub-panel of each level (sizes the shared memory of k_tri_inverse)
   std::vector<int> inv_lvl_ptr;            // sub-panels of level l: [inv_lvl_ptr[l], inv_lvl_ptr[l+1])
-  std::vector<int> inv_cls_ptr; int *d_inv_order = nullptr;   // sub-panels sorted by size class (k_tri_inverse launches)
+  std::vector<int> inv_cls_ptr[3]; int *d_inv_order = nullptr;   // sub-panels sorted by size class (k_tri_inverse launches): all / owned / not owned
   cudaStream_t stream_i = nullptr;         // low priority: triangle inversions underneath the factorization
   cudaEvent_t ev_inv = nullptr;
   // ---- FP64 tensor-core path (double / complex double, direct factorizations)
@@ -335,8 +335,19 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
       int k = 0; while (k + 1 < ncls && nb > bound[k]) ++k;
       byc[k].push_back(i);
     }
-    std::vector<int> order; h->inv_cls_ptr.assign(1, 0);
-    for (int k = 0; k < ncls; ++k) { order.insert(order.end(), byc[k].begin(), byc[k].end()); h->inv_cls_ptr.push_back((int)order.size()); }
+    // three lists per size class, one after the other: every sub-panel, the ones of the cblks this GPU owns (inverted
+    // inside the timed factorization of a multi-GPU run), the others (inverted after their panels have been pulled)
+    std::vector<int> order;
+    for (int which = 0; which < 3; ++which) {
+      h->inv_cls_ptr[which].assign(1, (int)order.size());
+      for (int k = 0; k < ncls; ++k) {
+        for (int i : byc[k]) {
+          const bool mine = h->plan.owner[tasks[i].cblk] == h->rank;
+          if (which == 0 || (which == 1) == mine) order.push_back(i);
+        }
+        h->inv_cls_ptr[which].push_back((int)order.size());
+      }
+    }
     int rc = upload(h, order, &h->d_inv_order); if (rc) return rc;
   }
   { int rc = upload(h, tasks, &h->d_slvtask); if (rc) return rc; }
@@ -725,12 +736,12 @@ extern "C" int pb200_create_opts(pb200_handle_t **out, const pb200_solver_t *s, 
   std::vector<int> lvl_cblk(C), fill(h->lvl_ptr.begin(), h->lvl_ptr.end() - 1);
   for (int64_t c = 0; c < C; ++c) lvl_cblk[fill[level[c]]++] = (int)c;
 
-  // up_down runs over every cblk on every GPU (factors are gathered after a distributed factorization)
-  { int rc = build_solve_schedule(h, lvl_cblk); if (rc) { pb200_destroy(h); return rc; } }
-
   // ---- multi-GPU: proportional subtree mapping; the factorization schedule keeps the owned cblks only
   h->plan = dist_plan(C, h->h_fblok.data(), h->h_fcblk.data(), h->h_width.data(), h->h_stride.data(), h->h_nrow.data(),
                       h->h_coefind.data(), nranks, factotype == PB200_FACT_LU);
+
+  // up_down runs over every cblk on every GPU (factors are gathered after a distributed factorization)
+  { int rc = build_solve_schedule(h, lvl_cblk); if (rc) { pb200_destroy(h); return rc; } }
   if (nranks > 1) {
     std::vector<int> optr(nl + 1, 0), ocblk;
     std::vector<FanTask> fan, pull;
@@ -950,7 +961,7 @@ extern "C" double pb200_norm1(int flttype, int64_t n, const int64_t *colptr, con
   return -1.0;
 }
 
-static int invert_dispatch(pb200_handle_t *h, cudaStream_t sm);
+static int invert_dispatch(pb200_handle_t *h, cudaStream_t sm, int which = 0);
 static int dist_barrier(pb200_handle_t *h);
 static int ensure_gathered(pb200_handle_t *h);
 // ------------------------------------------------------------------ dispatch helpers
@@ -1018,7 +1029,8 @@ static int gather_t(pb200_handle_t *h) {
     k_pull_panels<T><<<(unsigned)h->pull_tiles, 256, 0, h->stream>>>(h->S, h->peers, (T *)h->dL, (T *)h->dU, h->d_owner, h->d_pull, h->npull);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
-  return dist_check(h);
+  { int rc = dist_check(h); if (rc) return rc; }
+  return invert_dispatch(h, h->stream, 2);   // triangles of the panels that just arrived (ours were inverted at the end of the factorization)
 }
 static int gather_dispatch(pb200_handle_t *h) { DISPATCH_T(h, gather_t, h) }
 static int ensure_gathered(pb200_handle_t *h) {
@@ -1335,6 +1347,9 @@ extern "C" int pb200_factorize(pb200_handle_t *h, double critere, int64_t *nbpiv
     if (!h->inv_ready) rc = invert_dispatch(h, h->stream);   // diagonal triangles inverted once, for the up_down sweeps
     if (rc) return rc;
   } else {
+    // the same preparation of the up_down, for the cblks this GPU owns (N = 1 has all of it inside DPARM_FACT_TIME)
+    rc = invert_dispatch(h, h->stream, 1);
+    if (rc) return rc;
     k_dist_signal<<<1, 32, 0, h->stream>>>(h->d_flags, h->nlevels, h->epoch);   // our share of the factorization is done
     h->gathered = false;
   }
@@ -1394,26 +1409,28 @@ static int invert_range(pb200_handle_t *h, int sp0, int sp1, cudaStream_t sm, in
     k_tri_inverse<T><<<sp1 - sp0, 128, inv_smem<T>(nbmax), sm>>>((const T *)h->dU, h->d_slvtask + sp0, nullptr, (T *)h->d_inv_up, 0, ntri);
   return PB200_SUCCESS;
 }
-// all sub-panels, one launch per size class (the shared memory of a launch fits its widest triangle)
+// sub-panels (which = 0: all, 1: of the cblks this GPU owns, 2: the others), one launch per size class (the shared memory
+// of a launch fits its widest triangle)
 template <class T>
-static int invert_t(pb200_handle_t *h, cudaStream_t sm) {
+static int invert_t(pb200_handle_t *h, cudaStream_t sm, int which) {
   { int rc = inv_attr<T>(h); if (rc) return rc; }
   const int unit_down = (h->facto != PB200_FACT_LLT);
-  for (size_t k = 0; k + 1 < h->inv_cls_ptr.size(); ++k) {
-    const int n = h->inv_cls_ptr[k + 1] - h->inv_cls_ptr[k];
+  const std::vector<int> &ptr = h->inv_cls_ptr[which];
+  for (size_t k = 0; k + 1 < ptr.size(); ++k) {
+    const int n = ptr[k + 1] - ptr[k];
     if (n == 0) continue;
     const int nbmax = std::min(kInvClasses[k], (int)SlvCfg<T>::NB), ntri = nbmax * (nbmax + 1) / 2;
-    const int *ord = h->d_inv_order + h->inv_cls_ptr[k];
+    const int *ord = h->d_inv_order + ptr[k];
     k_tri_inverse<T><<<n, 128, inv_smem<T>(nbmax), sm>>>((const T *)h->dL, h->d_slvtask, ord, (T *)h->d_inv, unit_down, ntri);
     if (h->facto == PB200_FACT_LU)
       k_tri_inverse<T><<<n, 128, inv_smem<T>(nbmax), sm>>>((const T *)h->dU, h->d_slvtask, ord, (T *)h->d_inv_up, 0, ntri);
     h->last_launches += (h->facto == PB200_FACT_LU) ? 2 : 1;
   }
   CK(cudaGetLastError());
-  h->inv_ready = true;
+  if (which != 1) h->inv_ready = true;
   return PB200_SUCCESS;
 }
-static int invert_dispatch(pb200_handle_t *h, cudaStream_t sm) { DISPATCH_T(h, invert_t, h, sm) }
+static int invert_dispatch(pb200_handle_t *h, cudaStream_t sm, int which) { DISPATCH_T(h, invert_t, h, sm, which) }
 
 template <class T, int FACTO>
 static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {

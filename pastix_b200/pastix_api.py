@@ -246,11 +246,13 @@ class Pastix(PastixLib):
 
     def sopalin(self):
         """The GPU numeric phase behind this pastix_data as a `Sopalin` (borrowed handle)."""
-        from .sopalin import Sopalin
+        from .sopalin import Sopalin, SolverMatrix
         h = self.handle()
         if not h:
             raise RuntimeError("no device handle yet: run numfact() first")
-        return Sopalin.from_handle(h, self.prec, self.facto)
+        s = Sopalin.from_handle(h, self.prec, self.facto)
+        s.solver = SolverMatrix.from_dict(self.solver())      # panel shapes for get_cblk
+        return s
 
     def live_entries(self) -> int:
         """Number of SolverMatrix entries the shim's side table holds (this precision's library)."""
