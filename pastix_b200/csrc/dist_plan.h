@@ -31,6 +31,9 @@ struct DistPlan {
   int nranks = 1;
   std::vector<int> owner;          // per cblk
   std::vector<uint32_t> contrib;   // per cblk: bit p set <=> rank p != owner holds a cblk with a blok facing it
+  std::vector<uint32_t> contrib_priv;   // the same, counting only contributors that are NOT shared cblks (fan-out mode:
+                                   // the updates of a shared cblk are computed by the owners of their targets)
+  std::vector<char> shared;        // per cblk: 1 = column block of a shared top separator (candidate set > 1 GPU)
   std::vector<double> load;        // per rank: flops mapped to it
 };
 
@@ -41,6 +44,8 @@ inline DistPlan dist_plan(int64_t C, const int *fblok, const int *fcblk, const i
   P.nranks = nranks;
   P.owner.assign(C, 0);
   P.contrib.assign(C, 0u);
+  P.contrib_priv.assign(C, 0u);
+  P.shared.assign(C, 0);
   P.load.assign(nranks, 0.0);
   std::vector<double> cost(C), sub(C);
   std::vector<int> parent(C, -1);
@@ -103,6 +108,7 @@ inline DistPlan dist_plan(int64_t C, const int *fblok, const int *fcblk, const i
       }
       for (int k : small) subtrees.push_back({k, it.a, it.b});
     }
+    for (const Item &it : shared) P.shared[it.c] = 1;
     std::vector<double> L(nranks, 0.0);
     auto least = [&](int a2, int b2) { int best = a2; for (int p = a2 + 1; p < b2; ++p) if (L[p] < L[best]) best = p; return best; };
     auto place_subtree = [&](const Item &it) {
@@ -157,7 +163,10 @@ inline DistPlan dist_plan(int64_t C, const int *fblok, const int *fcblk, const i
     P.load[P.owner[c]] += cost[c];
     for (int b = fblok[c] + 1; b < fblok[c + 1]; ++b) {
       const int fc = fcblk[b];
-      if (P.owner[fc] != P.owner[c]) P.contrib[fc] |= 1u << P.owner[c];
+      if (P.owner[fc] != P.owner[c]) {
+        P.contrib[fc] |= 1u << P.owner[c];
+        if (!P.shared[c]) P.contrib_priv[fc] |= 1u << P.owner[c];
+      }
     }
   }
   return P;

@@ -132,7 +132,17 @@ struct pb200_handle_s {
   bool local_group = false;               // pb200_attach_local: the peers are handles of THIS process (no IPC mappings, no collective in destroy)
   unsigned int *d_flags = nullptr, *d_dist_err = nullptr;   // flags: [0,nlevels) level ready, [nlevels] factorization done, [nlevels+1] barrier
   unsigned int epoch = 0, bar_epoch = 0;
-  struct DistLevel { int sig = 0; unsigned int wait_mask = 0, late_mask = 0; int task0 = 0, ntasks = 0; long long ntiles = 0; };
+  struct DistLevel {
+    int sig = 0; unsigned int wait_mask = 0, late_mask = 0; int task0 = 0, ntasks = 0; long long ntiles = 0;
+    // fan-out of the shared top separators: psig = this GPU owns a shared cblk of the level whose targets live elsewhere
+    // (publish "panel factored"); fp_* = the shared cblks of the level owned elsewhere whose targets live here (pull)
+    int psig = 0; unsigned int fp_mask = 0; int fp_task0 = 0, fp_ntasks = 0; long long fp_tiles = 0;
+  };
+  std::vector<int> all_level, all_lvl_ptr, all_lvl_cblk, own_lvl_cblk;   // every cblk's level; level lists over all cblks / the owned ones
+  bool fanout = false;                     // multi-GPU tensor path: updates of shared cblks computed by the owners of their targets
+  std::vector<std::vector<int>> foreign;   // per level: shared cblks owned elsewhere that update cblks owned here
+  char *d_fanout = nullptr;                // per cblk: 1 = fan-out source (device copy of plan.shared)
+  FanTask *d_fpull = nullptr;
   cudaStream_t stream_g = nullptr;        // early part of the fan-in gathers (contributors that finished long before the level is due)
   std::vector<cudaEvent_t> gather_ev;     // per level
   std::vector<DistLevel> dist_lvl;
@@ -418,7 +428,7 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
     if (cudaMalloc((void **)&d_rm, nrow * sizeof(RowMap)) != cudaSuccess || cudaMalloc((void **)&d_cm, nrow * sizeof(ColMap)) != cudaSuccess)
       return fail(PB200_ERR_NOMEM, "cudaMalloc(scatter maps) failed");
     h->allocs.push_back(d_rm); h->allocs.push_back(d_cm); h->device_bytes += nrow * (sizeof(RowMap) + sizeof(ColMap));
-    k_build_maps<<<(unsigned)C, 128>>>(h->S, d_bt, d_rb, d_rm, d_cm);
+    k_build_maps<<<(unsigned)C, 128>>>(h->S, d_bt, d_rb, d_rm, d_cm, h->d_owner, h->fanout ? h->d_fanout : nullptr, h->rank);
     CK(cudaGetLastError());
     h->M.rmbase = d_rb; h->M.rm = d_rm; h->M.cm = d_cm;
   }
@@ -488,14 +498,25 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
       if (tiles > 0) h->steps.push_back({2, t0, (int)gemm.size() - t0, tiles, 0, l});
     }
     if (lu && rounds > 1) h->steps.push_back({6, q0, q1 - q0, 0, 0, l});   // complete the diagonal bloks of the multi-round cblks
+    // fan-out (multi-GPU): the shared panels factored here are published; the ones factored elsewhere whose targets
+    // live here are pulled into the local slab (same offsets) and take part in this GPU's update launches below
+    std::vector<int> srcs(lvl_cblk.begin() + q0, lvl_cblk.begin() + q1);
+    if (h->nranks > 1 && h->fanout) {
+      if (h->dist_lvl[l].psig) h->steps.push_back({7, 0, 1, 0, 0, l});
+      if (h->dist_lvl[l].fp_ntasks) {
+        h->steps.push_back({8, 0, 1, 0, 0, l});
+        srcs.insert(srcs.end(), h->foreign[l].begin(), h->foreign[l].end());
+      }
+    }
     // external update: fused GEMM + scatter, in two launches.  U1 = the column tiles that hit cblks of
     // the NEXT level (they gate that level's panel work) stays on the panel stream; U2 = everything else
     // runs on the second stream underneath the next level's diag/trsm chain.
     size_t first_p = level_first_step;
     for (int pass = 0; pass < 2; ++pass) {
       int t0 = (int)gemm.size(); long long tiles = 0;
-      for (int q = q0; q < q1; ++q) {
-        int c = lvl_cblk[q], w = h->h_width[c], ld = h->h_stride[c];
+      for (int c : srcs) {
+        const int w = h->h_width[c], ld = h->h_stride[c];
+        const bool filt = h->nranks > 1 && h->fanout && h->plan.shared[c];   // only the targets this GPU owns
         if (ld <= w) continue;
         int b = h->h_fblok[c] + 1;
         for (int a0 = w; a0 < ld; a0 += TM) {
@@ -510,10 +531,12 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
             if (tn < ntn) {
               int n_lo = w + tn * TN, n_hi = std::min(w + ncols, n_lo + TN);   // panel rows [n_lo, n_hi)
               while (h->h_coefind[cbk] + h->h_nrow[cbk] <= n_lo) ++cbk;
-              bool next = false;
-              for (int bb = cbk; bb < h->h_fblok[c + 1] && h->h_coefind[bb] < n_hi; ++bb)
-                if (level[h->h_fcblk[bb]] == l + 1) { next = true; break; }
-              want = (pass == 0) ? next : !next;
+              bool next = false, mine = !filt;
+              for (int bb = cbk; bb < h->h_fblok[c + 1] && h->h_coefind[bb] < n_hi; ++bb) {
+                if (level[h->h_fcblk[bb]] == l + 1) next = true;
+                if (h->plan.owner[h->h_fcblk[bb]] == h->rank) mine = true;
+              }
+              want = mine && ((pass == 0) ? next : !next);
             }
             if (want && run0 < 0) run0 = tn;
             if (!want && run0 >= 0) {
@@ -632,6 +655,69 @@ static int build_small_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
   return PB200_SUCCESS;
 }
 
+// ------------------------------------------------------------------ multi-GPU: per-level exchange lists
+// Owned cblks of every level, fan-in tasks (owned cblks with remote contributors), what this GPU publishes, and — in
+// fan-out mode — the shared cblks owned elsewhere whose factored panels are pulled to compute the updates of the
+// cblks owned here.  Rebuilt without fan-out when the tensor path turns out not to apply (incomplete factorization).
+static int build_dist_levels(pb200_handle_t *h, bool fanout) {
+  const int nl = h->nlevels, rank = h->rank;
+  const int64_t C = h->cblknbr;
+  const std::vector<int> &level = h->all_level, &lptr = h->all_lvl_ptr, &lcblk = h->all_lvl_cblk;
+  const std::vector<uint32_t> &contrib = fanout ? h->plan.contrib_priv : h->plan.contrib;
+  std::vector<int> optr(nl + 1, 0), ocblk;
+  std::vector<FanTask> fan, pull, fpull;
+  h->dist_lvl.assign(nl, pb200_handle_t::DistLevel());
+  h->foreign.assign(nl, std::vector<int>());
+  h->pull_tiles = 0;
+  for (int l = 0; l < nl; ++l) {
+    auto &D = h->dist_lvl[l];
+    D.task0 = (int)fan.size(); D.fp_task0 = (int)fpull.size();
+    for (int q = lptr[l]; q < lptr[l + 1]; ++q) {
+      const int c = lcblk[q];
+      const int64_t len = h->h_poff[c + 1] - h->h_poff[c];
+      const int nt = (int)((len + PB200_FAN_ELEMS - 1) / PB200_FAN_ELEMS);
+      bool tgt_here = false, tgt_else = false;   // (shared cblks) targets owned by this GPU / by others
+      if (fanout && h->plan.shared[c])
+        for (int b = h->h_fblok[c] + 1; b < h->h_fblok[c + 1]; ++b)
+          (h->plan.owner[h->h_fcblk[b]] == rank ? tgt_here : tgt_else) = true;
+      if (h->plan.owner[c] == rank) {
+        ocblk.push_back(c);
+        if (contrib[c]) {
+          fan.push_back({c, (int)D.ntiles, contrib[c], 0});
+          D.ntiles += nt; D.wait_mask |= contrib[c];
+        }
+        if (tgt_else) D.psig = 1;
+      } else {
+        if ((contrib[c] >> rank) & 1u) D.sig = 1;
+        pull.push_back({c, (int)h->pull_tiles, 0u, 0});
+        h->pull_tiles += nt;
+        if (tgt_here) {
+          h->foreign[l].push_back(c);
+          fpull.push_back({c, (int)D.fp_tiles, 0u, 0});
+          D.fp_tiles += nt; D.fp_mask |= 1u << h->plan.owner[c];
+        }
+      }
+    }
+    D.ntasks = (int)fan.size() - D.task0; D.fp_ntasks = (int)fpull.size() - D.fp_task0;
+    optr[l + 1] = (int)ocblk.size();
+  }
+  // contributors whose last contribution to a level comes from the level just before it (the hand-off on the
+  // critical path); everybody else can be pulled ahead of need
+  for (int64_t k = 0; k < C; ++k) {
+    if (h->plan.owner[k] == rank || (fanout && h->plan.shared[k])) continue;
+    for (int b = h->h_fblok[k] + 1; b < h->h_fblok[k + 1]; ++b) {
+      const int fc = h->h_fcblk[b];
+      if (h->plan.owner[fc] == rank && level[fc] == level[k] + 1) h->dist_lvl[level[fc]].late_mask |= 1u << h->plan.owner[k];
+    }
+  }
+  h->lvl_ptr = optr; h->own_lvl_cblk = ocblk;
+  h->npull = (int)pull.size();
+  { int rc = upload(h, fan, &h->d_fan); if (rc) return rc; }
+  { int rc = upload(h, pull, &h->d_pull); if (rc) return rc; }
+  { int rc = upload(h, fpull, &h->d_fpull); if (rc) return rc; }
+  return PB200_SUCCESS;
+}
+
 static int dist_barrier(pb200_handle_t *h);
 extern "C" int pb200_create(pb200_handle_t **out, const pb200_solver_t *s, int flttype, int factotype, int device) {
   return pb200_create_dist(out, s, flttype, factotype, device, 0, 1);
@@ -743,50 +829,23 @@ extern "C" int pb200_create_opts(pb200_handle_t **out, const pb200_solver_t *s, 
   // up_down runs over every cblk on every GPU (factors are gathered after a distributed factorization)
   { int rc = build_solve_schedule(h, lvl_cblk); if (rc) { pb200_destroy(h); return rc; } }
   if (nranks > 1) {
-    std::vector<int> optr(nl + 1, 0), ocblk;
-    std::vector<FanTask> fan, pull;
-    h->dist_lvl.assign(nl, pb200_handle_t::DistLevel());
-    for (int l = 0; l < nl; ++l) {
-      auto &D = h->dist_lvl[l];
-      D.task0 = (int)fan.size();
-      for (int q = h->lvl_ptr[l]; q < h->lvl_ptr[l + 1]; ++q) {
-        const int c = lvl_cblk[q];
-        const int64_t len = h->h_poff[c + 1] - h->h_poff[c];
-        const int nt = (int)((len + PB200_FAN_ELEMS - 1) / PB200_FAN_ELEMS);
-        if (h->plan.owner[c] == rank) {
-          ocblk.push_back(c);
-          if (h->plan.contrib[c]) {
-            fan.push_back({c, (int)D.ntiles, h->plan.contrib[c], 0});
-            D.ntiles += nt; D.wait_mask |= h->plan.contrib[c];
-          }
-        } else {
-          if ((h->plan.contrib[c] >> rank) & 1u) D.sig = 1;
-          pull.push_back({c, (int)h->pull_tiles, 0u, 0});
-          h->pull_tiles += nt;
-        }
-      }
-      D.ntasks = (int)fan.size() - D.task0;
-      optr[l + 1] = (int)ocblk.size();
-    }
-    // contributors whose last contribution to a level comes from the level just before it (the hand-off on the
-    // critical path); everybody else can be pulled ahead of need
-    for (int64_t k = 0; k < C; ++k) {
-      if (h->plan.owner[k] == rank) continue;
-      for (int b = h->h_fblok[k] + 1; b < h->h_fblok[k + 1]; ++b) {
-        const int fc = h->h_fcblk[b];
-        if (h->plan.owner[fc] == rank && level[fc] == level[k] + 1) h->dist_lvl[level[fc]].late_mask |= 1u << h->plan.owner[k];
-      }
-    }
+    // fan-out applies to the tensor path (double / complex double, direct factorizations); PB200_NO_FANOUT=1 keeps the
+    // owner-computes-everything scheme of round 1 for A/B runs
+    h->fanout = (flttype == PB200_REALDOUBLE || flttype == PB200_COMPLEXDOUBLE) && getenv("PB200_NO_FANOUT") == nullptr;
+    h->all_level = level; h->all_lvl_ptr = h->lvl_ptr; h->all_lvl_cblk = lvl_cblk;
+    int rc = build_dist_levels(h, h->fanout);
+    if (rc) { pb200_destroy(h); return rc; }
+    lvl_cblk = h->own_lvl_cblk;
     CK(cudaStreamCreateWithFlags(&h->stream_g, cudaStreamNonBlocking));
     h->gather_ev.resize(nl);
     for (auto &e : h->gather_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    h->lvl_ptr = optr; lvl_cblk = ocblk;
-    h->npull = (int)pull.size();
-    { int rc = upload(h, fan, &h->d_fan); if (rc) { pb200_destroy(h); return rc; } }
-    { int rc = upload(h, pull, &h->d_pull); if (rc) { pb200_destroy(h); return rc; } }
-    { int rc = upload(h, h->plan.owner, &h->d_owner); if (rc) { pb200_destroy(h); return rc; } }
-    CK(cudaMalloc((void **)&h->d_flags, (size_t)(nl + 2) * sizeof(unsigned int)));
-    CK(cudaMemset(h->d_flags, 0, (size_t)(nl + 2) * sizeof(unsigned int)));
+    { int rc2 = upload(h, h->plan.owner, &h->d_owner); if (rc2) { pb200_destroy(h); return rc2; } }
+    { std::vector<char> sh(h->plan.shared.begin(), h->plan.shared.end());
+      int rc2 = upload(h, sh, &h->d_fanout); if (rc2) { pb200_destroy(h); return rc2; } }
+    // flags: [0, nl) contributions into level l complete, [nl] factorization done, [nl + 1] barrier,
+    //        [nl + 2, 2 nl + 2) shared panels of level l factored (fan-out)
+    CK(cudaMalloc((void **)&h->d_flags, (size_t)(2 * nl + 2) * sizeof(unsigned int)));
+    CK(cudaMemset(h->d_flags, 0, (size_t)(2 * nl + 2) * sizeof(unsigned int)));
     CK(cudaMalloc((void **)&h->d_dist_err, sizeof(unsigned int)));
     CK(cudaMemset(h->d_dist_err, 0, sizeof(unsigned int)));
   }
@@ -853,6 +912,11 @@ extern "C" int pb200_create_opts(pb200_handle_t **out, const pb200_solver_t *s, 
 
   if (flttype == PB200_REALDOUBLE || flttype == PB200_COMPLEXDOUBLE) {
     int rc = build_mma_schedule(h, level, lvl_cblk);
+    if (rc) { pb200_destroy(h); return rc; }
+  }
+  if (!h->use_mma && h->nranks > 1 && h->fanout) {   // generic path: owner computes every update of its cblks
+    h->fanout = false;
+    int rc = build_dist_levels(h, false);
     if (rc) { pb200_destroy(h); return rc; }
   }
   if (!h->use_mma) {
@@ -1026,7 +1090,7 @@ template <class T>
 static int gather_t(pb200_handle_t *h) {
   k_dist_wait<<<1, 32, 0, h->stream>>>(h->peers, (1u << h->nranks) - 1u, h->nlevels, h->epoch, kDistTimeoutNs, h->d_dist_err);
   if (h->npull > 0)
-    k_pull_panels<T><<<(unsigned)h->pull_tiles, 256, 0, h->stream>>>(h->S, h->peers, (T *)h->dL, (T *)h->dU, h->d_owner, h->d_pull, h->npull);
+    k_pull_panels<T><<<(unsigned)h->pull_tiles, 256, 0, h->stream>>>(h->S, h->peers, (T *)h->dL, (T *)h->dU, (T *)nullptr, h->d_owner, h->d_pull, h->npull);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   { int rc = dist_check(h); if (rc) return rc; }
@@ -1193,7 +1257,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   }
   int64_t launches = 0;
   const bool prof = h->prof_on || getenv("PB200_PROFILE") != nullptr;
-  double tkind[7] = {0, 0, 0, 0, 0, 0, 0}; long long nk[7] = {0, 0, 0, 0, 0, 0, 0};
+  double tkind[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; long long nk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double tlevel_max = 0; int lvl_max = -1;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
@@ -1245,6 +1309,15 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
       case 5:
         launches += launch_fanin<T>(h, st.lvl, sm, !serial && getenv("PB200_EARLY_GATHER") != nullptr) - 1;   // opt-in: measured neutral at N=4 (r01)
         break;
+      case 7:   // fan-out: the shared panels of this level are factored (everything launched before on this stream)
+        k_dist_signal<<<1, 32, 0, sm>>>(h->d_flags, h->nlevels + 2 + st.lvl, h->epoch);
+        break;
+      case 8: { // fan-out: pull the shared panels of this level factored elsewhere (and their L*D copies)
+        const auto &D = h->dist_lvl[st.lvl];
+        k_dist_wait<<<1, 32, 0, sm>>>(h->peers, D.fp_mask, h->nlevels + 2 + st.lvl, h->epoch, kDistTimeoutNs, h->d_dist_err);
+        k_pull_panels<T><<<(unsigned)D.fp_tiles, 256, 0, sm>>>(h->S, h->peers, L, U, (T *)h->dW, h->d_owner, h->d_fpull + D.fp_task0, D.fp_ntasks);
+        ++launches;
+      } break;
       case 6:
         if (FACTO == F_LU)
           k_diag_complete_lu<T><<<dim3(8, std::min(st.ntasks, 65535)), dim3(32, 8), 0, sm>>>(h->S, L, U, h->d_lvl_cblk + st.task0, st.ntasks,
@@ -1275,7 +1348,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   }
   if (prof) {
     for (int q = 0; q < 4; ++q) { h->prof_ms[q] = tkind[q]; h->prof_n[q] = nk[q]; }
-    h->prof_ms[3] += tkind[5] + tkind[6]; h->prof_n[3] += nk[5] + nk[6];
+    h->prof_ms[3] += tkind[5] + tkind[6] + tkind[7] + tkind[8]; h->prof_n[3] += nk[5] + nk[6] + nk[7] + nk[8];
     if (getenv("PB200_PROFILE") != nullptr)
     fprintf(stderr, "[pb200 profile] diag %.3f ms (%lld)  trsm %.3f ms (%lld)  ext-update %.3f ms (%lld)  int-update/transpose %.3f ms (%lld)\n",
             tkind[0], nk[0], tkind[1], nk[1], tkind[2], nk[2], tkind[3], nk[3]);
@@ -1809,17 +1882,18 @@ extern "C" int pb200_dist_plan(const pb200_solver_t *s, int factotype, int nrank
   return PB200_SUCCESS;
 }
 
-extern "C" int pb200_ipc_size(void) { return (int)(3 * sizeof(cudaIpcMemHandle_t)); }
+extern "C" int pb200_ipc_size(void) { return (int)(4 * sizeof(cudaIpcMemHandle_t)); }
 
 extern "C" int pb200_ipc_export(pb200_handle_t *h, void *buf) {
   if (!h || !buf) return fail(PB200_ERR_BADARG, "null argument");
   if (h->nranks == 1) return fail(PB200_ERR_STATE, "not a multi-GPU handle");
   CK(cudaSetDevice(h->device));
   cudaIpcMemHandle_t *o = (cudaIpcMemHandle_t *)buf;
-  memset(o, 0, 3 * sizeof(cudaIpcMemHandle_t));
+  memset(o, 0, 4 * sizeof(cudaIpcMemHandle_t));
   CK(cudaIpcGetMemHandle(&o[0], h->dL));
   if (h->dU) CK(cudaIpcGetMemHandle(&o[1], h->dU));
   CK(cudaIpcGetMemHandle(&o[2], h->d_flags));
+  if (h->dW) CK(cudaIpcGetMemHandle(&o[3], h->dW));
   return PB200_SUCCESS;
 }
 
@@ -1831,13 +1905,14 @@ extern "C" int pb200_ipc_attach(pb200_handle_t *h, const void *all_handles) {
   const cudaIpcMemHandle_t *in = (const cudaIpcMemHandle_t *)all_handles;
   h->peers.rank = h->rank; h->peers.nranks = h->nranks;
   for (int p = 0; p < h->nranks; ++p) {
-    if (p == h->rank) { h->peers.L[p] = h->dL; h->peers.U[p] = h->dU; h->peers.flags[p] = h->d_flags; continue; }
+    if (p == h->rank) { h->peers.L[p] = h->dL; h->peers.U[p] = h->dU; h->peers.W[p] = h->dW; h->peers.flags[p] = h->d_flags; continue; }
     void *q = nullptr;
-    CK(cudaIpcOpenMemHandle(&q, in[3 * p + 0], cudaIpcMemLazyEnablePeerAccess)); h->ipc_opened.push_back(q); h->peers.L[p] = q;
-    h->peers.U[p] = nullptr;
-    if (h->dU) { CK(cudaIpcOpenMemHandle(&q, in[3 * p + 1], cudaIpcMemLazyEnablePeerAccess)); h->ipc_opened.push_back(q); h->peers.U[p] = q; }
-    CK(cudaIpcOpenMemHandle(&q, in[3 * p + 2], cudaIpcMemLazyEnablePeerAccess)); h->ipc_opened.push_back(q);
+    CK(cudaIpcOpenMemHandle(&q, in[4 * p + 0], cudaIpcMemLazyEnablePeerAccess)); h->ipc_opened.push_back(q); h->peers.L[p] = q;
+    h->peers.U[p] = nullptr; h->peers.W[p] = nullptr;
+    if (h->dU) { CK(cudaIpcOpenMemHandle(&q, in[4 * p + 1], cudaIpcMemLazyEnablePeerAccess)); h->ipc_opened.push_back(q); h->peers.U[p] = q; }
+    CK(cudaIpcOpenMemHandle(&q, in[4 * p + 2], cudaIpcMemLazyEnablePeerAccess)); h->ipc_opened.push_back(q);
     h->peers.flags[p] = (unsigned int *)q;
+    if (h->dW) { CK(cudaIpcOpenMemHandle(&q, in[4 * p + 3], cudaIpcMemLazyEnablePeerAccess)); h->ipc_opened.push_back(q); h->peers.W[p] = q; }
   }
   h->attached = true;
   return PB200_SUCCESS;
@@ -1870,7 +1945,7 @@ extern "C" int pb200_attach_local(pb200_handle_t **hs, int n) {
   for (int r = 0; r < n; ++r) {
     pb200_handle_t *h = hs[r];
     h->peers.rank = r; h->peers.nranks = n;
-    for (int q = 0; q < n; ++q) { h->peers.L[q] = hs[q]->dL; h->peers.U[q] = hs[q]->dU; h->peers.flags[q] = hs[q]->d_flags; }
+    for (int q = 0; q < n; ++q) { h->peers.L[q] = hs[q]->dL; h->peers.U[q] = hs[q]->dU; h->peers.W[q] = hs[q]->dW; h->peers.flags[q] = hs[q]->d_flags; }
     h->attached = true; h->local_group = true;
   }
   return PB200_SUCCESS;

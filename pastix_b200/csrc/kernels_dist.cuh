@@ -20,6 +20,7 @@ namespace pb200 {
 struct Peers {
   void *L[PB200_MAXRANKS];
   void *U[PB200_MAXRANKS];
+  void *W[PB200_MAXRANKS];      // LDLt / LDLh on the tensor path: the L*D copies beside the panels
   unsigned int *flags[PB200_MAXRANKS];
   int rank, nranks;
 };
@@ -96,9 +97,10 @@ k_fanin_gather(DevSym S, Peers P, T *L, T *U, const FanTask *__restrict__ tasks,
 
 // after the factorization: copy the factored panels of the other GPUs into the local slab so that
 // every GPU can run up_down on its share of the right-hand sides without further exchanges
+// (also the fan-out of a freshly factored shared panel to the GPUs that own its targets: then with the L*D copy W)
 template <class T>
 __global__ void __launch_bounds__(256)
-k_pull_panels(DevSym S, Peers P, T *L, T *U, const int *__restrict__ owner, const FanTask *__restrict__ tasks, int ntasks) {
+k_pull_panels(DevSym S, Peers P, T *L, T *U, T *W, const int *__restrict__ owner, const FanTask *__restrict__ tasks, int ntasks) {
   const int t = find_task(tasks, ntasks, (int)blockIdx.x);
   const FanTask tk = tasks[t];
   const int c = tk.cblk, o = owner[c];
@@ -106,12 +108,14 @@ k_pull_panels(DevSym S, Peers P, T *L, T *U, const int *__restrict__ owner, cons
   const int64_t e0 = (int64_t)(blockIdx.x - tk.tile0) * PB200_FAN_ELEMS;
   const T *pl = reinterpret_cast<const T *>(P.L[o]);
   const T *pu = reinterpret_cast<const T *>(P.U[o]);
+  const T *pw = reinterpret_cast<const T *>(P.W[o]);
 #pragma unroll
   for (int q = 0; q < PB200_FAN_ELEMS / 256; ++q) {
     const int64_t e = e0 + q * 256 + threadIdx.x;
     if (e >= len) break;
     L[base + e] = pl[base + e];
     if (U != nullptr) U[base + e] = pu[base + e];
+    if (W != nullptr) W[base + e] = pw[base + e];
   }
 }
 

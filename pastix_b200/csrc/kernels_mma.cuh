@@ -1021,8 +1021,11 @@ __global__ void k_diag_complete_lu(DevSym S, T *L, T *U, const int *__restrict__
 
 // ---------------------------------------------------------------- static scatter maps
 // one CTA per cblk, threads over its off-diagonal panel rows
+// fan-out (multi-GPU): the updates of a SHARED source cblk are computed by the GPUs owning their targets; on this GPU the
+// columns of such a source that face a cblk owned elsewhere get the "no column" mark (cb = INT_MAX fails every
+// rb >= cb test of the scatter), so a tile only writes what this GPU owns
 __global__ void k_build_maps(DevSym S, const BlokTgt *__restrict__ btgt, const int64_t *__restrict__ rmbase,
-                             RowMap *rm, ColMap *cm) {
+                             RowMap *rm, ColMap *cm, const int *__restrict__ owner, const char *__restrict__ fanout, int rank) {
   const int k = blockIdx.x;
   const int w = S.width[k], ld = S.stride[k], bf = S.fblok[k] + 1, be = S.fblok[k + 1];
   const int64_t base = rmbase[k];
@@ -1032,6 +1035,7 @@ __global__ void k_build_maps(DevSym S, const BlokTgt *__restrict__ btgt, const i
     const BlokTgt bt = btgt[b];
     RowMap r; r.rb = b - bf; r.roff = roff;
     ColMap c; c.ctgt = bt.tgt + (int64_t)roff * bt.tld; c.cb = b - bf; c.cj = bt.cj0 + roff; c.tw = bt.tw; c.tld = bt.tld;
+    if (fanout != nullptr && fanout[k] && owner[bt.fc] != rank) c.cb = 0x7fffffff;
     c.pad0 = c.pad1 = 0;
     rm[base + m - w] = r;
     cm[base + m - w] = c;

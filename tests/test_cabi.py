@@ -115,14 +115,15 @@ def test_flop_model_matches_reference_count():
             continue
         cb = g["cblknbr"]
         tot = 0.0
+        fm, fa = (6.0, 2.0) if g["prec"] in ("c", "z") else (1.0, 1.0)     # complex: 6 per multiply, 2 per add (flops.h:211-271)
         for c in range(cb):
             n = int(g["lcol"][c] - g["fcol"][c] + 1); ld = int(g["stride"][c]); m = ld - n
-            potrf = (n ** 3 / 6 + n ** 2 / 2 + n / 3) + (n ** 3 / 6 - n / 6)           # FMULS+FADDS_POTRF
-            trsm = m * n * (n + 1)                                   # FADDS_TRSM is defined as FMULS_TRMM (flops.h:99-100)
+            potrf = fm * (n ** 3 / 6 + n ** 2 / 2 + n / 3) + fa * (n ** 3 / 6 - n / 6)   # FMULS / FADDS_POTRF
+            trsm = (fm + fa) * m * n * (n + 1) / 2                   # FADDS_TRSM is defined as FMULS_TRMM (flops.h:99-100)
             gemm = 0.0
             for b in range(int(g["bloknum"][c]) + 1, int(g["bloknum"][c + 1])):
                 nk = int(g["lrow"][b] - g["frow"][b] + 1); mk = ld - int(g["coefind"][b])
-                gemm += 2.0 * mk * nk * n
+                gemm += (fm + fa) * mk * nk * n
             tot += potrf + trsm + gemm
         assert abs(tot - g["fact_flops"]) <= 1e-9 * g["fact_flops"], (name, tot, g["fact_flops"])
 
