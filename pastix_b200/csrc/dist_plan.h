@@ -12,10 +12,11 @@
 //   cost(c)    = PaStiX's flop model of the cblk (blend_symbol_cost.c:52-88, 382-430)
 //   candidates = contiguous rank interval, split among the children in proportion to subtree cost
 //   owner(c)   = the only candidate, or (shared cblk) dealt over the interval.
-// Two ways of dealing the shared column blocks (PB200_DIST_CHAIN, read by every rank):
-//   "deal"  (default) every shared cblk on its own, heaviest first to the least-loaded GPU of its interval: best flop
-//           balance, but consecutive cblks of one separator alternate between GPUs, so every level of the top chains is
-//           a hand-off (flag + fan-in pull) between two GPUs;
+// Ways of dealing the shared column blocks (PB200_DIST_CHAIN, read by every rank):
+//   default cyclic in elimination order over the candidate interval (1-D cyclic columns; with the fan-out of factored
+//           panels — engine.cu — the updates of a shared separator are spread over the GPUs that own their targets);
+//   "lpt"   (round 1) every shared cblk on its own, heaviest first to the least-loaded GPU of its interval: best flop
+//           balance of the owner-computes-all scheme;
 //   "group" the chain of shared cblks of one separator (same candidate interval, linked by parent) stays on ONE GPU:
 //           hand-offs only where the elimination tree branches, at the price of a coarser flop balance.
 #pragma once
@@ -64,7 +65,58 @@ inline DistPlan dist_plan(int64_t C, const int *fblok, const int *fcblk, const i
   child.resize(cptr[C]);
   { std::vector<int> fill(cptr.begin(), cptr.end() - 1);
     for (int64_t c = 0; c < C; ++c) if (parent[c] >= 0) child[fill[parent[c]]++] = (int)c; }
-  if (nranks > 1) {
+  const char *mode0 = getenv("PB200_DIST_CHAIN");
+  if (nranks > 1 && (mode0 == nullptr || !strcmp(mode0, "cyclic"))) {
+    // Default mapping (round 2).  The elimination tree over cblks is far from the balanced binary tree of the nested
+    // dissection: a separator split into 120-column cblks is a CHAIN, and sibling separators hang at different depths
+    // (C3: a 124-cblk top chain over subtrees of 0.53 / 0.16 / 0.16 of the flops).  Candidate intervals in proportion
+    // to cost then leave one GPU with 0.50 and the other with 0.32 of private work.  Instead: keep a set of private
+    // subtrees, place them heaviest-first on the least-loaded GPU (LPT), and while the private loads differ by more
+    // than PB200_DIST_EPS (default 6 %) of a fair share, open the heaviest subtree — its root cblk becomes SHARED, its
+    // children become subtrees.  Shared cblks are dealt cyclically over all GPUs in elimination order (1-D cyclic
+    // columns of the dense top); with the fan-out of factored panels (engine.cu) their updates are computed by the
+    // owners of the targets, so chain and update work of every top separator are spread over all GPUs.
+    double total = 0;
+    for (int64_t c = 0; c < C; ++c) if (parent[c] < 0) total += sub[c];
+    double eps = 0.06;
+    if (const char *e = getenv("PB200_DIST_EPS")) eps = atof(e);
+    std::vector<int> items;
+    for (int64_t c = 0; c < C; ++c) if (parent[c] < 0) items.push_back((int)c);
+    std::vector<int> shared_list;
+    std::vector<double> L(nranks, 0.0);
+    std::vector<int> where;
+    auto by_cost = [&](int x, int y) { return sub[x] != sub[y] ? sub[x] > sub[y] : x < y; };
+    for (;;) {
+      std::sort(items.begin(), items.end(), by_cost);
+      std::fill(L.begin(), L.end(), 0.0);
+      where.assign(items.size(), 0);
+      for (size_t i = 0; i < items.size(); ++i) {
+        int best = 0;
+        for (int p = 1; p < nranks; ++p) if (L[p] < L[best]) best = p;
+        where[i] = best; L[best] += sub[items[i]];
+      }
+      const double mx = *std::max_element(L.begin(), L.end()), mn = *std::min_element(L.begin(), L.end());
+      if (items.empty() || mx - mn <= eps * total / nranks) break;
+      const int k = items[0];                       // heaviest
+      if (cptr[k + 1] == cptr[k]) break;            // a leaf cblk: nothing left to open
+      shared_list.push_back(k);
+      items.erase(items.begin());
+      for (int q = cptr[k]; q < cptr[k + 1]; ++q) items.push_back(child[q]);
+    }
+    for (size_t i = 0; i < items.size(); ++i) {
+      std::vector<int> st2{items[i]};
+      while (!st2.empty()) {
+        const int c = st2.back(); st2.pop_back();
+        P.owner[c] = where[i];
+        for (int q = cptr[c]; q < cptr[c + 1]; ++q) st2.push_back(child[q]);
+      }
+    }
+    std::sort(shared_list.begin(), shared_list.end());
+    int nx = 0;
+    for (int p = 1; p < nranks; ++p) if (L[p] < L[nx]) nx = p;
+    for (int k : shared_list) { P.shared[k] = 1; P.owner[k] = nx; nx = (nx + 1) % nranks; }
+  } else if (nranks > 1) {
+    // Legacy mappings of round 1 (PB200_DIST_CHAIN=lpt|group).
     // Pass 1 (top-down): a subtree heavier than one GPU's fair share stays shared over a candidate interval
     // (several such children split the interval in proportion to their cost); lighter subtrees become
     // single-GPU subtrees, placed in pass 2.  Pass 2: subtrees, heaviest first, go to the least-loaded GPU
@@ -72,7 +124,13 @@ inline DistPlan dist_plan(int64_t C, const int *fblok, const int *fcblk, const i
     // of the flops, so they level what the subtrees left uneven.
     double total = 0;
     for (int64_t c = 0; c < C; ++c) if (parent[c] < 0) total += sub[c];
-    const double fair = total / nranks;
+    // A subtree is split over several GPUs only when it is heavier than a fair share by more than a tolerance
+    // (PB200_DIST_TOL, default 0: measured on C3, whose cblk tree is 0.53 / 0.16 / 0.16 under a 124-cblk top chain, splitting wins): the halves of a nested dissection are never exactly equal (100 = 50 + 49 + 1
+    // planes), and splitting the slightly heavier one shares its whole top separator chain between the GPUs — a
+    // serial chain of hand-offs (measured, C3 on 2 GPUs: 91 such levels) — to correct a 2 % imbalance.
+    double tolv = 0.0;
+    if (const char *e = getenv("PB200_DIST_TOL")) tolv = atof(e);
+    const double fair = (total / nranks) * (1.0 + tolv);
     struct Item { int c, a, b; };
     std::vector<Item> stack, subtrees, shared;
     {
@@ -152,15 +210,42 @@ inline DistPlan dist_plan(int64_t C, const int *fblok, const int *fcblk, const i
     }
     std::sort(subtrees.begin(), subtrees.end(), [&](const Item &x, const Item &y) { return sub[x.c] != sub[y.c] ? sub[x.c] > sub[y.c] : x.c < y.c; });
     for (const Item &it : subtrees) place_subtree(it);
-    std::sort(shared.begin(), shared.end(), [&](const Item &x, const Item &y) { return cost[x.c] != cost[y.c] ? cost[x.c] > cost[y.c] : x.c < y.c; });
-    for (const Item &it : shared) {
-      const int p = least(it.a, it.b);
-      L[p] += cost[it.c];
-      P.owner[it.c] = p;
+    if (mode && !strcmp(mode, "lpt")) {
+      // round 1: heaviest first to the least-loaded GPU of the interval (best flop balance of the owner-computes
+      // scheme; a whole separator chain may land on the one GPU that was behind)
+      std::sort(shared.begin(), shared.end(), [&](const Item &x, const Item &y) { return cost[x.c] != cost[y.c] ? cost[x.c] > cost[y.c] : x.c < y.c; });
+      for (const Item &it : shared) {
+        const int p = least(it.a, it.b);
+        L[p] += cost[it.c];
+        P.owner[it.c] = p;
+      }
+    } else {
+      // default: the shared cblks of every candidate interval are dealt CYCLICALLY in elimination order, starting at
+      // the least-loaded GPU — the 1-D cyclic column distribution of a dense factorization.  With the fan-out of the
+      // factored panels every GPU then updates the cblks it owns, so both the panel chain and the update work of a
+      // top separator are spread evenly, level after level.
+      std::sort(shared.begin(), shared.end(), [](const Item &x, const Item &y) { return x.c < y.c; });
+      std::vector<int> next((size_t)nranks * (nranks + 1), -1);
+      for (const Item &it : shared) {
+        int &nx = next[(size_t)it.a * (nranks + 1) + it.b];
+        if (nx < 0) nx = least(it.a, it.b);
+        const int p = nx;
+        nx = (nx + 1 - it.a) % (it.b - it.a) + it.a;
+        L[p] += cost[it.c];
+        P.owner[it.c] = p;
+      }
     }
   }
   for (int64_t c = 0; c < C; ++c) {
-    P.load[P.owner[c]] += cost[c];
+    // flops mapped to each GPU: a private cblk costs its owner everything; a shared one costs its owner the panel
+    // (diagonal block + TRSM) and the owners of its targets their updates (fan-out)
+    if (!P.shared[c]) P.load[P.owner[c]] += cost[c];
+    else {
+      const double w = width[c], m = stride[c] - width[c], f = lu ? 2.0 : 1.0;
+      P.load[P.owner[c]] += f * (w * w * w / 3.0 + m * w * w);
+      for (int b = fblok[c] + 1; b < fblok[c + 1]; ++b)
+        P.load[P.owner[fcblk[b]]] += f * 2.0 * (double)(stride[c] - coefind[b]) * nrow[b] * w;
+    }
     for (int b = fblok[c] + 1; b < fblok[c + 1]; ++b) {
       const int fc = fcblk[b];
       if (P.owner[fc] != P.owner[c]) {
