@@ -117,6 +117,7 @@ struct pb200_handle_s {
   double gemm_flops = 0;                 // algorithmic flops of the fused GEMM+scatter launches (PaStiX's GEMM term)
   cudaStream_t stream_u = nullptr;       // second stream: the bulk of the fused GEMM+scatter updates
   std::vector<cudaEvent_t> sched_ev;     // [l] panel(l) done, [nlevels + l] bulk update of level l done
+  std::vector<cudaEvent_t> tl_ev;        // PB200_TIMELINE: timed copies of the same points
   std::vector<int> h_gemm_modes;
   std::vector<void *> allocs;
   // ---- small-supernode path of the generic factorization (kernels_small.cuh)
@@ -524,6 +525,39 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
           while (h->h_coefind[b] + h->h_nrow[b] <= imax) ++b;   // blok holding the last row of this tile
           int ncols = h->h_coefind[b] + h->h_nrow[b] - w;
           int ntn = (ncols + TN - 1) / TN;
+          if (filt) {
+            // fan-out source: the column tiles are cut along the ownership of the facing cblks (maximal runs of
+            // consecutive bloks facing cblks owned here), so that no tile is computed on two GPUs
+            const int bend = h->h_fblok[c + 1], cend = w + ncols;
+            for (int bb = h->h_fblok[c] + 1; bb < bend && h->h_coefind[bb] < cend;) {
+              if (h->plan.owner[h->h_fcblk[bb]] != h->rank) { ++bb; continue; }
+              int be = bb;
+              while (be + 1 < bend && h->h_coefind[be + 1] < cend && h->plan.owner[h->h_fcblk[be + 1]] == h->rank) ++be;
+              const int s0 = h->h_coefind[bb], s1 = std::min(cend, h->h_coefind[be] + h->h_nrow[be]);
+              const int nts = (s1 - s0 + TN - 1) / TN;
+              int run0 = -1, cbk = bb;
+              for (int tn = 0; tn <= nts; ++tn) {
+                bool want = false;
+                if (tn < nts) {
+                  const int n_lo = s0 + tn * TN, n_hi = std::min(s1, n_lo + TN);
+                  while (h->h_coefind[cbk] + h->h_nrow[cbk] <= n_lo) ++cbk;
+                  bool next = false;
+                  for (int q = cbk; q <= be && h->h_coefind[q] < n_hi; ++q)
+                    if (level[h->h_fcblk[q]] == l + 1) next = true;
+                  want = (pass == 0) ? next : !next;
+                }
+                if (want && run0 < 0) run0 = tn;
+                if (!want && run0 >= 0) {
+                  const int rn = tn - run0;
+                  const int br0 = s0 + run0 * TN, br1 = std::min(s1, br0 + rn * TN);
+                  gemm.push_back({c, (int)tiles, rn, a0, ld, br0, br1, 0, w, 0, b, 0});
+                  tiles += rn; run0 = -1;
+                }
+              }
+              bb = be + 1;
+            }
+            continue;
+          }
           // classify the column tiles, emit maximal runs of the wanted class
           int run0 = -1, cbk = h->h_fblok[c] + 1;
           for (int tn = 0; tn <= ntn; ++tn) {
@@ -1262,7 +1296,8 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
   const bool serial = prof || getenv("PB200_SERIAL") != nullptr;
-  const bool diag_old = getenv("PB200_DIAG_OLD") != nullptr;   // A/B switch: the one-barrier-per-pivot kernel of round 1
+  const bool diag_old = getenv("PB200_DIAG_OLD") != nullptr;
+  const bool timeline = !serial && getenv("PB200_TIMELINE") != nullptr;   // A/B switch: the one-barrier-per-pivot kernel of round 1
   const bool overlap_inv = !serial && h->nranks == 1 && getenv("PB200_INV_OVERLAP") != nullptr;   // opt-in: measured slower (r01)
   // The schedule is a fixed sequence of launches on two streams joined by events: capture it once (per threshold value,
   // which is a by-value kernel argument) and replay it — kernel-to-kernel dependencies then resolve on the device
@@ -1326,6 +1361,10 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
     }
     ++launches;
     if (!serial && st.rec_ev >= 0) CK(cudaEventRecord(h->sched_ev[st.rec_ev], sm));
+    if (timeline && st.rec_ev >= 0) {   // dev aid: when the panel work (rec_ev < nlevels) / the bulk update of a level finished
+      if (h->tl_ev.size() != 2 * (size_t)h->nlevels) { h->tl_ev.resize(2 * (size_t)h->nlevels, nullptr); for (auto &e : h->tl_ev) cudaEventCreate(&e); }
+      cudaEventRecord(h->tl_ev[st.rec_ev], sm);
+    }
     if (overlap_inv && st.rec_ev >= 0 && st.rec_ev < h->nlevels) {
       // panel(l) is final: invert its diagonal triangles (up_down preparation) underneath the rest
       const int l = st.rec_ev;
@@ -1430,6 +1469,16 @@ extern "C" int pb200_factorize(pb200_handle_t *h, double critere, int64_t *nbpiv
   CK(cudaStreamSynchronize(h->stream));
   if (h->nranks > 1) { rc = dist_check(h); if (rc) return rc; }
   float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (!h->tl_ev.empty() && getenv("PB200_TIMELINE") != nullptr) {
+    if (h->stream_u) cudaStreamSynchronize(h->stream_u);
+    for (int l = 0; l < h->nlevels; ++l) {
+      float tp = -1.f, tu = -1.f;
+      if (cudaEventQuery(h->tl_ev[l]) == cudaSuccess) cudaEventElapsedTime(&tp, h->ev0, h->tl_ev[l]);
+      if (cudaEventQuery(h->tl_ev[h->nlevels + l]) == cudaSuccess) cudaEventElapsedTime(&tu, h->ev0, h->tl_ev[h->nlevels + l]);
+      fprintf(stderr, "[pb200 timeline] rank %d lvl %3d panel+U1 done %9.3f ms   bulk update done %9.3f ms\n", h->rank, l, tp, tu);
+    }
+    (void)cudaGetLastError();
+  }
   unsigned long long nb = 0;
   CK(cudaMemcpy(&nb, h->d_cnt, sizeof(nb), cudaMemcpyDeviceToHost));
   if (nbpivot) *nbpivot = (int64_t)nb;

@@ -33,6 +33,10 @@ for it in range(3):
         s.reassemble()
     s.factorize(crit)
     print(f"[rank {r}] plain run {it}: {s.fact_time * 1e3:.2f} ms", file=sys.stderr, flush=True)
+os.environ["PB200_TIMELINE"] = "1"
+s.reassemble(); s.factorize(crit)
+print(f"[rank {r}] timeline run: {s.fact_time * 1e3:.2f} ms", file=sys.stderr, flush=True)
+del os.environ["PB200_TIMELINE"]
 os.environ["PB200_PROFILE"] = "1"; os.environ["PB200_PROFILE_VERBOSE"] = "1"
 s.reassemble(); s.factorize(crit)
 print(f"[rank {r}] serialised run: {s.fact_time * 1e3:.2f} ms", file=sys.stderr, flush=True)
