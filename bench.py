@@ -279,12 +279,16 @@ def reference_arm(args):
         return None
     cores = os.cpu_count() or 1
     desc, kind, N, prec, facto, nrhs, over = WORKLOADS[args.workload]
-    r = run_reference_fact(args.workload, cores, args.steps, args.warmup, float(os.environ.get("PB200_REF_BUDGET_S", "240")))
+    # a step = the workload's numeric factorization when that runs in seconds on the host cores (c1, c2, c4s, c5s), else the
+    # same problem on a smaller grid (a bounded sample: GFLOP/s is the metric) — the arm must end within minutes
+    Ns, what = bounded_sample(args.workload)
+    r = run_reference_fact(args.workload, cores, args.steps, min(args.warmup, 1), float(os.environ.get("PB200_REF_BUDGET_S", "150")),
+                           N_override=Ns)
     if r is None:
         return {"impl": "reference", "unavailable": "oracle/_ref (the reference compiled from /root/reference) is not present"}
     gf = r["flops"] / r["fact_s"] / 1e9
     unit = "GFLOP/s"
-    sample = f"full numeric factorization of the workload, {r['steps_run']} timed step(s) (DPARM_FACT_TIME)"
+    sample = f"{what}, {r['steps_run']} timed step(s) (DPARM_FACT_TIME)"
     return {
         "impl": "reference", "metric": "numeric factorization throughput (PaStiX flop count)", "value": gf, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "steps_run": r["steps_run"], "warmup": args.warmup,
@@ -475,18 +479,18 @@ def our_arm_dist(args):
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     cpu_group = dist.new_group(backend="gloo")       # waits that must not occupy a GPU
     ctx = dict(torch=torch, dist=dist, rank=rank, world=world, local=local, cpu_group=cpu_group)
-    line = dist_case(args, args.workload, args.steps, args.warmup, ctx)
-    if args.workload == "c2" and not args.iparm and os.environ.get("PB200_ALSO", "1") != "0":
-        # the north_star target config beside the headline one, at the same N
+    line = dist_case(args, args.workload, args.steps if args.workload != "c3" else min(args.steps, 3), args.warmup, ctx)
+    if args.default_workload and not args.iparm and os.environ.get("PB200_ALSO", "1") != "0":
+        # the configuration the N = 1 line is quoted on, at the same N
         try:
-            l3 = dist_case(args, "c3", min(args.steps, 3), 3, ctx)
-            if line is not None and l3 is not None:
-                line["also"] = {"c3": {k: l3[k] for k in ("value", "unit", "fact_ms", "solve_ms_per_rhs", "backward_error", "ms_per_step",
-                                                         "gpu_launches", "e2e", "factor_relerr_vs_n1", "load_share", "device_bytes_per_gpu")}}
-                line["also"]["c3"]["workload"] = l3["config"]["workload"]
+            l2 = dist_case(args, "c2", args.steps, args.warmup, ctx)
+            if line is not None and l2 is not None:
+                line["also"] = {"c2": {k: l2[k] for k in ("value", "unit", "fact_ms", "solve_ms_per_rhs", "backward_error", "ms_per_step",
+                                                         "gpu_launches", "e2e", "factor_relerr_vs_n1", "n1_same_run", "load_share", "device_bytes_per_gpu")}}
+                line["also"]["c2"]["workload"] = l2["config"]["workload"]
         except Exception as e:
             if line is not None:
-                line["also"] = {"c3": {"error": repr(e)}}
+                line["also"] = {"c2": {"error": repr(e)}}
     dist.barrier(group=cpu_group)
     dist.destroy_process_group()
     return line
@@ -552,13 +556,18 @@ def dist_case(args, workload, steps, warmup, ctx):
     xs = unpermute_solution(xh.T if xh.ndim == 2 else xh.reshape(n, 1), permtab)
     berr_dev = float(np.linalg.norm(Af @ xs.reshape(n, -1) - b) / np.linalg.norm(b))
     # ---- the same factors as one GPU computes: sampled cblks of this run against a single-GPU factorization
-    rel_n1 = None
+    rel_n1 = None; n1_same_run = None
     if rank == 0 and 2.2 * s.device_bytes > 170e9:
         rel_n1 = "skipped: a second, single-GPU copy of the factors does not fit beside this rank's slab"
     elif rank == 0:
         try:
             s1 = Sopalin(solver, prec, facto, device=local)
             s1.assemble(csc["colptr"], csc["rows"], csc["values"], csc["tvalues"]); s1.factorize(crit)
+            t1 = []
+            for _ in range(2):
+                s1.reassemble(); s1.factorize(crit); t1.append(s1.fact_time)
+            n1_same_run = {"fact_ms": min(t1) * 1e3, "value": flops / min(t1) / 1e9, "unit": "GFLOP/s",
+                           "what": "the same factorization on ONE of these GPUs (rank 0), same process, same run"}
             num, den = 0.0, 1e-300
             for c in sample_cblks(solver["cblknbr"]):
                 w = int(solver["lcolnum"][c] - solver["fcolnum"][c] + 1)
@@ -613,10 +622,21 @@ def dist_case(args, workload, steps, warmup, ctx):
             "load_share": [float(v) for v in load / load.sum()], "device_bytes_per_gpu": dev_bytes,
             "fact_ms": fact_mean * 1e3, "solve_ms_per_rhs": solve_mean * 1e3 / nrhs, "backward_error": berr_dev,
             "fact_ms_covers": "numeric factorization + inversion of the diagonal triangles of the owned cblks (what N = 1 times)",
-            "factor_relerr_vs_n1": rel_n1,
+            "factor_relerr_vs_n1": rel_n1, "n1_same_run": n1_same_run,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None, "clocks": clocks, "analysis_s": t_analysis,
         }
     return line
+
+
+def bounded_sample(workload: str):
+    """(grid size override or None, description) of what the CPU arm factorizes for this workload."""
+    if workload == "c3":
+        return 64, "same 27-point LDLt problem on a 64^3 grid (bounded sample of the 100^3 workload)"
+    if workload in ("c4", "c4s"):
+        return 32, "same complex LU problem on a 32^3 grid (bounded sample)"
+    if workload == "c5":
+        return 64, "same ILU(2) problem on a 64^3 grid (bounded sample)"
+    return None, "the full workload's numeric factorization"
 
 
 def cpu_baseline_for(args, gpu=None, x_gpu=None):
@@ -626,14 +646,8 @@ def cpu_baseline_for(args, gpu=None, x_gpu=None):
     cores = os.cpu_count() or 1
     desc, kind, N, prec, facto, nrhs, over = WORKLOADS[args.workload]
     # bounded sample: the full workload when it is <= ~1e12 flop, else the same stencil on a smaller grid
-    Ns = None
-    sample = "the full workload's numeric factorization, one run"
-    if args.workload == "c3":
-        Ns = 64; sample = "same 27-point LDLt problem on a 64^3 grid (bounded sample), one run"
-    elif args.workload in ("c4", "c4s"):
-        Ns = 32; sample = "same complex LU problem on a 32^3 grid (bounded sample), one run"
-    elif args.workload == "c5":
-        Ns = 64; sample = "same ILU(2) problem on a 64^3 grid (bounded sample), one run"
+    Ns, sample = bounded_sample(args.workload)
+    sample += ", one run"
     try:
         r = run_reference_fact(args.workload, cores, 1, 0, 120.0, N_override=Ns)
     except Exception as e:  # pragma: no cover
@@ -675,12 +689,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=os.environ.get("PB200_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("PB200_WORKLOAD"), choices=sorted(WORKLOADS),
+                    help="default: c2 (BASELINE.json configs[1], the configuration the metric is quoted on) at --gpus 1; "
+                         "c3 (configs[2], 100^3 27-point LDLt 'on 1 and 8 B200') when ONE factorization is spread over "
+                         "N > 1 GPUs — C2 holds 0.43 TFLOP, 23 ms on one GPU, nothing to spread; the other one rides in `also`")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--iparm", action="append", default=[], metavar="IPARM_NAME=VALUE",
                     help="extra iparm override for the analysis (e.g. IPARM_MAX_BLOCKSIZE=240); applied to both arms")
     args = ap.parse_args()
+    args.default_workload = args.workload is None
+    if args.workload is None:
+        args.workload = "c2" if args.gpus == 1 else "c3"
     if args.iparm:
         d, k, N, p, f, nr, over = WORKLOADS[args.workload]
         over = dict(over)
@@ -706,7 +726,7 @@ def main():
         if line is not None:
             line.setdefault("cpu_baseline", None)
     # the north_star target config beside the headline one (N=1 default run only): C3 = 100^3 27-point LDLt
-    if (args.impl == "ours" and line is not None and args.gpus == 1 and args.workload == "c2" and not args.iparm
+    if (args.impl == "ours" and line is not None and args.gpus == 1 and args.workload == "c2" and args.default_workload and not args.iparm
             and os.environ.get("PB200_ALSO", "1") != "0"):
         try:
             a2 = argparse.Namespace(**vars(args)); a2.workload = "c3"; a2.steps = min(args.steps, 3)

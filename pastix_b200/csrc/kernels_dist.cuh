@@ -108,14 +108,17 @@ k_pull_panels(DevSym S, Peers P, T *L, T *U, T *W, const int *__restrict__ owner
   const int64_t e0 = (int64_t)(blockIdx.x - tk.tile0) * PB200_FAN_ELEMS;
   const T *pl = reinterpret_cast<const T *>(P.L[o]);
   const T *pu = reinterpret_cast<const T *>(P.U[o]);
-  const T *pw = reinterpret_cast<const T *>(P.W[o]);
+  const int ld = S.stride[c];
 #pragma unroll
   for (int q = 0; q < PB200_FAN_ELEMS / 256; ++q) {
     const int64_t e = e0 + q * 256 + threadIdx.x;
     if (e >= len) break;
-    L[base + e] = pl[base + e];
+    const T l = pl[base + e];
+    L[base + e] = l;
     if (U != nullptr) U[base + e] = pu[base + e];
-    if (W != nullptr) W[base + e] = pw[base + e];
+    // LDLt / LDLh: the L*D copy is rebuilt here from the pulled column and its pivot (one more peer load per element,
+    // broadcast over the column) instead of crossing NVLink a second time
+    if (W != nullptr) { const int64_t j = e / ld; W[base + e] = l * pl[base + j * (int64_t)(ld + 1)]; }
   }
 }
 
