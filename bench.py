@@ -39,6 +39,8 @@ WORKLOADS = {
     "c1": ("1-D Laplacian n=100 LLt double (example/bin/simple -lap 100)", "lap1d", 100, "d", "llt", 1, {}),
     "c2": ("3-D 7-point Laplacian 64^3 (n=262144) LLt double, nested dissection", "lap7", 64, "d", "llt", 1, {}),
     "c3": ("3-D 27-point Laplacian 100^3 (n=1000000) LDLt double, nested dissection", "lap27", 100, "d", "ldlt", 1, {}),
+    "c2s": ("3-D 7-point Laplacian 64^3 (n=262144) LLt SINGLE precision, nested dissection", "lap7", 64, "s", "llt", 1, {}),
+    "c3s": ("3-D 27-point Laplacian 100^3 (n=1000000) LDLt SINGLE precision, nested dissection", "lap27", 100, "s", "ldlt", 1, {}),
     "c4s": ("complex-double convection-diffusion 64^3 LU static pivoting (config 4 at single-GPU size)", "cd", 64, "z", "lu", 1, {}),
     "c4": ("complex-double convection-diffusion 128^3 LU static pivoting", "cd", 128, "z", "lu", 1, {}),
     "c5s": ("blockwise ILU(2) + 64-RHS solve, 3-D 7-point Laplacian 64^3", "lap7", 64, "d", "llt", 64,
@@ -146,6 +148,37 @@ def measure_fp64_peak(device: int) -> dict:
     out["cublas_dgemm_tflops"] = 2.0 * n ** 3 / best / 1e9
     out["peak_tflops"] = max(out["dmma_probe_tflops"], out["cublas_dgemm_tflops"])
     out["source"] = "measured live in bench.py (max of own DMMA probe and cuBLAS DGEMM 8192^3 burst); MEASURED_PEAKS.json has no FP64 figure"
+    return out
+
+
+def measure_fp32_peak(device: int) -> dict:
+    """Single-precision roofs, measured live: cuBLAS SGEMM 8192^3 in true FP32 (the SGEMM-class roof the s / c path is
+    held against) and with TF32 tensor cores allowed (our kernels issue THREE tf32 MMAs per FP32 product — 3xTF32 —
+    so a third of that figure is their tensor-pipe ceiling)."""
+    import torch
+    n = 8192
+    a = torch.randn(n, n, device=f"cuda:{device}", dtype=torch.float32)
+    b = torch.randn(n, n, device=f"cuda:{device}", dtype=torch.float32)
+    out = {}
+    old = torch.backends.cuda.matmul.allow_tf32
+    for name, tf in (("cublas_sgemm_fp32_tflops", False), ("cublas_sgemm_tf32_tflops", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf
+        for _ in range(2):
+            c = a @ b
+        torch.cuda.synchronize(device)
+        best = 1e30
+        for _ in range(3):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); c = a @ b; e1.record(); torch.cuda.synchronize(device)
+            best = min(best, e0.elapsed_time(e1))
+        out[name] = 2.0 * n ** 3 / best / 1e9
+    torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b, c
+    torch.cuda.empty_cache()
+    out["tf32_over_3_tflops"] = out["cublas_sgemm_tf32_tflops"] / 3.0
+    out["peak_tflops"] = out["cublas_sgemm_fp32_tflops"]
+    out["source"] = ("measured live in bench.py: cuBLAS SGEMM 8192^3 burst in true FP32 (allow_tf32 = False); the TF32 figure / 3 is "
+                     "the ceiling of the 3xTF32 tensor path")
     return out
 
 
@@ -412,16 +445,16 @@ def our_arm(args, with_cpu_baseline: bool = False):
         prof = s.get_profile()
         s.set_profile(False)
         s.reassemble(); s.factorize(crit)
-        peak = measure_fp64_peak(local)
+        peak = measure_fp64_peak(local) if prec in ("d", "z") else measure_fp32_peak(local)
         gms = prof["ms"]["gemm_scatter"]
         tot = sum(prof["ms"].values())
         ach = prof["gemm_flops"] / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         traf = ncu_traffic(args.workload)
-        roof = {"kernel": "k_gemm_scatter (fused DMMA GEMM + scatter-add into facing cblks)", "bound": "tensor",
+        roof = {"kernel": "k_gemm_scatter (fused %s GEMM + scatter-add into facing cblks)" % ("DMMA" if prec in ("d", "z") else "3xTF32 MMA"), "bound": "tensor",
                 "achieved": ach, "peak": peak["peak_tflops"], "unit": "TFLOP/s", "frac": ach / peak["peak_tflops"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (the largest one captured by ncu --set full;
                 # which launch, its duration and pipe utilisation are in traffic_capture)
-                "traffic": traf["dram_bytes"] if traf else None, "traffic_capture": traf, "peak_source": peak["source"], "fp64_peaks": {k: v for k, v in peak.items() if k.endswith("tflops")},
+                "traffic": traf["dram_bytes"] if traf else None, "traffic_capture": traf, "peak_source": peak["source"], "measured_peaks": {k: v for k, v in peak.items() if k.endswith("tflops")},
                 "kernel_share_of_step": gms / tot if tot > 0 else None,
                 "kind_ms_serialised": prof["ms"], "kind_launches": prof["launches"],
                 "algorithmic_flops_per_factorization": prof["gemm_flops"]}
@@ -443,7 +476,7 @@ def our_arm(args, with_cpu_baseline: bool = False):
                         "factor_slab_GB": s.coefnbr * ESIZE[prec] * (2 if facto == "lu" else 1) / 1e9},
             "fact_ms": fact_mean * 1e3, "assemble_ms": float(np.mean(asm_s)) * 1e3,
             "solve_ms_per_rhs": solve_mean * 1e3 / nrhs,
-            "pct_fp64_peak": 100.0 * (flops / fact_mean / 1e12) / roof["peak"],
+            ("pct_fp64_peak" if prec in ("d", "z") else "pct_fp32_sgemm_peak"): 100.0 * (flops / fact_mean / 1e12) / roof["peak"],
             "backward_error": berr_dev,
             "e2e": {"value": world * flops / e2e_fact_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "numfact_call_ms": e2e_fact_s * 1e3, "solve_call_ms": e2e_solve_s * 1e3,

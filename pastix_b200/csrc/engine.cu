@@ -382,11 +382,14 @@ static int build_solve_schedule(pb200_handle_t *h, const std::vector<int> &lvl_c
 // Levels of the elimination tree; inside a level, cblks wider than NBMAX are walked sub-panel by
 // sub-panel ("rounds"): diag -> trsm -> internal update; then one fused GEMM+scatter launch for the level.
 static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, const std::vector<int> &lvl_cblk) {
-  const bool cx = (h->flt == PB200_COMPLEXDOUBLE);
+  const bool cx = (h->flt == PB200_COMPLEXDOUBLE || h->flt == PB200_COMPLEXSINGLE);
   const bool lu = (h->facto == PB200_FACT_LU);
-  const int NBMAX = cx ? SubCfg<cdouble>::NBMAX : SubCfg<double>::NBMAX;
-  const int TM = cx ? UpdCfg<cdouble>::TM : UpdCfg<double>::TM;
-  const int TN = cx ? UpdCfg<cdouble>::TN : UpdCfg<double>::TN;
+  const int NBMAX = h->flt == PB200_REALDOUBLE ? SubCfg<double>::NBMAX : h->flt == PB200_COMPLEXDOUBLE ? SubCfg<cdouble>::NBMAX
+                  : h->flt == PB200_REALSINGLE ? SubCfg<float>::NBMAX : SubCfg<cfloat>::NBMAX;
+  static_assert(UpdCfg<double>::TM == 64 && UpdCfg<cdouble>::TM == 64 && UpdCfg<float>::TM == 64 && UpdCfg<cfloat>::TM == 64 &&
+                UpdCfg<double>::TN == 64 && UpdCfg<cdouble>::TN == 64 && UpdCfg<float>::TN == 64 && UpdCfg<cfloat>::TN == 64,
+                "one tile shape for the four precisions (the schedule and the tile descriptors are built once)");
+  const int TM = 64, TN = 64;
   const int64_t C = h->cblknbr;
   // pair tables
   std::vector<int64_t> pairbase(C + 1, 0);
@@ -614,8 +617,7 @@ static int build_mma_schedule(pb200_handle_t *h, const std::vector<int> &level, 
     for (const auto &st : h->steps) {
       if (st.kind != 2 || st.ntiles == 0) continue;
       const int n = (int)st.ntiles;
-      if (cx) k_build_tiledesc<UpdCfg<cdouble>::TM, UpdCfg<cdouble>::TN><<<(n + 127) / 128, 128>>>(h->S, h->M, h->d_gemm + st.task0, h->d_t2t + st.t2t0, n, h->d_desc + st.t2t0);
-      else k_build_tiledesc<UpdCfg<double>::TM, UpdCfg<double>::TN><<<(n + 127) / 128, 128>>>(h->S, h->M, h->d_gemm + st.task0, h->d_t2t + st.t2t0, n, h->d_desc + st.t2t0);
+      k_build_tiledesc<64, 64><<<(n + 127) / 128, 128>>>(h->S, h->M, h->d_gemm + st.task0, h->d_t2t + st.t2t0, n, h->d_desc + st.t2t0);
     }
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
@@ -865,7 +867,8 @@ extern "C" int pb200_create_opts(pb200_handle_t **out, const pb200_solver_t *s, 
   if (nranks > 1) {
     // fan-out applies to the tensor path (double / complex double, direct factorizations); PB200_NO_FANOUT=1 keeps the
     // owner-computes-everything scheme of round 1 for A/B runs
-    h->fanout = (flttype == PB200_REALDOUBLE || flttype == PB200_COMPLEXDOUBLE) && getenv("PB200_NO_FANOUT") == nullptr;
+    h->fanout = (flttype == PB200_REALDOUBLE || flttype == PB200_COMPLEXDOUBLE || getenv("PB200_NO_MMA_SINGLE") == nullptr) &&
+                getenv("PB200_NO_FANOUT") == nullptr;
     h->all_level = level; h->all_lvl_ptr = h->lvl_ptr; h->all_lvl_cblk = lvl_cblk;
     int rc = build_dist_levels(h, h->fanout);
     if (rc) { pb200_destroy(h); return rc; }
@@ -944,7 +947,9 @@ extern "C" int pb200_create_opts(pb200_handle_t **out, const pb200_solver_t *s, 
   { int rc = upload(h, slv, &h->d_slv); if (rc) { pb200_destroy(h); return rc; } }
   { int rc = upload(h, upd, &h->d_upd); if (rc) { pb200_destroy(h); return rc; } }
 
-  if (flttype == PB200_REALDOUBLE || flttype == PB200_COMPLEXDOUBLE) {
+  // tensor-core path for the four precisions (double: DMMA, single: 3xTF32); PB200_NO_MMA_SINGLE=1 keeps s / c on the
+  // generic SIMT kernels of round 1 for A/B runs
+  if (flttype == PB200_REALDOUBLE || flttype == PB200_COMPLEXDOUBLE || getenv("PB200_NO_MMA_SINGLE") == nullptr) {
     int rc = build_mma_schedule(h, level, lvl_cblk);
     if (rc) { pb200_destroy(h); return rc; }
   }
@@ -1419,7 +1424,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
 
 template <class T>
 static int factorize_t(pb200_handle_t *h, double crit) {
-  if constexpr (std::is_same<T, double>::value || std::is_same<T, cdouble>::value) {
+  {
     if (h->use_mma) {
       switch (h->facto) {
         case PB200_FACT_LLT: return factorize_mma<T, F_LLT>(h, crit);

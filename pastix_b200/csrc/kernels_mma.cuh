@@ -105,6 +105,19 @@ template <> struct UpdCfg<cdouble> {
   static constexpr bool TMA = PB200_UPD_TMA != 0;
   static constexpr int CPY = TM;   // 16-byte elements: always aligned
 };
+// single precision: the same kernels on TF32 tensor cores with the 3xTF32 split (mma.cuh)
+template <> struct UpdCfg<float> {
+  static constexpr int TM = 64, TN = 64, KC = 16, STG = 2, WM = 2, WN = 2, PADA = 4, PADB = 4;
+  static constexpr int NT = WM * WN * 32, CTAS = 4;
+  static constexpr bool TMA = PB200_UPD_TMA != 0;
+  static constexpr int CPY = TM + 4;   // 4-byte elements: the aligned address lies up to 3 elements below
+};
+template <> struct UpdCfg<cfloat> {
+  static constexpr int TM = 64, TN = 64, KC = 16, STG = 3, WM = 4, WN = 2, PADA = 2, PADB = 2;
+  static constexpr int NT = WM * WN * 32, CTAS = 2;
+  static constexpr bool TMA = PB200_UPD_TMA != 0;
+  static constexpr int CPY = TM + 2;
+};
 #ifndef PB200_TABMAX
 #define PB200_TABMAX 1536
 #endif
@@ -123,6 +136,9 @@ constexpr size_t upd_smem_bytes() {
 __device__ __forceinline__ double neg_bits(double v) { return __longlong_as_double(__double_as_longlong(v) ^ (long long)0x8000000000000000ULL); }
 __device__ __forceinline__ void red_sub(double *p, double v) { atomicAdd(p, neg_bits(v)); }
 __device__ __forceinline__ void red_sub(cdouble *p, cdouble v) { atomicAdd(&p->x, neg_bits(v.x)); atomicAdd(&p->y, neg_bits(v.y)); }
+__device__ __forceinline__ float neg_bits(float v) { return __int_as_float(__float_as_int(v) ^ (int)0x80000000); }
+__device__ __forceinline__ void red_sub(float *p, float v) { atomicAdd(p, neg_bits(v)); }
+__device__ __forceinline__ void red_sub(cfloat *p, cfloat v) { atomicAdd(&p->x, neg_bits(v.x)); atomicAdd(&p->y, neg_bits(v.y)); }
 
 // last index i in [0, n) with key[i] <= v (keys ascending, key[0] <= v assumed)
 __device__ __forceinline__ int upper_le_s(const int *key, int n, int v) {
@@ -144,6 +160,7 @@ template <class T, int FACTO>
 __global__ void __launch_bounds__(UpdCfg<T>::NT, UpdCfg<T>::CTAS)
 k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__restrict__ descs) {
   using C = UpdCfg<T>;
+  using RT = typename ST<T>::real;
   constexpr bool CX = ST<T>::is_complex;
   constexpr int TM = C::TM, TN = C::TN, KC = C::KC, STG = C::STG, NT = C::NT;
   constexpr int LDA = TM + C::PADA, LDB = TN + C::PADB;
@@ -175,7 +192,7 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
 
   int *s_tab = reinterpret_cast<int *>(s_rm + TM);
   const int ktot = tk.k1 - tk.k0;
-  Acc<CX> acc[MI][NI];
+  Acc<CX, RT> acc[MI][NI];
 #pragma unroll
   for (int a = 0; a < MI; ++a)
 #pragma unroll
@@ -216,10 +233,11 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
     static_assert((LDA * sizeof(T)) % 16 == 0 && (LDB * sizeof(T)) % 16 == 0 && LDA >= C::CPY && LDB >= C::CPY, "bulk copy alignment");
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_tab + PB200_TABMAX);
     constexpr unsigned CPYB = C::CPY * sizeof(T);
-    // parity (0/1 element) of the first element of column k0 of each operand, and of the stride
-    const int ldpar = (sizeof(T) == 8) ? (ld & 1) : 0;
+    // offset (in elements, below 16 bytes) of the first element of column k0 of each operand, and of the stride
+    constexpr int EPM = 16 / (int)sizeof(T) - 1;   // 0, 1 or 3
+    const int ldpar = ld & EPM;
     const int64_t eA = tk.poff + (int64_t)tk.k0 * ld + m0, eB = tk.poff + (int64_t)tk.k0 * ld + n0;
-    const int parA = (sizeof(T) == 8) ? (int)(eA & 1) : 0, parB = (sizeof(T) == 8) ? (int)(eB & 1) : 0;
+    const int parA = (int)(eA & EPM), parB = (int)(eB & EPM);
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < STG; ++s) mbar_init(bar + s, 1);
@@ -247,7 +265,7 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
       const int q = warp * CPW + lane, kk = q & (KC - 1), isb = q / KC;
       if (lane < CPW && kk < nk) {
         const int k = c * KC + kk;
-        const int par = ((isb ? parB : parA) + k * ldpar) & 1;
+        const int par = ((isb ? parB : parA) + k * ldpar) & EPM;
         const T *src = (isb ? Bp : Ap) + (size_t)(tk.k0 + k) * ld + (isb ? n0 : m0) - par;
         T *dst = (isb ? sB + stg * KC * LDB + kk * LDB : sA + stg * KC * LDA + kk * LDA);
         bulk_g2s(dst, src, CPYB, bar + stg);
@@ -256,7 +274,7 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
     for (int c = 0; c < STG && c < nchunks; ++c) issue(c);
     // this thread's fragment columns are k = (even) + t4 (+4): one parity per operand for the whole tile
     const int t4f = lane & 3;
-    const int pa = (parA + t4f * ldpar) & 1, pb = (parB + t4f * ldpar) & 1;
+    const int pa = (parA + t4f * ldpar) & EPM, pb = (parB + t4f * ldpar) & EPM;   // (k - t4 is a multiple of 4)
     cp_async_wait<0>();
     for (int c = 0; c < nchunks; ++c) {
       const int stg = c % STG;
@@ -266,8 +284,8 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
 #pragma unroll
       for (int ks = 0; ks < KC; ks += 8) {
         if (ks < nk8) {
-          FragA<CX> fa[MI];
-          FragB<CX> fb[NI];
+          FragA<CX, RT> fa[MI];
+          FragB<CX, RT> fb[NI];
 #pragma unroll
           for (int x = 0; x < MI; ++x) load_frag_a<T>(fa[x], a, LDA, wm0 + x * 16, ks, lane);
 #pragma unroll
@@ -319,8 +337,8 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
     const T *a = sA + stg * KC * LDA, *b = sB + stg * KC * LDB;
 #pragma unroll
     for (int ks = 0; ks < KC; ks += 8) {
-      FragA<CX> fa[MI];
-      FragB<CX> fb[NI];
+      FragA<CX, RT> fa[MI];
+      FragB<CX, RT> fb[NI];
 #pragma unroll
       for (int x = 0; x < MI; ++x) load_frag_a<T>(fa[x], a, LDA, wm0 + x * 16, ks, lane);
 #pragma unroll
@@ -355,7 +373,7 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
       c_tgt[y][e] = cmv.ctgt;
     }
   auto value = [&](int x, int y, int hh, int e) -> T {
-    if constexpr (CX) return cdouble(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
+    if constexpr (CX) return T(acc[x][y].re[hh * 2 + e], acc[x][y].im[hh * 2 + e]);
     else return acc[x][y].re[hh * 2 + e];
   };
   if (tk.mode == 1) {
@@ -379,7 +397,7 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
                 if (roff == c_cj[y][e]) {
                   T *p = TA + c_tgt[y][e] + roff;
                   atomicAdd(&p->x, neg_bits(value(x, y, hh, e).x));
-                  p->y = 0.0;
+                  p->y = RT(0);
                   continue;
                 }
               }
@@ -446,6 +464,8 @@ template <class T> struct SubCfg;
 #endif
 template <> struct SubCfg<double> { static constexpr int NBMAX = PB200_NBMAX_D, PADW = 4, PADX = 4; };
 template <> struct SubCfg<cdouble> { static constexpr int NBMAX = 64, PADW = 2, PADX = 2; };
+template <> struct SubCfg<float> { static constexpr int NBMAX = 64, PADW = 4, PADX = 4; };
+template <> struct SubCfg<cfloat> { static constexpr int NBMAX = 64, PADW = 2, PADX = 2; };
 
 template <class T>
 __host__ __device__ constexpr int trsm_ldw(int nbp) {
@@ -461,6 +481,7 @@ inline size_t trsm_smem_bytes(int nb) {
 template <class T, int FACTO>
 __global__ void __launch_bounds__(128)
 k_trsm_mma(DevSym S, T *L, T *U, T *W, const SubTask *__restrict__ tasks, int ntasks) {
+  using RT = typename ST<T>::real;
   constexpr bool CX = ST<T>::is_complex;
   constexpr int TM = PB200_TRSM_TM, LDX = TM + SubCfg<T>::PADX;
   constexpr bool UNIT_SYM = (FACTO == F_LDLT || FACTO == F_LDLH);
@@ -540,9 +561,9 @@ k_trsm_mma(DevSym S, T *L, T *U, T *W, const SubTask *__restrict__ tasks, int nt
   const int r0 = warp * 16, g = lane >> 2, t4 = lane & 3;
   if (r0 < mrows) {
     for (int jb = 0; jb < nbp / 8; ++jb) {
-      Acc<CX> a0, a1;
+      Acc<CX, RT> a0, a1;
       a0.zero(); a1.zero();
-      FragA<CX> fa; FragB<CX> fb;
+      FragA<CX, RT> fa; FragB<CX, RT> fb;
       int kb = 0;
       for (; kb + 1 < jb; kb += 2) {
         load_frag_a<T>(fa, Xs, LDX, r0, kb * 8, lane);
@@ -563,7 +584,7 @@ k_trsm_mma(DevSym S, T *L, T *U, T *W, const SubTask *__restrict__ tasks, int nt
         const int i = r0 + g + ((q & 2) ? 8 : 0), kc = jb * 8 + t4 * 2 + (q & 1);
         T *p = Xs + (size_t)kc * LDX + i;
         T s;
-        if constexpr (CX) s = cdouble(a0.re[q] + a1.re[q], a0.im[q] + a1.im[q]);
+        if constexpr (CX) s = T(a0.re[q] + a1.re[q], a0.im[q] + a1.im[q]);
         else s = a0.re[q] + a1.re[q];
         *p = *p - s;
       }
@@ -577,7 +598,7 @@ k_trsm_mma(DevSym S, T *L, T *U, T *W, const SubTask *__restrict__ tasks, int nt
       for (int q = 0; q < 4; ++q) {
         const int i = r0 + g + ((q & 2) ? 8 : 0), kc = jb * 8 + t4 * 2 + (q & 1);
         T s;
-        if constexpr (CX) s = cdouble(a0.re[q], a0.im[q]);
+        if constexpr (CX) s = T(a0.re[q], a0.im[q]);
         else s = a0.re[q];
         Xs[(size_t)kc * LDX + i] = s;
       }
@@ -610,7 +631,15 @@ k_trsm_mma(DevSym S, T *L, T *U, T *W, const SubTask *__restrict__ tasks, int nt
 template <class T> __device__ __forceinline__ bool below_crit(T d, double crit);
 template <> __device__ __forceinline__ bool below_crit<double>(double d, double crit) { return fabs(d) < crit; }
 template <> __device__ __forceinline__ bool below_crit<cdouble>(cdouble d, double crit) {
-  return d.x * d.x + d.y * d.y < crit * crit;
+  return hypot(d.x, d.y) < crit;   // (squaring the threshold would underflow for tiny values)
+}
+template <> __device__ __forceinline__ bool below_crit<float>(float d, double crit) { return fabs((double)d) < crit; }
+template <> __device__ __forceinline__ bool below_crit<cfloat>(cfloat d, double crit) {
+  return hypot((double)d.x, (double)d.y) < crit;
+}
+__device__ __forceinline__ float shfl_t(unsigned m, float v, int src) { return __shfl_sync(m, v, src); }
+__device__ __forceinline__ cfloat shfl_t(unsigned m, cfloat v, int src) {
+  return cfloat(__shfl_sync(m, v.x, src), __shfl_sync(m, v.y, src));
 }
 __device__ __forceinline__ double shfl_t(unsigned m, double v, int src) { return __shfl_sync(m, v, src); }
 __device__ __forceinline__ cdouble shfl_t(unsigned m, cdouble v, int src) {
@@ -621,6 +650,14 @@ __device__ __forceinline__ cdouble shfl_t(unsigned m, cdouble v, int src) {
 template <int FACTO> __device__ __forceinline__ void pivot_inv(double &d, double &inv) {
   if (FACTO == F_LLT) { inv = rsqrt(d); d = d * inv; inv = inv + inv * fma(-d, inv, 1.0); }   // one Newton step on 1/sqrt
   else inv = __drcp_rn(d);
+}
+template <int FACTO> __device__ __forceinline__ void pivot_inv(float &d, float &inv) {
+  if (FACTO == F_LLT) d = sqrtf(d);
+  inv = 1.0f / d;
+}
+template <int FACTO> __device__ __forceinline__ void pivot_inv(cfloat &d, cfloat &inv) {
+  if (FACTO == F_LLT) d = ST<cfloat>::sqrt(d);
+  inv = cfloat(1.0f, 0.0f) / d;
 }
 template <int FACTO> __device__ __forceinline__ void pivot_inv(cdouble &d, cdouble &inv) {
   if (FACTO == F_LLT) d = ST<cdouble>::sqrt(d);

@@ -61,55 +61,95 @@ __device__ __forceinline__ void ld_parts(const cdouble *p, double &re, double &i
   const double2 v = *reinterpret_cast<const double2 *>(p);
   re = v.x; im = v.y;
 }
-__device__ __forceinline__ double mk(double re, double, double *) { return re; }
-__device__ __forceinline__ cdouble mk(double re, double im, cdouble *) { return cdouble(re, im); }
+__device__ __forceinline__ void ld_parts(const float *p, float &re, float &im) { re = *p; im = 0.f; }
+__device__ __forceinline__ void ld_parts(const cfloat *p, float &re, float &im) {
+  const float2 v = *reinterpret_cast<const float2 *>(p);
+  re = v.x; im = v.y;
+}
 
-// accumulator tile of one m16n8 MMA in T's arithmetic
-template <bool CX> struct Acc;
-template <> struct Acc<false> {
-  double re[4];
-  __device__ __forceinline__ void zero() { re[0] = re[1] = re[2] = re[3] = 0.0; }
+// ---- operand registers and the m16n8k8 product in the two real arithmetics.
+// double: mma.sync.m16n8k8.f64 (DMMA).  float: the SAME fragment layout exists for tf32 operands
+// (mma.sync.m16n8k8.f32.tf32.tf32.f32), and FP32 accuracy is recovered by the 3xTF32 split: x = hi + lo with
+// hi = tf32(x), lo = tf32(x - hi); C += A_lo B_hi + A_hi B_lo + A_hi B_hi (the lo*lo term is below the FP32 ulp).
+__device__ __forceinline__ unsigned f2tf32(float x) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void smma(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <class R> struct Mma;
+template <> struct Mma<double> {
+  struct A { double v[4]; };
+  struct B { double v[2]; };
+  static __device__ __forceinline__ void set(A &f, int q, double x) { f.v[q] = x; }
+  static __device__ __forceinline__ void set(B &f, int q, double x) { f.v[q] = x; }
+  static __device__ __forceinline__ void mma(double (&c)[4], const A &a, const B &b) { dmma(c, a.v, b.v); }
 };
-template <> struct Acc<true> {
-  double re[4], im[4];
-  __device__ __forceinline__ void zero() {
-    re[0] = re[1] = re[2] = re[3] = 0.0; im[0] = im[1] = im[2] = im[3] = 0.0;
+template <> struct Mma<float> {
+  struct A { unsigned hi[4], lo[4]; };
+  struct B { unsigned hi[2], lo[2]; };
+  static __device__ __forceinline__ void set(A &f, int q, float x) {
+    const unsigned h = f2tf32(x); f.hi[q] = h; f.lo[q] = f2tf32(x - __uint_as_float(h));
+  }
+  static __device__ __forceinline__ void set(B &f, int q, float x) {
+    const unsigned h = f2tf32(x); f.hi[q] = h; f.lo[q] = f2tf32(x - __uint_as_float(h));
+  }
+  static __device__ __forceinline__ void mma(float (&c)[4], const A &a, const B &b) {
+    smma(c, a.lo, b.hi); smma(c, a.hi, b.lo); smma(c, a.hi, b.hi);   // small terms first
   }
 };
-template <bool CX> struct FragA;
-template <> struct FragA<false> { double re[4]; };
-template <> struct FragA<true> { double re[4], im[4]; };
-template <bool CX> struct FragB;
-template <> struct FragB<false> { double re[2]; };
-template <> struct FragB<true> { double re[2], im[2], nim[2]; };
 
-__device__ __forceinline__ void mma_acc(Acc<false> &c, const FragA<false> &a, const FragB<false> &b) {
-  dmma(c.re, a.re, b.re);
+// accumulator tile of one m16n8 MMA in T's arithmetic (R = the real type of T)
+template <bool CX, class R> struct Acc;
+template <class R> struct Acc<false, R> {
+  R re[4];
+  __device__ __forceinline__ void zero() { re[0] = re[1] = re[2] = re[3] = R(0); }
+};
+template <class R> struct Acc<true, R> {
+  R re[4], im[4];
+  __device__ __forceinline__ void zero() {
+    re[0] = re[1] = re[2] = re[3] = R(0); im[0] = im[1] = im[2] = im[3] = R(0);
+  }
+};
+template <bool CX, class R> struct FragA;
+template <class R> struct FragA<false, R> { typename Mma<R>::A re; };
+template <class R> struct FragA<true, R> { typename Mma<R>::A re, im; };
+template <bool CX, class R> struct FragB;
+template <class R> struct FragB<false, R> { typename Mma<R>::B re; };
+template <class R> struct FragB<true, R> { typename Mma<R>::B re, im, nim; };
+
+template <class R>
+__device__ __forceinline__ void mma_acc(Acc<false, R> &c, const FragA<false, R> &a, const FragB<false, R> &b) {
+  Mma<R>::mma(c.re, a.re, b.re);
 }
-__device__ __forceinline__ void mma_acc(Acc<true> &c, const FragA<true> &a, const FragB<true> &b) {
-  dmma(c.re, a.re, b.re);
-  dmma(c.re, a.im, b.nim);
-  dmma(c.im, a.re, b.im);
-  dmma(c.im, a.im, b.re);
+template <class R>
+__device__ __forceinline__ void mma_acc(Acc<true, R> &c, const FragA<true, R> &a, const FragB<true, R> &b) {
+  Mma<R>::mma(c.re, a.re, b.re);
+  Mma<R>::mma(c.re, a.im, b.nim);
+  Mma<R>::mma(c.im, a.re, b.im);
+  Mma<R>::mma(c.im, a.im, b.re);
 }
 
 // A fragment from a k-major tile: element (row i, k) at s[k * ld + i]
 template <class T>
-__device__ __forceinline__ void load_frag_a(FragA<ST<T>::is_complex> &f, const T *s, int ld, int row0, int k0, int lane) {
+__device__ __forceinline__ void load_frag_a(FragA<ST<T>::is_complex, typename ST<T>::real> &f, const T *s, int ld, int row0, int k0, int lane) {
+  using R = typename ST<T>::real;
   const int g = lane >> 2, t = lane & 3;
-  double re, im;
+  R re, im;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int i = row0 + g + ((q & 1) ? 8 : 0), k = k0 + t + ((q & 2) ? 4 : 0);
     ld_parts(s + (size_t)k * ld + i, re, im);
-    f.re[q] = re;
-    if constexpr (ST<T>::is_complex) f.im[q] = im;
+    Mma<R>::set(f.re, q, re);
+    if constexpr (ST<T>::is_complex) Mma<R>::set(f.im, q, im);
   }
 }
 // B fragment from a k-major tile: element (k, n) at s[k * ld + n]; `scale` (optional, per k) and conj applied here
 template <class T, bool CONJ, bool SCALE>
-__device__ __forceinline__ void load_frag_b(FragB<ST<T>::is_complex> &f, const T *s, int ld, int n0, int k0, int lane,
+__device__ __forceinline__ void load_frag_b(FragB<ST<T>::is_complex, typename ST<T>::real> &f, const T *s, int ld, int n0, int k0, int lane,
                                             const T *dk) {
+  using R = typename ST<T>::real;
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -117,9 +157,10 @@ __device__ __forceinline__ void load_frag_b(FragB<ST<T>::is_complex> &f, const T
     T v = s[(size_t)k * ld + n0 + g];
     if (SCALE) v = v * dk[k];
     if constexpr (ST<T>::is_complex) {
-      f.re[q] = v.x; f.im[q] = CONJ ? -v.y : v.y; f.nim[q] = -f.im[q];
+      const R im = CONJ ? -v.y : v.y;
+      Mma<R>::set(f.re, q, v.x); Mma<R>::set(f.im, q, im); Mma<R>::set(f.nim, q, -im);
     } else {
-      f.re[q] = v;
+      Mma<R>::set(f.re, q, v);
     }
   }
 }
