@@ -185,11 +185,11 @@ def measure_fp32_peak(device: int) -> dict:
 def ncu_traffic(workload: str = "c2"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (k_gemm_scatter: the largest
     captured launch) and of the two up_down sweeps, from the committed `ncu --set full` captures
-    (profiles/r01/r01c_full_*_summary.json, written by tools/gpu_profile.sh + tools/ncu_summary.py); None when absent."""
+    (profiles/r02/r02_full_*_summary.json, written by tools/gpu_profile.sh r02 + tools/ncu_summary.py); None when absent."""
     wl = workload if workload in ("c2", "c3") else "c2"
     out = None
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01", f"r01c_full_gemm_scatter_{wl}_summary.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02", f"r02_full_gemm_scatter_{wl}_summary.json")))
         k = max(d, key=lambda x: x.get("grid", 0))
         out = {"dram_bytes": k["dram_read_bytes"] + k["dram_write_bytes"], "launch_tiles": int(k["grid"]),
                "launch_ms": k["duration_us"] * 1e-3, "dmma_pipe_active_pct": k.get("dmma_pipe_pct"),
@@ -197,7 +197,7 @@ def ncu_traffic(workload: str = "c2"):
     except Exception:
         pass
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01", "r01c_full_updown_c2_summary.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02", "r02_full_updown_c2_summary.json")))
         if out is not None and wl == "c2":
             out["updown_sweeps"] = [{"kernel": k["kernel"].replace("void ", "").split("<")[0], "dram_bytes": k["dram_read_bytes"] + k["dram_write_bytes"],
                                      "launch_ms": k["duration_us"] * 1e-3} for k in d]
@@ -730,7 +730,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--iparm", action="append", default=[], metavar="IPARM_NAME=VALUE",
                     help="extra iparm override for the analysis (e.g. IPARM_MAX_BLOCKSIZE=240); applied to both arms")
+    ap.add_argument("--tuned", action="store_true",
+                    help="GPU-aware block sizes for blend (IPARM_MIN/MAX_BLOCKSIZE = 120/240 instead of the reference's 60/120; "
+                         "pb200_tune_iparm) — applied to both arms, like --iparm")
     args = ap.parse_args()
+    if args.tuned:
+        from pastix_b200.pastix_api import TUNED_IPARM
+        args.iparm = list(args.iparm) + [f"{k}={v}" for k, v in TUNED_IPARM.items()]
     args.default_workload = args.workload is None
     if args.workload is None:
         args.workload = "c2" if args.gpus == 1 else "c3"

@@ -133,7 +133,12 @@ constexpr size_t upd_smem_bytes() {
 // fire-and-forget reductions (RED.ADD.F64 at L2): the reference serialises these adds with
 // mutex_blok (sopalin_compute.c:563-580)
 // (the sign is flipped on the integer pipe: a DADD would compete with the DMMAs for the FP64 pipe)
-__device__ __forceinline__ double neg_bits(double v) { return __longlong_as_double(__double_as_longlong(v) ^ (long long)0x8000000000000000ULL); }
+// (inline PTX on the high word: a plain xor of the bit pattern is recognised by the compiler and comes back as DADD -RZ, -R)
+__device__ __forceinline__ double neg_bits(double v) {
+  double r;
+  asm("{\n.reg .b32 lo, hi;\nmov.b64 {lo, hi}, %1;\nxor.b32 hi, hi, 0x80000000;\nmov.b64 %0, {lo, hi};\n}" : "=d"(r) : "d"(v));
+  return r;
+}
 __device__ __forceinline__ void red_sub(double *p, double v) { atomicAdd(p, neg_bits(v)); }
 __device__ __forceinline__ void red_sub(cdouble *p, cdouble v) { atomicAdd(&p->x, neg_bits(v.x)); atomicAdd(&p->y, neg_bits(v.y)); }
 __device__ __forceinline__ float neg_bits(float v) { return __int_as_float(__float_as_int(v) ^ (int)0x80000000); }

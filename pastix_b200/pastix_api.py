@@ -24,6 +24,11 @@ def dropin_path(prec: str, int_bits: int = 64) -> str:
     return os.path.join(LIBDIR, f"libpastix_dropin_{prec}{'_i32' if int_bits == 32 else ''}.so")
 
 
+# GPU-aware block sizes for blend (pb200_tune_iparm in shim/shim_hooks.c): same analysis
+# code, different parameters.  The reference's defaults are 60 / 120.
+TUNED_IPARM = {"IPARM_MIN_BLOCKSIZE": 120, "IPARM_MAX_BLOCKSIZE": 240}
+
+
 def load_enums(path: str = None) -> dict:
     return json.load(open(path or os.path.join(LIBDIR, "api_enums.json")))
 

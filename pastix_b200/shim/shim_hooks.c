@@ -187,6 +187,17 @@ void pb200_shim_release_data(void *pastix_data)
 }
 int pb200_shim_live(void) { return pb200_shim_live_entries(); }
 
+/* GPU-aware block sizes for blend.  The reference's defaults IPARM_MIN/MAX_BLOCKSIZE =
+ * 60 / 120 (pastix.c:375-376) were chosen for CPU BLAS; on the B200 every scattered update tile pays a fixed
+ * prologue / epilogue whatever the contraction length, so wider column blocks (K = 120 .. 240) raise the useful work per
+ * tile — measured in profiles/r02/README.md.  Same analysis code, different parameters: call this between
+ * API_TASK_INIT (which fills the defaults) and API_TASK_ANALYSE, or set the two iparm entries yourself. */
+void pb200_tune_iparm(PASTIX_INT *iparm)
+{
+  iparm[IPARM_MIN_BLOCKSIZE] = 120;
+  iparm[IPARM_MAX_BLOCKSIZE] = 240;
+}
+
 /* The factors where the reference leaves them: cblktab[].coeftab / .ucoeftab (solver.h:94-117) filled from HBM on
  * demand, allocated like CoefMatrix_Allocate does (coefinit.c:104-160) so that CoefMatrix_Free / solverExit release
  * them.  For consumers that read the panels directly (dump_all / PASTIX_DUMP_FACTO, user code walking the
