@@ -132,7 +132,7 @@ class Sopalin:
     # -- multi-GPU plumbing ----------------------------------------------------
     def attach(self, dist=None):
         """Exchange the CUDA IPC blobs of the slabs over torch.distributed (any backend; the blobs are
-        192 opaque bytes per rank) and map every peer's slab (pb200_ipc_attach).  Collective."""
+        pb200_ipc_size() = 256 opaque bytes per rank) and map every peer's slab (pb200_ipc_attach).  Collective."""
         if self.nranks == 1:
             return self
         import torch
