@@ -16,6 +16,7 @@
 #include "kernels_factor.cuh"
 #include "kernels_solve.cuh"
 #include "kernels_solve_dag.cuh"
+#include "kernels_solve_dag2.cuh"
 #include "kernels_mma.cuh"
 #include "kernels_dist.cuh"
 #include "kernels_small.cuh"
@@ -81,6 +82,8 @@ struct pb200_handle_s {
   unsigned int *d_slv_cnt = nullptr;
   // persistent counter-ordered sweeps (kernels_solve_dag.cuh)
   bool dag_ok = false; int dag_tiles = 0, dag_nbs = 0;
+  int dag_rows = PB200_DAG2_ROWS;                                // panel rows per T ticket: 32 (k_dag2), 64 (k_fwd_dag / k_bwd_dag, PB200_DAG_V1=1)
+  unsigned long long *d_dag_trace = nullptr;                     // PB200_DAG_TRACE=<file>: per-ticket time stamps of the last solve
   DagTick *d_dag_ticks = nullptr; int *d_dag_tgt = nullptr;
   unsigned int *d_dag_need = nullptr, *d_dag_state = nullptr;   // state: arrived[nsp] ready[nsp] done[nsp] cnt[nsp] ticket[2] err[1]
   unsigned int *h_dag_err = nullptr;                             // pinned
@@ -188,6 +191,8 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
   const int NB = (h->flt == PB200_COMPLEXDOUBLE) ? SlvCfg<cdouble>::NB : SlvCfg<double>::NB;
   const int64_t C = h->cblknbr;
   const int nsp = (int)tasks.size();
+  h->dag_rows = getenv("PB200_DAG_V1") != nullptr ? PB200_DAG_ROWS : PB200_DAG2_ROWS;
+  const int DROWS = h->dag_rows;
   // (cblk, round) -> sub-panel id, and the sub-panel width of each cblk
   std::vector<int> sp_ptr(C + 1, 0), sw(C, 1);
   for (int64_t c = 0; c < C; ++c) {
@@ -214,7 +219,7 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
     spid[sp_ptr[tk.cblk] + tk.c0 / sw[tk.cblk]] = i;
     if (tk.cblk == sc) continue;
     nbs = std::max(nbs, tk.c1 - tk.c0);
-    nticks += (std::max(mend[tk.cblk], tk.c1) - tk.c1 + PB200_DAG_ROWS - 1) / PB200_DAG_ROWS;
+    nticks += (std::max(mend[tk.cblk], tk.c1) - tk.c1 + DROWS - 1) / DROWS;
   }
   if (nticks >= (1LL << 24)) return PB200_SUCCESS;   // millions of tiny tickets: the level sweeps batch them better
   std::vector<DagTick> ticks; ticks.reserve((size_t)nticks);
@@ -226,7 +231,7 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
     if (tk.cblk == sc) continue;
     const int c = tk.cblk, w = tk.w, ld = tk.ld, nb = tk.c1 - tk.c0;
     const int me = std::max(mend[c], tk.c1);   // rows [c1, me) of the panel take part
-    const int nt = (me - tk.c1 + PB200_DAG_ROWS - 1) / PB200_DAG_ROWS;
+    const int nt = (me - tk.c1 + DROWS - 1) / DROWS;
     DagTick d{};
     d.src = tk.invoff; d.aux = tk.poff + (int64_t)tk.c0 * (ld + 1); d.ld = ld; d.nb = nb; d.mrows = -1; d.sp = tk.sp;
     d.xcol = tk.fcol + tk.c0; d.nsib = nt;
@@ -235,7 +240,7 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
     const int be = h->h_fblok[c + 1];
     for (int t = 0; t < nt; ++t) {
       const long long g = (long long)ticks.size();
-      const int m0 = tk.c1 + t * PB200_DAG_ROWS, m1 = std::min(me, m0 + PB200_DAG_ROWS);
+      const int m0 = tk.c1 + t * DROWS, m1 = std::min(me, m0 + DROWS);
       DagTick k{};
       k.src = tk.poff + (int64_t)tk.c0 * ld + m0; k.aux = tk.rgbase + m0; k.ld = ld; k.nb = nb; k.mrows = m1 - m0; k.sp = tk.sp;
       k.xcol = tk.fcol + tk.c0; k.grow0 = tk.fcol + m0; k.wrem = w - m0; k.tptr = (int)tgt.size();
@@ -255,6 +260,7 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
     }
   }
   if (tgt.size() >= (size_t)INT32_MAX) return PB200_SUCCESS;
+  for (auto &k : ticks) if (k.mrows < 0) k.pad0 = (int)need[k.sp];
   for (int s : tgt) if (s < 0) return fail(PB200_ERR_STRUCT, "up_down dependency table: row without an owning sub-panel");
   { int rc = upload(h, ticks, &h->d_dag_ticks); if (rc) return rc; }
   { int rc = upload(h, tgt, &h->d_dag_tgt); if (rc) return rc; }
@@ -1598,7 +1604,62 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
     ++launches;
   }
   if (h->dag_ok) {
-    // one persistent launch per sweep, ordered by device-side contribution counters (kernels_solve_dag.cuh)
+    // one persistent launch per sweep, ordered by device-side contribution counters
+    const size_t nsp = (size_t)h->nsubpanels;
+    DagArgs A;
+    A.ticks = h->d_dag_ticks; A.tgt = h->d_dag_tgt; A.need = h->d_dag_need;
+    A.arrived = h->d_dag_state; A.ready = A.arrived + nsp; A.done = A.ready + nsp; A.cnt = A.done + nsp;
+    A.ticket = A.cnt + nsp; A.err = A.ticket + 2; A.rowglob = h->d_rowglob;
+    A.G = h->dag_tiles; A.nbs = h->dag_nbs; A.trace = nullptr;
+    CK(cudaMemsetAsync(h->d_dag_state, 0, (4 * nsp + 4) * sizeof(unsigned int), h->stream));
+    if (h->dag_rows == PB200_DAG2_ROWS) {
+      // second generation (kernels_solve_dag2.cuh): three tickets in flight per CTA, one or NRMAX right-hand sides per pass
+      const char *trf = getenv("PB200_DAG_TRACE");
+      if (trf && !h->d_dag_trace) {
+        const size_t tb = (size_t)2 * A.G * 4 * sizeof(unsigned long long);
+        CK(cudaMalloc((void **)&h->d_dag_trace, tb));
+        h->allocs.push_back(h->d_dag_trace); h->device_bytes += tb;
+      }
+      if (trf) { A.trace = h->d_dag_trace; CK(cudaMemsetAsync(h->d_dag_trace, 0, (size_t)2 * A.G * 4 * sizeof(unsigned long long), h->stream)); }
+      constexpr int NRM = Dag2Cfg<T>::NRMAX;
+      const bool one = nrhs == 1;
+      const size_t smem = one ? Dag2Cfg<T>::bytes(1) : Dag2Cfg<T>::bytes(NRM);
+      if (!(h->attr_mask & 64u)) {
+        CK(cudaFuncSetAttribute(k_dag2<T, FACTO, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Dag2Cfg<T>::bytes(1)));
+        CK(cudaFuncSetAttribute(k_dag2<T, FACTO, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Dag2Cfg<T>::bytes(1)));
+        CK(cudaFuncSetAttribute(k_dag2<T, FACTO, 0, NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Dag2Cfg<T>::bytes(NRM)));
+        CK(cudaFuncSetAttribute(k_dag2<T, FACTO, 1, NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Dag2Cfg<T>::bytes(NRM)));
+        CK(cudaFuncSetAttribute(k_dag2<T, FACTO, 0, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(k_dag2<T, FACTO, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(k_dag2<T, FACTO, 0, NRM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(k_dag2<T, FACTO, 1, NRM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        h->attr_mask |= 64u;
+      }
+      int occ = 0;
+      if (one) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dag2<T, FACTO, 0, 1>, PB200_DAG2_NT, smem));
+      else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dag2<T, FACTO, 0, NRM>, PB200_DAG2_NT, smem));
+      if (occ < 1) return fail(PB200_ERR_CUDA, "persistent up_down kernels do not fit on this device");
+      const unsigned grid = (unsigned)std::min<long long>(A.G, (long long)h->sm_count * occ);
+      if (one) {
+        k_dag2<T, FACTO, 0, 1><<<grid, PB200_DAG2_NT, smem, h->stream>>>(L, inv, x, y, ldx, nrhs, A);
+        k_dag2<T, FACTO, 1, 1><<<grid, PB200_DAG2_NT, smem, h->stream>>>(Mup, inv_up, x, y, ldx, nrhs, A);
+      } else {
+        k_dag2<T, FACTO, 0, NRM><<<grid, PB200_DAG2_NT, smem, h->stream>>>(L, inv, x, y, ldx, nrhs, A);
+        k_dag2<T, FACTO, 1, NRM><<<grid, PB200_DAG2_NT, smem, h->stream>>>(Mup, inv_up, x, y, ldx, nrhs, A);
+      }
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(h->h_dag_err, A.err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+      if (getenv("PB200_DAG_VERBOSE")) fprintf(stderr, "[pb200 dag2] tickets %d, widest sub-panel %d, smem %zu B, CTAs/SM %d\n", A.G, A.nbs, smem, occ);
+      if (trf) {
+        // debugging aid: [sweep][ticket] = {taken, dependencies met, done, (sm << 32) | queue depth << 8 | is-diagonal} (ns, %globaltimer)
+        CK(cudaStreamSynchronize(h->stream));
+        std::vector<unsigned long long> tr((size_t)2 * A.G * 4);
+        CK(cudaMemcpy(tr.data(), h->d_dag_trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(trf, "wb")) { fwrite(tr.data(), sizeof(unsigned long long), tr.size(), f); fclose(f); }
+      }
+      h->last_launches = 2;
+      return PB200_SUCCESS;
+    }
     const size_t smem = DagSmem<T>::bytes(h->dag_nbs), belems = DagSmem<T>::buf_elems(h->dag_nbs);
     if (!(h->attr_mask & 32u)) {
       CK(cudaFuncSetAttribute(k_fwd_dag<T, FACTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DagSmem<T>::bytes(SlvCfg<T>::NB)));
@@ -1611,13 +1672,6 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_fwd_dag<T, FACTO>, PB200_DAG_NT, smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bwd_dag<T, FACTO>, PB200_DAG_NT, smem));
     if (occ_f < 1 || occ_b < 1) return fail(PB200_ERR_CUDA, "persistent up_down kernels do not fit on this device");
-    const size_t nsp = (size_t)h->nsubpanels;
-    DagArgs A;
-    A.ticks = h->d_dag_ticks; A.tgt = h->d_dag_tgt; A.need = h->d_dag_need;
-    A.arrived = h->d_dag_state; A.ready = A.arrived + nsp; A.done = A.ready + nsp; A.cnt = A.done + nsp;
-    A.ticket = A.cnt + nsp; A.err = A.ticket + 2; A.rowglob = h->d_rowglob;
-    A.G = h->dag_tiles; A.nbs = h->dag_nbs;
-    CK(cudaMemsetAsync(h->d_dag_state, 0, (4 * nsp + 4) * sizeof(unsigned int), h->stream));
     const unsigned gf = (unsigned)std::min<long long>(A.G, (long long)h->sm_count * occ_f);
     const unsigned gb = (unsigned)std::min<long long>(A.G, (long long)h->sm_count * occ_b);
     k_fwd_dag<T, FACTO><<<gf, PB200_DAG_NT, smem, h->stream>>>(L, inv, x, y, ldx, nrhs, A, belems);

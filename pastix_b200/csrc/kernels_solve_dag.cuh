@@ -44,7 +44,7 @@ struct DagTick {
   int wrem;        // T: leading tile rows that are inside the diagonal block (<= 0: none)
   int nsib;        // D: T tickets of the sub-panel
   int tptr, ntgt;  // T: sub-panels owning the rows of the tile: tgt[tptr .. tptr+ntgt)
-  int pad0, pad1;
+  int pad0, pad1;  // pad0: D: contributions x_J waits for in the down step (= need[sp], carried in the record for k_dag2)
 };
 static_assert(sizeof(DagTick) == 64, "DagTick is one 64-byte record");
 
@@ -60,6 +60,7 @@ struct DagArgs {
   unsigned *err;
   const int *rowglob;
   int G, nbs;               // tickets; widest sub-panel
+  unsigned long long *trace; // optional [2][G][4] time stamps per ticket (PB200_DAG_TRACE, k_dag2 only), else null
 };
 
 template <int BYTES>

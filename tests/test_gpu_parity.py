@@ -189,3 +189,32 @@ def test_persistent_updown_equals_level_sweeps(name, monkeypatch):
         out.append(X)
         s.close()
     assert relerr(out[0], out[1]) <= 50 * tol(g["prec"])
+
+
+@pytest.mark.parametrize("name", ["lap7_8_llt_d", "lap27_6_ldlt_d", "cd_8_lu_d", "cd_6_lu_c", "lap7_10_llt_d_bs16",
+                                  "lap7_6_llt_s", "lap7her_6_ldlh_z", "cd_6_lu_z"])
+@pytest.mark.parametrize("nrhs", [1, 5])
+def test_second_generation_sweeps_equal_the_first(name, nrhs, monkeypatch):
+    """k_dag2 (kernels_solve_dag2.cuh: three tickets in flight per CTA, 32-row tiles, block-task triangle product)
+    against k_fwd_dag / k_bwd_dag (PB200_DAG_V1=1, 64-row tiles) on the same factors: single right-hand side (the
+    NR = 1 instantiation) and 5 (one full pass + a partial one of the NRMAX instantiation)."""
+    from pastix_b200 import Sopalin
+    from pastix_b200.csc import permute_rhs
+    import os
+    if not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", name + ".npz")):
+        pytest.skip("golden not present")
+    g = load_golden(name)
+    b1 = permute_rhs(g["b"], g["permtab"]).reshape(-1, 1)
+    out = []
+    for v1 in (False, True):
+        if v1:
+            monkeypatch.setenv("PB200_DAG_V1", "1")
+        s = Sopalin(g, g["prec"], g["facto"])
+        s.assemble(g["colptr"], g["rows"], g["values"], g["tvalues"])
+        s.factorize(g["critere"])
+        X = np.asfortranarray(b1 * (1.0 + 0.5 * np.arange(nrhs))[None, :]).astype(s.dtype, order="F")
+        s.solve(X)
+        assert s.last_launches() == 2, "persistent path not taken"
+        out.append(X)
+        s.close()
+    assert relerr(out[0], out[1]) <= 50 * tol(g["prec"])
