@@ -226,21 +226,27 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
   std::vector<int> tgt; tgt.reserve((size_t)nticks * 3);
   std::vector<unsigned int> need(nsp, 0);
   std::vector<long long> stamp(nsp, -1);
-  for (int i = 0; i < nsp; ++i) {
+  std::vector<int> ntk(nsp, 0);                    // T tickets of each sub-panel
+  auto emit_D = [&](int i) {
     const SlvTask &tk = tasks[i];
-    if (tk.cblk == sc) continue;
-    const int c = tk.cblk, w = tk.w, ld = tk.ld, nb = tk.c1 - tk.c0;
-    const int me = std::max(mend[c], tk.c1);   // rows [c1, me) of the panel take part
-    const int nt = (me - tk.c1 + DROWS - 1) / DROWS;
+    const int ld = tk.ld, nb = tk.c1 - tk.c0;
     DagTick d{};
     d.src = tk.invoff; d.aux = tk.poff + (int64_t)tk.c0 * (ld + 1); d.ld = ld; d.nb = nb; d.mrows = -1; d.sp = tk.sp;
-    d.xcol = tk.fcol + tk.c0; d.nsib = nt;
+    d.xcol = tk.fcol + tk.c0; d.nsib = 0;
     ticks.push_back(d);
+  };
+  // T tickets of sub-panel i, `trows` panel rows each
+  auto emit_T = [&](int i, int trows) {
+    const SlvTask &tk = tasks[i];
+    const int c = tk.cblk, w = tk.w, ld = tk.ld, nb = tk.c1 - tk.c0;
+    const int me = std::max(mend[c], tk.c1);   // rows [c1, me) of the panel take part
+    const int nt = (me - tk.c1 + trows - 1) / trows;
+    ntk[i] = nt;
     int b = h->h_fblok[c] + 1;                    // first off-diagonal blok
     const int be = h->h_fblok[c + 1];
     for (int t = 0; t < nt; ++t) {
       const long long g = (long long)ticks.size();
-      const int m0 = tk.c1 + t * DROWS, m1 = std::min(me, m0 + DROWS);
+      const int m0 = tk.c1 + t * trows, m1 = std::min(me, m0 + trows);
       DagTick k{};
       k.src = tk.poff + (int64_t)tk.c0 * ld + m0; k.aux = tk.rgbase + m0; k.ld = ld; k.nb = nb; k.mrows = m1 - m0; k.sp = tk.sp;
       k.xcol = tk.fcol + tk.c0; k.grow0 = tk.fcol + m0; k.wrem = w - m0; k.tptr = (int)tgt.size();
@@ -258,7 +264,33 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
       k.ntgt = (int)tgt.size() - k.tptr;
       ticks.push_back(k);
     }
+  };
+  if (DROWS == PB200_DAG_ROWS) {
+    // first generation: D(J) followed by its own T tickets, 64 rows each
+    for (int i = 0; i < nsp; ++i) {
+      if (tasks[i].cblk == sc) continue;
+      emit_D(i); emit_T(i, DROWS);
+    }
+  } else {
+    // second generation: per (level, round) step all the D tickets, then all the T tickets — a ticket and the ones it waits
+    // for are a whole block of independent tickets apart wherever a level is wide, so the three-deep queues of the CTAs
+    // never hold a runnable ticket behind a blocked one there.  T tickets grow to up to 8 sub-tiles of 32 rows in steps
+    // with thousands of sub-tiles (the per-ticket cost — atomics, polls, fence — is paid once per 256 rows) and stay one
+    // sub-tile where a step is a link of the dependency chain.
+    for (const auto &st : h->slv_steps) {
+      long long subt = 0;
+      for (int i = st.task0; i < st.task0 + st.ntasks; ++i) {
+        if (tasks[i].cblk == sc) continue;
+        const int c = tasks[i].cblk;
+        subt += (std::max(mend[c], tasks[i].c1) - tasks[i].c1 + DROWS - 1) / DROWS;
+      }
+      int nsub = 1;
+      while (nsub < 8 && subt / (2 * nsub) >= 1024) nsub *= 2;
+      for (int i = st.task0; i < st.task0 + st.ntasks; ++i) if (tasks[i].cblk != sc) emit_D(i);
+      for (int i = st.task0; i < st.task0 + st.ntasks; ++i) if (tasks[i].cblk != sc) emit_T(i, DROWS * nsub);
+    }
   }
+  for (auto &k : ticks) if (k.mrows < 0) k.nsib = ntk[k.sp];
   if (tgt.size() >= (size_t)INT32_MAX) return PB200_SUCCESS;
   for (auto &k : ticks) if (k.mrows < 0) k.pad0 = (int)need[k.sp];
   for (int s : tgt) if (s < 0) return fail(PB200_ERR_STRUCT, "up_down dependency table: row without an owning sub-panel");
@@ -1616,11 +1648,11 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
       // second generation (kernels_solve_dag2.cuh): three tickets in flight per CTA, one or NRMAX right-hand sides per pass
       const char *trf = getenv("PB200_DAG_TRACE");
       if (trf && !h->d_dag_trace) {
-        const size_t tb = (size_t)2 * A.G * 4 * sizeof(unsigned long long);
+        const size_t tb = (size_t)2 * A.G * 8 * sizeof(unsigned long long);
         CK(cudaMalloc((void **)&h->d_dag_trace, tb));
         h->allocs.push_back(h->d_dag_trace); h->device_bytes += tb;
       }
-      if (trf) { A.trace = h->d_dag_trace; CK(cudaMemsetAsync(h->d_dag_trace, 0, (size_t)2 * A.G * 4 * sizeof(unsigned long long), h->stream)); }
+      if (trf) { A.trace = h->d_dag_trace; CK(cudaMemsetAsync(h->d_dag_trace, 0, (size_t)2 * A.G * 8 * sizeof(unsigned long long), h->stream)); }
       constexpr int NRM = Dag2Cfg<T>::NRMAX;
       const bool one = nrhs == 1;
       const size_t smem = one ? Dag2Cfg<T>::bytes(1) : Dag2Cfg<T>::bytes(NRM);
@@ -1651,9 +1683,10 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
       CK(cudaMemcpyAsync(h->h_dag_err, A.err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
       if (getenv("PB200_DAG_VERBOSE")) fprintf(stderr, "[pb200 dag2] tickets %d, widest sub-panel %d, smem %zu B, CTAs/SM %d\n", A.G, A.nbs, smem, occ);
       if (trf) {
-        // debugging aid: [sweep][ticket] = {taken, dependencies met, done, (sm << 32) | queue depth << 8 | is-diagonal} (ns, %globaltimer)
+        // debugging aid: [sweep][ticket] = {taken, dependencies met, done, (sm << 32) | sub-tiles << 16 | stages in flight << 8 | is-diagonal,
+        // copies landed, input vector in shared memory, partial sums written, before the fence} (ns, %globaltimer)
         CK(cudaStreamSynchronize(h->stream));
-        std::vector<unsigned long long> tr((size_t)2 * A.G * 4);
+        std::vector<unsigned long long> tr((size_t)2 * A.G * 8);
         CK(cudaMemcpy(tr.data(), h->d_dag_trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         if (FILE *f = fopen(trf, "wb")) { fwrite(tr.data(), sizeof(unsigned long long), tr.size(), f); fclose(f); }
       }

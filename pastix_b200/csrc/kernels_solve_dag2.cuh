@@ -90,13 +90,14 @@ __device__ __forceinline__ void dag2_tri_task(T (&acc)[NR], const T *buf, const 
   }
 }
 
-// DIR 0: down + diagonal step over coeftab;  DIR 1: up step over coeftab (ucoeftab for LU), tickets in reverse
+// DIR 0: down + diagonal step over coeftab;  DIR 1: up step over coeftab (ucoeftab for LU), tickets in reverse.
+// A T ticket covers up to 8 sub-tiles of 32 panel rows (the host picks the size per level: large where a level has
+// thousands of tiles, one sub-tile where the level is a link of the dependency chain); the ring holds sub-tiles.
 template <class T, int FACTO, int DIR, int NR>
 __global__ void __launch_bounds__(PB200_DAG2_NT, 2)
 k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t ldx, int nrhs, DagArgs A) {
   using C = Dag2Cfg<T>;
   constexpr int NB = C::NB, SLOT = C::SLOT, ROWS = PB200_DAG2_ROWS, LDT = PB200_DAG2_LDT, NT = PB200_DAG2_NT, DEPTH = PB200_DAG2_DEPTH;
-  constexpr int PARTS = PB200_DAG2_PARTS;
   constexpr bool LDL = (FACTO == F_LDLT || FACTO == F_LDLH);
   constexpr bool CONJ = (DIR == 1 && FACTO == F_LDLH);
   constexpr bool OVERLAY = (NR > 1);
@@ -105,23 +106,30 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
   T *xs = slots + (size_t)DEPTH * SLOT;                       // input vector [NR][NB] (tiles of the up step: [NR][32])
   T *parts = OVERLAY ? xs : xs + NB;                          // [task][NR][32] or [H][NR][NB]
   DagTick *ent = reinterpret_cast<DagTick *>(xs + C::work_elems(NR));
-  int *e_grow = reinterpret_cast<int *>(ent + DEPTH);         // [DEPTH][32] global row of each tile row
-  int *e_tgt = e_grow + DEPTH * 32;                           // [DEPTH][32] sub-panels owning the rows of the tile
-  int *e_g = e_tgt + DEPTH * 32;                              // [DEPTH] ticket number (>= G: none left)
+  int *s_grow = reinterpret_cast<int *>(ent + DEPTH);         // [slot][32] global row of each row of the sub-tile in the slot
+  int *e_tgt = s_grow + DEPTH * 32;                           // [entry][32] first 32 sub-panels owning rows of the ticket
+  int *e_g = e_tgt + DEPTH * 32;                              // [entry] ticket number (>= G: none left)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const T zero = ST<T>::zero();
 
-  // queue of taken tickets: entry (hd + k) % DEPTH, k < nq, occupies slots [off_k, off_k + use_k)
-  int hd = 0, nq = 0, used = 0, wr = 0;
+  // tickets taken: entries (ehd + k) % DEPTH, k < enq; the newest one is being issued sub-tile by sub-tile (iss_*);
+  // stages = sub-tiles / triangles in flight, oldest first, in slots [off_k, off_k + use_k); pk = sub-tile of the head
+  // ticket the oldest stage holds
+  int ehd = 0, enq = 0, iss_e = 0, iss_k = 0, iss_n = 0, pk = 0;
+  int snq = 0, used = 0, wr = 0;
   int off0 = 0, off1 = 0, off2 = 0, use0 = 0, use1 = 0, use2 = 0;
-  bool pending = false, exhausted = false;
+  bool exhausted = false;
+  T bacc[NR];                                                 // up step: column sums carried across the sub-tiles of a ticket
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) bacc[rr] = zero;
+  unsigned long long t_dep = 0, t_cpw = 0, t_b1 = 0, t_b2 = 0, t_fin = 0;
 
   for (;;) {
-    // ------------------------------------------------------------ top up: take tickets, issue their copies
+    // ------------------------------------------------------------ fill: take tickets, issue copies
     for (;;) {
-      const int e = (hd + nq) % DEPTH;
-      if (!pending) {
-        if (exhausted || nq == DEPTH) break;
+      if (iss_k == iss_n) {
+        if (exhausted || enq == DEPTH) break;
+        const int e = (ehd + enq) % DEPTH;
         if (warp == 0) {
           unsigned g = 0;
           if (lane == 0) g = atomicAdd(A.ticket + DIR, 1u);
@@ -132,19 +140,21 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
           }
           if (lane == 0) {
             e_g[e] = (int)min(g, (unsigned)A.G);
-            if (A.trace && g < (unsigned)A.G) A.trace[(size_t)(DIR * (size_t)A.G + g) * 4 + 0] = dag_gtime();
+            if (A.trace && g < (unsigned)A.G) A.trace[(size_t)(DIR * (size_t)A.G + g) * 8 + 0] = dag_gtime();
           }
         }
         __syncthreads();
         if (e_g[e] >= A.G) { exhausted = true; break; }
-        pending = true;
+        ++enq; iss_e = e; iss_k = 0;
+        const int mr = ent[e].mrows;
+        iss_n = mr < 0 ? 1 : (mr + ROWS - 1) / ROWS;
       }
-      const DagTick tk = ent[e];
+      const DagTick tk = ent[iss_e];
       const int nb = tk.nb;
       const bool isD = tk.mrows < 0;
       const int tri = (nb * (nb + 1)) >> 1;
       const bool wide = isD && (tri + (LDL && DIR == 0 ? nb : 0)) > SLOT;
-      if (wide ? nq > 0 : used + 1 > DEPTH) break;              // no room yet: keep it pending
+      if (wide ? snq > 0 : used + 1 > DEPTH) break;             // no room yet
       int off, use;
       if (wide) { off = 0; use = 2; wr = 2; }
       else { off = wr; use = 1; wr = (wr + 1) % DEPTH; }
@@ -163,34 +173,37 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
         }
         if (LDL && DIR == 0 && tid < nb) dag_cp_async<sizeof(T)>(buf + tri + tid, M + tk.aux + (size_t)tid * (tk.ld + 1));
       } else {
-        const T *P0 = M + tk.src;
-        const int mrows = tk.mrows;
-        if (lane < mrows)
+        const int rk = iss_k * ROWS, mr = min(ROWS, tk.mrows - rk);
+        const T *P0 = M + tk.src + rk;
+        if (lane < mr)
           for (int j = warp; j < nb; j += NT / 32) dag_cp_async<sizeof(T)>(buf + j * LDT + lane, P0 + (size_t)j * tk.ld + lane);
         if (warp == 0) {
-          if (lane < mrows) {
-            if (lane < tk.wrem) e_grow[e * 32 + lane] = tk.grow0 + lane;
-            else dag_cp_async<4>(e_grow + e * 32 + lane, A.rowglob + tk.aux + lane);
+          if (lane < mr) {
+            if (rk + lane < tk.wrem) s_grow[off * 32 + lane] = tk.grow0 + rk + lane;
+            else dag_cp_async<4>(s_grow + off * 32 + lane, A.rowglob + tk.aux + rk + lane);
           }
-          if (lane < tk.ntgt) dag_cp_async<4>(e_tgt + e * 32 + lane, A.tgt + tk.tptr + lane);
+          if (iss_k == 0 && lane < tk.ntgt) dag_cp_async<4>(e_tgt + iss_e * 32 + lane, A.tgt + tk.tptr + lane);
         }
       }
       dag_cp_commit();
-      if (nq == 0) { off0 = off; use0 = use; } else if (nq == 1) { off1 = off; use1 = use; } else { off2 = off; use2 = use; }
-      ++nq; used += use; pending = false;
+      if (snq == 0) { off0 = off; use0 = use; } else if (snq == 1) { off1 = off; use1 = use; } else { off2 = off; use2 = use; }
+      ++snq; used += use; ++iss_k;
     }
-    if (nq == 0) {
-      if (exhausted) return;
+    if (snq == 0) {
+      if (exhausted && enq == 0) return;
       continue;
     }
-    // ------------------------------------------------------------ process the head of the queue
-    const int e = hd;
+    // ------------------------------------------------------------ process the oldest stage
+    const int e = ehd;
     const DagTick tk = ent[e];
     const int nb = tk.nb;
-    T *buf = slots + (size_t)off0 * SLOT;
-    if (nq == 1) dag_cp_wait<0>(); else if (nq == 2) dag_cp_wait<1>(); else dag_cp_wait<2>();
+    const int sl = off0;
+    T *buf = slots + (size_t)sl * SLOT;
+    if (snq == 1) dag_cp_wait<0>(); else if (snq == 2) dag_cp_wait<1>(); else dag_cp_wait<2>();
     const bool isD = tk.mrows < 0;
-    unsigned long long t_dep = 0;
+    const int nsub = isD ? 1 : (tk.mrows + ROWS - 1) / ROWS;
+    const bool first = pk == 0, last = pk == nsub - 1;
+    if (A.trace && tid == 0 && first) t_cpw = dag_gtime();
 
     if (isD) {
       // ---------------- D(J).  down: x_J <- inv(L_JJ) x_J, y_J <- x_J (/ D_JJ);  up: x_J <- inv(W_JJ)^T y_J
@@ -213,6 +226,7 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
           }
         }
         __syncthreads();
+        if (A.trace && tid == 0 && r0 == 0) t_b1 = dag_gtime();
         // block tasks (row block, column block) of the lower triangle, 32 x 32 each; warp w: first task -> part w,
         // second task (the two warps that hold two triangles) -> parts 8, 9
         //   w: 0 (3,0)  1 (3,1)  2 (3,2)  3 (3,3)+(0,0)  4 (2,0)  5 (2,1)  6 (2,2)+(1,1)  7 (1,0)
@@ -234,6 +248,7 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
           if (warp == 6) parts[(9 * NR + rr) * 32 + lane] = acc1[rr];
         }
         __syncthreads();
+        if (A.trace && tid == 0 && r0 == 0) t_b2 = dag_gtime();
         if (warp == 0) {
 #pragma unroll
           for (int ob = 0; ob < 4; ++ob) {
@@ -264,30 +279,33 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
         if (OVERLAY || r0 + NR < nrhs) __syncthreads();
       }
       if (warp == 0) {
+        if (A.trace && lane == 0) t_fin = dag_gtime();
         __threadfence();
         if (lane == 0) atomicAdd((DIR == 0 ? A.ready : A.done) + tk.sp, 1u);
       }
     } else if (DIR == 0) {
       // ---------------- T(J,t), down: x[rows] -= P[rows, J] x_J
-      const int mrows = tk.mrows;
+      const int mr = min(ROWS, tk.mrows - pk * ROWS);
       const int cw = (nb + NT / 32 - 1) / (NT / 32);
       const int j0 = warp * cw, j1 = min(nb, j0 + cw);
       for (int r0 = 0; r0 < nrhs; r0 += NR) {
         const int nr = min(NR, nrhs - r0);
         if (warp == 0) {
-          if (r0 == 0) {
+          if (first && r0 == 0) {
             if (lane == 0) {
               dag_wait_ge(A.ready + tk.sp, 1u, A.err);
               if (A.trace) t_dep = dag_gtime();
             }
             __syncwarp();
           }
-          for (int k = lane; k < NR * NB; k += 32) {
-            const int rr = k / NB, j = k % NB;
-            xs[k] = (rr < nr && j < nb) ? ld_cg(&x[(size_t)(r0 + rr) * ldx + tk.xcol + j]) : zero;
-          }
+          if (first || NR > 1)        // one right-hand side: x_J stays in shared memory for all the sub-tiles of the ticket
+            for (int k = lane; k < NR * NB; k += 32) {
+              const int rr = k / NB, j = k % NB;
+              xs[k] = (rr < nr && j < nb) ? ld_cg(&x[(size_t)(r0 + rr) * ldx + tk.xcol + j]) : zero;
+            }
         }
         __syncthreads();
+        if (A.trace && tid == 0 && r0 == 0 && last) t_b1 = dag_gtime();
         T acc[NR];
 #pragma unroll
         for (int rr = 0; rr < NR; ++rr) acc[rr] = zero;
@@ -304,8 +322,9 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
 #pragma unroll
         for (int rr = 0; rr < NR; ++rr) parts[(warp * NR + rr) * 32 + lane] = acc[rr];
         __syncthreads();
-        if (warp == 0 && lane < mrows) {
-          const int grow = e_grow[e * 32 + lane];
+        if (A.trace && tid == 0 && r0 == 0 && last) t_b2 = dag_gtime();
+        if (warp == 0 && lane < mr) {
+          const int grow = s_grow[sl * 32 + lane];
           for (int rr = 0; rr < nr; ++rr) {
             T v = parts[rr * 32 + lane];
 #pragma unroll
@@ -315,32 +334,36 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
         }
         if (OVERLAY || r0 + NR < nrhs) __syncthreads();
       }
-      if (warp == 0) {
+      if (last && warp == 0) {
+        if (A.trace && lane == 0) t_fin = dag_gtime();
         __threadfence();
-        if (lane < tk.ntgt) atomicAdd(A.arrived + e_tgt[e * 32 + lane], 1u);
+        for (int q = lane; q < tk.ntgt; q += 32) atomicAdd(A.arrived + (q < 32 ? e_tgt[e * 32 + q] : A.tgt[tk.tptr + q]), 1u);
       }
     } else {
       // ---------------- T(J,t), up: y_J -= P[rows, J]^T x[rows]
       constexpr int H = NT / NB, RG = ROWS / H;
-      const int mrows = tk.mrows;
+      const int mr = min(ROWS, tk.mrows - pk * ROWS);
       const int p = tid % NB, hh = tid / NB;
-      const int i0 = hh * RG, i1 = min(mrows, i0 + RG);
+      const int i0 = hh * RG, i1 = min(mr, i0 + RG);
+      const bool single = nrhs <= NR;          // one pass: the column sums stay in registers until the last sub-tile
       for (int r0 = 0; r0 < nrhs; r0 += NR) {
         const int nr = min(NR, nrhs - r0);
         if (warp == 0) {
-          if (r0 == 0) {
-            if (lane < tk.ntgt) dag_wait_ge(A.done + e_tgt[e * 32 + lane], 1u, A.err);
+          if (first && r0 == 0) {
+            for (int q = lane; q < tk.ntgt; q += 32) dag_wait_ge(A.done + (q < 32 ? e_tgt[e * 32 + q] : A.tgt[tk.tptr + q]), 1u, A.err);
             __syncwarp();
             if (A.trace && lane == 0) t_dep = dag_gtime();
           }
-          const int grow = lane < mrows ? e_grow[e * 32 + lane] : 0;
+          const int grow = lane < mr ? s_grow[sl * 32 + lane] : 0;
 #pragma unroll
-          for (int rr = 0; rr < NR; ++rr) xs[rr * 32 + lane] = (lane < mrows && rr < nr) ? ld_cg(&x[(size_t)(r0 + rr) * ldx + grow]) : zero;
+          for (int rr = 0; rr < NR; ++rr) xs[rr * 32 + lane] = (lane < mr && rr < nr) ? ld_cg(&x[(size_t)(r0 + rr) * ldx + grow]) : zero;
         }
         __syncthreads();
-        T acc[NR];
+        if (A.trace && tid == 0 && r0 == 0 && last) t_b1 = dag_gtime();
+        if (!single || first) {
 #pragma unroll
-        for (int rr = 0; rr < NR; ++rr) acc[rr] = zero;
+          for (int rr = 0; rr < NR; ++rr) bacc[rr] = zero;
+        }
         if (p < nb) {
           const T *a = buf + p * LDT;
 #pragma unroll 4
@@ -348,13 +371,15 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
             T av = a[i];
             if (CONJ) av = ST<T>::conj(av);
 #pragma unroll
-            for (int rr = 0; rr < NR; ++rr) fma_acc(acc[rr], av, xs[rr * 32 + i]);
+            for (int rr = 0; rr < NR; ++rr) fma_acc(bacc[rr], av, xs[rr * 32 + i]);
           }
         }
+        if (single && !last) { __syncthreads(); continue; }     // slot and x[rows] may be reused; sums carried on
         if (OVERLAY) __syncthreads();
 #pragma unroll
-        for (int rr = 0; rr < NR; ++rr) parts[(hh * NR + rr) * NB + p] = acc[rr];
+        for (int rr = 0; rr < NR; ++rr) parts[(hh * NR + rr) * NB + p] = bacc[rr];
         __syncthreads();
+        if (A.trace && tid == 0 && r0 == 0 && last) t_b2 = dag_gtime();
         if (warp == 0)
           for (int c = lane; c < nb; c += 32)
             for (int rr = 0; rr < nr; ++rr) {
@@ -365,20 +390,22 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
             }
         if (OVERLAY || r0 + NR < nrhs) __syncthreads();
       }
-      if (warp == 0) {
+      if (last && warp == 0) {
+        if (A.trace && lane == 0) t_fin = dag_gtime();
         __threadfence();
         if (lane == 0) atomicAdd(A.cnt + tk.sp, 1u);
       }
     }
-    if (A.trace && tid == 0) {
-      unsigned long long *tr = A.trace + (size_t)(DIR * (size_t)A.G + (size_t)e_g[e]) * 4;
+    if (A.trace && tid == 0 && last) {
+      unsigned long long *tr = A.trace + (size_t)(DIR * (size_t)A.G + (size_t)e_g[e]) * 8;
       unsigned sm;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-      tr[1] = t_dep; tr[2] = dag_gtime(); tr[3] = ((unsigned long long)sm << 32) | (unsigned)(isD ? 1 : 0) | ((unsigned)nq << 8);
+      tr[1] = t_dep; tr[2] = dag_gtime(); tr[3] = ((unsigned long long)sm << 32) | (unsigned)(isD ? 1 : 0) | ((unsigned)snq << 8) | ((unsigned)nsub << 16);
+      tr[4] = t_cpw; tr[5] = t_b1; tr[6] = t_b2; tr[7] = t_fin;
     }
-    // pop
-    used -= use0; off0 = off1; use0 = use1; off1 = off2; use1 = use2;
-    hd = (hd + 1) % DEPTH; --nq;
+    // pop the stage; the ticket with its last sub-tile
+    used -= use0; off0 = off1; use0 = use1; off1 = off2; use1 = use2; --snq;
+    if (last) { pk = 0; ehd = (ehd + 1) % DEPTH; --enq; } else ++pk;
   }
 }
 

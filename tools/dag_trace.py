@@ -1,13 +1,14 @@
 """Dev tool: read the per-ticket time stamps k_dag2 writes with PB200_DAG_TRACE=<file> (engine.cu, solve_tf) and say
 where a sweep spends its time.  usage: python tools/dag_trace.py trace.bin
-record = {taken, dependencies met, done, (sm << 32) | queue depth << 8 | is-diagonal}, ns of %globaltimer."""
+record = {taken, dependencies met, done, (sm << 32) | sub-tiles << 16 | stages in flight << 8 | is-diagonal, copies landed,
+input vector in shared memory, partial sums written, before the fence}, ns of %globaltimer."""
 import sys
 
 import numpy as np
 
 
 def main():
-    tr = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(2, -1, 4)
+    tr = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(2, -1, 8)
     G = tr.shape[1]
     for d, name in enumerate(("down", "up")):
         t = tr[d]
@@ -24,6 +25,8 @@ def main():
             if not m.any():
                 continue
             w = (dep - take)[m]; p = (end - dep)[m]
+            ph = [np.median((t[ok, b].astype(np.int64) - t[ok, a].astype(np.int64))[m]) / 1e3 for a, b in ((1, 5), (5, 6), (6, 7), (7, 2))]
+            print(f"  {lab}: dep->vector in smem {ph[0]:.2f} | product {ph[1]:.2f} | combine+stores {ph[2]:.2f} | fence+signal {ph[3]:.2f} us (medians, last sub-tile)")
             print(f"  {lab}: n={m.sum():6d}  wait(dep-take) med {np.median(w) / 1e3:7.2f} p90 {np.percentile(w, 90) / 1e3:7.2f} us | "
                   f"work(end-dep) med {np.median(p) / 1e3:6.2f} p90 {np.percentile(p, 90) / 1e3:6.2f} max {p.max() / 1e3:6.2f} us | queue depth mean {nq[m].mean():.2f}")
         # progress of the ticket frontier: when was ticket k finished
