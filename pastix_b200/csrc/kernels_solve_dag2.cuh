@@ -42,7 +42,7 @@ template <class T> struct Dag2Cfg {
   // work region: input vector + partial sums; with several right-hand sides the partial sums overlay the vector
   __host__ __device__ static constexpr size_t work_elems(int NR) { return NR == 1 ? (size_t)NB + PB200_DAG2_PARTS : (size_t)PB200_DAG2_PARTS * NR; }
   __host__ __device__ static constexpr size_t bytes(int NR) {
-    return ((size_t)PB200_DAG2_DEPTH * SLOT + work_elems(NR)) * sizeof(T) + PB200_DAG2_DEPTH * (sizeof(DagTick) + 2 * 32 * sizeof(int) + sizeof(int)) + 16;
+    return ((size_t)PB200_DAG2_DEPTH * SLOT + work_elems(NR)) * sizeof(T) + PB200_DAG2_DEPTH * (sizeof(DagTick) + 2 * 32 * sizeof(int) + sizeof(int) + sizeof(unsigned long long)) + 32;
   }
 };
 
@@ -93,6 +93,14 @@ __device__ __forceinline__ void dag2_tri_task(T (&acc)[NR], const T *buf, const 
 // DIR 0: down + diagonal step over coeftab;  DIR 1: up step over coeftab (ucoeftab for LU), tickets in reverse.
 // A T ticket covers up to 8 sub-tiles of 32 panel rows (the host picks the size per level: large where a level has
 // thousands of tiles, one sub-tile where the level is a link of the dependency chain); the ring holds sub-tiles.
+//
+// Three warps carry the latency chains, so that they overlap instead of adding up (measured on the first cut of this
+// kernel, tools/dag_trace.py: 1.2 us to take a ticket, 0.5-1 us from "dependency met" to "vector in shared memory",
+// 0.6-0.7 us for fence + signal — 4.4 us per ticket and CTA when one warp did them in turn):
+//   warp 2 (take)  has the NEXT ticket number and its 64-byte record on their way while the current ones are worked on;
+//   warp 1 (head)  polls the dependency of the next stage and loads its input vector from L2 — with one right-hand side
+//                  it does so while
+//   warp 0 (tail)  is still reducing, fencing and signalling the current one.
 template <class T, int FACTO, int DIR, int NR>
 __global__ void __launch_bounds__(PB200_DAG2_NT, 2)
 k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t ldx, int nrhs, DagArgs A) {
@@ -101,6 +109,8 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
   constexpr bool LDL = (FACTO == F_LDLT || FACTO == F_LDLH);
   constexpr bool CONJ = (DIR == 1 && FACTO == F_LDLH);
   constexpr bool OVERLAY = (NR > 1);
+  constexpr bool PIPE = (NR == 1);                            // head of the next stage overlaps the tail of this one
+  constexpr int WT = 0, WH = 1, WK = 2;
   extern __shared__ __align__(16) unsigned char dag2_smem[];
   T *slots = reinterpret_cast<T *>(dag2_smem);
   T *xs = slots + (size_t)DEPTH * SLOT;                       // input vector [NR][NB] (tiles of the up step: [NR][32])
@@ -109,6 +119,7 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
   int *s_grow = reinterpret_cast<int *>(ent + DEPTH);         // [slot][32] global row of each row of the sub-tile in the slot
   int *e_tgt = s_grow + DEPTH * 32;                           // [entry][32] first 32 sub-panels owning rows of the ticket
   int *e_g = e_tgt + DEPTH * 32;                              // [entry] ticket number (>= G: none left)
+  unsigned long long *e_dep = reinterpret_cast<unsigned long long *>(e_g + DEPTH + 1);   // [entry] trace: dependencies met
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const T zero = ST<T>::zero();
 
@@ -118,11 +129,68 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
   int ehd = 0, enq = 0, iss_e = 0, iss_k = 0, iss_n = 0, pk = 0;
   int snq = 0, used = 0, wr = 0;
   int off0 = 0, off1 = 0, off2 = 0, use0 = 0, use1 = 0, use2 = 0;
-  bool exhausted = false;
+  bool exhausted = false, head_done = false;
   T bacc[NR];                                                 // up step: column sums carried across the sub-tiles of a ticket
 #pragma unroll
   for (int rr = 0; rr < NR; ++rr) bacc[rr] = zero;
   unsigned long long t_dep = 0, t_cpw = 0, t_b1 = 0, t_b2 = 0, t_fin = 0;
+
+  // warp WK: ticket taken ahead (number + one word of its record per lane)
+  unsigned nx_g = (unsigned)A.G; int nx_w = 0;
+  auto pretake = [&]() {
+    unsigned g = 0;
+    if (lane == 0) g = atomicAdd(A.ticket + DIR, 1u);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    nx_g = min(g, (unsigned)A.G);
+    if (g < (unsigned)A.G && lane < 16) {
+      const int gi = DIR ? A.G - 1 - (int)g : (int)g;
+      nx_w = __ldg(reinterpret_cast<const int *>(A.ticks + gi) + lane);
+    }
+  };
+  if (warp == WK) pretake();
+
+  // head of a stage (warp WH): dependency of the ticket (first sub-tile), input vector of pass r0 into shared memory
+  auto head = [&](const DagTick &tk, int eh, int sh, int kh, int r0) {
+    const int nb = tk.nb, nr = min(NR, nrhs - r0);
+    if (tk.mrows < 0) {
+      if (r0 == 0) {
+        if (lane == 0) {
+          if (DIR == 0) dag_wait_ge(A.arrived + tk.sp, (unsigned)tk.pad0, A.err);
+          else dag_wait_ge(A.cnt + tk.sp, (unsigned)tk.nsib, A.err);
+          if (A.trace) e_dep[eh] = dag_gtime();
+        }
+        __syncwarp();
+      }
+      const T *vin = DIR == 0 ? x : y;
+      for (int k = lane; k < NR * NB; k += 32) {
+        const int rr = k / NB, j = k % NB;
+        xs[k] = (rr < nr && j < nb) ? ld_cg(&vin[(size_t)(r0 + rr) * ldx + tk.xcol + j]) : zero;
+      }
+    } else if (DIR == 0) {
+      if (kh == 0 && r0 == 0) {
+        if (lane == 0) {
+          dag_wait_ge(A.ready + tk.sp, 1u, A.err);
+          if (A.trace) e_dep[eh] = dag_gtime();
+        }
+        __syncwarp();
+      }
+      if (kh == 0 || NR > 1)          // one right-hand side: x_J stays in shared memory for all the sub-tiles of the ticket
+        for (int k = lane; k < NR * NB; k += 32) {
+          const int rr = k / NB, j = k % NB;
+          xs[k] = (rr < nr && j < nb) ? ld_cg(&x[(size_t)(r0 + rr) * ldx + tk.xcol + j]) : zero;
+        }
+    } else {
+      const int mr = min(ROWS, tk.mrows - kh * ROWS);
+      if (kh == 0 && r0 == 0) {
+        for (int q = lane; q < tk.ntgt; q += 32) dag_wait_ge(A.done + (q < 32 ? e_tgt[eh * 32 + q] : A.tgt[tk.tptr + q]), 1u, A.err);
+        __syncwarp();
+        if (A.trace && lane == 0) e_dep[eh] = dag_gtime();
+      }
+      const int grow = lane < mr ? s_grow[sh * 32 + lane] : 0;
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) xs[rr * 32 + lane] = (lane < mr && rr < nr) ? ld_cg(&x[(size_t)(r0 + rr) * ldx + grow]) : zero;
+    }
+  };
 
   for (;;) {
     // ------------------------------------------------------------ fill: take tickets, issue copies
@@ -130,18 +198,14 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
       if (iss_k == iss_n) {
         if (exhausted || enq == DEPTH) break;
         const int e = (ehd + enq) % DEPTH;
-        if (warp == 0) {
-          unsigned g = 0;
-          if (lane == 0) g = atomicAdd(A.ticket + DIR, 1u);
-          g = __shfl_sync(0xffffffffu, g, 0);
-          if (g < (unsigned)A.G && lane < 16) {
-            const int gi = DIR ? A.G - 1 - (int)g : (int)g;
-            reinterpret_cast<int *>(ent + e)[lane] = __ldg(reinterpret_cast<const int *>(A.ticks + gi) + lane);
-          }
+        if (warp == WK) {
+          const bool valid = nx_g < (unsigned)A.G;
+          if (valid && lane < 16) reinterpret_cast<int *>(ent + e)[lane] = nx_w;
           if (lane == 0) {
-            e_g[e] = (int)min(g, (unsigned)A.G);
-            if (A.trace && g < (unsigned)A.G) A.trace[(size_t)(DIR * (size_t)A.G + g) * 8 + 0] = dag_gtime();
+            e_g[e] = (int)nx_g;
+            if (A.trace && valid) A.trace[(size_t)(DIR * (size_t)A.G + nx_g) * 8 + 0] = dag_gtime();
           }
+          if (valid) pretake();
         }
         __syncthreads();
         if (e_g[e] >= A.G) { exhausted = true; break; }
@@ -177,7 +241,7 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
         const T *P0 = M + tk.src + rk;
         if (lane < mr)
           for (int j = warp; j < nb; j += NT / 32) dag_cp_async<sizeof(T)>(buf + j * LDT + lane, P0 + (size_t)j * tk.ld + lane);
-        if (warp == 0) {
+        if (warp == WH) {                        // read back by the head warp before any barrier: its own copies
           if (lane < mr) {
             if (rk + lane < tk.wrem) s_grow[off * 32 + lane] = tk.grow0 + rk + lane;
             else dag_cp_async<4>(s_grow + off * 32 + lane, A.rowglob + tk.aux + rk + lane);
@@ -196,6 +260,7 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
     // ------------------------------------------------------------ process the oldest stage
     const int e = ehd;
     const DagTick tk = ent[e];
+    const int my_g = e_g[e];
     const int nb = tk.nb;
     const int sl = off0;
     T *buf = slots + (size_t)sl * SLOT;
@@ -203,33 +268,29 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
     const bool isD = tk.mrows < 0;
     const int nsub = isD ? 1 : (tk.mrows + ROWS - 1) / ROWS;
     const bool first = pk == 0, last = pk == nsub - 1;
+    const int mr = isD ? 0 : min(ROWS, tk.mrows - pk * ROWS);
     if (A.trace && tid == 0 && first) t_cpw = dag_gtime();
+    // what the tail needs from tables the next stages may overwrite while it runs: read after the first barrier
+    int my_grow = 0, my_tgt = 0;
+    T dreg[4];
+#pragma unroll
+    for (int ob = 0; ob < 4; ++ob) dreg[ob] = ST<T>::from_real(1.0);
 
-    if (isD) {
-      // ---------------- D(J).  down: x_J <- inv(L_JJ) x_J, y_J <- x_J (/ D_JJ);  up: x_J <- inv(W_JJ)^T y_J
-      const T *vin = DIR == 0 ? x : y;
-      const int tri = (nb * (nb + 1)) >> 1;
-      for (int r0 = 0; r0 < nrhs; r0 += NR) {
-        const int nr = min(NR, nrhs - r0);
-        if (warp == 0) {
-          if (r0 == 0) {
-            if (lane == 0) {
-              if (DIR == 0) dag_wait_ge(A.arrived + tk.sp, (unsigned)tk.pad0, A.err);
-              else dag_wait_ge(A.cnt + tk.sp, (unsigned)tk.nsib, A.err);
-              if (A.trace) t_dep = dag_gtime();
-            }
-            __syncwarp();
-          }
-          for (int k = lane; k < NR * NB; k += 32) {
-            const int rr = k / NB, j = k % NB;
-            xs[k] = (rr < nr && j < nb) ? ld_cg(&vin[(size_t)(r0 + rr) * ldx + tk.xcol + j]) : zero;
-          }
-        }
-        __syncthreads();
-        if (A.trace && tid == 0 && r0 == 0) t_b1 = dag_gtime();
+    for (int r0 = 0; r0 < nrhs; r0 += NR) {
+      const int nr = min(NR, nrhs - r0);
+      if (warp == WH && !(r0 == 0 && head_done)) head(tk, e, sl, pk, r0);
+      __syncthreads();
+      if (A.trace && tid == 0 && r0 == 0 && last) { t_b1 = dag_gtime(); t_dep = e_dep[e]; }
+      if (warp == WT && r0 == 0) {
+        if (!isD && lane < mr) my_grow = s_grow[sl * 32 + lane];
+        if (!isD && lane < min(tk.ntgt, 32)) my_tgt = e_tgt[e * 32 + lane];
+      }
+      if (isD) {
+        // ---------------- D(J).  down: x_J <- inv(L_JJ) x_J, y_J <- x_J (/ D_JJ);  up: x_J <- inv(W_JJ)^T y_J
         // block tasks (row block, column block) of the lower triangle, 32 x 32 each; warp w: first task -> part w,
         // second task (the two warps that hold two triangles) -> parts 8, 9
         //   w: 0 (3,0)  1 (3,1)  2 (3,2)  3 (3,3)+(0,0)  4 (2,0)  5 (2,1)  6 (2,2)+(1,1)  7 (1,0)
+        const int tri = (nb * (nb + 1)) >> 1;
         T acc0[NR], acc1[NR];
 #pragma unroll
         for (int rr = 0; rr < NR; ++rr) acc0[rr] = acc1[rr] = zero;
@@ -237,9 +298,10 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
         if (warp == 3) dag2_tri_task<T, NR, DIR, CONJ>(acc1, buf, xs, nb, 0, 0, lane);
         if (warp == 6) dag2_tri_task<T, NR, DIR, CONJ>(acc1, buf, xs, nb, 1, 1, lane);
         // the diagonal of LDLt sits behind the triangle in the slot: read it before the slot can be handed on
-        T dreg[4];
+        if (LDL && DIR == 0 && warp == WT && r0 == 0) {
 #pragma unroll
-        for (int ob = 0; ob < 4; ++ob) dreg[ob] = (LDL && DIR == 0 && warp == 0 && 32 * ob + lane < nb) ? buf[tri + 32 * ob + lane] : ST<T>::from_real(1.0);
+          for (int ob = 0; ob < 4; ++ob) if (32 * ob + lane < nb) dreg[ob] = buf[tri + 32 * ob + lane];
+        }
         if (OVERLAY) __syncthreads();
 #pragma unroll
         for (int rr = 0; rr < NR; ++rr) {
@@ -247,9 +309,56 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
           if (warp == 3) parts[(8 * NR + rr) * 32 + lane] = acc1[rr];
           if (warp == 6) parts[(9 * NR + rr) * 32 + lane] = acc1[rr];
         }
-        __syncthreads();
-        if (A.trace && tid == 0 && r0 == 0) t_b2 = dag_gtime();
-        if (warp == 0) {
+      } else if (DIR == 0) {
+        // ---------------- T(J,t), down: x[rows] -= P[rows, J] x_J
+        const int cw = (nb + NT / 32 - 1) / (NT / 32);
+        const int j0 = warp * cw, j1 = min(nb, j0 + cw);
+        T acc[NR];
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) acc[rr] = zero;
+        {
+          const T *a = buf + j0 * LDT + lane;
+#pragma unroll 4
+          for (int j = j0; j < j1; ++j, a += LDT) {
+            const T av = *a;
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) fma_acc(acc[rr], av, xs[rr * NB + j]);
+          }
+        }
+        if (OVERLAY) __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) parts[(warp * NR + rr) * 32 + lane] = acc[rr];
+      } else {
+        // ---------------- T(J,t), up: y_J -= P[rows, J]^T x[rows]
+        constexpr int H = NT / NB, RG = ROWS / H;
+        const int p = tid % NB, hh = tid / NB;
+        const int i0 = hh * RG, i1 = min(mr, i0 + RG);
+        const bool single = nrhs <= NR;        // one pass: the column sums stay in registers until the last sub-tile
+        if (!single || first) {
+#pragma unroll
+          for (int rr = 0; rr < NR; ++rr) bacc[rr] = zero;
+        }
+        if (p < nb) {
+          const T *a = buf + p * LDT;
+#pragma unroll 4
+          for (int i = i0; i < i1; ++i) {
+            T av = a[i];
+            if (CONJ) av = ST<T>::conj(av);
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) fma_acc(bacc[rr], av, xs[rr * 32 + i]);
+          }
+        }
+        if (!(single && !last)) {
+          if (OVERLAY) __syncthreads();
+#pragma unroll
+          for (int rr = 0; rr < NR; ++rr) parts[(hh * NR + rr) * NB + p] = bacc[rr];
+        }
+      }
+      __syncthreads();       // products done: the slot and the vector may be reused, the partial sums are visible
+      if (A.trace && tid == 0 && r0 == 0 && last) t_b2 = dag_gtime();
+      // ---- reductions and stores of this pass (tail warp)
+      if (warp == WT) {
+        if (isD) {
 #pragma unroll
           for (int ob = 0; ob < 4; ++ob) {
             const int p = 32 * ob + lane;
@@ -275,112 +384,16 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
               if (DIR == 0) y[(size_t)(r0 + rr) * ldx + tk.xcol + p] = LDL ? v / d : v;
             }
           }
-        }
-        if (OVERLAY || r0 + NR < nrhs) __syncthreads();
-      }
-      if (warp == 0) {
-        if (A.trace && lane == 0) t_fin = dag_gtime();
-        __threadfence();
-        if (lane == 0) atomicAdd((DIR == 0 ? A.ready : A.done) + tk.sp, 1u);
-      }
-    } else if (DIR == 0) {
-      // ---------------- T(J,t), down: x[rows] -= P[rows, J] x_J
-      const int mr = min(ROWS, tk.mrows - pk * ROWS);
-      const int cw = (nb + NT / 32 - 1) / (NT / 32);
-      const int j0 = warp * cw, j1 = min(nb, j0 + cw);
-      for (int r0 = 0; r0 < nrhs; r0 += NR) {
-        const int nr = min(NR, nrhs - r0);
-        if (warp == 0) {
-          if (first && r0 == 0) {
-            if (lane == 0) {
-              dag_wait_ge(A.ready + tk.sp, 1u, A.err);
-              if (A.trace) t_dep = dag_gtime();
+        } else if (DIR == 0) {
+          if (lane < mr)
+            for (int rr = 0; rr < nr; ++rr) {
+              T v = parts[rr * 32 + lane];
+#pragma unroll
+              for (int q = 1; q < NT / 32; ++q) v += parts[(q * NR + rr) * 32 + lane];
+              atomic_sub(&x[(size_t)(r0 + rr) * ldx + my_grow], v);
             }
-            __syncwarp();
-          }
-          if (first || NR > 1)        // one right-hand side: x_J stays in shared memory for all the sub-tiles of the ticket
-            for (int k = lane; k < NR * NB; k += 32) {
-              const int rr = k / NB, j = k % NB;
-              xs[k] = (rr < nr && j < nb) ? ld_cg(&x[(size_t)(r0 + rr) * ldx + tk.xcol + j]) : zero;
-            }
-        }
-        __syncthreads();
-        if (A.trace && tid == 0 && r0 == 0 && last) t_b1 = dag_gtime();
-        T acc[NR];
-#pragma unroll
-        for (int rr = 0; rr < NR; ++rr) acc[rr] = zero;
-        {
-          const T *a = buf + j0 * LDT + lane;
-#pragma unroll 4
-          for (int j = j0; j < j1; ++j, a += LDT) {
-            const T av = *a;
-#pragma unroll
-            for (int rr = 0; rr < NR; ++rr) fma_acc(acc[rr], av, xs[rr * NB + j]);
-          }
-        }
-        if (OVERLAY) __syncthreads();
-#pragma unroll
-        for (int rr = 0; rr < NR; ++rr) parts[(warp * NR + rr) * 32 + lane] = acc[rr];
-        __syncthreads();
-        if (A.trace && tid == 0 && r0 == 0 && last) t_b2 = dag_gtime();
-        if (warp == 0 && lane < mr) {
-          const int grow = s_grow[sl * 32 + lane];
-          for (int rr = 0; rr < nr; ++rr) {
-            T v = parts[rr * 32 + lane];
-#pragma unroll
-            for (int q = 1; q < NT / 32; ++q) v += parts[(q * NR + rr) * 32 + lane];
-            atomic_sub(&x[(size_t)(r0 + rr) * ldx + grow], v);
-          }
-        }
-        if (OVERLAY || r0 + NR < nrhs) __syncthreads();
-      }
-      if (last && warp == 0) {
-        if (A.trace && lane == 0) t_fin = dag_gtime();
-        __threadfence();
-        for (int q = lane; q < tk.ntgt; q += 32) atomicAdd(A.arrived + (q < 32 ? e_tgt[e * 32 + q] : A.tgt[tk.tptr + q]), 1u);
-      }
-    } else {
-      // ---------------- T(J,t), up: y_J -= P[rows, J]^T x[rows]
-      constexpr int H = NT / NB, RG = ROWS / H;
-      const int mr = min(ROWS, tk.mrows - pk * ROWS);
-      const int p = tid % NB, hh = tid / NB;
-      const int i0 = hh * RG, i1 = min(mr, i0 + RG);
-      const bool single = nrhs <= NR;          // one pass: the column sums stay in registers until the last sub-tile
-      for (int r0 = 0; r0 < nrhs; r0 += NR) {
-        const int nr = min(NR, nrhs - r0);
-        if (warp == 0) {
-          if (first && r0 == 0) {
-            for (int q = lane; q < tk.ntgt; q += 32) dag_wait_ge(A.done + (q < 32 ? e_tgt[e * 32 + q] : A.tgt[tk.tptr + q]), 1u, A.err);
-            __syncwarp();
-            if (A.trace && lane == 0) t_dep = dag_gtime();
-          }
-          const int grow = lane < mr ? s_grow[sl * 32 + lane] : 0;
-#pragma unroll
-          for (int rr = 0; rr < NR; ++rr) xs[rr * 32 + lane] = (lane < mr && rr < nr) ? ld_cg(&x[(size_t)(r0 + rr) * ldx + grow]) : zero;
-        }
-        __syncthreads();
-        if (A.trace && tid == 0 && r0 == 0 && last) t_b1 = dag_gtime();
-        if (!single || first) {
-#pragma unroll
-          for (int rr = 0; rr < NR; ++rr) bacc[rr] = zero;
-        }
-        if (p < nb) {
-          const T *a = buf + p * LDT;
-#pragma unroll 4
-          for (int i = i0; i < i1; ++i) {
-            T av = a[i];
-            if (CONJ) av = ST<T>::conj(av);
-#pragma unroll
-            for (int rr = 0; rr < NR; ++rr) fma_acc(bacc[rr], av, xs[rr * 32 + i]);
-          }
-        }
-        if (single && !last) { __syncthreads(); continue; }     // slot and x[rows] may be reused; sums carried on
-        if (OVERLAY) __syncthreads();
-#pragma unroll
-        for (int rr = 0; rr < NR; ++rr) parts[(hh * NR + rr) * NB + p] = bacc[rr];
-        __syncthreads();
-        if (A.trace && tid == 0 && r0 == 0 && last) t_b2 = dag_gtime();
-        if (warp == 0)
+        } else if (!(nrhs <= NR && !last)) {
+          constexpr int H = NT / NB;
           for (int c = lane; c < nb; c += 32)
             for (int rr = 0; rr < nr; ++rr) {
               T v = parts[rr * NB + c];
@@ -388,20 +401,40 @@ k_dag2(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, int64_t l
               for (int q = 1; q < H; ++q) v += parts[(q * NR + rr) * NB + c];
               atomic_sub(&y[(size_t)(r0 + rr) * ldx + tk.xcol + c], v);
             }
-        if (OVERLAY || r0 + NR < nrhs) __syncthreads();
+        }
       }
-      if (last && warp == 0) {
-        if (A.trace && lane == 0) t_fin = dag_gtime();
-        __threadfence();
+      if (OVERLAY || r0 + NR < nrhs) __syncthreads();
+    }
+    // ---- the ticket is complete with its last sub-tile: fence + signal (tail warp) ...
+    if (last && warp == WT) {
+      if (A.trace && lane == 0) t_fin = dag_gtime();
+      __threadfence();
+      if (isD) {
+        if (lane == 0) atomicAdd((DIR == 0 ? A.ready : A.done) + tk.sp, 1u);
+      } else if (DIR == 0) {
+        if (lane < min(tk.ntgt, 32)) atomicAdd(A.arrived + my_tgt, 1u);
+        for (int q = 32 + lane; q < tk.ntgt; q += 32) atomicAdd(A.arrived + A.tgt[tk.tptr + q], 1u);
+      } else {
         if (lane == 0) atomicAdd(A.cnt + tk.sp, 1u);
       }
+      if (A.trace && lane == 0) {
+        unsigned long long *tr = A.trace + (size_t)(DIR * (size_t)A.G + (size_t)my_g) * 8;
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        tr[1] = t_dep; tr[2] = dag_gtime(); tr[3] = ((unsigned long long)sm << 32) | (unsigned)(isD ? 1 : 0) | ((unsigned)snq << 8) | ((unsigned)nsub << 16);
+        tr[4] = t_cpw; tr[5] = t_b1; tr[6] = t_b2; tr[7] = t_fin;
+      }
     }
-    if (A.trace && tid == 0 && last) {
-      unsigned long long *tr = A.trace + (size_t)(DIR * (size_t)A.G + (size_t)e_g[e]) * 8;
-      unsigned sm;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-      tr[1] = t_dep; tr[2] = dag_gtime(); tr[3] = ((unsigned long long)sm << 32) | (unsigned)(isD ? 1 : 0) | ((unsigned)snq << 8) | ((unsigned)nsub << 16);
-      tr[4] = t_cpw; tr[5] = t_b1; tr[6] = t_b2; tr[7] = t_fin;
+    // ---- ... while the head warp already polls and loads for the next stage in the queue (one right-hand side)
+    head_done = false;
+    if (PIPE && snq >= 2) {
+      const int e2 = last ? (e + 1) % DEPTH : e, k2 = last ? 0 : pk + 1;
+      if (warp == WH) {
+        if (snq == 2) dag_cp_wait<0>(); else dag_cp_wait<1>();      // its own copies of that stage (row numbers, dependents)
+        const DagTick tk2 = ent[e2];
+        head(tk2, e2, off1, k2, 0);
+      }
+      head_done = true;
     }
     // pop the stage; the ticket with its last sub-tile
     used -= use0; off0 = off1; use0 = use1; off1 = off2; use1 = use2; --snq;
