@@ -8,7 +8,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "lib", "libpastix_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("engine.cu", "csc_build.cu", "probe.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("scalar.cuh", "symbol.cuh", "kernels_factor.cuh", "kernels_solve.cuh", "kernels_solve_dag.cuh", "kernels_solve_dag2.cuh", "kernels_small.cuh", "kernels_raff.cuh", "kernels_mma.cuh", "mma.cuh", "kernels_dist.cuh", "dist_plan.h", "csc_build.h")] + \
+HEADERS = [os.path.join(_HERE, "csrc", f) for f in ("scalar.cuh", "symbol.cuh", "kernels_factor.cuh", "kernels_solve.cuh", "kernels_solve_dag.cuh", "kernels_solve_dag2.cuh", "kernels_solve_dag3.cuh", "kernels_small.cuh", "kernels_raff.cuh", "kernels_mma.cuh", "mma.cuh", "kernels_dist.cuh", "dist_plan.h", "csc_build.h")] + \
           [os.path.join(_HERE, "..", "include", "pastix_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--threads", "4"]

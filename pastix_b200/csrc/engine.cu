@@ -17,6 +17,7 @@
 #include "kernels_solve.cuh"
 #include "kernels_solve_dag.cuh"
 #include "kernels_solve_dag2.cuh"
+#include "kernels_solve_dag3.cuh"
 #include "kernels_mma.cuh"
 #include "kernels_dist.cuh"
 #include "kernels_small.cuh"
@@ -82,7 +83,9 @@ struct pb200_handle_s {
   unsigned int *d_slv_cnt = nullptr;
   // persistent counter-ordered sweeps (kernels_solve_dag.cuh)
   bool dag_ok = false; int dag_tiles = 0, dag_nbs = 0;
-  int dag_rows = PB200_DAG2_ROWS;                                // panel rows per T ticket: 32 (k_dag2), 64 (k_fwd_dag / k_bwd_dag, PB200_DAG_V1=1)
+  int dag_rows = PB200_DAG_ROWS;                                 // panel rows per T sub-tile of the general list: 64 (k_fwd_dag / k_bwd_dag), 32 (k_dag2, PB200_DAG_V2=1)
+  bool dag3_ok = false; int dag3_GD = 0, dag3_GT = 0;            // third generation (one right-hand side): D and T ticket lists
+  DagTick *d_dag3_ticksD = nullptr, *d_dag3_ticksT = nullptr; int *d_dag3_tgt = nullptr;
   unsigned long long *d_dag_trace = nullptr;                     // PB200_DAG_TRACE=<file>: per-ticket time stamps of the last solve
   DagTick *d_dag_ticks = nullptr; int *d_dag_tgt = nullptr;
   unsigned int *d_dag_need = nullptr, *d_dag_state = nullptr;   // state: arrived[nsp] ready[nsp] done[nsp] cnt[nsp] ticket[2] err[1]
@@ -191,8 +194,7 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
   const int NB = (h->flt == PB200_COMPLEXDOUBLE) ? SlvCfg<cdouble>::NB : SlvCfg<double>::NB;
   const int64_t C = h->cblknbr;
   const int nsp = (int)tasks.size();
-  h->dag_rows = getenv("PB200_DAG_V1") != nullptr ? PB200_DAG_ROWS : PB200_DAG2_ROWS;
-  const int DROWS = h->dag_rows;
+  const int DROWS = 32;      // finest tiling any generation uses (ticket count bound below)
   // (cblk, round) -> sub-panel id, and the sub-panel width of each cblk
   std::vector<int> sp_ptr(C + 1, 0), sw(C, 1);
   for (int64_t c = 0; c < C; ++c) {
@@ -222,87 +224,110 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
     nticks += (std::max(mend[tk.cblk], tk.c1) - tk.c1 + DROWS - 1) / DROWS;
   }
   if (nticks >= (1LL << 24)) return PB200_SUCCESS;   // millions of tiny tickets: the level sweeps batch them better
-  std::vector<DagTick> ticks; ticks.reserve((size_t)nticks);
-  std::vector<int> tgt; tgt.reserve((size_t)nticks * 3);
-  std::vector<unsigned int> need(nsp, 0);
-  std::vector<long long> stamp(nsp, -1);
-  std::vector<int> ntk(nsp, 0);                    // T tickets of each sub-panel
-  auto emit_D = [&](int i) {
-    const SlvTask &tk = tasks[i];
-    const int ld = tk.ld, nb = tk.c1 - tk.c0;
-    DagTick d{};
-    d.src = tk.invoff; d.aux = tk.poff + (int64_t)tk.c0 * (ld + 1); d.ld = ld; d.nb = nb; d.mrows = -1; d.sp = tk.sp;
-    d.xcol = tk.fcol + tk.c0; d.nsib = 0;
-    ticks.push_back(d);
-  };
-  // T tickets of sub-panel i, `trows` panel rows each
-  auto emit_T = [&](int i, int trows) {
-    const SlvTask &tk = tasks[i];
-    const int c = tk.cblk, w = tk.w, ld = tk.ld, nb = tk.c1 - tk.c0;
-    const int me = std::max(mend[c], tk.c1);   // rows [c1, me) of the panel take part
-    const int nt = (me - tk.c1 + trows - 1) / trows;
-    ntk[i] = nt;
-    int b = h->h_fblok[c] + 1;                    // first off-diagonal blok
-    const int be = h->h_fblok[c + 1];
-    for (int t = 0; t < nt; ++t) {
-      const long long g = (long long)ticks.size();
-      const int m0 = tk.c1 + t * trows, m1 = std::min(me, m0 + trows);
-      DagTick k{};
-      k.src = tk.poff + (int64_t)tk.c0 * ld + m0; k.aux = tk.rgbase + m0; k.ld = ld; k.nb = nb; k.mrows = m1 - m0; k.sp = tk.sp;
-      k.xcol = tk.fcol + tk.c0; k.grow0 = tk.fcol + m0; k.wrem = w - m0; k.tptr = (int)tgt.size();
-      auto add = [&](int s) { if (stamp[s] != g) { stamp[s] = g; tgt.push_back(s); ++need[s]; } };
-      // rows still inside the diagonal block: later sub-panels of the same cblk
-      for (int m = m0; m < std::min(m1, w); m = (m / sw[c] + 1) * sw[c]) add(spid[sp_ptr[c] + m / sw[c]]);
-      // off-diagonal rows: the bloks crossing [m0, m1)
-      while (b < be && h->h_coefind[b] + h->h_nrow[b] <= m0) ++b;
-      for (int bb = b; bb < be && h->h_coefind[bb] < m1; ++bb) {
-        const int fc = h->h_fcblk[bb];
-        const int lo = std::max(m0, h->h_coefind[bb]), hi = std::min(m1, h->h_coefind[bb] + h->h_nrow[bb]);   // panel rows [lo, hi)
-        const int o0 = h->h_frow[bb] + (lo - h->h_coefind[bb]) - h->h_fcol[fc], o1 = h->h_frow[bb] + (hi - 1 - h->h_coefind[bb]) - h->h_fcol[fc];
-        for (int r = o0 / sw[fc]; r <= o1 / sw[fc]; ++r) add(spid[sp_ptr[fc] + r]);
+  // One ticket list.  rows: panel rows per sub-tile; blocked: per (level, round) step all D tickets, then all T tickets,
+  // T tickets grown to up to 8 sub-tiles where a step has thousands of them (second and third generation); split:
+  // D and T tickets in two lists (third generation).  need[] = T tickets contributing to each sub-panel.
+  struct DagList { std::vector<DagTick> ticks, ticksT; std::vector<int> tgt; std::vector<unsigned int> need; };
+  auto build_list = [&](int rows, bool blocked, bool split, long long grow_at, DagList &L) {
+    L.ticks.reserve((size_t)nticks); L.tgt.reserve((size_t)nticks * 3);
+    L.need.assign(nsp, 0);
+    std::vector<DagTick> &tt = split ? L.ticksT : L.ticks;
+    std::vector<long long> stamp(nsp, -1);
+    std::vector<int> ntk(nsp, 0);                    // T tickets of each sub-panel
+    long long serial = 0;
+    auto emit_D = [&](int i) {
+      const SlvTask &tk = tasks[i];
+      const int ld = tk.ld, nb = tk.c1 - tk.c0;
+      DagTick d{};
+      d.src = tk.invoff; d.aux = tk.poff + (int64_t)tk.c0 * (ld + 1); d.ld = ld; d.nb = nb; d.mrows = -1; d.sp = tk.sp;
+      d.xcol = tk.fcol + tk.c0; d.nsib = 0;
+      L.ticks.push_back(d);
+    };
+    // T tickets of sub-panel i, `trows` panel rows each
+    auto emit_T = [&](int i, int trows) {
+      const SlvTask &tk = tasks[i];
+      const int c = tk.cblk, w = tk.w, ld = tk.ld, nb = tk.c1 - tk.c0;
+      const int me = std::max(mend[c], tk.c1);   // rows [c1, me) of the panel take part
+      const int nt = (me - tk.c1 + trows - 1) / trows;
+      ntk[i] = nt;
+      int b = h->h_fblok[c] + 1;                    // first off-diagonal blok
+      const int be = h->h_fblok[c + 1];
+      for (int t = 0; t < nt; ++t) {
+        const long long g = serial++;
+        const int m0 = tk.c1 + t * trows, m1 = std::min(me, m0 + trows);
+        DagTick k{};
+        k.src = tk.poff + (int64_t)tk.c0 * ld + m0; k.aux = tk.rgbase + m0; k.ld = ld; k.nb = nb; k.mrows = m1 - m0; k.sp = tk.sp;
+        k.xcol = tk.fcol + tk.c0; k.grow0 = tk.fcol + m0; k.wrem = w - m0; k.tptr = (int)L.tgt.size();
+        auto add = [&](int s) { if (stamp[s] != g) { stamp[s] = g; L.tgt.push_back(s); ++L.need[s]; } };
+        // rows still inside the diagonal block: later sub-panels of the same cblk
+        for (int m = m0; m < std::min(m1, w); m = (m / sw[c] + 1) * sw[c]) add(spid[sp_ptr[c] + m / sw[c]]);
+        // off-diagonal rows: the bloks crossing [m0, m1)
+        while (b < be && h->h_coefind[b] + h->h_nrow[b] <= m0) ++b;
+        for (int bb = b; bb < be && h->h_coefind[bb] < m1; ++bb) {
+          const int fc = h->h_fcblk[bb];
+          const int lo = std::max(m0, h->h_coefind[bb]), hi = std::min(m1, h->h_coefind[bb] + h->h_nrow[bb]);   // panel rows [lo, hi)
+          const int o0 = h->h_frow[bb] + (lo - h->h_coefind[bb]) - h->h_fcol[fc], o1 = h->h_frow[bb] + (hi - 1 - h->h_coefind[bb]) - h->h_fcol[fc];
+          for (int r = o0 / sw[fc]; r <= o1 / sw[fc]; ++r) add(spid[sp_ptr[fc] + r]);
+        }
+        k.ntgt = (int)L.tgt.size() - k.tptr;
+        tt.push_back(k);
       }
-      k.ntgt = (int)tgt.size() - k.tptr;
-      ticks.push_back(k);
-    }
-  };
-  if (DROWS == PB200_DAG_ROWS) {
-    // first generation: D(J) followed by its own T tickets, 64 rows each
-    for (int i = 0; i < nsp; ++i) {
-      if (tasks[i].cblk == sc) continue;
-      emit_D(i); emit_T(i, DROWS);
-    }
-  } else {
-    // second generation: per (level, round) step all the D tickets, then all the T tickets — a ticket and the ones it waits
-    // for are a whole block of independent tickets apart wherever a level is wide, so the three-deep queues of the CTAs
-    // never hold a runnable ticket behind a blocked one there.  T tickets grow to up to 8 sub-tiles of 32 rows in steps
-    // with thousands of sub-tiles (the per-ticket cost — atomics, polls, fence — is paid once per 256 rows) and stay one
-    // sub-tile where a step is a link of the dependency chain.
-    for (const auto &st : h->slv_steps) {
-      long long subt = 0;
-      for (int i = st.task0; i < st.task0 + st.ntasks; ++i) {
+    };
+    if (!blocked) {
+      // first generation: D(J) followed by its own T tickets
+      for (int i = 0; i < nsp; ++i) {
         if (tasks[i].cblk == sc) continue;
-        const int c = tasks[i].cblk;
-        subt += (std::max(mend[c], tasks[i].c1) - tasks[i].c1 + DROWS - 1) / DROWS;
+        emit_D(i); emit_T(i, rows);
       }
-      int nsub = 1;
-      while (nsub < 8 && subt / (2 * nsub) >= 1024) nsub *= 2;
-      for (int i = st.task0; i < st.task0 + st.ntasks; ++i) if (tasks[i].cblk != sc) emit_D(i);
-      for (int i = st.task0; i < st.task0 + st.ntasks; ++i) if (tasks[i].cblk != sc) emit_T(i, DROWS * nsub);
+    } else {
+      // per (level, round) step all the D tickets, then all the T tickets — a ticket and the ones it waits for are a whole
+      // block of independent tickets apart wherever a level is wide.  T tickets grow to up to 8 sub-tiles in steps with
+      // thousands of sub-tiles (the per-ticket cost — atomics, polls, fence — is paid once per 256 rows) and stay one
+      // sub-tile where a step is a link of the dependency chain.
+      for (const auto &st : h->slv_steps) {
+        long long subt = 0;
+        for (int i = st.task0; i < st.task0 + st.ntasks; ++i) {
+          if (tasks[i].cblk == sc) continue;
+          const int c = tasks[i].cblk;
+          subt += (std::max(mend[c], tasks[i].c1) - tasks[i].c1 + rows - 1) / rows;
+        }
+        int nsub = 1;
+        while (nsub < 8 && subt / (2 * nsub) >= grow_at) nsub *= 2;
+        for (int i = st.task0; i < st.task0 + st.ntasks; ++i) if (tasks[i].cblk != sc) emit_D(i);
+        for (int i = st.task0; i < st.task0 + st.ntasks; ++i) if (tasks[i].cblk != sc) emit_T(i, rows * nsub);
+      }
+    }
+    for (auto &k : L.ticks) if (k.mrows < 0) { k.nsib = ntk[k.sp]; k.pad0 = (int)L.need[k.sp]; }
+  };
+  // which kernels: PB200_DAG_V1 = first generation for everything, PB200_DAG_V2 = second generation for everything;
+  // default: third generation (kernels_solve_dag3.cuh) for one right-hand side, first generation for several
+  const bool v1only = getenv("PB200_DAG_V1") != nullptr, v2only = !v1only && getenv("PB200_DAG_V2") != nullptr;
+  h->dag_rows = v2only ? PB200_DAG2_ROWS : PB200_DAG_ROWS;
+  h->dag3_ok = false;
+  DagList LA;
+  build_list(h->dag_rows, v2only, false, 1024, LA);
+  if (LA.tgt.size() >= (size_t)INT32_MAX) return PB200_SUCCESS;
+  for (int s : LA.tgt) if (s < 0) return fail(PB200_ERR_STRUCT, "up_down dependency table: row without an owning sub-panel");
+  { int rc = upload(h, LA.ticks, &h->d_dag_ticks); if (rc) return rc; }
+  { int rc = upload(h, LA.tgt, &h->d_dag_tgt); if (rc) return rc; }
+  { int rc = upload(h, LA.need, &h->d_dag_need); if (rc) return rc; }
+  if (!v1only && !v2only) {
+    DagList L3;
+    build_list(32, true, true, 2048, L3);
+    if (L3.tgt.size() < (size_t)INT32_MAX && !L3.ticks.empty()) {
+      h->dag3_GD = (int)L3.ticks.size(); h->dag3_GT = (int)L3.ticksT.size();
+      { int rc = upload(h, L3.ticks, &h->d_dag3_ticksD); if (rc) return rc; }
+      { int rc = upload(h, L3.ticksT, &h->d_dag3_ticksT); if (rc) return rc; }
+      { int rc = upload(h, L3.tgt, &h->d_dag3_tgt); if (rc) return rc; }
+      h->dag3_ok = true;
     }
   }
-  for (auto &k : ticks) if (k.mrows < 0) k.nsib = ntk[k.sp];
-  if (tgt.size() >= (size_t)INT32_MAX) return PB200_SUCCESS;
-  for (auto &k : ticks) if (k.mrows < 0) k.pad0 = (int)need[k.sp];
-  for (int s : tgt) if (s < 0) return fail(PB200_ERR_STRUCT, "up_down dependency table: row without an owning sub-panel");
-  { int rc = upload(h, ticks, &h->d_dag_ticks); if (rc) return rc; }
-  { int rc = upload(h, tgt, &h->d_dag_tgt); if (rc) return rc; }
-  { int rc = upload(h, need, &h->d_dag_need); if (rc) return rc; }
-  const size_t sb = ((size_t)4 * nsp + 4) * sizeof(unsigned int);
+  const size_t sb = ((size_t)4 * nsp + 8) * sizeof(unsigned int);
   CK(cudaMalloc((void **)&h->d_dag_state, sb));
   h->allocs.push_back(h->d_dag_state); h->device_bytes += sb;
   CK(cudaHostAlloc((void **)&h->h_dag_err, sizeof(unsigned int), cudaHostAllocDefault));
   *h->h_dag_err = 0;
-  h->dag_tiles = (int)ticks.size(); h->dag_nbs = nbs; h->dag_ok = true;
+  h->dag_tiles = (int)LA.ticks.size(); h->dag_nbs = nbs; h->dag_ok = true;
   return PB200_SUCCESS;
 }
 
@@ -1641,9 +1666,50 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
     DagArgs A;
     A.ticks = h->d_dag_ticks; A.tgt = h->d_dag_tgt; A.need = h->d_dag_need;
     A.arrived = h->d_dag_state; A.ready = A.arrived + nsp; A.done = A.ready + nsp; A.cnt = A.done + nsp;
-    A.ticket = A.cnt + nsp; A.err = A.ticket + 2; A.rowglob = h->d_rowglob;
+    A.ticket = A.cnt + nsp; A.err = A.ticket + 4; A.rowglob = h->d_rowglob;
     A.G = h->dag_tiles; A.nbs = h->dag_nbs; A.trace = nullptr;
-    CK(cudaMemsetAsync(h->d_dag_state, 0, (4 * nsp + 4) * sizeof(unsigned int), h->stream));
+    CK(cudaMemsetAsync(h->d_dag_state, 0, (4 * nsp + 8) * sizeof(unsigned int), h->stream));
+    if (h->dag3_ok && nrhs == 1) {
+      // third generation (kernels_solve_dag3.cuh): one right-hand side, independent tile workers + a diagonal team per SM
+      Dag3Args B;
+      B.ticksD = h->d_dag3_ticksD; B.ticksT = h->d_dag3_ticksT; B.GD = h->dag3_GD; B.GT = h->dag3_GT; B.tgt = h->d_dag3_tgt;
+      B.arrived = A.arrived; B.ready = A.ready; B.done = A.done; B.cnt = A.cnt; B.ticket = A.ticket; B.err = A.ticket + 4;
+      B.rowglob = h->d_rowglob; B.trace = nullptr;
+      const char *trf = getenv("PB200_DAG_TRACE");
+      const size_t tb = (size_t)2 * ((size_t)B.GD + B.GT) * 8 * sizeof(unsigned long long);
+      if (trf && !h->d_dag_trace) {
+        CK(cudaMalloc((void **)&h->d_dag_trace, tb));
+        h->allocs.push_back(h->d_dag_trace); h->device_bytes += tb;
+      }
+      if (trf) { B.trace = h->d_dag_trace; CK(cudaMemsetAsync(h->d_dag_trace, 0, tb, h->stream)); }
+      const size_t smem = Dag3Cfg<T>::bytes;
+      if (!(h->attr_mask & 128u)) {
+        CK(cudaFuncSetAttribute(k_dag3<T, FACTO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_dag3<T, FACTO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_dag3<T, FACTO, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(k_dag3<T, FACTO, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        h->attr_mask |= 128u;
+      }
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dag3<T, FACTO, 0>, PB200_DAG3_NT, smem));
+      if (occ < 1) return fail(PB200_ERR_CUDA, "persistent up_down kernels do not fit on this device");
+      const unsigned grid = (unsigned)(h->sm_count * occ);
+      k_dag3<T, FACTO, 0><<<grid, PB200_DAG3_NT, smem, h->stream>>>(L, inv, x, y, B);
+      k_dag3<T, FACTO, 1><<<grid, PB200_DAG3_NT, smem, h->stream>>>(Mup, inv_up, x, y, B);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(h->h_dag_err, B.err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+      if (getenv("PB200_DAG_VERBOSE")) fprintf(stderr, "[pb200 dag3] D tickets %d, T tickets %d, smem %zu B, CTAs/SM %d\n", B.GD, B.GT, smem, occ);
+      if (trf) {
+        // debugging aid: [sweep][D tickets, then T tickets] = {taken, dependencies met, done, (sm << 32) | sub-tiles << 16 | is-diagonal,
+        // taken, first data in shared memory, partial sums written, before the fence} (ns, %globaltimer)
+        CK(cudaStreamSynchronize(h->stream));
+        std::vector<unsigned long long> tr(tb / sizeof(unsigned long long));
+        CK(cudaMemcpy(tr.data(), h->d_dag_trace, tb, cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(trf, "wb")) { fwrite(tr.data(), sizeof(unsigned long long), tr.size(), f); fclose(f); }
+      }
+      h->last_launches = 2;
+      return PB200_SUCCESS;
+    }
     if (h->dag_rows == PB200_DAG2_ROWS) {
       // second generation (kernels_solve_dag2.cuh): three tickets in flight per CTA, one or NRMAX right-hand sides per pass
       const char *trf = getenv("PB200_DAG_TRACE");

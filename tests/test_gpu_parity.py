@@ -195,9 +195,10 @@ def test_persistent_updown_equals_level_sweeps(name, monkeypatch):
                                   "lap7_6_llt_s", "lap7her_6_ldlh_z", "cd_6_lu_z"])
 @pytest.mark.parametrize("nrhs", [1, 5])
 def test_second_generation_sweeps_equal_the_first(name, nrhs, monkeypatch):
-    """k_dag2 (kernels_solve_dag2.cuh: three tickets in flight per CTA, 32-row tiles, block-task triangle product)
-    against k_fwd_dag / k_bwd_dag (PB200_DAG_V1=1, 64-row tiles) on the same factors: single right-hand side (the
-    NR = 1 instantiation) and 5 (one full pass + a partial one of the NRMAX instantiation)."""
+    """The three generations of the persistent sweeps on the same factors: the default (k_dag3, kernels_solve_dag3.cuh:
+    independent tile workers + a diagonal team per SM, for one right-hand side; k_fwd_dag / k_bwd_dag for several),
+    k_dag2 (PB200_DAG_V2=1: three stages in flight per CTA, 32-row sub-tiles, NR = 1 and NRMAX instantiations) and
+    k_fwd_dag / k_bwd_dag for everything (PB200_DAG_V1=1, 64-row tiles)."""
     from pastix_b200 import Sopalin
     from pastix_b200.csc import permute_rhs
     import os
@@ -206,9 +207,11 @@ def test_second_generation_sweeps_equal_the_first(name, nrhs, monkeypatch):
     g = load_golden(name)
     b1 = permute_rhs(g["b"], g["permtab"]).reshape(-1, 1)
     out = []
-    for v1 in (False, True):
-        if v1:
-            monkeypatch.setenv("PB200_DAG_V1", "1")
+    for var in (None, "PB200_DAG_V2", "PB200_DAG_V1"):
+        monkeypatch.delenv("PB200_DAG_V2", raising=False)
+        monkeypatch.delenv("PB200_DAG_V1", raising=False)
+        if var:
+            monkeypatch.setenv(var, "1")
         s = Sopalin(g, g["prec"], g["facto"])
         s.assemble(g["colptr"], g["rows"], g["values"], g["tvalues"])
         s.factorize(g["critere"])
@@ -217,4 +220,5 @@ def test_second_generation_sweeps_equal_the_first(name, nrhs, monkeypatch):
         assert s.last_launches() == 2, "persistent path not taken"
         out.append(X)
         s.close()
-    assert relerr(out[0], out[1]) <= 50 * tol(g["prec"])
+    assert relerr(out[0], out[2]) <= 50 * tol(g["prec"])
+    assert relerr(out[1], out[2]) <= 50 * tol(g["prec"])

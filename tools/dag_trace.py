@@ -25,8 +25,8 @@ def main():
             if not m.any():
                 continue
             w = (dep - take)[m]; p = (end - dep)[m]
-            ph = [np.median((t[ok, b].astype(np.int64) - t[ok, a].astype(np.int64))[m]) / 1e3 for a, b in ((1, 5), (5, 6), (6, 7), (7, 2))]
-            print(f"  {lab}: dep->vector in smem {ph[0]:.2f} | product {ph[1]:.2f} | combine+stores {ph[2]:.2f} | fence+signal {ph[3]:.2f} us (medians, last sub-tile)")
+            ph = [np.median((t[ok, b].astype(np.int64) - t[ok, a].astype(np.int64))[m]) / 1e3 for a, b in ((0, 2), (1, 5), (5, 7), (7, 2))]
+            print(f"  {lab}: take->done {ph[0]:.2f} | dep->first data/vector in smem {ph[1]:.2f} | products+reductions {ph[2]:.2f} | fence+signal {ph[3]:.2f} us (medians)")
             print(f"  {lab}: n={m.sum():6d}  wait(dep-take) med {np.median(w) / 1e3:7.2f} p90 {np.percentile(w, 90) / 1e3:7.2f} us | "
                   f"work(end-dep) med {np.median(p) / 1e3:6.2f} p90 {np.percentile(p, 90) / 1e3:6.2f} max {p.max() / 1e3:6.2f} us | queue depth mean {nq[m].mean():.2f}")
         # progress of the ticket frontier: when was ticket k finished

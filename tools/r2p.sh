@@ -10,7 +10,7 @@ run() { timeout 300 python tools/run_case.py "$@" 2>&1 | grep -E 'factorize|solv
 echo "== C2 v2"; PB200_DAG_VERBOSE=1 run 64 7 llt d --reps=1
 echo "== C2 v2 trace"; PB200_DAG_TRACE=gpurun_out/${T}_trace_c2.bin run 64 7 llt d --reps=1
 python tools/dag_trace.py gpurun_out/${T}_trace_c2.bin
-echo "== C2 v2 64 rhs"; run 64 7 llt d 64 --reps=1
+echo "== C2 v2 64 rhs"; PB200_DAG_V2=1 run 64 7 llt d 64 --reps=1; echo "== C2 64 rhs default"; run 64 7 llt d 64 --reps=1
 echo "== C3 v2"; run 100 27 ldlt d --reps=1
 echo "== C3 v2 trace"; PB200_DAG_TRACE=gpurun_out/${T}_trace_c3.bin run 100 27 ldlt d --reps=1
 python tools/dag_trace.py gpurun_out/${T}_trace_c3.bin
