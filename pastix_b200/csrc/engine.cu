@@ -313,7 +313,7 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
   { int rc = upload(h, LA.need, &h->d_dag_need); if (rc) return rc; }
   if (!v1only && !v2only) {
     DagList L3;
-    build_list(32, true, true, 2048, L3);
+    build_list(32, true, true, getenv("PB200_DAG3_GROW") ? atoll(getenv("PB200_DAG3_GROW")) : 1024, L3);
     if (L3.tgt.size() < (size_t)INT32_MAX && !L3.ticks.empty()) {
       h->dag3_GD = (int)L3.ticks.size(); h->dag3_GT = (int)L3.ticksT.size();
       { int rc = upload(h, L3.ticks, &h->d_dag3_ticksD); if (rc) return rc; }
@@ -1691,11 +1691,11 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
         h->attr_mask |= 128u;
       }
       int occ = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dag3<T, FACTO, 0>, PB200_DAG3_NT, smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dag3<T, FACTO, 0>, Dag3Cfg<T>::NT, smem));
       if (occ < 1) return fail(PB200_ERR_CUDA, "persistent up_down kernels do not fit on this device");
       const unsigned grid = (unsigned)(h->sm_count * occ);
-      k_dag3<T, FACTO, 0><<<grid, PB200_DAG3_NT, smem, h->stream>>>(L, inv, x, y, B);
-      k_dag3<T, FACTO, 1><<<grid, PB200_DAG3_NT, smem, h->stream>>>(Mup, inv_up, x, y, B);
+      k_dag3<T, FACTO, 0><<<grid, Dag3Cfg<T>::NT, smem, h->stream>>>(L, inv, x, y, B);
+      k_dag3<T, FACTO, 1><<<grid, Dag3Cfg<T>::NT, smem, h->stream>>>(Mup, inv_up, x, y, B);
       CK(cudaGetLastError());
       CK(cudaMemcpyAsync(h->h_dag_err, B.err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
       if (getenv("PB200_DAG_VERBOSE")) fprintf(stderr, "[pb200 dag3] D tickets %d, T tickets %d, smem %zu B, CTAs/SM %d\n", B.GD, B.GT, smem, occ);

@@ -11,15 +11,12 @@
 // of independent chains in flight, not by bytes in flight per chain.
 //
 // So here nothing is CTA-wide.  One CTA per SM, no __syncthreads after the prologue:
-//   * warps 4..7 are four independent TILE WORKERS.  A worker takes T tickets from its own counter (the next ticket
+//   * warps 4.. are eight (four for complex double) independent TILE WORKERS.  A worker takes T tickets from its own counter (the next ticket
 //     number and record are always on their way while the current ticket is worked on), streams the ticket's
-//     32-row sub-tiles through its private double buffer in chunks of 32 rows x NB/2 columns — one TMA bulk copy
-//     (cp.async.bulk, completion on the buffer's mbarrier) per panel-column segment, issued by two lanes each, the next
-//     chunk in flight while the current one is multiplied.  Panel columns are only element-aligned: a copy starts at
-//     the 16-byte boundary at or below the segment and the consumer shifts its row index by the column's parity
-//     (the k_gemm_scatter staging, kernels_mma.cuh) — lane = panel row in the down step (one RED per row and
+//     32-row sub-tiles through its private double buffer in chunks of 32 rows x 32 columns (cp.async, the next chunk
+//     in flight while the current one is multiplied), lane = panel row in the down step (one RED per row and
 //     sub-tile), lane = columns {lane, lane+32, ..} in the up step (sums kept in registers for the whole ticket),
-//     then fences and signals — warp-level synchronisation only.  592 chains on the device instead of 296 or 444.
+//     then fences and signals — warp-level synchronisation only.  1184 chains on the device instead of 296 or 444.
 //   * warps 0..3 are the DIAGONAL TEAM: D tickets from a second counter, the packed inverted triangle of a sub-panel
 //     (up to 66 KB) in a slot of their own, the product as ten 32 x 32 block tasks over four warps with independent
 //     accumulators, a 128-thread named barrier.
@@ -29,12 +26,9 @@
 // Several right-hand sides keep the first-generation kernels (a panel tile is reused across right-hand sides there).
 #pragma once
 #include "kernels_solve_dag2.cuh"
-#include "mma.cuh"
 
 namespace pb200 {
 
-#define PB200_DAG3_NT 256
-#define PB200_DAG3_WORKERS 4
 
 struct Dag3Args {
   const DagTick *ticksD, *ticksT;   // forward order
@@ -49,16 +43,16 @@ struct Dag3Args {
 
 template <class T> struct Dag3Cfg {
   static constexpr int NB = SlvCfg<T>::NB;
-  static constexpr int CC = NB / 2;                                   // columns per chunk
-  static constexpr int E16 = 16 / (int)sizeof(T) > 0 ? 16 / (int)sizeof(T) : 1;   // elements per 16 bytes
-  static constexpr int CPY = ((32 + E16 - 1) + E16 - 1) / E16 * E16;   // elements per column copy: 32 rows + alignment slack, 16-byte multiple
-  static constexpr int LDT = CPY;                                     // leading dimension of a chunk buffer (columns 16-byte aligned)
+  static constexpr int CC = 32;                                       // columns per chunk
+  static constexpr int WORKERS = sizeof(T) >= 16 ? 4 : 8;             // tile-worker warps per CTA
+  static constexpr int NT = 128 + 32 * WORKERS;
+  static constexpr int LDT = 33;
   static constexpr int HALF = CC * LDT;                               // elements of one chunk buffer
   static constexpr int DSLOT = (NB * (NB + 1)) / 2 + NB;              // packed triangle + LDLt diagonal
   // per worker: two chunk buffers, x_J [NB], x[rows] [32], record
-  static constexpr size_t worker_bytes = ((((size_t)2 * HALF + NB + 32) * sizeof(T) + sizeof(DagTick) + 16) + 63) / 64 * 64;
+  static constexpr size_t worker_bytes = ((((size_t)2 * HALF + NB + 32) * sizeof(T) + sizeof(DagTick)) + 63) / 64 * 64;
   static constexpr size_t team_bytes = ((((size_t)DSLOT + NB + 10 * 32) * sizeof(T) + sizeof(DagTick) + 16) + 63) / 64 * 64;
-  static constexpr size_t bytes = team_bytes + PB200_DAG3_WORKERS * worker_bytes;
+  static constexpr size_t bytes = team_bytes + WORKERS * worker_bytes;
 };
 
 __device__ __forceinline__ void dag3_team_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -88,7 +82,7 @@ __device__ __forceinline__ T dag3_tri_task(const T *buf, const T *xs, int nb, in
 }
 
 template <class T, int FACTO, int DIR>
-__global__ void __launch_bounds__(PB200_DAG3_NT, 1)
+__global__ void __launch_bounds__(Dag3Cfg<T>::NT, 1)
 k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args A) {
   using C = Dag3Cfg<T>;
   constexpr int NB = C::NB, CC = C::CC, LDT = C::LDT, HALF = C::HALF, ROWS = 32;
@@ -210,11 +204,6 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
   T *xs = hs + 2 * HALF;                           // down: x_J [NB]
   T *xr = xs + NB;                                 // up: x[rows of the sub-tile] [32]
   int *rec = reinterpret_cast<int *>(xr + 32);     // the ticket record
-  uint64_t *bar = reinterpret_cast<uint64_t *>(rec + 16);   // [2] one mbarrier per chunk buffer
-  constexpr int E16 = C::E16, CPY = C::CPY;
-  if (lane == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_fence_init(); }
-  __syncwarp();
-  unsigned uses0 = 0, uses1 = 0;                   // completed phases of the two mbarriers
   unsigned nx_g = (unsigned)A.GT; int nx_w = 0;
   auto pretake = [&]() {
     unsigned g = 0;
@@ -238,32 +227,29 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
     const T *P0 = M + tk.src;
     // sub-panels owning rows of the ticket: counters to bump (down) / flags to wait for (up)
     int my_tgt = lane < tk.ntgt ? __ldg(A.tgt + tk.tptr + lane) : 0;
-    const int ldpar = tk.ld & (E16 - 1);
-    // parity (in elements) of the 16-byte alignment of row rk of column j: (src + j * ld + rk) mod E16
-    auto par_of = [&](int rk, int j) -> int { return (int)((tk.src + rk + (int64_t)j * ldpar) & (E16 - 1)); };
     auto issue = [&](int q) {
       const int k = q / ncc, c = q - k * ncc;
-      const int rk = k * ROWS;
-      const int j0 = c * CC, ncol = min(nb, j0 + CC) - j0;
-      uint64_t *b = bar + (q & 1);
-      if (lane == 0) mbar_arrive_expect_tx(b, (unsigned)ncol * CPY * (unsigned)sizeof(T));
-      __syncwarp();
-      for (int jl = lane; jl < ncol; jl += 32) {
-        const int j = j0 + jl;
-        const T *src = P0 + (size_t)j * tk.ld + rk - par_of(rk, j);
-        bulk_g2s(hs + (q & 1) * HALF + jl * LDT, src, (unsigned)(CPY * sizeof(T)), b);
-      }
+      const int rk = k * ROWS, mr = min(ROWS, tk.mrows - rk);
+      const int j0 = c * CC, j1 = min(nb, j0 + CC);
+      T *dst = hs + (q & 1) * HALF + lane;
+      const T *src = P0 + (size_t)j0 * tk.ld + rk + lane;
+      if (lane < mr)
+        for (int j = j0; j < j1; ++j, dst += LDT, src += tk.ld) dag_cp_async<sizeof(T)>(dst, src);
+      dag_cp_commit();
     };
     auto grow_of = [&](int k) -> int {
       const int r = k * ROWS + lane;
       if (r >= tk.mrows) return 0;
       return r < tk.wrem ? tk.grow0 + r : __ldg(A.rowglob + tk.aux + r);
     };
+    // the first look at the dependency flag travels while the copies of the first chunk are being issued
+    unsigned early = 0;
+    if (DIR == 0 && lane == 0) early = dag_ld_acquire(A.ready + tk.sp);
     issue(0);
     int grow = grow_of(0);
     // ---- dependency, input vector
     if (DIR == 0) {
-      if (lane == 0) dag_wait_ge(A.ready + tk.sp, 1u, A.err);
+      if (lane == 0 && early < 1u) dag_wait_ge(A.ready + tk.sp, 1u, A.err);
       __syncwarp();
       if (A.trace && lane == 0) t_dep = dag_gtime();
       for (int j = lane; j < NB; j += 32) xs[j] = j < nb ? ld_cg(&x[tk.xcol + j]) : zero;
@@ -282,8 +268,7 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
       const int k = q / ncc, c = q - k * ncc;
       const int mr = min(ROWS, tk.mrows - k * ROWS);
       const int j0 = c * CC, ncol = min(nb, j0 + CC) - j0;
-      if (q + 1 < total) issue(q + 1);
-      if (q & 1) { mbar_wait(bar + 1, uses1 & 1); ++uses1; } else { mbar_wait(bar, uses0 & 1); ++uses0; }
+      if (q + 1 < total) { issue(q + 1); dag_cp_wait<1>(); } else dag_cp_wait<0>();
       if (c == 0) {
         if (k > 0) grow = grow_next;
         if (k + 1 < nsub) grow_next = grow_of(k + 1);
@@ -296,18 +281,14 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
         // lane = panel row: sum over the columns of the chunk
         const T *a = h + lane;
         const T *xv = xs + j0;
-        const int rk = k * ROWS;
-        int p0 = par_of(rk, j0);                  // parity of column j0 + j: advances by ldpar per column
         int j = 0;
         for (; j + 4 <= ncol; j += 4) {
-          const int q0 = p0, q1 = (p0 + ldpar) & (E16 - 1), q2 = (p0 + 2 * ldpar) & (E16 - 1), q3 = (p0 + 3 * ldpar) & (E16 - 1);
-          fma_acc(acc0, a[(j + 0) * LDT + q0], xv[j + 0]);
-          fma_acc(acc1, a[(j + 1) * LDT + q1], xv[j + 1]);
-          fma_acc(acc2, a[(j + 2) * LDT + q2], xv[j + 2]);
-          fma_acc(acc3, a[(j + 3) * LDT + q3], xv[j + 3]);
-          p0 = (p0 + 4 * ldpar) & (E16 - 1);
+          fma_acc(acc0, a[(j + 0) * LDT], xv[j + 0]);
+          fma_acc(acc1, a[(j + 1) * LDT], xv[j + 1]);
+          fma_acc(acc2, a[(j + 2) * LDT], xv[j + 2]);
+          fma_acc(acc3, a[(j + 3) * LDT], xv[j + 3]);
         }
-        for (; j < ncol; ++j) { fma_acc(acc0, a[j * LDT + p0], xv[j]); p0 = (p0 + ldpar) & (E16 - 1); }
+        for (; j < ncol; ++j) fma_acc(acc0, a[j * LDT], xv[j]);
         if (c == ncc - 1) {
           if (lane < mr) atomic_sub(&x[grow], (acc0 + acc1) + (acc2 + acc3));
           acc0 = acc1 = acc2 = acc3 = zero;
@@ -319,7 +300,7 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
           if (t / CPL != c) continue;
           const int pl = (t % CPL) * 32 + lane;
           if (pl >= ncol) continue;
-          const T *a = h + pl * LDT + par_of(k * ROWS, j0 + pl);
+          const T *a = h + pl * LDT;
           T s0 = zero, s1 = zero;
           int i = 0;
           for (; i + 2 <= mr; i += 2) {
