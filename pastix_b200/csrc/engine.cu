@@ -228,6 +228,7 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
   // T tickets grown to up to 8 sub-tiles where a step has thousands of them (second and third generation); split:
   // D and T tickets in two lists (third generation).  need[] = T tickets contributing to each sub-panel.
   struct DagList { std::vector<DagTick> ticks, ticksT; std::vector<int> tgt; std::vector<unsigned int> need; };
+  const long long csplit_below = getenv("PB200_DAG3_CSPLIT") ? atoll(getenv("PB200_DAG3_CSPLIT")) : 600;   // steps with at most this many sub-tiles: T tickets also split by columns
   auto build_list = [&](int rows, bool blocked, bool split, long long grow_at, DagList &L) {
     L.ticks.reserve((size_t)nticks); L.tgt.reserve((size_t)nticks * 3);
     L.need.assign(nsp, 0);
@@ -244,7 +245,7 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
       L.ticks.push_back(d);
     };
     // T tickets of sub-panel i, `trows` panel rows each
-    auto emit_T = [&](int i, int trows) {
+    auto emit_T = [&](int i, int trows, int ccols) {
       const SlvTask &tk = tasks[i];
       const int c = tk.cblk, w = tk.w, ld = tk.ld, nb = tk.c1 - tk.c0;
       const int me = std::max(mend[c], tk.c1);   // rows [c1, me) of the panel take part
@@ -270,14 +271,25 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
           for (int r = o0 / sw[fc]; r <= o1 / sw[fc]; ++r) add(spid[sp_ptr[fc] + r]);
         }
         k.ntgt = (int)L.tgt.size() - k.tptr;
-        tt.push_back(k);
+        if (ccols <= 0 || ccols >= nb) { tt.push_back(k); continue; }
+        // column split (links of the dependency chain): the same rows, ccols columns of the sub-panel per ticket — each is
+        // a narrower sub-panel to the kernels (x_J slice, panel columns), all of them count for the same sub-panels
+        const int ncs = (nb + ccols - 1) / ccols;
+        for (int cs = 0; cs < ncs; ++cs) {
+          DagTick kc = k;
+          const int j0 = cs * ccols, j1 = std::min(nb, j0 + ccols);
+          kc.src = k.src + (int64_t)j0 * ld; kc.xcol = k.xcol + j0; kc.nb = j1 - j0;
+          tt.push_back(kc);
+        }
+        for (int q = 0; q < k.ntgt; ++q) L.need[L.tgt[k.tptr + q]] += (unsigned)(ncs - 1);
+        ntk[i] += ncs - 1;
       }
     };
     if (!blocked) {
       // first generation: D(J) followed by its own T tickets
       for (int i = 0; i < nsp; ++i) {
         if (tasks[i].cblk == sc) continue;
-        emit_D(i); emit_T(i, rows);
+        emit_D(i); emit_T(i, rows, 0);
       }
     } else {
       // per (level, round) step all the D tickets, then all the T tickets — a ticket and the ones it waits for are a whole
@@ -294,7 +306,8 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
         int nsub = 1;
         while (nsub < 8 && subt / (2 * nsub) >= grow_at) nsub *= 2;
         for (int i = st.task0; i < st.task0 + st.ntasks; ++i) if (tasks[i].cblk != sc) emit_D(i);
-        for (int i = st.task0; i < st.task0 + st.ntasks; ++i) if (tasks[i].cblk != sc) emit_T(i, rows * nsub);
+        const int ccols = (split && subt <= csplit_below) ? 32 : 0;
+        for (int i = st.task0; i < st.task0 + st.ntasks; ++i) if (tasks[i].cblk != sc) emit_T(i, rows * nsub, ccols);
       }
     }
     for (auto &k : L.ticks) if (k.mrows < 0) { k.nsib = ntk[k.sp]; k.pad0 = (int)L.need[k.sp]; }
@@ -1669,7 +1682,12 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
     A.ticket = A.cnt + nsp; A.err = A.ticket + 4; A.rowglob = h->d_rowglob;
     A.G = h->dag_tiles; A.nbs = h->dag_nbs; A.trace = nullptr;
     CK(cudaMemsetAsync(h->d_dag_state, 0, (4 * nsp + 8) * sizeof(unsigned int), h->stream));
-    if (h->dag3_ok && nrhs == 1) {
+    // one right-hand side: the independent-worker kernels where the sweeps are throughput-bound (measured: 100^3 LDLt
+    // 12.2 -> 8.9 ms), the first generation where they are a dependency chain (64^3 LLt: 2.5 vs 2.75 ms); the factor
+    // size tells the two apart.  PB200_DAG3=1 / 0 forces the choice.
+    bool use3 = h->dag3_ok && nrhs == 1 && (size_t)h->coefnbr * h->esize * (h->facto == PB200_FACT_LU ? 2 : 1) >= ((size_t)4 << 30);
+    if (const char *f3 = getenv("PB200_DAG3")) use3 = h->dag3_ok && nrhs == 1 && atoi(f3) != 0;
+    if (use3) {
       // third generation (kernels_solve_dag3.cuh): one right-hand side, independent tile workers + a diagonal team per SM
       Dag3Args B;
       B.ticksD = h->d_dag3_ticksD; B.ticksT = h->d_dag3_ticksT; B.GD = h->dag3_GD; B.GT = h->dag3_GT; B.tgt = h->d_dag3_tgt;

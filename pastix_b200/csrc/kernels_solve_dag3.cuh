@@ -57,7 +57,8 @@ template <class T> struct Dag3Cfg {
 
 __device__ __forceinline__ void dag3_team_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// 32 x 32 block task of a triangle product with four independent accumulators (see dag2_tri_task for the layouts)
+// 32 x 32 block task of a triangle product with four independent accumulators (see dag2_tri_task for the layouts);
+// off-diagonal blocks run without predicates, the index of column / row j is a closed form of j
 template <class T, int DIR, bool CONJ>
 __device__ __forceinline__ T dag3_tri_task(const T *buf, const T *xs, int nb, int rb, int cb, int lane) {
   T a0 = ST<T>::zero(), a1 = a0, a2 = a0, a3 = a0;
@@ -65,19 +66,22 @@ __device__ __forceinline__ T dag3_tri_task(const T *buf, const T *xs, int nb, in
   const int j0 = 32 * (DIR == 0 ? cb : rb), j1 = min(j0 + 32, nb);
   const int p = 32 * (DIR == 0 ? rb : cb) + lane;
   if (p >= nb) return a0;
-  auto term = [&](int j, T &acc) {
-    if (DIR == 0) {
-      if (j <= p && j < j1) fma_acc(acc, buf[j * nb - ((j * (j - 1)) >> 1) - j + p], xs[j]);
-    } else {
-      if (j >= p && j < j1) {
-        T a = buf[((j * (j + 1)) >> 1) + p];
-        if (CONJ) a = ST<T>::conj(a);
-        fma_acc(acc, a, xs[j]);
-      }
-    }
+  // element of summation index j that belongs to output p
+  auto at = [&](int j) -> T {
+    T a = DIR == 0 ? buf[j * nb - ((j * (j + 1)) >> 1) + p] : buf[((j * (j + 1)) >> 1) + p];
+    if (CONJ) a = ST<T>::conj(a);
+    return a;
   };
+  if (rb != cb && j1 == j0 + 32) {
 #pragma unroll 2
-  for (int j = j0; j < j1; j += 4) { term(j, a0); term(j + 1, a1); term(j + 2, a2); term(j + 3, a3); }
+    for (int j = j0; j < j1; j += 4) {
+      fma_acc(a0, at(j), xs[j]); fma_acc(a1, at(j + 1), xs[j + 1]); fma_acc(a2, at(j + 2), xs[j + 2]); fma_acc(a3, at(j + 3), xs[j + 3]);
+    }
+  } else {
+    auto term = [&](int j, T &acc) { if (j < j1 && (DIR == 0 ? j <= p : j >= p)) fma_acc(acc, at(j), xs[j]); };
+#pragma unroll 2
+    for (int j = j0; j < j1; j += 4) { term(j, a0); term(j + 1, a1); term(j + 2, a2); term(j + 3, a3); }
+  }
   return (a0 + a1) + (a2 + a3);
 }
 
