@@ -1682,11 +1682,10 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
     A.ticket = A.cnt + nsp; A.err = A.ticket + 4; A.rowglob = h->d_rowglob;
     A.G = h->dag_tiles; A.nbs = h->dag_nbs; A.trace = nullptr;
     CK(cudaMemsetAsync(h->d_dag_state, 0, (4 * nsp + 8) * sizeof(unsigned int), h->stream));
-    // one right-hand side: the independent-worker kernels where the sweeps are throughput-bound (measured: 100^3 LDLt
-    // 12.2 -> 8.9 ms), the first generation where they are a dependency chain (64^3 LLt: 2.5 vs 2.75 ms); the factor
-    // size tells the two apart.  PB200_DAG3=1 / 0 forces the choice.
-    bool use3 = h->dag3_ok && nrhs == 1 && (size_t)h->coefnbr * h->esize * (h->facto == PB200_FACT_LU ? 2 : 1) >= ((size_t)4 << 30);
-    if (const char *f3 = getenv("PB200_DAG3")) use3 = h->dag3_ok && nrhs == 1 && atoi(f3) != 0;
+    // one right-hand side: the independent-worker kernels (measured against the first generation: 64^3 LLt 2.51 -> 2.18 ms,
+    // 100^3 LDLt 12.2 -> 7.8 ms, 64^3 complex LU 4.03 -> 3.78 ms); PB200_DAG3=0 keeps the first generation for A/B
+    bool use3 = h->dag3_ok && nrhs == 1;
+    if (const char *f3 = getenv("PB200_DAG3")) use3 = use3 && atoi(f3) != 0;
     if (use3) {
       // third generation (kernels_solve_dag3.cuh): one right-hand side, independent tile workers + a diagonal team per SM
       Dag3Args B;

@@ -152,15 +152,19 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
       dag_cp_wait<0>();
       dag3_team_bar();
       if (A.trace && tid == 0) t_b1 = dag_gtime();
-      // block tasks: w0: (3,0) (2,0) (0,0)t   w1: (3,1) (2,1) (1,1)t   w2: (3,2) (1,0) (2,2)t   w3: (3,3)t
+      // block tasks, 64 "units" per warp (a full 32 x 32 block = 32, a triangle = 16):
+      //   w0: (3,0) (3,1)   w1: (3,2) (2,0)   w2: (2,1) (1,0)   w3: the four triangles (3,3) (2,2) (1,1) (0,0)
       // part ids: (3,c) -> c, (2,c) -> 4 + c, (1,0) -> 7, (0,0) -> 8, (1,1) -> 9
       T dreg[4];
 #pragma unroll
       for (int ob = 0; ob < 4; ++ob) dreg[ob] = (LDL && DIR == 0 && warp == 0 && 32 * ob + lane < nb) ? buf[tri + 32 * ob + lane] : ST<T>::from_real(1.0);
-      dparts[warp * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, warp, lane);
-      if (warp == 0) { dparts[4 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 0, lane); dparts[8 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 0, 0, lane); }
-      if (warp == 1) { dparts[5 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 1, lane); dparts[9 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 1, 1, lane); }
-      if (warp == 2) { dparts[7 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 1, 0, lane); dparts[6 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 2, lane); }
+      if (warp == 0) { dparts[0 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 0, lane); dparts[1 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 1, lane); }
+      if (warp == 1) { dparts[2 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 2, lane); dparts[4 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 0, lane); }
+      if (warp == 2) { dparts[5 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 1, lane); dparts[7 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 1, 0, lane); }
+      if (warp == 3) {
+        dparts[3 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 3, lane); dparts[6 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 2, lane);
+        dparts[9 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 1, 1, lane); dparts[8 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 0, 0, lane);
+      }
       dag3_team_bar();
       if (warp == 0) {
         if (A.trace && lane == 0) t_b2 = dag_gtime();

@@ -9,7 +9,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
 # 2. --set full of the dominant kernel (first 16 launches = the wide low levels) and of the two up_down sweeps, C2
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_gemm_scatter -c 12 \
   -o $O/${TAG}_full_gemm_scatter_c2 -f python tools/profile_step.py c2 > $O/${TAG}_full_gemm_c2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_.wd_dag -c 2 \
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_dag3 -c 2 \
   -o $O/${TAG}_full_updown_c2 -f python tools/profile_step.py c2 > $O/${TAG}_full_updown_c2.log 2>&1
 for f in full_gemm_scatter_c2 full_updown_c2; do
   ncu -i $O/${TAG}_$f.ncu-rep --page raw --csv > $O/${TAG}_${f}_raw.csv 2>/dev/null
