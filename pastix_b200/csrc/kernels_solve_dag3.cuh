@@ -57,31 +57,25 @@ template <class T> struct Dag3Cfg {
 
 __device__ __forceinline__ void dag3_team_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// 32 x 32 block task of a triangle product with four independent accumulators (see dag2_tri_task for the layouts);
-// off-diagonal blocks run without predicates, the index of column / row j is a closed form of j
+// 32 x 32 block task of a triangle product with four independent accumulators (see dag2_tri_task for the layouts).
+// Branch-free: every lane walks all 32 summation indices; where the term does not exist (above the diagonal of a
+// diagonal block, past the sub-panel's width) the load goes to a valid element anyway and a select drops it.
 template <class T, int DIR, bool CONJ>
 __device__ __forceinline__ T dag3_tri_task(const T *buf, const T *xs, int nb, int rb, int cb, int lane) {
-  T a0 = ST<T>::zero(), a1 = a0, a2 = a0, a3 = a0;
-  if (32 * rb >= nb) return a0;
+  const T zero = ST<T>::zero();
+  T a0 = zero, a1 = zero, a2 = zero, a3 = zero;
+  if (32 * rb >= nb) return zero;
   const int j0 = 32 * (DIR == 0 ? cb : rb), j1 = min(j0 + 32, nb);
-  const int p = 32 * (DIR == 0 ? rb : cb) + lane;
-  if (p >= nb) return a0;
-  // element of summation index j that belongs to output p
-  auto at = [&](int j) -> T {
-    T a = DIR == 0 ? buf[j * nb - ((j * (j + 1)) >> 1) + p] : buf[((j * (j + 1)) >> 1) + p];
+  const int p = min(32 * (DIR == 0 ? rb : cb) + lane, nb - 1);      // lanes past the width redo the last output (never stored)
+  auto term = [&](int j, T &acc) {
+    const int jj = min(j, j1 - 1);
+    T a = DIR == 0 ? buf[jj * nb - ((jj * (jj + 1)) >> 1) + p] : buf[((jj * (jj + 1)) >> 1) + p];
     if (CONJ) a = ST<T>::conj(a);
-    return a;
+    const bool ok = j < j1 && (DIR == 0 ? j <= p : j >= p);
+    fma_acc(acc, ok ? a : zero, xs[jj]);
   };
-  if (rb != cb && j1 == j0 + 32) {
-#pragma unroll 2
-    for (int j = j0; j < j1; j += 4) {
-      fma_acc(a0, at(j), xs[j]); fma_acc(a1, at(j + 1), xs[j + 1]); fma_acc(a2, at(j + 2), xs[j + 2]); fma_acc(a3, at(j + 3), xs[j + 3]);
-    }
-  } else {
-    auto term = [&](int j, T &acc) { if (j < j1 && (DIR == 0 ? j <= p : j >= p)) fma_acc(acc, at(j), xs[j]); };
-#pragma unroll 2
-    for (int j = j0; j < j1; j += 4) { term(j, a0); term(j + 1, a1); term(j + 2, a2); term(j + 3, a3); }
-  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) { term(j0 + j, a0); term(j0 + j + 1, a1); term(j0 + j + 2, a2); term(j0 + j + 3, a3); }
   return (a0 + a1) + (a2 + a3);
 }
 
@@ -152,19 +146,22 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
       dag_cp_wait<0>();
       dag3_team_bar();
       if (A.trace && tid == 0) t_b1 = dag_gtime();
-      // block tasks, 64 "units" per warp (a full 32 x 32 block = 32, a triangle = 16):
-      //   w0: (3,0) (3,1)   w1: (3,2) (2,0)   w2: (2,1) (1,0)   w3: the four triangles (3,3) (2,2) (1,1) (0,0)
+      // ten block tasks (every one costs the same: branch-free), 3 + 3 + 2 + 2 over the four warps:
+      //   w0: (3,0) (2,0) (0,0)   w1: (3,1) (2,1) (1,1)   w2: (3,2) (1,0)   w3: (3,3) (2,2)
       // part ids: (3,c) -> c, (2,c) -> 4 + c, (1,0) -> 7, (0,0) -> 8, (1,1) -> 9
       T dreg[4];
 #pragma unroll
       for (int ob = 0; ob < 4; ++ob) dreg[ob] = (LDL && DIR == 0 && warp == 0 && 32 * ob + lane < nb) ? buf[tri + 32 * ob + lane] : ST<T>::from_real(1.0);
-      if (warp == 0) { dparts[0 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 0, lane); dparts[1 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 1, lane); }
-      if (warp == 1) { dparts[2 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 2, lane); dparts[4 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 0, lane); }
-      if (warp == 2) { dparts[5 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 1, lane); dparts[7 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 1, 0, lane); }
-      if (warp == 3) {
-        dparts[3 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 3, lane); dparts[6 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 2, lane);
-        dparts[9 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 1, 1, lane); dparts[8 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 0, 0, lane);
+      if (warp == 0) {
+        dparts[0 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 0, lane); dparts[4 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 0, lane);
+        dparts[8 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 0, 0, lane);
       }
+      if (warp == 1) {
+        dparts[1 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 1, lane); dparts[5 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 1, lane);
+        dparts[9 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 1, 1, lane);
+      }
+      if (warp == 2) { dparts[2 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 2, lane); dparts[7 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 1, 0, lane); }
+      if (warp == 3) { dparts[3 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 3, 3, lane); dparts[6 * 32 + lane] = dag3_tri_task<T, DIR, CONJ>(buf, dxs, nb, 2, 2, lane); }
       dag3_team_bar();
       if (warp == 0) {
         if (A.trace && lane == 0) t_b2 = dag_gtime();
