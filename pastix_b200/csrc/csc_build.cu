@@ -307,6 +307,15 @@ extern "C" int pb200_csc_fetch(pb200_csc_t *c, int64_t *colptr, int64_t *rows, v
   return PB200_SUCCESS;
 }
 
+extern "C" int pb200_csc_fetch_colptr(pb200_csc_t *c, int64_t *colptr) {
+  if (!c || !colptr) return cfail(PB200_ERR_BADARG, "null argument");
+  if (!c->valid) return cfail(PB200_ERR_STATE, "no internal CSC built");
+  CCK(cudaSetDevice(c->device));
+  CCK(cudaMemcpyAsync(colptr, c->d_colptr, (size_t)(c->n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  CCK(cudaStreamSynchronize(c->stream));
+  return PB200_SUCCESS;
+}
+
 extern "C" int pb200_csc_norm1(pb200_csc_t *c, double *norm) {
   if (!c || !norm) return cfail(PB200_ERR_BADARG, "null argument");
   if (!c->valid) return cfail(PB200_ERR_STATE, "no internal CSC built");
