@@ -213,6 +213,9 @@ int pb200_csc_destroy(pb200_csc_t *c);
 int pb200_csc_build(pb200_csc_t *c, char type, int64_t n, const int64_t *colptr, const int64_t *rows,
                     const void *values, const int64_t *permtab, int trans, int64_t *nnz_out);
 int pb200_csc_fetch(pb200_csc_t *c, int64_t *colptr, int64_t *rows, void *values, void *tvalues);
+/* the column pointers alone (what CSC_COLTAB of every column block is filled from, csc_intern_build.c:520-532): the
+ * drop-in copies rows / values back only when a host-side reader of the CscMatrix shows up. */
+int pb200_csc_fetch_colptr(pb200_csc_t *c, int64_t *colptr);
 /* CscNorm1 (sopalin/src/csc_intern_compute.c:120-176) of the CSC in HBM: max_j sum_i |a_ij|, each column summed in
  * storage order like the reference's loop (identical result for real types; complex |.| is the device hypot). */
 int pb200_csc_norm1(pb200_csc_t *c, double *norm);

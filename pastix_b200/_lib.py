@@ -17,7 +17,7 @@ SYMBOLS = [
     "pb200_create_dist", "pb200_ipc_size", "pb200_ipc_export", "pb200_ipc_attach", "pb200_dist_barrier", "pb200_dist_plan",
     "pb200_vec_alloc", "pb200_vec_free", "pb200_vec_set", "pb200_vec_get", "pb200_vec_zero", "pb200_vec_copy", "pb200_vec_scal",
     "pb200_vec_axpy", "pb200_vec_dot", "pb200_csc_ax", "pb200_precond",
-    "pb200_csc_create", "pb200_csc_destroy", "pb200_csc_build", "pb200_csc_fetch", "pb200_csc_norm1", "pb200_assemble_csc",
+    "pb200_csc_create", "pb200_csc_destroy", "pb200_csc_build", "pb200_csc_fetch", "pb200_csc_fetch_colptr", "pb200_csc_norm1", "pb200_assemble_csc",
     "pb200_create_opts", "pb200_get_cblk", "pb200_set_hermitian", "pb200_attach_local", "pb200_destroy_group",
 ]
 
@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
     L.pb200_csc_build.argtypes = [C.c_void_p, C.c_char, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.POINTER(C.c_int64)]
     L.pb200_csc_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pb200_csc_fetch_colptr.argtypes = [C.c_void_p, C.c_void_p]
     L.pb200_assemble_csc.argtypes = [C.c_void_p, C.c_void_p]
     L.pb200_csc_norm1.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.pb200_factorize.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_double)]

@@ -89,7 +89,8 @@ for PP in $PRECS; do
   if [ "$SYM" != "CscOrdistrib" ]; then objcopy --redefine-sym "CscOrdistrib=$SYM" "$OBJ/x_shim_csc.o" || exit 1; fi
   # the reference's release points (coefinit.c:479 CoefMatrix_Free, solverRealloc.c:217 solverExit) stay linked as
   # *_hostref; shim_hooks.c defines the public names, drops the device state of that SolverMatrix and calls them
-  for FN in CoefMatrix_Free:p_coefinit solverExit:b_solverRealloc; do
+  # Csc2updown (csc_intern_updown.c:339) likewise: shim_hooks.c brings the host copy of the internal CSC up to date first
+  for FN in CoefMatrix_Free:p_coefinit solverExit:b_solverRealloc Csc2updown:p_csc_intern_updown; do
     F=${FN%%:*}; O=${FN##*:}
     SYM=$(nm "$OBJ/$O.o" | awk -v f="$F" '$2=="T" && $3 ~ (f "$") {print $3}' | head -1)
     [ -n "$SYM" ] || { echo "[$P] $F not found in the reference object $O.o"; exit 1; }

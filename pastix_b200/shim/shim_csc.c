@@ -65,6 +65,7 @@ void CscOrdistrib(CscMatrix *thecsc, char *Type, PASTIX_FLOAT **transcsc, const 
     return;
   }
   e->csc_fresh = 0;
+  e->host_stale = 0;
   if (e->csc == NULL && pb200_csc_create(&e->csc, PB200_FLT, -1) != PB200_SUCCESS) {
     errorPrint("pastix_b200: pb200_csc_create: %s", pb200_last_error());
     EXIT(MOD_SOPALIN, INTERNAL_ERR);
@@ -87,9 +88,23 @@ void CscOrdistrib(CscMatrix *thecsc, char *Type, PASTIX_FLOAT **transcsc, const 
   MALLOC_INTERN(CSC_VALTAB(thecsc), nnz, PASTIX_FLOAT);
   MALLOC_INTERN(gcol, Ncol + 1, int64_t);
   if (trans == 1) { MALLOC_INTERN(*transcsc, nnz, PASTIX_FLOAT); }
-  if (pb200_csc_fetch(e->csc, gcol, (int64_t *)CSC_ROWTAB(thecsc), CSC_VALTAB(thecsc), trans == 1 ? *transcsc : NULL) != PB200_SUCCESS) {
-    errorPrint("pastix_b200: pb200_csc_fetch: %s", pb200_last_error());
-    EXIT(MOD_SOPALIN, INTERNAL_ERR);
+  if (getenv("PB200_EAGER_CSC") != NULL) {
+    if (pb200_csc_fetch(e->csc, gcol, (int64_t *)CSC_ROWTAB(thecsc), CSC_VALTAB(thecsc), trans == 1 ? *transcsc : NULL) != PB200_SUCCESS) {
+      errorPrint("pastix_b200: pb200_csc_fetch: %s", pb200_last_error());
+      EXIT(MOD_SOPALIN, INTERNAL_ERR);
+    }
+  } else {
+    /* the numeric phase, the static-pivot threshold and the refinement read the copy in HBM; the host arrays are
+     * allocated (CscExit frees them as usual) and filled when a host-side reader of the CscMatrix shows up:
+     * Csc2updown (right-hand side generated from the matrix, pastix.c:716), the host statistics of the refinement,
+     * the test hooks — pb200_shim_csc_host.  Saves the 16 * nnz byte copy on every API_TASK_NUMFACT. */
+    if (pb200_csc_fetch_colptr(e->csc, gcol) != PB200_SUCCESS) {
+      errorPrint("pastix_b200: pb200_csc_fetch_colptr: %s", pb200_last_error());
+      EXIT(MOD_SOPALIN, INTERNAL_ERR);
+    }
+    e->lazy_ncol = (int64_t)Ncol; e->lazy_rows = CSC_ROWTAB(thecsc); e->lazy_vals = CSC_VALTAB(thecsc);
+    e->lazy_tvals = trans == 1 ? (void *)*transcsc : NULL;
+    e->host_stale = 1;
   }
   if (trans == 2) *transcsc = CSC_VALTAB(thecsc);                /* CSC_ALLOC, csc_intern_build.c:163-170 */
   for (index = 0; index < solvmtx->cblknbr; index++) {
@@ -104,7 +119,7 @@ void CscOrdistrib(CscMatrix *thecsc, char *Type, PASTIX_FLOAT **transcsc, const 
   e->csc_fresh = 1;
   t2 = clockGet();
   if (getenv("PB200_SHIM_TIMING") != NULL)
-    fprintf(stderr, "[pb200 shim] CscOrdistrib on the device: upload + sort + gather %.1f ms, copy back + CscMatrix %.1f ms (nnz %ld)\n",
+    fprintf(stderr, "[pb200 shim] CscOrdistrib on the device: upload + sort + gather %.1f ms, CscMatrix (host rows / values on demand) %.1f ms (nnz %ld)\n",
             (t1 - t0) * 1e3, (t2 - t1) * 1e3, (long)nnz);
   (void)Nrow; (void)Nnzero; (void)procnum;
 }

@@ -113,6 +113,7 @@ void pb200_shim_fingerprint(const SolverMatrix *m, uint64_t fp[2])
 /* ---- the reference's release points.  The reference objects keep their own routines under *_hostref names. */
 void CoefMatrix_Free_hostref(SopalinParam *sopar, SolverMatrix *datacode, PASTIX_INT factotype);
 void solverExit_hostref(SolverMatrix *solvmtx);
+void Csc2updown_hostref(const CscMatrix *cscmtx, UpDownVector *updovct, const SolverMatrix *solvmtx, int mode, MPI_Comm comm);
 
 /* CoefMatrix_Free (coefinit.c:479): the host panels go away — before a new blend on the same pastix_data
  * (pastix.c:2716) and before every re-fill of the coefficients (pastix.c:3391).  The factors on the device are void
@@ -134,6 +135,28 @@ void solverExit(SolverMatrix *solvmtx)
 }
 
 static pb200_shim_entry_t *hook_find(const SolverMatrix *m) { return pb200_shim_entry(m, 0); }
+
+/* ---- host copy of the internal CSC on demand (shim_csc.c leaves rows / values in HBM) */
+void pb200_shim_csc_host(const SolverMatrix *m)
+{
+  pb200_shim_entry_t *e = hook_find(m);
+  int64_t *gcol;
+  if (e == NULL || !e->host_stale || e->csc == NULL) return;
+  gcol = (int64_t *)malloc(sizeof(int64_t) * (size_t)(e->lazy_ncol + 1));
+  if (gcol == NULL || pb200_csc_fetch(e->csc, gcol, (int64_t *)e->lazy_rows, e->lazy_vals, e->lazy_tvals) != PB200_SUCCESS) {
+    errorPrint("pastix_b200: internal CSC -> host: %s", gcol ? pb200_last_error() : "out of memory");
+    EXIT(MOD_SOPALIN, INTERNAL_ERR);
+  }
+  free(gcol);
+  e->host_stale = 0;
+}
+/* Csc2updown (csc_intern_updown.c:339): b = A * (1 | i) read off the HOST CscMatrix when IPARM_RHS_MAKING asks for a
+ * generated right-hand side (pastix.c:716) — the one reader of the CSC values inside the unchanged pastix.c */
+void Csc2updown(const CscMatrix *cscmtx, UpDownVector *updovct, const SolverMatrix *solvmtx, int mode, MPI_Comm comm)
+{
+  pb200_shim_csc_host(solvmtx);
+  Csc2updown_hostref(cscmtx, updovct, solvmtx, mode, comm);
+}
 
 /* pb200_handle_t* behind a pastix_data_t (NULL before the first API_TASK_NUMFACT) */
 void *pb200_shim_get_handle(void *pastix_data)
@@ -238,6 +261,7 @@ int pb200_shim_csc_get(void *pastix_data, int64_t *colptr, int64_t *rows, void *
   pastix_data_t *pd = (pastix_data_t *)pastix_data;
   CscMatrix *c = &pd->cscmtx;
   PASTIX_INT i, j, col = 0, nnz = 0;
+  pb200_shim_csc_host(&pd->solvmatr);
   for (i = 0; i < CSC_FNBR(c); i++) {
     for (j = 0; j < CSC_COLNBR(c, i); j++) colptr[col++] = CSC_COL(c, i, j);
     nnz = CSC_COL(c, i, CSC_COLNBR(c, i));

@@ -141,6 +141,8 @@ void Pastix_End(void *arg, PASTIX_FLOAT tmp, PASTIX_INT nb_iter, double t, PASTI
     SYNCHRO_THREAD;
     r = (PASTIX_FLOAT *)sopalin_data->ptr_raff[0];
     s = (PASTIX_FLOAT *)sopalin_data->ptr_raff[1];
+    if (me == 0) pb200_shim_csc_host(datacode);       /* the host statistics read the host CscMatrix */
+    SYNCHRO_THREAD;
     MULTITHREAD_BEGIN;
     CscbMAx(sopalin_data, me, r, sopar->b, sopar->cscmtx, &(datacode->updovct), datacode, PASTIX_COMM,
             sopar->iparm[IPARM_TRANSPOSE_SOLVE]);

@@ -24,11 +24,17 @@ typedef struct pb200_shim_entry_s {
   int                 csc_fresh;  /* set by CscOrdistrib, consumed by the next numeric factorization */
   uint64_t            fp[2];      /* fingerprint of the SolverMatrix the handle was built for */
   int                 herm;       /* internal CSC type 'H' (conjugated transposed values) */
+  /* host copy of the internal CSC filled on demand: CscOrdistrib (shim_csc.c) allocates CSC_ROWTAB / CSC_VALTAB /
+   * transcsc and fills CSC_COLTAB, the rows / values stay in HBM until a host-side reader asks (pb200_shim_csc_host) */
+  int                 host_stale;
+  int64_t             lazy_ncol;
+  void               *lazy_rows, *lazy_vals, *lazy_tvals;
 } pb200_shim_entry_t;
 #define pb200_shim_entry        PASTIX_PREFIX_F(pb200_shim_entry)
 #define pb200_shim_entry_drop   PASTIX_PREFIX_F(pb200_shim_entry_drop)
 #define pb200_shim_fingerprint  PASTIX_PREFIX_F(pb200_shim_fingerprint)
 #define pb200_shim_live_entries PASTIX_PREFIX_F(pb200_shim_live_entries)
+#define pb200_shim_csc_host     PASTIX_PREFIX_F(pb200_shim_csc_host)
 /* entry of SolverMatrix m (created empty when absent and `create` is set); entries never move */
 pb200_shim_entry_t *pb200_shim_entry(const SolverMatrix *m, int create);
 /* destroy the handle / device CSC of m's entry and forget it */
@@ -36,4 +42,6 @@ void pb200_shim_entry_drop(const SolverMatrix *m);
 /* cblknbr, bloknbr, coefnbr and a hash of every cblktab / bloktab field the device schedule is derived from */
 void pb200_shim_fingerprint(const SolverMatrix *m, uint64_t fp[2]);
 int  pb200_shim_live_entries(void);
+/* make the host arrays of m's internal CSC valid (no-op unless CscOrdistrib left them to be filled on demand) */
+void pb200_shim_csc_host(const SolverMatrix *m);
 #endif

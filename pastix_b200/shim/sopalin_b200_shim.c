@@ -273,8 +273,10 @@ static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
   if (e->csc != NULL && e->csc_fresh) {        /* CscOrdistrib of this call left the internal CSC in HBM (shim_csc.c) */
     dev_csc = 1;
     e->csc_fresh = 0;
-  } else
+  } else {
+    pb200_shim_csc_host(datacode);
     shim_flatten_csc(sopar, &colptr, &rows);
+  }
   t2 = clockGet();
   crit = shim_critere(datacode, sopar, dev_csc ? e->csc : NULL);
   t3 = clockGet();

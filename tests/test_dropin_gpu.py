@@ -450,3 +450,34 @@ def test_refinement_on_device_vectors_matches_reference(kind, N, prec, facto, sy
     assert res <= 50 * eps, res
     assert abs(itg - itr) <= 1 and (ilu is None or itg >= 1), (itg, itr)
     assert relerr(xg, xr) <= 1e3 * eps
+
+
+@pytest.mark.parametrize("prec,kind,facto,sym", [("d", "lap7", "llt", "yes"), ("z", "cd", "lu", "no")])
+def test_generated_rhs_reads_the_host_csc_on_demand(prec, kind, facto, sym, monkeypatch):
+    """IPARM_RHS_MAKING = API_RHS_1: pastix.c:716 builds b = A * 1 from the HOST CscMatrix (Csc2updown,
+    csc_intern_updown.c:339) — the one reader of the internal CSC values inside the unchanged pastix.c.  The drop-in
+    leaves rows / values in HBM after CscOrdistrib and fills the host arrays when such a reader shows up
+    (shim_csc.c, pb200_shim_csc_host): the solution must be the vector of ones, like the reference's, and equal to what
+    the eager copy (PB200_EAGER_CSC=1) gives."""
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    if not available(prec):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix(kind, 10, DT[prec])
+    n = A.shape[0]
+    E = Pastix(prec).E
+    over = {"IPARM_RHS_MAKING": E["API_RHS_1"]}
+    ref = RefPastix(prec, threads=1).setup(A, perm0, facto, sym=sym, iparm_over=over).analyze().numfact()
+    xr = ref.solve(np.zeros(n, dtype=DT[prec]))
+    ref.clean()
+    out = []
+    for eager in (False, True):
+        if eager:
+            monkeypatch.setenv("PB200_EAGER_CSC", "1")
+        gpu = Pastix(prec, threads=1).setup(A, perm0, facto, sym=sym, iparm_over=over).analyze().numfact()
+        out.append(gpu.solve(np.zeros(n, dtype=DT[prec])))
+        gpu.clean()
+    assert np.abs(xr - 1.0).max() <= 1e-8, "the reference itself does not return the vector of ones"
+    assert relerr(out[0], xr) <= 50 * tol(prec)
+    assert relerr(out[0], out[1]) <= 50 * tol(prec)
