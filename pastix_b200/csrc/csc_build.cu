@@ -173,6 +173,14 @@ static void launch_gather(pb200_csc_t *c, int64_t nnz, int rb, bool want_t) {
                                                                        reinterpret_cast<int *>(c->d_extra + 2));
 }
 
+// Pageable host -> device copies of the user's CSC (the arrays pastix() receives: nothing is known about their
+// lifetime, so they are not registered).  A plain cudaMemcpy stages them through the driver's pinned buffer with ONE
+// thread (~12 GB/s: 2.1 of the 27 ms a pastix(API_TASK_NUMFACT) call takes on the 64^3 problem, 23 ms of 300 on the
+// 100^3 one); here the same host threads and pinned pieces as parallel_d2h copy 1 MB chunks of all the arrays into
+// pinned memory and hand them to the DMA engine on their own streams, eight chunks in flight per thread.
+struct H2DSeg { void *dst; const void *src; size_t bytes; };
+static int parallel_h2d(pb200_csc_t *c, const H2DSeg *segs, int nseg);
+
 extern "C" int pb200_csc_build(pb200_csc_t *c, char type, int64_t n, const int64_t *colptr, const int64_t *rows, const void *values,
                                const int64_t *permtab, int trans, int64_t *nnz_out) {
   if (!c || !colptr || !rows || !values || !permtab || !nnz_out) return cfail(PB200_ERR_BADARG, "null argument");
@@ -198,10 +206,11 @@ extern "C" int pb200_csc_build(pb200_csc_t *c, char type, int64_t n, const int64
     if ((rc = ensure(&c->d_colptr, &c->cap_colptr, (size_t)(n + 1) * 8))) return rc;
     if ((rc = ensure(&c->d_extra, &c->cap_extra, 4 * 8))) return rc;
   }
-  CCK(cudaMemcpyAsync(c->d_ucolptr, colptr, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  CCK(cudaMemcpyAsync(c->d_perm, permtab, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-  CCK(cudaMemcpyAsync(c->d_urows, rows, (size_t)unz * 8, cudaMemcpyHostToDevice, c->stream));
-  CCK(cudaMemcpyAsync(c->d_uvals, values, (size_t)unz * c->esize, cudaMemcpyHostToDevice, c->stream));
+  {
+    const H2DSeg segs[4] = {{c->d_ucolptr, colptr, (size_t)(n + 1) * 8}, {c->d_perm, permtab, (size_t)n * 8},
+                            {c->d_urows, rows, (size_t)unz * 8}, {c->d_uvals, values, (size_t)unz * c->esize}};
+    if (parallel_h2d(c, segs, 4)) return cfail(PB200_ERR_CUDA, "host -> device copy of the user's CSC failed");
+  }
   CCK(cudaMemsetAsync(c->d_extra, 0, 4 * 8, c->stream));
   int *d_bad = reinterpret_cast<int *>(c->d_extra + 2);
   k_csc_expand<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, c->d_ucolptr, c->d_urows, c->d_perm, (int)type, trans, rb,
@@ -287,6 +296,50 @@ static int parallel_d2h(pb200_csc_t *c, void *dst, const void *src, size_t bytes
   for (auto &t : th) t.join();
   for (int r : rc) if (r) return 1;
   return 0;
+}
+
+static int parallel_h2d(pb200_csc_t *c, const H2DSeg *segs, int nseg) {
+  static const size_t kChunk = (size_t)1 << 20;
+  size_t total = 0;
+  for (int k = 0; k < nseg; ++k) total += segs[k].bytes;
+  unsigned nt = std::min<unsigned>(PB200_CSC_NPIN, std::max(1u, std::thread::hardware_concurrency()));
+  nt = (unsigned)std::min<size_t>(nt, (total + 4 * kChunk - 1) / (4 * kChunk));
+  if (total < ((size_t)8 << 20) || nt < 2 || getenv("PB200_PLAIN_H2D") != nullptr) {
+    for (int k = 0; k < nseg; ++k)
+      if (segs[k].bytes && cudaMemcpyAsync(segs[k].dst, segs[k].src, segs[k].bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return 1;
+    return 0;
+  }
+  for (unsigned i = 0; i < nt; ++i)
+    if (!c->pin[i]) {
+      if (cudaHostAlloc(&c->pin[i], kPiece, cudaHostAllocDefault) != cudaSuccess) { c->pin[i] = nullptr; return 1; }
+      if (cudaStreamCreateWithFlags(&c->pstream[i], cudaStreamNonBlocking) != cudaSuccess) return 1;
+    }
+  // chunk list over all segments; thread i takes chunks i, i + nt, ...
+  struct Chunk { char *dst; const char *src; size_t n; };
+  std::vector<Chunk> chunks;
+  for (int k = 0; k < nseg; ++k)
+    for (size_t off = 0; off < segs[k].bytes; off += kChunk)
+      chunks.push_back({(char *)segs[k].dst + off, (const char *)segs[k].src + off, std::min(kChunk, segs[k].bytes - off)});
+  std::vector<std::thread> th;
+  std::vector<int> rc(nt, 0);
+  const int device = c->device;
+  const size_t slots = kPiece / kChunk;
+  for (unsigned i = 0; i < nt; ++i)
+    th.emplace_back([&, i]() {
+      if (cudaSetDevice(device) != cudaSuccess) { rc[i] = 1; return; }
+      size_t used = 0;
+      for (size_t q = i; q < chunks.size(); q += nt) {
+        if (used == slots) { if (cudaStreamSynchronize(c->pstream[i]) != cudaSuccess) { rc[i] = 1; return; } used = 0; }
+        char *p = (char *)c->pin[i] + used * kChunk;
+        memcpy(p, chunks[q].src, chunks[q].n);
+        if (cudaMemcpyAsync(chunks[q].dst, p, chunks[q].n, cudaMemcpyHostToDevice, c->pstream[i]) != cudaSuccess) { rc[i] = 1; return; }
+        ++used;
+      }
+      if (cudaStreamSynchronize(c->pstream[i]) != cudaSuccess) rc[i] = 1;
+    });
+  for (auto &t : th) t.join();
+  for (int r : rc) if (r) return 1;
+  return 0;   // every copy has completed: the kernels on c->stream that follow see the data
 }
 
 extern "C" int pb200_csc_fetch(pb200_csc_t *c, int64_t *colptr, int64_t *rows, void *values, void *tvalues) {

@@ -309,6 +309,7 @@ static void shim_numfact(SolverMatrix *datacode, SopalinParam *sopar)
       sopar->transcsc = NULL;                  /* alias of CSC_VALTAB (forcetrans) */
     else
       memFree_null(sopar->transcsc);
+    e->lazy_tvals = NULL;                      /* a later on-demand copy of the internal CSC has nowhere to put them */
   }
   if (getenv("PB200_SHIM_TIMING") != NULL)
     fprintf(stderr, "[pb200 shim] create %.1f ms, CSC flatten %.1f ms, CscNorm1 %.1f ms, assembly + factorization on %d GPU(s) %.1f ms\n",
