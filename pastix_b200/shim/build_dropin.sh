@@ -97,6 +97,16 @@ for PP in $PRECS; do
     objcopy --redefine-sym "$SYM=${F}_hostref" "$OBJ/$O.o" || exit 1
     if [ "$SYM" != "$F" ]; then objcopy --redefine-sym "$F=$SYM" "$OBJ/x_shim_hooks.o" || exit 1; fi
   done
+  # the host SpMV routines that read the HOST CscMatrix (csc_intern_compute.c: CscbMAx, CscAxPb — static-pivot refinement,
+  # host statistics) stay linked as <variant>_*_hostref; sopalin_b200_shim.c defines the public names (host copy of the
+  # internal CSC on demand)
+  for V in po ge sy he; do
+    for F in CscbMAx CscAxPb; do
+      SYM=$(nm "$OBJ/p_csc_intern_compute_$V.o" | awk -v f="_$F" '$2=="T" && $3 ~ (f "$") {print $3}' | head -1)
+      [ -n "$SYM" ] || { echo "[$P] $F not found in p_csc_intern_compute_$V.o"; exit 1; }
+      objcopy --redefine-sym "$SYM=${SYM}_hostref" "$OBJ/p_csc_intern_compute_$V.o" || exit 1
+    done
+  done
   gcc -shared -o "$LIB" "$OBJ"/*.o -L"$OUT" -lpastix_b200 "$BLASLIB" -lpthread -lm \
       -Wl,--disable-new-dtags -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$BLASDIR" -Wl,-rpath-link,"$BLASDIR" -Wl,--no-undefined 2> "$OBJ/link.log" \
       || { echo "[$P] link failed"; head -30 "$OBJ/link.log"; exit 1; }

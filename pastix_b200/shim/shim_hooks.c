@@ -139,18 +139,23 @@ void solverExit(SolverMatrix *solvmtx)
 static pb200_shim_entry_t *hook_find(const SolverMatrix *m) { return pb200_shim_entry(m, 0); }
 
 /* ---- host copy of the internal CSC on demand (shim_csc.c leaves rows / values in HBM) */
+static pthread_mutex_t csc_host_mutex = PTHREAD_MUTEX_INITIALIZER;
 void pb200_shim_csc_host(const SolverMatrix *m)
 {
   pb200_shim_entry_t *e = hook_find(m);
   int64_t *gcol;
   if (e == NULL || !e->host_stale || e->csc == NULL) return;
-  gcol = (int64_t *)malloc(sizeof(int64_t) * (size_t)(e->lazy_ncol + 1));
-  if (gcol == NULL || pb200_csc_fetch(e->csc, gcol, (int64_t *)e->lazy_rows, e->lazy_vals, e->lazy_tvals) != PB200_SUCCESS) {
-    errorPrint("pastix_b200: internal CSC -> host: %s", gcol ? pb200_last_error() : "out of memory");
-    EXIT(MOD_SOPALIN, INTERNAL_ERR);
+  pthread_mutex_lock(&csc_host_mutex);          /* the readers may be the threads of a refinement (raff_pivot.c) */
+  if (e->host_stale) {
+    gcol = (int64_t *)malloc(sizeof(int64_t) * (size_t)(e->lazy_ncol + 1));
+    if (gcol == NULL || pb200_csc_fetch(e->csc, gcol, (int64_t *)e->lazy_rows, e->lazy_vals, e->lazy_tvals) != PB200_SUCCESS) {
+      errorPrint("pastix_b200: internal CSC -> host: %s", gcol ? pb200_last_error() : "out of memory");
+      EXIT(MOD_SOPALIN, INTERNAL_ERR);
+    }
+    free(gcol);
+    e->host_stale = 0;
   }
-  free(gcol);
-  e->host_stale = 0;
+  pthread_mutex_unlock(&csc_host_mutex);
 }
 /* Csc2updown (csc_intern_updown.c:339): b = A * (1 | i) read off the HOST CscMatrix when IPARM_RHS_MAKING asks for a
  * generated right-hand side (pastix.c:716) — the one reader of the CSC values inside the unchanged pastix.c */

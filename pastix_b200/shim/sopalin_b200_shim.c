@@ -431,3 +431,26 @@ void API_CALL(sopalin_updo_bicgstab_thread)(SolverMatrix *m, SopalinParam *sopap
   shim_updown(m, sopaparam);
   API_CALL(bicgstab_thread)(m, sopaparam);
 }
+
+/* ---- host-side readers of the internal CSC inside the reference code that stays linked.  CscbMAx / CscAxPb
+ * (csc_intern_compute.c) walk the HOST CscMatrix; the static-pivot refinement (raff_pivot.c:133-139, included above)
+ * and the host statistics of the other drivers (shim_raff.c) call them.  The reference objects keep their routines as
+ * <variant>_CscbMAx_hostref / _CscAxPb_hostref (build_dropin.sh, objcopy); these bring the host copy up to date first
+ * (shim_csc.c leaves rows / values in HBM, pb200_shim_csc_host). */
+void API_CALL(CscbMAx_hostref)(Sopalin_Data_t *sopalin_data, int me, volatile PASTIX_FLOAT *r, const volatile PASTIX_FLOAT *b,
+                               const CscMatrix *cscmtx, const UpDownVector *updovct, const SolverMatrix *solvmtx, MPI_Comm comm,
+                               PASTIX_INT transpose);
+void API_CALL(CscAxPb_hostref)(Sopalin_Data_t *sopalin_data, int me, PASTIX_FLOAT *r, const PASTIX_FLOAT *b, const CscMatrix *cscmtx,
+                               const UpDownVector *updovct, const SolverMatrix *solvmtx, MPI_Comm comm, PASTIX_INT transpose);
+void CscbMAx(Sopalin_Data_t *sopalin_data, int me, volatile PASTIX_FLOAT *r, const volatile PASTIX_FLOAT *b, const CscMatrix *cscmtx,
+             const UpDownVector *updovct, const SolverMatrix *solvmtx, MPI_Comm comm, PASTIX_INT transpose)
+{
+  pb200_shim_csc_host(solvmtx);
+  API_CALL(CscbMAx_hostref)(sopalin_data, me, r, b, cscmtx, updovct, solvmtx, comm, transpose);
+}
+void CscAxPb(Sopalin_Data_t *sopalin_data, int me, PASTIX_FLOAT *r, const PASTIX_FLOAT *b, const CscMatrix *cscmtx,
+             const UpDownVector *updovct, const SolverMatrix *solvmtx, MPI_Comm comm, PASTIX_INT transpose)
+{
+  pb200_shim_csc_host(solvmtx);
+  API_CALL(CscAxPb_hostref)(sopalin_data, me, r, b, cscmtx, updovct, solvmtx, comm, transpose);
+}
