@@ -45,6 +45,8 @@ WORKLOADS = {
     "c4": ("complex-double convection-diffusion 128^3 LU static pivoting", "cd", 128, "z", "lu", 1, {}),
     "c5s": ("blockwise ILU(2) + 64-RHS solve, 3-D 7-point Laplacian 64^3", "lap7", 64, "d", "llt", 64,
             {"IPARM_INCOMPLETE": 1, "IPARM_LEVEL_OF_FILL": 2}),
+    "c5m": ("blockwise ILU(2) + 64-RHS solve, 3-D 7-point Laplacian 100^3 (the largest size whose ILU(2) host analysis fits a GPU lease)", "lap7", 100, "d", "llt", 64,
+            {"IPARM_INCOMPLETE": 1, "IPARM_LEVEL_OF_FILL": 2}),
     "c5": ("blockwise ILU(2) + 64-RHS solve, 3-D 7-point Laplacian 200^3", "lap7", 200, "d", "llt", 64,
            {"IPARM_INCOMPLETE": 1, "IPARM_LEVEL_OF_FILL": 2}),
 }
@@ -664,11 +666,13 @@ def dist_case(args, workload, steps, warmup, ctx):
 
 def bounded_sample(workload: str):
     """(grid size override or None, description) of what the CPU arm factorizes for this workload."""
+    if workload == "c3" and os.environ.get("PB200_REF_FULL"):
+        return None, "the full workload's numeric factorization (PB200_REF_FULL=1)"
     if workload == "c3":
         return 64, "same 27-point LDLt problem on a 64^3 grid (bounded sample of the 100^3 workload)"
     if workload in ("c4", "c4s"):
         return 32, "same complex LU problem on a 32^3 grid (bounded sample)"
-    if workload == "c5":
+    if workload in ("c5", "c5m"):
         return 64, "same ILU(2) problem on a 64^3 grid (bounded sample)"
     return None, "the full workload's numeric factorization"
 
