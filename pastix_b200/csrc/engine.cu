@@ -171,6 +171,20 @@ static int upload(pb200_handle_t *h, const std::vector<V> &v, V **d) {
   return 0;
 }
 
+// Launch of a panel-chain kernel, optionally with programmatic stream serialization (kernels_mma.cuh, pdl_wait): the
+// launch may be scheduled while its predecessor in the stream still runs.  Only kernels that execute
+// griddepcontrol.wait before touching panels may take the attribute.
+template <class... KArgs, class... Args>
+static cudaError_t launch_chain(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static size_t elem_size(int flt) {
   switch (flt) {
     case PB200_REALSINGLE: return 4;
@@ -1384,6 +1398,9 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   // which is a by-value kernel argument) and replay it — kernel-to-kernel dependencies then resolve on the device
   // without the stream scheduler in between.  Multi-GPU schedules carry an epoch argument and stay on streams.
   const bool use_graph = !serial && !overlap_inv && h->nranks == 1 && h->nlevels > 0 && getenv("PB200_GRAPH") != nullptr;
+  // programmatic dependent launch of the chain kernels (PB200_PDL=0: plain stream order, for A/B); per-launch event
+  // timing (profile mode) needs the plain order
+  const bool pdl = !prof && !use_graph && (getenv("PB200_PDL") == nullptr || atoi(getenv("PB200_PDL")) != 0);
   if (use_graph && h->fact_graph && h->fact_graph_crit == crit) {
     CK(cudaGraphLaunch(h->fact_graph, h->stream));
     h->last_launches = h->fact_graph_launches;
@@ -1406,17 +1423,18 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
         if (diag_old)
           k_diag_sub<T, FACTO><<<st.ntasks, 256, 0, sm>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
         else if (st.nbmax <= 64)
-          k_diag_blk<T, FACTO, 4><<<st.ntasks, 256, 0, sm>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
+          CK(launch_chain(pdl, k_diag_blk<T, FACTO, 4>, dim3(st.ntasks), dim3(256), 0, sm, h->S, L, U, (const SubTask *)(h->d_sub + st.task0), crit, h->d_cnt));
         else if constexpr (SubCfg<T>::NBMAX > 64)
-          k_diag_blk<T, FACTO, SubCfg<T>::NBMAX / 16><<<st.ntasks, 256, 0, sm>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
+          CK(launch_chain(pdl, k_diag_blk<T, FACTO, SubCfg<T>::NBMAX / 16>, dim3(st.ntasks), dim3(256), 0, sm, h->S, L, U,
+                          (const SubTask *)(h->d_sub + st.task0), crit, h->d_cnt));
       } break;
       case 1:
-        k_trsm_mma<T, FACTO><<<(unsigned)(st.ntiles * lu), 128, trsm_smem_bytes<T>(st.nbmax), sm>>>(
-            h->S, L, U, (T *)h->dW, h->d_sub + st.task0, st.ntasks);
+        CK(launch_chain(pdl, k_trsm_mma<T, FACTO>, dim3((unsigned)(st.ntiles * lu)), dim3(128), trsm_smem_bytes<T>(st.nbmax), sm,
+                        h->S, L, U, (T *)h->dW, (const SubTask *)(h->d_sub + st.task0), (int)st.ntasks));
         break;
       case 2:
-        k_gemm_scatter<T, FACTO><<<(unsigned)(st.ntiles * lu), UpdCfg<T>::NT, upd_smem_bytes<T>(), sm>>>(
-            h->M, L, U, (const T *)h->dW, h->d_desc + st.t2t0);
+        CK(launch_chain(pdl, k_gemm_scatter<T, FACTO>, dim3((unsigned)(st.ntiles * lu)), dim3(UpdCfg<T>::NT), upd_smem_bytes<T>(), sm,
+                        h->M, L, U, (const T *)h->dW, (const TileDesc *)(h->d_desc + st.t2t0)));
         break;
       case 3:
         if (FACTO == F_LU)

@@ -161,6 +161,13 @@ __device__ __forceinline__ void cp_async_raw(void *smem_dst, const void *gmem_sr
   asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(gmem_src), "n"(BYTES));
 }
 
+// Programmatic dependent launch (sm_90+): the kernels of the panel chain let the NEXT launch of their stream be scheduled
+// while they run (its CTAs become resident, read their static task record and stop at pdl_wait) and themselves wait for
+// the previous launch to have completed — memory included — before touching panels.  Without the launch attribute
+// (engine.cu, launch_chain) both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <class T, int FACTO>
 __global__ void __launch_bounds__(UpdCfg<T>::NT, UpdCfg<T>::CTAS)
 k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__restrict__ descs) {
@@ -184,7 +191,9 @@ k_gemm_scatter(DevMap M, T *L, T *U, const T *__restrict__ W, const TileDesc *__
   if (FACTO == F_LU) { part = tile & 1; tile >>= 1; }
   // the whole tile description in one (broadcast) load: no dependent index chasing before the first
   // operand bytes are requested
+  pdl_launch_dependents();
   const TileDesc tk = descs[tile];
+  pdl_wait();
   const int ld = tk.ld;
   const int m0 = tk.m0, mrows = tk.mrows;
   const int n0 = tk.n0, ncols = tk.ncols;
@@ -494,7 +503,9 @@ k_trsm_mma(DevSym S, T *L, T *U, T *W, const SubTask *__restrict__ tasks, int nt
   int tile = blockIdx.x, part = 0;
   if (FACTO == F_LU) { part = tile & 1; tile >>= 1; }
   const int ti = find_task(tasks, ntasks, tile);
+  pdl_launch_dependents();
   const SubTask tk = tasks[ti];
+  pdl_wait();
   const int k = tk.cblk, ld = S.stride[k], c0 = tk.c0, nb = tk.c1 - tk.c0, nbp = (nb + 7) & ~7;
   const int LDW = trsm_ldw<T>(nbp);
   const int r_base = tk.c1 + (tile - tk.tile0) * TM, mrows = min(TM, ld - r_base);
@@ -957,7 +968,9 @@ k_diag_blk(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, double crit,
   __shared__ T X[BS][NBP];
   __shared__ T Y[(LU || LDL) ? BS : 1][(LU || LDL) ? NBP : 1];
   __shared__ T Dout[BS][BS];
+  pdl_launch_dependents();
   const SubTask tk = tasks[blockIdx.x];
+  pdl_wait();
   const int c = tk.cblk, ld = S.stride[c], nb = tk.c1 - tk.c0;
   T *A = L + S.poff[c] + (size_t)tk.c0 * (ld + 1);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
