@@ -1398,9 +1398,11 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   // which is a by-value kernel argument) and replay it — kernel-to-kernel dependencies then resolve on the device
   // without the stream scheduler in between.  Multi-GPU schedules carry an epoch argument and stay on streams.
   const bool use_graph = !serial && !overlap_inv && h->nranks == 1 && h->nlevels > 0 && getenv("PB200_GRAPH") != nullptr;
-  // programmatic dependent launch of the chain kernels (PB200_PDL=0: plain stream order, for A/B); per-launch event
-  // timing (profile mode) needs the plain order
-  const bool pdl = !prof && !use_graph && (getenv("PB200_PDL") == nullptr || atoi(getenv("PB200_PDL")) != 0);
+  // programmatic dependent launch of the chain kernels: PB200_PDL=0 plain stream order, 1 every chain kernel, 2 only
+  // launches of at most one wave of CTAs (default: the CTAs of an early-scheduled large launch sit on SM resources the
+  // OTHER stream's kernels could use — measured slower, profiles/README.md); per-launch event timing needs the plain order
+  const int pdl_mode = (prof || use_graph) ? 0 : (getenv("PB200_PDL") ? atoi(getenv("PB200_PDL")) : 2);
+  const long long pdl_max = pdl_mode == 1 ? (1LL << 40) : (long long)h->sm_count;
   if (use_graph && h->fact_graph && h->fact_graph_crit == crit) {
     CK(cudaGraphLaunch(h->fact_graph, h->stream));
     h->last_launches = h->fact_graph_launches;
@@ -1423,17 +1425,17 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
         if (diag_old)
           k_diag_sub<T, FACTO><<<st.ntasks, 256, 0, sm>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
         else if (st.nbmax <= 64)
-          CK(launch_chain(pdl, k_diag_blk<T, FACTO, 4>, dim3(st.ntasks), dim3(256), 0, sm, h->S, L, U, (const SubTask *)(h->d_sub + st.task0), crit, h->d_cnt));
+          CK(launch_chain(pdl_mode && st.ntasks <= pdl_max, k_diag_blk<T, FACTO, 4>, dim3(st.ntasks), dim3(256), 0, sm, h->S, L, U, (const SubTask *)(h->d_sub + st.task0), crit, h->d_cnt));
         else if constexpr (SubCfg<T>::NBMAX > 64)
-          CK(launch_chain(pdl, k_diag_blk<T, FACTO, SubCfg<T>::NBMAX / 16>, dim3(st.ntasks), dim3(256), 0, sm, h->S, L, U,
+          CK(launch_chain(pdl_mode && st.ntasks <= pdl_max, k_diag_blk<T, FACTO, SubCfg<T>::NBMAX / 16>, dim3(st.ntasks), dim3(256), 0, sm, h->S, L, U,
                           (const SubTask *)(h->d_sub + st.task0), crit, h->d_cnt));
       } break;
       case 1:
-        CK(launch_chain(pdl, k_trsm_mma<T, FACTO>, dim3((unsigned)(st.ntiles * lu)), dim3(128), trsm_smem_bytes<T>(st.nbmax), sm,
+        CK(launch_chain(pdl_mode && st.ntiles * lu <= pdl_max, k_trsm_mma<T, FACTO>, dim3((unsigned)(st.ntiles * lu)), dim3(128), trsm_smem_bytes<T>(st.nbmax), sm,
                         h->S, L, U, (T *)h->dW, (const SubTask *)(h->d_sub + st.task0), (int)st.ntasks));
         break;
       case 2:
-        CK(launch_chain(pdl, k_gemm_scatter<T, FACTO>, dim3((unsigned)(st.ntiles * lu)), dim3(UpdCfg<T>::NT), upd_smem_bytes<T>(), sm,
+        CK(launch_chain(pdl_mode && st.ntiles * lu <= pdl_max, k_gemm_scatter<T, FACTO>, dim3((unsigned)(st.ntiles * lu)), dim3(UpdCfg<T>::NT), upd_smem_bytes<T>(), sm,
                         h->M, L, U, (const T *)h->dW, (const TileDesc *)(h->d_desc + st.t2t0)));
         break;
       case 3:
