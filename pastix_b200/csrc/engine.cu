@@ -1402,7 +1402,7 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   // launches of at most one wave of CTAs (default: the CTAs of an early-scheduled large launch sit on SM resources the
   // OTHER stream's kernels could use — measured slower, profiles/README.md); per-launch event timing needs the plain order
   const int pdl_mode = (prof || use_graph) ? 0 : (getenv("PB200_PDL") ? atoi(getenv("PB200_PDL")) : 2);
-  const long long pdl_max = pdl_mode == 1 ? (1LL << 40) : (long long)h->sm_count;
+  const long long pdl_max = pdl_mode == 1 ? (1LL << 40) : (getenv("PB200_PDL_MAX") ? atoll(getenv("PB200_PDL_MAX")) : (long long)h->sm_count);
   if (use_graph && h->fact_graph && h->fact_graph_crit == crit) {
     CK(cudaGraphLaunch(h->fact_graph, h->stream));
     h->last_launches = h->fact_graph_launches;

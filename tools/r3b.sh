@@ -1,12 +1,11 @@
 #!/bin/bash
 set -x
 export PYTHONUNBUFFERED=1
-T=${1:-r3b}
-timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_parity_scale.py -m gpu -q -x > gpurun_out/${T}_pytest_gpu_1gpu.log 2>&1; echo rc=$?
-tail -4 gpurun_out/${T}_pytest_gpu_1gpu.log
-run() { timeout 300 python tools/run_case.py "$@" 2>&1 | grep -E 'factorize|backward|rror' | tail -3; }
-for P in 2 0; do
-echo "== C2 pdl=$P"; PB200_PDL=$P run 64 7 llt d --reps=4
-echo "== C3 pdl=$P"; PB200_PDL=$P run 100 27 ldlt d --reps=2
-echo "== c4s pdl=$P"; PB200_PDL=$P run 64 cd lu z --reps=2
+run() { timeout 300 python tools/run_case.py "$@" 2>&1 | grep -E 'factorize' | tail -2; }
+for M in 8 32 74 148 296; do
+echo "== C2 pdlmax=$M"; PB200_PDL_MAX=$M run 64 7 llt d --reps=3
+echo "== c4s pdlmax=$M"; PB200_PDL_MAX=$M run 64 cd lu z --reps=2
 done
+echo "== C3 pdlmax=32"; PB200_PDL_MAX=32 run 100 27 ldlt d --reps=2
+echo "== C2 pdl=0"; PB200_PDL=0 run 64 7 llt d --reps=3
+echo "== c4s pdl=0"; PB200_PDL=0 run 64 cd lu z --reps=2
