@@ -1399,10 +1399,11 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   // without the stream scheduler in between.  Multi-GPU schedules carry an epoch argument and stay on streams.
   const bool use_graph = !serial && !overlap_inv && h->nranks == 1 && h->nlevels > 0 && getenv("PB200_GRAPH") != nullptr;
   // programmatic dependent launch of the chain kernels: PB200_PDL=0 plain stream order, 1 every chain kernel, 2 only
-  // launches of at most one wave of CTAs (default: the CTAs of an early-scheduled large launch sit on SM resources the
+  // launches of at most PB200_PDL_MAX CTAs (default: half the SMs; measured on C2 / 64^3 z-LU: 8: 21.66 / 133.5 ms, 32: 21.54 / 132.4,
+  // 74: 21.37 / 133.9, 148: 21.50 / 137.9, 296: 21.82 / 142.5, every launch: 23.35 / 147.4, none: 22.14 / 133.5 — the CTAs of an early-scheduled large launch sit on SM resources the
   // OTHER stream's kernels could use — measured slower, profiles/README.md); per-launch event timing needs the plain order
   const int pdl_mode = (prof || use_graph) ? 0 : (getenv("PB200_PDL") ? atoi(getenv("PB200_PDL")) : 2);
-  const long long pdl_max = pdl_mode == 1 ? (1LL << 40) : (getenv("PB200_PDL_MAX") ? atoll(getenv("PB200_PDL_MAX")) : (long long)h->sm_count);
+  const long long pdl_max = pdl_mode == 1 ? (1LL << 40) : (getenv("PB200_PDL_MAX") ? atoll(getenv("PB200_PDL_MAX")) : (long long)h->sm_count / 2);
   if (use_graph && h->fact_graph && h->fact_graph_crit == crit) {
     CK(cudaGraphLaunch(h->fact_graph, h->stream));
     h->last_launches = h->fact_graph_launches;
