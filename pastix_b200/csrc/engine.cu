@@ -1402,6 +1402,8 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   // launches of at most PB200_PDL_MAX CTAs (default: half the SMs; measured on C2 / 64^3 z-LU: 8: 21.66 / 133.5 ms, 32: 21.54 / 132.4,
   // 74: 21.37 / 133.9, 148: 21.50 / 137.9, 296: 21.82 / 142.5, every launch: 23.35 / 147.4, none: 22.14 / 133.5 — the CTAs of an early-scheduled large launch sit on SM resources the
   // OTHER stream's kernels could use — measured slower, profiles/README.md); per-launch event timing needs the plain order
+  // compact shared-memory diagonal kernel for real LLt / LDLt (PB200_DIAG_CMP=0: the register-resident k_diag_blk)
+  const bool diag_cmp = getenv("PB200_DIAG_CMP") == nullptr || atoi(getenv("PB200_DIAG_CMP")) != 0;
   const int pdl_mode = (prof || use_graph) ? 0 : (getenv("PB200_PDL") ? atoi(getenv("PB200_PDL")) : 2);
   const long long pdl_max = pdl_mode == 1 ? (1LL << 40) : (getenv("PB200_PDL_MAX") ? atoll(getenv("PB200_PDL_MAX")) : (long long)h->sm_count / 2);
   if (use_graph && h->fact_graph && h->fact_graph_crit == crit) {
@@ -1425,7 +1427,11 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
       case 0: {
         if (diag_old)
           k_diag_sub<T, FACTO><<<st.ntasks, 256, 0, sm>>>(h->S, L, U, h->d_sub + st.task0, crit, h->d_cnt);
-        else if (st.nbmax <= 64)
+        else if (diag_cmp && st.nbmax <= 64 && !ST<T>::is_complex && (FACTO == F_LLT || FACTO == F_LDLT)) {
+          if constexpr (!ST<T>::is_complex && (FACTO == F_LLT || FACTO == F_LDLT))
+            CK(launch_chain(pdl_mode && st.ntasks <= pdl_max, k_diag_cmp<T, FACTO>, dim3(st.ntasks), dim3(256), 0, sm, h->S, L,
+                            (const SubTask *)(h->d_sub + st.task0), crit, h->d_cnt));
+        } else if (st.nbmax <= 64)
           CK(launch_chain(pdl_mode && st.ntasks <= pdl_max, k_diag_blk<T, FACTO, 4>, dim3(st.ntasks), dim3(256), 0, sm, h->S, L, U, (const SubTask *)(h->d_sub + st.task0), crit, h->d_cnt));
         else if constexpr (SubCfg<T>::NBMAX > 64)
           CK(launch_chain(pdl_mode && st.ntasks <= pdl_max, k_diag_blk<T, FACTO, SubCfg<T>::NBMAX / 16>, dim3(st.ntasks), dim3(256), 0, sm, h->S, L, U,

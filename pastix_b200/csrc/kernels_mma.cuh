@@ -1016,6 +1016,136 @@ k_diag_blk(DevSym S, T *L, T *U, const SubTask *__restrict__ tasks, double crit,
   }
 }
 
+// ---- compact diagonal-block kernel (real types, LLt / LDLt, sub-blocks of at most 64 columns).
+// Same reference (factor_diag: PASTIX_potrf_block / PASTIX_sytrf_block, compute_diag.c) and the same 8-pivot steps as
+// k_diag_blk, but the block lives in SHARED memory and the steps are a real loop: k_diag_blk keeps the block in
+// registers, which forces every step to be unrolled with its own static indices — 5 640 SASS instructions of
+// straight-line code executed once per launch by one CTA, and ncu shows that CTA waiting for instructions
+// (stall_no_inst) more than for pivots.  Here the whole kernel is a few hundred instructions that stay in the
+// instruction cache across the eight steps.
+//   per step: warp 0 factors the 8 x 8 diagonal block in the registers of every lane (no shuffle between pivots, static-
+//   pivot rule per pivot in order), each lane solves its two rows of the block column against it and publishes them
+//   (and l * d for LDLt); then all 256 threads apply the rank-8 update to the trailing lower triangle, 4 x 4 elements
+//   per thread from register copies of their rows / columns of the panel.
+template <class T, int FACTO>
+__global__ void __launch_bounds__(256)
+k_diag_cmp(DevSym S, T *L, const SubTask *__restrict__ tasks, double crit, unsigned long long *nbpivot) {
+  constexpr int NB = 64, LD = 65, BS = 8;
+  constexpr bool LDL = (FACTO == F_LDLT);
+  __shared__ T A[NB * LD];                 // column-major, A[c * LD + r]
+  __shared__ T Y[BS][NB];                  // LDLt: l * d of the panel columns (the second factor of the update)
+  pdl_launch_dependents();
+  const SubTask tk = tasks[blockIdx.x];
+  pdl_wait();
+  const int c = tk.cblk, ld = S.stride[c], nb = tk.c1 - tk.c0;
+  T *Ag = L + S.poff[c] + (size_t)tk.c0 * (ld + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T one = ST<T>::from_real(1.0), zero = ST<T>::zero();
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e & (NB - 1), cc = e >> 6;
+    // padding: identity, so that the blocked steps need no edge cases
+    A[cc * LD + r] = (r < nb && cc < nb && r >= cc) ? Ag[(size_t)cc * ld + r] : (r == cc ? one : zero);
+  }
+  __syncthreads();
+  const int nsteps = (nb + BS - 1) / BS;
+  for (int s = 0; s < nsteps; ++s) {
+    const int J0 = s * BS, J1 = J0 + BS;
+    if (warp == 0) {
+      // 1. the BS x BS diagonal block, factored by every lane in registers (d[r][q] = element (J0 + r, J0 + q), r >= q)
+      T d[BS][BS], invd[BS], piv[BS];
+#pragma unroll
+      for (int q = 0; q < BS; ++q)
+#pragma unroll
+        for (int r = q; r < BS; ++r) d[r][q] = A[(J0 + q) * LD + J0 + r];
+#pragma unroll
+      for (int k = 0; k < BS; ++k) {
+        T pv = d[k][k];
+        if (below_crit<T>(pv, crit)) {
+          pv = ST<T>::from_real(crit);
+          if (lane == 0 && J0 + k < nb) atomicAdd(nbpivot, 1ULL);
+        }
+        T inv;
+        pivot_inv<FACTO>(pv, inv);
+        d[k][k] = pv; invd[k] = inv; piv[k] = pv;
+        T wk[BS];
+#pragma unroll
+        for (int r = k + 1; r < BS; ++r) {
+          const T l = d[r][k] * inv;
+          d[r][k] = l;
+          wk[r] = LDL ? pv * l : l;
+        }
+#pragma unroll
+        for (int cc = k + 1; cc < BS; ++cc)
+#pragma unroll
+          for (int r = cc; r < BS; ++r) d[r][cc] = d[r][cc] - d[r][k] * wk[cc];
+      }
+      // 2. lanes 0..7 put row `lane` of the factored block back
+      if (lane < BS) {
+#pragma unroll
+        for (int r = 0; r < BS; ++r)
+#pragma unroll
+          for (int q = 0; q <= r; ++q)
+            if (r == lane) A[(J0 + q) * LD + J0 + r] = d[r][q];
+      }
+      // 3. rows below the block: x L11^T = p (LLt);  w L11^T = p, l = w / d (LDLt) — two rows per lane
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = J1 + lane + 32 * h;
+        if (r < NB) {
+          T x[BS];
+#pragma unroll
+          for (int q = 0; q < BS; ++q) {
+            T acc = A[(J0 + q) * LD + r];
+#pragma unroll
+            for (int qq = 0; qq < q; ++qq) acc = acc - x[qq] * d[q][qq];
+            if (LDL) {
+              x[q] = acc;                              // w = l * d
+              const T l = acc * invd[q];
+              A[(J0 + q) * LD + r] = l;
+              Y[q][r] = piv[q] * l;
+            } else {
+              x[q] = acc * invd[q];
+              A[(J0 + q) * LD + r] = x[q];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // 4. rank-BS update of the trailing lower triangle: thread (tx, ty) owns rows J1 + tx + 16 i, columns J1 + ty + 16 j
+    if (J1 < NB) {
+      const int tx = tid & 15, ty = tid >> 4;
+      T xr[4][BS], yc[4][BS];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = J1 + tx + 16 * i, cc = J1 + ty + 16 * i;
+#pragma unroll
+        for (int q = 0; q < BS; ++q) {
+          xr[i][q] = r < NB ? A[(J0 + q) * LD + r] : zero;
+          yc[i][q] = cc < NB ? (LDL ? Y[q][cc] : A[(J0 + q) * LD + cc]) : zero;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = J1 + tx + 16 * i, cc = J1 + ty + 16 * j;
+          if (r < NB && cc <= r) {
+            T acc = zero;
+#pragma unroll
+            for (int q = 0; q < BS; ++q) acc += xr[i][q] * yc[j][q];
+            A[cc * LD + r] -= acc;
+          }
+        }
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e & (NB - 1), cc = e >> 6;
+    if (r < nb && cc < nb && r >= cc) Ag[(size_t)cc * ld + r] = A[cc * LD + r];
+  }
+}
+
 // LU: ucoeftab's diagonal blok <- transpose of coeftab's, for every cblk of the level about to be
 // factored (all external contributions have landed in coeftab by then).
 template <class T>

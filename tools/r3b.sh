@@ -1,11 +1,11 @@
 #!/bin/bash
 set -x
 export PYTHONUNBUFFERED=1
-run() { timeout 300 python tools/run_case.py "$@" 2>&1 | grep -E 'factorize' | tail -2; }
-for M in 8 32 74 148 296; do
-echo "== C2 pdlmax=$M"; PB200_PDL_MAX=$M run 64 7 llt d --reps=3
-echo "== c4s pdlmax=$M"; PB200_PDL_MAX=$M run 64 cd lu z --reps=2
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r3f_pytest_gpu_1gpu.log 2>&1; echo rc=$?
+tail -4 gpurun_out/r3f_pytest_gpu_1gpu.log
+run() { timeout 300 python tools/run_case.py "$@" 2>&1 | grep -E 'factorize|backward' | tail -3; }
+for P in 1 0; do
+echo "== C2 cmp=$P"; PB200_DIAG_CMP=$P run 64 7 llt d --reps=3
+echo "== C3 cmp=$P"; PB200_DIAG_CMP=$P run 100 27 ldlt d --reps=2
+echo "== c2s cmp=$P"; PB200_DIAG_CMP=$P run 64 7 llt s --reps=2
 done
-echo "== C3 pdlmax=32"; PB200_PDL_MAX=32 run 100 27 ldlt d --reps=2
-echo "== C2 pdl=0"; PB200_PDL=0 run 64 7 llt d --reps=3
-echo "== c4s pdl=0"; PB200_PDL=0 run 64 cd lu z --reps=2
