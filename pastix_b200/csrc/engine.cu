@@ -86,6 +86,7 @@ struct pb200_handle_s {
   int dag_rows = PB200_DAG_ROWS;                                 // panel rows per T sub-tile of the general list: 64 (k_fwd_dag / k_bwd_dag), 32 (k_dag2, PB200_DAG_V2=1)
   bool dag3_ok = false; int dag3_GD = 0, dag3_GT = 0;            // third generation (one right-hand side): D and T ticket lists
   DagTick *d_dag3_ticksD = nullptr, *d_dag3_ticksT = nullptr; int *d_dag3_tgt = nullptr;
+  unsigned long long *d_dag3_xpub = nullptr; unsigned dag3_epoch = 0;   // solved unknowns published with the flag in the data (kernels_solve_dag3.cuh)
   unsigned long long *d_dag_trace = nullptr;                     // PB200_DAG_TRACE=<file>: per-ticket time stamps of the last solve
   DagTick *d_dag_ticks = nullptr; int *d_dag_tgt = nullptr;
   unsigned int *d_dag_need = nullptr, *d_dag_state = nullptr;   // state: arrived[nsp] ready[nsp] done[nsp] cnt[nsp] ticket[2] err[1]
@@ -346,6 +347,12 @@ static int build_solve_dag(pb200_handle_t *h, const std::vector<SlvTask> &tasks)
       { int rc = upload(h, L3.ticks, &h->d_dag3_ticksD); if (rc) return rc; }
       { int rc = upload(h, L3.ticksT, &h->d_dag3_ticksT); if (rc) return rc; }
       { int rc = upload(h, L3.tgt, &h->d_dag3_tgt); if (rc) return rc; }
+      {
+        const size_t pb = (size_t)h->n * (h->esize / 4) * sizeof(unsigned long long);
+        CK(cudaMalloc((void **)&h->d_dag3_xpub, pb));
+        CK(cudaMemset(h->d_dag3_xpub, 0, pb));     // epoch 0 = never published
+        h->allocs.push_back(h->d_dag3_xpub); h->device_bytes += pb;
+      }
       h->dag3_ok = true;
     }
   }
@@ -1402,8 +1409,9 @@ static int factorize_mma(pb200_handle_t *h, double crit) {
   // launches of at most PB200_PDL_MAX CTAs (default: half the SMs; measured on C2 / 64^3 z-LU: 8: 21.66 / 133.5 ms, 32: 21.54 / 132.4,
   // 74: 21.37 / 133.9, 148: 21.50 / 137.9, 296: 21.82 / 142.5, every launch: 23.35 / 147.4, none: 22.14 / 133.5 — the CTAs of an early-scheduled large launch sit on SM resources the
   // OTHER stream's kernels could use — measured slower, profiles/README.md); per-launch event timing needs the plain order
-  // compact shared-memory diagonal kernel for real LLt / LDLt (PB200_DIAG_CMP=0: the register-resident k_diag_blk)
-  const bool diag_cmp = getenv("PB200_DIAG_CMP") == nullptr || atoi(getenv("PB200_DIAG_CMP")) != 0;
+  // compact shared-memory diagonal kernel for real LLt / LDLt: opt-in (PB200_DIAG_CMP=1) — measured SLOWER than the
+  // register-resident k_diag_blk (C2 22.75 vs 21.43 ms, C3 271.1 vs 268.4 ms: one warp per panel, the rest at a barrier)
+  const bool diag_cmp = getenv("PB200_DIAG_CMP") != nullptr && atoi(getenv("PB200_DIAG_CMP")) != 0;
   const int pdl_mode = (prof || use_graph) ? 0 : (getenv("PB200_PDL") ? atoi(getenv("PB200_PDL")) : 2);
   const long long pdl_max = pdl_mode == 1 ? (1LL << 40) : (getenv("PB200_PDL_MAX") ? atoll(getenv("PB200_PDL_MAX")) : (long long)h->sm_count / 2);
   if (use_graph && h->fact_graph && h->fact_graph_crit == crit) {
@@ -1719,6 +1727,10 @@ static int solve_tf(pb200_handle_t *h, T *x, int64_t ldx, int nrhs) {
       B.ticksD = h->d_dag3_ticksD; B.ticksT = h->d_dag3_ticksT; B.GD = h->dag3_GD; B.GT = h->dag3_GT; B.tgt = h->d_dag3_tgt;
       B.arrived = A.arrived; B.ready = A.ready; B.done = A.done; B.cnt = A.cnt; B.ticket = A.ticket; B.err = A.ticket + 4;
       B.rowglob = h->d_rowglob; B.trace = nullptr;
+      B.xpub = h->d_dag3_xpub;
+      h->dag3_epoch = (h->dag3_epoch + 2u) & 0x7ffffffeu;
+      if (h->dag3_epoch == 0) { CK(cudaMemsetAsync(h->d_dag3_xpub, 0, (size_t)h->n * (h->esize / 4) * sizeof(unsigned long long), h->stream)); h->dag3_epoch = 2u; }
+      B.epoch_down = h->dag3_epoch - 1u; B.epoch_up = h->dag3_epoch;
       const char *trf = getenv("PB200_DAG_TRACE");
       const size_t tb = (size_t)2 * ((size_t)B.GD + B.GT) * 8 * sizeof(unsigned long long);
       if (trf && !h->d_dag_trace) {

@@ -39,6 +39,8 @@ struct Dag3Args {
   unsigned *err;
   const int *rowglob;
   unsigned long long *trace;        // optional [2][GD + GT][8]
+  unsigned long long *xpub;         // [n][sizeof(T) / 4] {32-bit word of x, 32-bit epoch}: x published with the flag in the data
+  unsigned epoch_down, epoch_up;    // tags of this solve's two sweeps (never 0)
 };
 
 template <class T> struct Dag3Cfg {
@@ -56,6 +58,61 @@ template <class T> struct Dag3Cfg {
 };
 
 __device__ __forceinline__ void dag3_team_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ---- flag-in-data publication of solved unknowns.  A D ticket used to store x_J, fence, and bump a flag; the T tickets
+// waiting for it polled the flag (acquire) and only then loaded x_J: three L2 round trips on the D -> T hop of the
+// dependency chain.  Here every 32-bit word of a published value travels in ONE 8-byte store together with the
+// sweep's epoch ({word, epoch}: 8-byte accesses are single-copy atomic), so the consumer's load of the value IS its
+// poll — no fence, no flag, one round trip — and a value is valid exactly when all its words carry the epoch
+// (the LL protocol of NCCL, applied to a solution vector).
+template <class T> struct PubCfg { static constexpr int W = (int)sizeof(T) / 4; };
+template <class T>
+__device__ __forceinline__ void pub_store(unsigned long long *xpub, size_t idx, T v, unsigned epoch) {
+  constexpr int W = PubCfg<T>::W;
+  unsigned w[W];
+  memcpy(w, &v, sizeof(T));
+  unsigned long long *p = xpub + idx * W;
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const unsigned long long u = ((unsigned long long)epoch << 32) | w[k];
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p + k), "l"(u) : "memory");
+  }
+}
+// one look: true (and v filled) when every word of element idx carries `epoch`
+template <class T>
+__device__ __forceinline__ bool pub_try_load(const unsigned long long *xpub, size_t idx, unsigned epoch, T &v) {
+  constexpr int W = PubCfg<T>::W;
+  unsigned w[W];
+  bool ok = true;
+  const unsigned long long *p = xpub + idx * W;
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    unsigned long long u;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(u) : "l"(p + k) : "memory");
+    ok = ok && (unsigned)(u >> 32) == epoch;
+    w[k] = (unsigned)u;
+  }
+  memcpy(&v, w, sizeof(T));
+  return ok;
+}
+// all lanes of a warp spin until each has its element (lanes with !want pass); raises *err after the watchdog time
+template <class T>
+__device__ __forceinline__ T pub_wait_load(const unsigned long long *xpub, size_t idx, bool want, unsigned epoch, unsigned *err) {
+  T v = ST<T>::zero();
+  bool have = !want;
+  if (!have) have = pub_try_load<T>(xpub, idx, epoch, v);
+  if (__all_sync(0xffffffffu, have)) return v;
+  const long long t0 = clock64();
+  for (unsigned it = 1;; ++it) {
+    if (!have) have = pub_try_load<T>(xpub, idx, epoch, v);
+    if (__all_sync(0xffffffffu, have)) return v;
+    if ((it & 63u) == 0) {
+      bool stop = *reinterpret_cast<volatile unsigned *>(err) != 0;
+      if (!stop && clock64() - t0 > PB200_DAG_TIMEOUT) { atomicExch(err, 1u); stop = true; }
+      if (__any_sync(0xffffffffu, stop)) return v;
+    }
+  }
+}
 
 // 32 x 32 block task of a triangle product with four independent accumulators (see dag2_tri_task for the layouts).
 // Branch-free: every lane walks all 32 summation indices; where the term does not exist (above the diagonal of a
@@ -183,13 +240,13 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
             else v = dparts[96 + lane];
           }
           x[tk.xcol + p] = v;
+          // what the T tickets of the sweep wait for, value and flag in one store each
+          pub_store<T>(A.xpub, (size_t)(tk.xcol + p), v, DIR == 0 ? A.epoch_down : A.epoch_up);
           // LDLt / LDLh: the diagonal step x_k /= D_kk folded into the write-back (updo.c:948-984)
           if (DIR == 0) y[tk.xcol + p] = LDL ? v / dreg[ob] : v;
         }
         if (A.trace && lane == 0) t_fin = dag_gtime();
-        __threadfence();
         if (lane == 0) {
-          atomicAdd((DIR == 0 ? A.ready : A.done) + tk.sp, 1u);
           if (A.trace) {
             unsigned long long *tr = A.trace + ((size_t)DIR * (A.GD + A.GT) + (size_t)g) * 8;
             unsigned sm;
@@ -247,21 +304,14 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
       if (r >= tk.mrows) return 0;
       return r < tk.wrem ? tk.grow0 + r : __ldg(A.rowglob + tk.aux + r);
     };
-    // the first look at the dependency flag travels while the copies of the first chunk are being issued
-    unsigned early = 0;
-    if (DIR == 0 && lane == 0) early = dag_ld_acquire(A.ready + tk.sp);
     issue(0);
     int grow = grow_of(0);
-    // ---- dependency, input vector
+    // ---- dependency = the data itself: x_J of the sub-panel (down), x[rows] per sub-tile (up, below)
     if (DIR == 0) {
-      if (lane == 0 && early < 1u) dag_wait_ge(A.ready + tk.sp, 1u, A.err);
-      __syncwarp();
-      if (A.trace && lane == 0) t_dep = dag_gtime();
-      for (int j = lane; j < NB; j += 32) xs[j] = j < nb ? ld_cg(&x[tk.xcol + j]) : zero;
-    } else {
-      if (lane < min(tk.ntgt, 32)) dag_wait_ge(A.done + my_tgt, 1u, A.err);
-      for (int q = 32 + lane; q < tk.ntgt; q += 32) dag_wait_ge(A.done + __ldg(A.tgt + tk.tptr + q), 1u, A.err);
-      __syncwarp();
+      for (int j = lane; j < NB; j += 32) {          // NB / 32 uniform rounds
+        const T v = pub_wait_load<T>(A.xpub, (size_t)(tk.xcol + j), j < nb, A.epoch_down, A.err);
+        xs[j] = j < nb ? v : zero;
+      }
       if (A.trace && lane == 0) t_dep = dag_gtime();
     }
     T acc0 = zero, acc1 = zero, acc2 = zero, acc3 = zero;     // down: row sums of the current sub-tile (4 chains)
@@ -277,7 +327,11 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
       if (c == 0) {
         if (k > 0) grow = grow_next;
         if (k + 1 < nsub) grow_next = grow_of(k + 1);
-        if (DIR == 1) xr[lane] = lane < mr ? ld_cg(&x[grow]) : zero;
+        if (DIR == 1) {
+          const T v = pub_wait_load<T>(A.xpub, (size_t)grow, lane < mr, A.epoch_up, A.err);
+          xr[lane] = lane < mr ? v : zero;
+          if (A.trace && lane == 0 && q == 0) t_dep = dag_gtime();
+        }
       }
       __syncwarp();
       if (A.trace && lane == 0 && q == 0) t_b1 = dag_gtime();
