@@ -187,7 +187,7 @@ def measure_fp32_peak(device: int) -> dict:
 def ncu_traffic(workload: str = "c2"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (k_gemm_scatter: the largest
     captured launch) and of the two up_down sweeps, from the committed `ncu --set full` captures
-    (profiles/r02/r02_full_gemm_scatter_*_summary.json and r02b_full_updown_c2_summary.json — the k_dag3 sweeps —, written by
+    (profiles/r02/r02_full_gemm_scatter_*_summary.json and r02c_full_updown_c2_summary.json — the k_dag3 sweeps —, written by
     tools/gpu_profile.sh + tools/ncu_summary.py); None when absent."""
     wl = workload if workload in ("c2", "c3") else "c2"
     out = None
@@ -200,7 +200,7 @@ def ncu_traffic(workload: str = "c2"):
     except Exception:
         pass
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r02", "r02b_full_updown_c2_summary.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02", "r02c_full_updown_c2_summary.json")))
         if out is not None and wl == "c2":
             out["updown_sweeps"] = [{"kernel": k["kernel"].replace("void ", "").split("<")[0], "dram_bytes": k["dram_read_bytes"] + k["dram_write_bytes"],
                                      "launch_ms": k["duration_us"] * 1e-3} for k in d]
