@@ -222,3 +222,24 @@ def test_second_generation_sweeps_equal_the_first(name, nrhs, monkeypatch):
         s.close()
     assert relerr(out[0], out[2]) <= 50 * tol(g["prec"])
     assert relerr(out[1], out[2]) <= 50 * tol(g["prec"])
+
+
+@pytest.mark.parametrize("name", ["lap7_8_llt_d", "lap27_6_ldlt_d", "cd_8_lu_d", "cd_6_lu_z", "lap7_10_llt_d_bs16", "lap7_6_llt_s",
+                                  "lap7sing_6_ldlt_d"])
+@pytest.mark.parametrize("var,val", [("PB200_PDL", "0"), ("PB200_PDL", "1"), ("PB200_DIAG_CMP", "1")])
+def test_launch_and_diagonal_kernel_variants_give_the_same_factors(name, var, val, monkeypatch):
+    """The panel chain with plain stream order (PB200_PDL=0), with EVERY chain launch programmatically dependent
+    (PB200_PDL=1; default: only launches of at most half a wave), and with the compact shared-memory diagonal kernel
+    (PB200_DIAG_CMP=1, real LLt / LDLt; opt-in) against the default schedule: same factors, same pivot count (the
+    static-pivot case included)."""
+    g = load_golden(name)
+    s0, _, (L0, U0), nb0 = run_cuda(g)
+    s0.close()
+    monkeypatch.setenv(var, val)
+    s1, _, (L1, U1), nb1 = run_cuda(g)
+    s1.close()
+    m = lower_mask(g) if g["facto"] != "lu" else slice(None)
+    assert nb1 == nb0
+    assert relerr(L1[m], L0[m]) <= tol(g["prec"]), (name, var, val)
+    if U0 is not None:
+        assert relerr(U1, U0) <= tol(g["prec"]), (name, var, val)
