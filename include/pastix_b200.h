@@ -120,7 +120,16 @@ int pb200_destroy(pb200_handle_t *h);
  *           the interior system is solved and the Schur unknowns keep their right-hand side. */
 typedef struct pb200_options_s {
   int32_t schur;
-  int32_t reserved[7];
+  int32_t reserved0;
+  /* owner : optional [cblknbr] column block -> rank map for nranks > 1 (NULL: the mapping computed inside).  The
+   *         drop-in passes the reference's OWN proportional mapping when asked (PB200_DIST_MAP=blend): blend maps the
+   *         COMP_1D task of every column block to one of its IPARM_THREAD_NBR "local threads" with the same
+   *         propMappTree / distribPart machinery that maps them to processes (blend/src/splitpart.c:752-1012,
+   *         distribPart.c; result in SolverMatrix.ttsktab, blend/src/solver.h:158-159), and thread t becomes rank
+   *         t * nranks / thrdnbr.  A column block whose subtree spans several ranks is treated as a shared
+   *         top-separator block (fan-out), everything else as private (fan-in). */
+  const int32_t *owner;
+  int32_t reserved[4];
 } pb200_options_t;
 /* pb200_create / pb200_create_dist with options (rank 0 of 1 for a single GPU). */
 int pb200_create_opts(pb200_handle_t **h, const pb200_solver_t *solver, int flttype, int factotype,

@@ -40,7 +40,7 @@ struct DistPlan {
 
 // fblok[C+1], fcblk[B], width[C], stride[C], nrow[B], coefind[B]
 inline DistPlan dist_plan(int64_t C, const int *fblok, const int *fcblk, const int *width, const int *stride,
-                          const int *nrow, const int *coefind, int nranks, bool lu) {
+                          const int *nrow, const int *coefind, int nranks, bool lu, const int32_t *ext_owner = nullptr) {
   DistPlan P;
   P.nranks = nranks;
   P.owner.assign(C, 0);
@@ -66,7 +66,16 @@ inline DistPlan dist_plan(int64_t C, const int *fblok, const int *fcblk, const i
   { std::vector<int> fill(cptr.begin(), cptr.end() - 1);
     for (int64_t c = 0; c < C; ++c) if (parent[c] >= 0) child[fill[parent[c]]++] = (int)c; }
   const char *mode0 = getenv("PB200_DIST_CHAIN");
-  if (nranks > 1 && (mode0 == nullptr || !strcmp(mode0, "cyclic"))) {
+  if (nranks > 1 && ext_owner != nullptr) {
+    // Mapping handed in by the caller (the reference's own: blend's task-to-thread map, pastix_b200.h pb200_options_t).
+    // A cblk whose subtree is not owned by a single rank is a shared top-separator block (its updates are computed by the
+    // owners of their targets, fan-out), the rest is private (fan-in).
+    std::vector<int> uni(C);
+    for (int64_t c = 0; c < C; ++c) { P.owner[c] = std::min(std::max((int)ext_owner[c], 0), nranks - 1); uni[c] = P.owner[c]; }
+    for (int64_t c = 0; c < C; ++c)        // ascending = children first
+      if (parent[c] >= 0 && uni[parent[c]] != uni[c]) uni[parent[c]] = -1;
+    for (int64_t c = 0; c < C; ++c) P.shared[c] = uni[c] < 0;
+  } else if (nranks > 1 && (mode0 == nullptr || !strcmp(mode0, "cyclic"))) {
     // Default mapping (round 2).  The elimination tree over cblks is far from the balanced binary tree of the nested
     // dissection: a separator split into 120-column cblks is a CHAIN, and sibling separators hang at different depths
     // (C3: a 124-cblk top chain over subtrees of 0.53 / 0.16 / 0.16 of the flops).  Candidate intervals in proportion

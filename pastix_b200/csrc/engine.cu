@@ -957,7 +957,7 @@ extern "C" int pb200_create_opts(pb200_handle_t **out, const pb200_solver_t *s, 
 
   // ---- multi-GPU: proportional subtree mapping; the factorization schedule keeps the owned cblks only
   h->plan = dist_plan(C, h->h_fblok.data(), h->h_fcblk.data(), h->h_width.data(), h->h_stride.data(), h->h_nrow.data(),
-                      h->h_coefind.data(), nranks, factotype == PB200_FACT_LU);
+                      h->h_coefind.data(), nranks, factotype == PB200_FACT_LU, (opts && nranks > 1) ? opts->owner : nullptr);
 
   // up_down runs over every cblk on every GPU (factors are gathered after a distributed factorization)
   { int rc = build_solve_schedule(h, lvl_cblk); if (rc) { pb200_destroy(h); return rc; } }

@@ -251,6 +251,26 @@ int pb200_shim_fetch_coeftab(void *pastix_data)
   return 0;
 }
 
+/* the reference's own task-to-thread mapping as a cblk -> rank map for `nranks` GPUs (what PB200_DIST_MAP=blend hands to
+ * pb200_create_opts, sopalin_b200_shim.c): owner[cblknbr]; returns the number of blend threads, -1 when the task list is
+ * not a complete 1-D one.  Host only (tests/test_dist.py compares it with the mapping computed in the CUDA layer). */
+int pb200_shim_blend_owner(void *pastix_data, int nranks, int32_t *owner)
+{
+  pastix_data_t *pd = (pastix_data_t *)pastix_data;
+  SolverMatrix *m = &pd->solvmatr;
+  PASTIX_INT i, t, k, C = m->cblknbr;
+  if (m->ttsktab == NULL || m->thrdnbr <= 0 || nranks <= 0) return -1;
+  for (i = 0; i < C; i++) owner[i] = -1;
+  for (t = 0; t < m->thrdnbr; t++)
+    for (k = 0; k < m->ttsknbr[t]; k++) {
+      const Task *tk = &m->tasktab[m->ttsktab[t][k]];
+      if ((tk->taskid == COMP_1D || tk->taskid == DIAG) && tk->cblknum >= 0 && tk->cblknum < C)
+        owner[tk->cblknum] = (int32_t)((t * nranks) / m->thrdnbr);
+    }
+  for (i = 0; i < C; i++) if (owner[i] < 0) return -1;
+  return (int)m->thrdnbr;
+}
+
 /* internal CSC of this pastix_data_t (CscMatrix, blend/src/csc.h) flattened: sizes = {ncol, nnz, has transcsc, filled};
  * colptr 0-based with ncol+1 entries.  Used by the parity tests of the device-side CscOrdistrib (shim_csc.c). */
 void pb200_shim_csc_sizes(void *pastix_data, int64_t *out)

@@ -127,9 +127,30 @@ static pb200_handle_t *shim_create(SolverMatrix *datacode, int schur, int rank, 
   s.frownum = frow; s.lrownum = lrow; s.cblknum = fcb; s.coefind = cind;
   memset(&opts, 0, sizeof(opts));
   opts.schur = schur;
+  /* PB200_DIST_MAP=blend: the GPUs take the reference's own proportional mapping — the thread blend assigned the
+   * COMP_1D task of every column block to (SolverMatrix.ttsktab, blend/src/solver.h:158-159; built by the same
+   * propMappTree / distribPart code that maps tasks to processes, splitpart.c:752-1012) — instead of the mapping
+   * computed in the CUDA layer.  Meaningful when IPARM_THREAD_NBR was the number of GPUs at analysis time. */
+  int32_t *own = NULL;
+  if (nranks > 1 && getenv("PB200_DIST_MAP") != NULL && strcmp(getenv("PB200_DIST_MAP"), "blend") == 0 &&
+      datacode->ttsktab != NULL && datacode->thrdnbr > 0) {
+    PASTIX_INT t, k;
+    own = (int32_t *)malloc(sizeof(int32_t) * (size_t)(C + 1));
+    if (own == NULL) { errorPrint("pastix_b200: out of memory"); EXIT(MOD_SOPALIN, OUTOFMEMORY_ERR); }
+    for (i = 0; i < C; i++) own[i] = -1;
+    for (t = 0; t < datacode->thrdnbr; t++)
+      for (k = 0; k < datacode->ttsknbr[t]; k++) {
+        const Task *tk = &datacode->tasktab[datacode->ttsktab[t][k]];
+        if ((tk->taskid == COMP_1D || tk->taskid == DIAG) && tk->cblknum >= 0 && tk->cblknum < C)
+          own[tk->cblknum] = (int32_t)((t * nranks) / datacode->thrdnbr);
+      }
+    for (i = 0; i < C; i++) if (own[i] < 0) { free(own); own = NULL; break; }   /* not a complete 1-D task list: keep ours */
+    opts.owner = own;
+  }
   /* one GPU: the current device; a group: devices 0 .. nranks-1 of the box */
   if (pb200_create_opts(&h, &s, PB200_FLT, PB200_FACTO, nranks > 1 ? rank : -1, rank, nranks, &opts) != PB200_SUCCESS)
     shim_fatal("pb200_create_opts");
+  if (own) free(own);
   free(buf);
   return h;
 }

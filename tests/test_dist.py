@@ -10,6 +10,8 @@ import pytest
 
 from conftest import load_golden, lower_mask, relerr, tol
 
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -97,6 +99,8 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
 import numpy as np, torch, torch.distributed as dist
 from conftest import load_golden, lower_mask, relerr, tol
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
 from pastix_b200 import Sopalin
 from pastix_b200.csc import permute_rhs, unpermute_solution
 local = int(os.environ["LOCAL_RANK"]); torch.cuda.set_device(local)
@@ -205,3 +209,87 @@ def test_pastix_with_iparm_cuda_nbr_matches_reference(kind, N, prec, facto, nrhs
     multi.clean(); one.clean()
     assert multi.live_entries() == 0
     ref.clean()
+
+
+@pytest.mark.parametrize("G", [2, 4])
+def test_reference_thread_mapping_as_gpu_mapping(G):
+    """PB200_DIST_MAP=blend (CPU part): the cblk -> GPU map the drop-in derives from the reference's OWN proportional
+    mapping — blend's task-to-thread map with IPARM_THREAD_NBR = G (SolverMatrix.ttsktab, solver.h:158-159;
+    splitpart.c:752-1012) — is a complete map onto G ranks, balanced in PaStiX's flop model about as well as blend
+    balances its threads, and a subtree-to-processor mapping: going up the elimination tree the owner only changes into
+    column blocks whose subtree spans several ranks (the shared top separators).  Reported beside it: how the mapping
+    computed in the CUDA layer (dist_plan.h) compares."""
+    import ctypes as C
+    from make_golden import case_matrix, DT
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import Sopalin
+    A, perm0 = case_matrix("lap7", 24, DT["d"])
+    r = Pastix("d", threads=G).setup(A, perm0, "llt", sym="yes").analyze()
+    s = r.solver()
+    cb = s["cblknbr"]
+    owner = np.full(cb, -9, dtype=np.int32)
+    f = r.lib.pb200_shim_blend_owner
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    f.restype = C.c_int
+    nthr = f(r.pd, G, owner.ctypes.data)
+    assert nthr == G, nthr
+    assert owner.min() >= 0 and owner.max() == G - 1 and len(np.unique(owner)) == G
+    # flop model per cblk (blend_symbol_cost.c:382-430, symmetric): w^3/3 + m w^2 + sum over bloks of 2 (rows from b on) nrow(b) w
+    w = (s["lcolnum"][:cb] - s["fcolnum"][:cb] + 1).astype(float)
+    m = s["stride"][:cb].astype(float) - w
+    cost = w ** 3 / 3 + m * w * w
+    par = np.full(cb, -1)
+    for c in range(cb):
+        b0, b1 = int(s["bloknum"][c]), int(s["bloknum"][c + 1])
+        if b1 - b0 > 1:
+            par[c] = int(s["cblknum"][b0 + 1])
+        for b in range(b0 + 1, b1):
+            cost[c] += 2.0 * (s["stride"][c] - s["coefind"][b]) * (s["lrownum"][b] - s["frownum"][b] + 1) * w[c]
+    share = np.array([cost[owner == p].sum() for p in range(G)]) / cost.sum()
+    assert share.min() >= 0.5 / G and share.max() <= 2.0 / G, share
+    # subtree property: uni[c] = the single owner of c's subtree, or -1
+    uni = owner.astype(int).copy()
+    for c in range(cb):
+        if par[c] >= 0 and uni[par[c]] != uni[c]:
+            uni[par[c]] = -1
+    for c in range(cb):
+        if par[c] >= 0 and owner[par[c]] != owner[c]:
+            assert uni[par[c]] == -1
+    g = dict(cblknbr=cb, bloknbr=s["bloknbr"], fcol=s["fcolnum"], lcol=s["lcolnum"], bloknum=s["bloknum"], stride=s["stride"],
+             frow=s["frownum"], lrow=s["lrownum"], fcblk=s["cblknum"], coefind=s["coefind"])
+    ours, _, load = Sopalin.dist_plan(g, "llt", G)
+    print(f"G={G}: blend thread mapping shares {np.round(share, 3)}, dist_plan shares {np.round(load / load.sum(), 3)}, "
+          f"same owner on {np.mean(ours == owner) * 100:.0f} % of the cblks (up to a relabelling of the ranks: not compared)")
+    r.clean()
+
+
+@pytest.mark.gpu
+def test_factorization_with_the_reference_mapping(monkeypatch):
+    """PB200_DIST_MAP=blend (GPU part, 2 GPUs through pastix() with IPARM_CUDA_NBR = IPARM_THREAD_NBR = 2): factors and
+    solution with the GPUs mapped like blend's threads equal the reference's."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import scipy.sparse as sp
+    from make_golden import case_matrix, DT
+    from oracle.refpastix import RefPastix, available
+    from pastix_b200.pastix_api import Pastix
+    from pastix_b200 import generators as G
+    if not available("d"):
+        pytest.skip("oracle/_ref not built")
+    A, perm0 = case_matrix("lap7", 24, DT["d"])
+    b = G.rhs_vector(A.shape[0], 1, DT["d"])[:, 0].copy()
+    ref = RefPastix("d", threads=2).setup(A, perm0, "llt", sym="yes").analyze().numfact()
+    xr = ref.solve(b)
+    Lr, _ = ref.coef()
+    sol = ref.solver()
+    ref.clean()
+    monkeypatch.setenv("PB200_DIST_MAP", "blend")
+    E = Pastix("d").E
+    gpu = Pastix("d", threads=2).setup(A, perm0, "llt", sym="yes", iparm_over={"IPARM_CUDA_NBR": 2}).analyze().numfact()
+    xg = gpu.solve(b)
+    Lg, _ = gpu.sopalin().get_coeftab()
+    m = lower_mask(sol)
+    assert relerr(Lg[m], Lr[m]) <= tol("d")
+    assert relerr(xg, xr) <= 50 * tol("d")
+    gpu.clean()
