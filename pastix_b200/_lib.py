@@ -36,7 +36,7 @@ class Info(C.Structure):
 
 class Options(C.Structure):
     """pb200_options_t"""
-    _fields_ = [("schur", C.c_int32), ("reserved", C.c_int32 * 7)]
+    _fields_ = [("schur", C.c_int32), ("reserved0", C.c_int32), ("owner", C.c_void_p), ("reserved", C.c_int32 * 4)]
 
 
 _lib = None
