@@ -12,8 +12,7 @@
 //
 // So here nothing is CTA-wide.  One CTA per SM, no __syncthreads after the prologue:
 //   * warps 4.. are eight (four for complex double) independent TILE WORKERS.  A worker takes T tickets from its own counter (the next ticket
-//     number and record are always on their way while the current ticket is worked on, and its first chunk is requested
-//     during the last chunk of the current one), streams the ticket's
+//     number and record are always on their way while the current ticket is worked on), streams the ticket's
 //     32-row sub-tiles through its private double buffer in chunks of 32 rows x 32 columns (cp.async, the next chunk
 //     in flight while the current one is multiplied), lane = panel row in the down step (one RED per row and
 //     sub-tile), lane = columns {lane, lane+32, ..} in the up step (sums kept in registers for the whole ticket),
@@ -53,7 +52,7 @@ template <class T> struct Dag3Cfg {
   static constexpr int HALF = CC * LDT;                               // elements of one chunk buffer
   static constexpr int DSLOT = (NB * (NB + 1)) / 2 + NB;              // packed triangle + LDLt diagonal
   // per worker: two chunk buffers, x_J [NB], x[rows] [32], record
-  static constexpr size_t worker_bytes = ((((size_t)2 * HALF + NB + 32) * sizeof(T) + 2 * sizeof(DagTick)) + 63) / 64 * 64;
+  static constexpr size_t worker_bytes = ((((size_t)2 * HALF + NB + 32) * sizeof(T) + sizeof(DagTick)) + 63) / 64 * 64;
   static constexpr size_t team_bytes = ((((size_t)DSLOT + NB + 10 * 32) * sizeof(T) + sizeof(DagTick) + 16) + 63) / 64 * 64;
   static constexpr size_t bytes = team_bytes + WORKERS * worker_bytes;
 };
@@ -266,7 +265,7 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
   T *hs = reinterpret_cast<T *>(wbase);            // [2][HALF]
   T *xs = hs + 2 * HALF;                           // down: x_J [NB]
   T *xr = xs + NB;                                 // up: x[rows of the sub-tile] [32]
-  int *rec = reinterpret_cast<int *>(xr + 32);     // two ticket records: the current ticket and the one taken ahead
+  int *rec = reinterpret_cast<int *>(xr + 32);     // the ticket record
   unsigned nx_g = (unsigned)A.GT; int nx_w = 0;
   auto pretake = [&]() {
     unsigned g = 0;
@@ -275,44 +274,37 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
     nx_g = min(g, (unsigned)A.GT);
     if (g < (unsigned)A.GT && lane < 16) nx_w = __ldg(reinterpret_cast<const int *>(A.ticksT + (DIR ? A.GT - 1 - (int)g : (int)g)) + lane);
   };
-  // chunk q of ticket t into chunk buffer `buf`
-  auto issue = [&](const DagTick &t, int q, unsigned buf) {
-    const int ncc = (t.nb + CC - 1) / CC;
-    const int k = q / ncc, c = q - k * ncc;
-    const int rk = k * ROWS, mr = min(ROWS, t.mrows - rk);
-    const int j0 = c * CC, j1 = min(t.nb, j0 + CC);
-    T *dst = hs + (buf & 1u) * HALF + lane;
-    const T *src = M + t.src + (size_t)j0 * t.ld + rk + lane;
-    if (lane < mr)
-      for (int j = j0; j < j1; ++j, dst += LDT, src += t.ld) dag_cp_async<sizeof(T)>(dst, src);
-    dag_cp_commit();
-  };
-  // materialise the ticket taken ahead as record slot `slot`, take the next one ahead
-  auto adopt = [&](int slot) -> DagTick {
-    __syncwarp();
-    if (lane < 16) rec[slot * 16 + lane] = nx_w;
-    __syncwarp();
-    const DagTick t = *reinterpret_cast<const DagTick *>(rec + slot * 16);
-    pretake();
-    return t;
-  };
   pretake();
-  if (nx_g >= (unsigned)A.GT) return;
-  int g = (int)nx_g, cb = 0;
-  unsigned gq0 = 0;                                // running chunk number: chunk q of the ticket sits in buffer (gq0 + q) & 1
-  DagTick tk = adopt(cb);
-  issue(tk, 0, gq0);                               // the first chunk of a ticket is always on its way before the ticket starts
   for (;;) {
+    if (nx_g >= (unsigned)A.GT) return;
+    const int g = (int)nx_g;
+    __syncwarp();
+    if (lane < 16) rec[lane] = nx_w;
+    __syncwarp();
+    const DagTick tk = *reinterpret_cast<const DagTick *>(rec);
     unsigned long long t_take = 0, t_dep = 0, t_b1 = 0, t_fin = 0;
     if (A.trace && lane == 0) t_take = dag_gtime();
+    pretake();
     const int nb = tk.nb, nsub = (tk.mrows + ROWS - 1) / ROWS, ncc = (nb + CC - 1) / CC, total = nsub * ncc;
-    // sub-panels owning rows of the ticket: counters to bump (down)
+    const T *P0 = M + tk.src;
+    // sub-panels owning rows of the ticket: counters to bump (down) / flags to wait for (up)
     int my_tgt = lane < tk.ntgt ? __ldg(A.tgt + tk.tptr + lane) : 0;
+    auto issue = [&](int q) {
+      const int k = q / ncc, c = q - k * ncc;
+      const int rk = k * ROWS, mr = min(ROWS, tk.mrows - rk);
+      const int j0 = c * CC, j1 = min(nb, j0 + CC);
+      T *dst = hs + (q & 1) * HALF + lane;
+      const T *src = P0 + (size_t)j0 * tk.ld + rk + lane;
+      if (lane < mr)
+        for (int j = j0; j < j1; ++j, dst += LDT, src += tk.ld) dag_cp_async<sizeof(T)>(dst, src);
+      dag_cp_commit();
+    };
     auto grow_of = [&](int k) -> int {
       const int r = k * ROWS + lane;
       if (r >= tk.mrows) return 0;
       return r < tk.wrem ? tk.grow0 + r : __ldg(A.rowglob + tk.aux + r);
     };
+    issue(0);
     int grow = grow_of(0);
     // ---- dependency = the data itself: x_J of the sub-panel (down), x[rows] per sub-tile (up, below)
     if (DIR == 0) {
@@ -322,7 +314,6 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
       }
       if (A.trace && lane == 0) t_dep = dag_gtime();
     }
-    bool have_next = false; int g_next = 0; DagTick tkn = tk;
     T acc0 = zero, acc1 = zero, acc2 = zero, acc3 = zero;     // down: row sums of the current sub-tile (4 chains)
     T bacc[NBL];                                              // up: column sums of the ticket
 #pragma unroll
@@ -332,15 +323,7 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
       const int k = q / ncc, c = q - k * ncc;
       const int mr = min(ROWS, tk.mrows - k * ROWS);
       const int j0 = c * CC, ncol = min(nb, j0 + CC) - j0;
-      if (q + 1 < total) { issue(tk, q + 1, gq0 + q + 1); dag_cp_wait<1>(); }
-      else if (nx_g < (unsigned)A.GT) {
-        // last chunk: the ticket taken ahead becomes the next one and ITS first chunk is requested now, so that it
-        // travels during this chunk's product, the reductions, the fence and the signal
-        have_next = true; g_next = (int)nx_g;
-        tkn = adopt(cb ^ 1);
-        issue(tkn, 0, gq0 + total);
-        dag_cp_wait<1>();
-      } else dag_cp_wait<0>();
+      if (q + 1 < total) { issue(q + 1); dag_cp_wait<1>(); } else dag_cp_wait<0>();
       if (c == 0) {
         if (k > 0) grow = grow_next;
         if (k + 1 < nsub) grow_next = grow_of(k + 1);
@@ -352,7 +335,7 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
       }
       __syncwarp();
       if (A.trace && lane == 0 && q == 0) t_b1 = dag_gtime();
-      const T *h = hs + ((gq0 + q) & 1u) * HALF;
+      const T *h = hs + (q & 1) * HALF;
       if (DIR == 0) {
         // lane = panel row: sum over the columns of the chunk
         const T *a = h + lane;
@@ -409,8 +392,6 @@ k_dag3(const T *__restrict__ M, const T *__restrict__ inv, T *x, T *y, Dag3Args 
       tr[0] = t_take; tr[1] = t_dep; tr[2] = dag_gtime(); tr[3] = ((unsigned long long)sm << 32) | ((unsigned)nsub << 16);
       tr[4] = t_take; tr[5] = t_b1; tr[6] = t_b1; tr[7] = t_fin;
     }
-    if (!have_next) return;
-    tk = tkn; g = g_next; cb ^= 1; gq0 += (unsigned)total;
   }
 }
 
