@@ -1654,14 +1654,22 @@ static int invert_t(pb200_handle_t *h, cudaStream_t sm, int which) {
   { int rc = inv_attr<T>(h); if (rc) return rc; }
   const int unit_down = (h->facto != PB200_FACT_LLT);
   const std::vector<int> &ptr = h->inv_cls_ptr[which];
+  const bool pdl_inv = getenv("PB200_PDL") == nullptr || atoi(getenv("PB200_PDL")) != 0;
+  bool first = true;
   for (size_t k = 0; k + 1 < ptr.size(); ++k) {
     const int n = ptr[k + 1] - ptr[k];
     if (n == 0) continue;
     const int nbmax = std::min(kInvClasses[k], (int)SlvCfg<T>::NB), ntri = nbmax * (nbmax + 1) / 2;
     const int *ord = h->d_inv_order + ptr[k];
-    k_tri_inverse<T><<<n, 128, inv_smem<T>(nbmax), sm>>>((const T *)h->dL, h->d_slvtask, ord, (T *)h->d_inv, unit_down, ntri);
+    // the first launch of the pass waits for everything before it in the stream (the factorization); the others only for
+    // the previous class to have STARTED (programmatic launch without a griddepcontrol.wait: the classes are independent),
+    // so the six launches run as one — PB200_PDL=0 keeps them in plain stream order
+    CK(launch_chain(pdl_inv && !first, k_tri_inverse<T>, dim3(n), dim3(128), inv_smem<T>(nbmax), sm, (const T *)h->dL,
+                    (const SlvTask *)h->d_slvtask, (const int *)ord, (T *)h->d_inv, unit_down, ntri));
+    first = false;
     if (h->facto == PB200_FACT_LU)
-      k_tri_inverse<T><<<n, 128, inv_smem<T>(nbmax), sm>>>((const T *)h->dU, h->d_slvtask, ord, (T *)h->d_inv_up, 0, ntri);
+      CK(launch_chain(pdl_inv, k_tri_inverse<T>, dim3(n), dim3(128), inv_smem<T>(nbmax), sm, (const T *)h->dU,
+                      (const SlvTask *)h->d_slvtask, (const int *)ord, (T *)h->d_inv_up, 0, ntri));
     h->last_launches += (h->facto == PB200_FACT_LU) ? 2 : 1;
   }
   CK(cudaGetLastError());

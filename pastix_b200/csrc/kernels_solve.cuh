@@ -71,6 +71,9 @@ template <class T>
 __global__ void __launch_bounds__(128)
 k_tri_inverse(const T *__restrict__ M, const SlvTask *__restrict__ tasks, const int *__restrict__ order, T *inv, int unit, int ntri) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // the size-classed launches of one inversion pass are independent of each other: a launch with the programmatic
+  // attribute (engine.cu, invert_t) may start as soon as the CTAs of the previous class have all started
+  asm volatile("griddepcontrol.launch_dependents;");
   T *Ws = reinterpret_cast<T *>(smem_raw);
   T *Xs = Ws + ntri;
   const SlvTask tk = tasks[order ? order[blockIdx.x] : blockIdx.x];
