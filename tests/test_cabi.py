@@ -150,3 +150,20 @@ def test_int32_dropin_analysis_gives_the_golden_structures(name, kind, N):
         assert np.array_equal(s[k][:len(g[k2])], g[k2]), k
     assert np.array_equal(permtab, g["permtab"])
     assert p.out()["fact_flops"] == g["fact_flops"] and p.out()["nnzeros"] == g["nnzeros"]
+
+
+def test_options_struct_layout_matches_the_python_binding(tmp_path):
+    """pb200_options_t (include/pastix_b200.h) as a C compiler lays it out against the ctypes mirror the harness uses:
+    same size, `owner` at the same offset (the struct grew a pointer in round 2 inside its reserved space)."""
+    import subprocess
+    from pastix_b200 import _lib
+    src = tmp_path / "o.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pastix_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu\\n", sizeof(pb200_options_t), offsetof(pb200_options_t, schur), '
+                   'offsetof(pb200_options_t, owner));return 0;}\n')
+    exe = tmp_path / "o"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    size, off_schur, off_owner = map(int, subprocess.check_output([str(exe)]).split())
+    assert size == C.sizeof(_lib.Options) == 32
+    assert off_schur == _lib.Options.schur.offset == 0
+    assert off_owner == _lib.Options.owner.offset == 8
